@@ -1,0 +1,24 @@
+# Builds libpaimon_gpu.so (sm_100a only) in-tree, and the parity oracle.
+NVCC ?= /usr/local/cuda/bin/nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Iinclude -Ipaimon_b200/csrc
+SRCS := paimon_b200/csrc/merge.cu paimon_b200/csrc/api.cu
+HDRS := include/paimon_gpu.h paimon_b200/csrc/pg_internal.h
+LIB := paimon_b200/libpaimon_gpu.so
+
+all: $(LIB) oracle
+
+$(LIB): $(SRCS) $(HDRS)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRCS)
+
+ptxas-info: $(SRCS) $(HDRS)
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c -o /dev/null paimon_b200/csrc/merge.cu
+
+oracle:
+	$(MAKE) -C oracle -s
+
+clean:
+	rm -f $(LIB)
+	$(MAKE) -C oracle clean
+
+.PHONY: all oracle clean ptxas-info

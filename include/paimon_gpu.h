@@ -1,0 +1,190 @@
+/*
+ * paimon_gpu.h — C ABI of libpaimon_gpu.so, the B200 (sm_100a) implementation of Apache
+ * Paimon's merge-on-read / compaction hot path:
+ *
+ *     sorted-run columnar batches -> k-way merge by (key, sequence) -> per-key MergeFunction
+ *
+ * This is the drop-in boundary.  Plain C, plain pointers and sizes, opaque
+ * uint64 handles, every call returns a status (0 = OK) and leaves a message for
+ * pg_last_error() otherwise; no C++/torch types cross it.  A JNI shim (jni/paimon_gpu_jni.cc)
+ * binds one Java native method per function; see INTEGRATION.md.
+ *
+ * Reference interfaces each entry point replaces (paths under /root/reference/):
+ *   pg_merge_spec_create  <- MergeFunctionFactory.create(readType)
+ *                            paimon-core/.../mergetree/compact/MergeFunctionFactory.java:29-41 and the
+ *                            option parsing in PartialUpdateMergeFunction.java:389-489,
+ *                            aggregate/AggregateMergeFunction.java:146-204
+ *   pg_run_open           <- one sorted run's RecordReader<KeyValue>:
+ *                            paimon-core/.../mergetree/MergeTreeReaders.java:94-101 (readerForRun)
+ *   pg_merge_open         <- SortMergeReader.createSortMergeReader(readers, keyComparator,
+ *                            userDefinedSeqComparator, mergeFunctionWrapper, sortEngine)
+ *                            paimon-core/.../mergetree/compact/SortMergeReader.java:41-57
+ *                            (+ DropDeleteReader, paimon-core/.../mergetree/DropDeleteReader.java:50-68)
+ *   pg_merge_execute/next <- RecordReader.readBatch()  paimon-common/.../reader/RecordReader.java:40-72;
+ *                            like SortMergeReaderWithLoserTree.java:67-73 the merge yields ONE batch
+ *   pg_merge_release      <- RecordIterator.releaseBatch()
+ *   pg_*_free             <- RecordReader.close()
+ *   pg_interval_partition <- IntervalPartition.partition()
+ *                            paimon-core/.../mergetree/compact/IntervalPartition.java:67-125
+ *   pg_parquet_*          <- FormatReaderFactory.createReader / FileRecordReader.readBatch
+ *                            paimon-common/.../format/FormatReaderFactory.java:33-57,
+ *                            paimon-format/.../parquet/ParquetReaderFactory.java:113-148
+ *
+ * Threading: the library is re-entrant across handles; one merge handle (one CUDA stream) per
+ * Java reader thread, like the reference's thread-confined readers.
+ */
+#ifndef PAIMON_GPU_H
+#define PAIMON_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_ABI_VERSION 1
+#define PG_MAX_RUNS 32          /* runs merged by one call; more => merge in rounds on the host */
+#define PG_MAX_KEY_FIELDS 4
+
+typedef int32_t pg_status;
+enum {
+    PG_OK = 0,
+    PG_ERR_INVALID = 1,         /* bad argument / handle */
+    PG_ERR_UNSUPPORTED = 2,     /* spec refused at plan time (no CPU fallback) */
+    PG_ERR_CUDA = 3,
+    PG_ERR_MERGE_FUNCTION = 4,  /* the Java MergeFunction would have thrown; message says which */
+    PG_ERR_INTERNAL = 5,
+    PG_ERR_FORMAT = 6           /* malformed / unsupported file bytes */
+};
+
+/* physical column types; Paimon DATE/TIME -> INT32, TIMESTAMP(p<=6)/DECIMAL(p<=18) -> INT64,
+ * CHAR/VARCHAR -> STRING, BINARY/VARBINARY -> BINARY, BOOLEAN -> one byte per value */
+typedef enum {
+    PG_INT8 = 1, PG_INT16 = 2, PG_INT32 = 3, PG_INT64 = 4,
+    PG_FLOAT = 5, PG_DOUBLE = 6, PG_BOOL = 7, PG_STRING = 8, PG_BINARY = 9
+} pg_type;
+
+/* RowKind.toByteValue, paimon-api/.../types/RowKind.java:35-56 */
+enum { PG_INSERT = 0, PG_UPDATE_BEFORE = 1, PG_UPDATE_AFTER = 2, PG_DELETE = 3 };
+
+/* CoreOptions.MergeEngine */
+enum { PG_ENGINE_DEDUPLICATE = 0, PG_ENGINE_PARTIAL_UPDATE = 1, PG_ENGINE_AGGREGATE = 2,
+       PG_ENGINE_FIRST_ROW = 3 };
+
+/* fields.<f>.aggregate-function */
+enum {
+    PG_AGG_NONE = 0, PG_AGG_SUM = 1, PG_AGG_PRODUCT = 2, PG_AGG_MAX = 3, PG_AGG_MIN = 4,
+    PG_AGG_BOOL_AND = 5, PG_AGG_BOOL_OR = 6, PG_AGG_LAST_VALUE = 7, PG_AGG_LAST_NON_NULL_VALUE = 8,
+    PG_AGG_FIRST_VALUE = 9, PG_AGG_FIRST_NON_NULL_VALUE = 10, PG_AGG_PRIMARY_KEY = 11
+};
+
+enum { PG_MEM_HOST = 0, PG_MEM_DEVICE = 1 };
+
+typedef struct {
+    int32_t type;       /* pg_type */
+    int32_t nullable;
+} pg_field;
+
+/* file schema [_KEY_*..., _SEQUENCE_NUMBER BIGINT, _VALUE_KIND TINYINT, value...]
+ * (paimon-core/.../KeyValue.java:130-138) */
+typedef struct {
+    int32_t n_key;
+    int32_t n_val;
+    const pg_field *key_fields;
+    const pg_field *val_fields;
+} pg_schema_desc;
+
+/* declarative MergeFunction: what the reference factories derive from table options */
+typedef struct {
+    int32_t engine;
+    int32_t ignore_delete;              /* 'ignore-delete' */
+    int32_t remove_record_on_delete;    /* partial-update.* / aggregation.remove-record-on-delete */
+    int32_t drop_delete;                /* wrap the merge in DropDeleteReader */
+    int32_t n_seq_fields;               /* 'sequence.field' (value-field indexes), 0 = none */
+    const int32_t *seq_fields;
+    int32_t seq_ascending;              /* 'sequence.field.sort-order' */
+    const int32_t *agg;                 /* [n_val] PG_AGG_*; NULL = all NONE */
+    const uint8_t *ignore_retract;      /* [n_val]; NULL = all false */
+    int32_t n_sequence_groups;          /* partial-update sequence groups; must be 0 in ABI v1 */
+} pg_merge_spec;
+
+/* one column, Arrow buffer layout */
+typedef struct {
+    const void *data;          /* fixed width: values[n_rows]; var-len: bytes */
+    const int32_t *offsets;    /* var-len: int32[n_rows + 1], else NULL */
+    const uint8_t *validity;   /* bitmap LSB-first, or NULL when the column has no nulls */
+} pg_column;
+
+typedef struct {
+    int64_t n_rows;
+    const pg_column *cols;     /* n_key + 2 + n_val columns in file order */
+} pg_run_desc;
+
+typedef struct {
+    void *data;
+    int32_t *offsets;
+    uint8_t *validity;         /* NULL for NOT NULL columns */
+    int64_t data_bytes;        /* bytes in data (var-len: payload bytes) */
+} pg_out_column;
+
+typedef struct {
+    int64_t n_rows;
+    int32_t n_cols;
+    const pg_out_column *cols; /* owned by the merge handle, valid until pg_merge_release/free */
+} pg_batch;
+
+typedef struct {
+    int64_t rows_in;
+    int64_t rows_out;
+    int64_t bytes_h2d;
+    int64_t bytes_d2h;
+    int64_t bytes_out;             /* device bytes of the output batch */
+    int32_t n_tiles;
+    int32_t n_levels;              /* sampled partition levels above level 0 */
+    float ms_partition;            /* CUDA-event times of the last execute, on the handle's stream */
+    float ms_plan;
+    float ms_emit;
+    float ms_total;
+    int32_t launches;              /* kernels launched by the last execute */
+} pg_stats;
+
+const char *pg_last_error(void);
+int32_t pg_abi_version(void);
+
+/* bind the calling thread's library state to a device; idempotent */
+pg_status pg_init(int32_t device_ordinal);
+pg_status pg_shutdown(void);
+
+pg_status pg_schema_create(const pg_schema_desc *desc, uint64_t *out_schema);
+pg_status pg_schema_free(uint64_t schema);
+
+pg_status pg_merge_spec_create(uint64_t schema, const pg_merge_spec *spec, uint64_t *out_spec);
+pg_status pg_merge_spec_free(uint64_t spec);
+
+/* Register one sorted run.  PG_MEM_HOST: the buffers are copied to the device now (they may be
+ * freed after the call).  PG_MEM_DEVICE: the pointers are device pointers that the caller keeps
+ * alive until pg_run_free. */
+pg_status pg_run_open(uint64_t schema, const pg_run_desc *run, int32_t mem, uint64_t *out_run);
+pg_status pg_run_free(uint64_t run);
+
+/* k-way merge of `k` runs (all of `schema`) with the merge function of `spec`. */
+pg_status pg_merge_open(uint64_t spec, const uint64_t *runs, int32_t k, uint64_t *out_merge);
+/* run the kernels; asynchronous on the handle's stream except for one size read-back */
+pg_status pg_merge_execute(uint64_t merge);
+/* the single output batch, device-resident (pointers are device pointers) */
+pg_status pg_merge_device_batch(uint64_t merge, pg_batch *out);
+/* copy the output batch into caller-allocated host buffers (sizes from pg_merge_device_batch) */
+pg_status pg_merge_fetch(uint64_t merge, const pg_out_column *host_cols, int32_t n_cols);
+pg_status pg_merge_release(uint64_t merge);      /* releaseBatch(): drop the output buffers */
+pg_status pg_merge_stats(uint64_t merge, pg_stats *out);
+pg_status pg_merge_stream(uint64_t merge, void **out_cuda_stream);
+pg_status pg_merge_free(uint64_t merge);
+
+/* IntervalPartition over int64 (min,max) key bounds of data files: section and run id per file */
+pg_status pg_interval_partition(int32_t n_files, const int64_t *min_key, const int64_t *max_key,
+                                int32_t *section_of, int32_t *run_of, int32_t *n_sections);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,797 @@
+// api.cu — host side of libpaimon_gpu.so: handle tables, plan-time validation of merge specs,
+// device descriptors, and the launch sequence of one merge (partition levels -> plan -> scan ->
+// emit).  Everything the Java side sees goes through the extern "C" functions at the bottom
+// (include/paimon_gpu.h).  There is no CPU fallback anywhere in this file: a spec the kernels do not
+// implement is refused with PG_ERR_UNSUPPORTED.
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <queue>
+#include <unordered_map>
+
+#include "pg_internal.h"
+
+namespace pg {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string &msg) { g_last_error = msg; }
+pg_status fail(pg_status code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+
+static int type_width(int t) {
+    switch (t) {
+        case PG_INT8: case PG_BOOL: return 1;
+        case PG_INT16: return 2;
+        case PG_INT32: case PG_FLOAT: return 4;
+        case PG_INT64: case PG_DOUBLE: return 8;
+        default: return 0;
+    }
+}
+static bool type_ok(int t) { return t >= PG_INT8 && t <= PG_BINARY; }
+static bool is_varlen(int t) { return t == PG_STRING || t == PG_BINARY; }
+
+struct Merge {
+    const Spec *spec = nullptr;
+    const Schema *schema = nullptr;
+    std::vector<const Run *> runs;
+    int k = 0;
+    int64_t n_in = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    KeyDesc key{};
+    MergeFlags flags{};
+    std::vector<ColDesc> cols;
+    std::vector<int32_t> varlen_cols;
+    // persistent device descriptors
+    void *d_desc = nullptr;            // one allocation holding all descriptor arrays
+    const void **d_key_ptrs = nullptr;
+    const int64_t **d_seq_ptrs = nullptr;
+    const int8_t **d_kind_ptrs = nullptr;
+    DevColumn *d_run_cols = nullptr;
+    ColDesc *d_cols = nullptr;
+    int32_t *d_varlen_cols = nullptr;
+    pg_out_column *d_out_cols = nullptr;
+    int64_t *d_totals = nullptr;       // [1 + n_varlen]
+    int32_t *d_err = nullptr;
+    // pinned host mirror of totals + err
+    int64_t *h_totals = nullptr;
+    int32_t *h_err = nullptr;
+    // output of the last execute
+    std::vector<pg_out_column> out_cols;
+    std::vector<void *> out_allocs;
+    int64_t n_out = 0;
+    bool has_batch = false;
+    pg_stats stats{};
+};
+
+// ------------------------------------------------------------------ handle tables
+
+template <typename T>
+struct Table {
+    std::mutex mu;
+    std::unordered_map<uint64_t, std::unique_ptr<T>> map;
+    uint64_t next = 1;
+    uint64_t tag;
+    explicit Table(uint64_t t) : tag(t << 56) {}
+    uint64_t put(std::unique_ptr<T> p) {
+        std::lock_guard<std::mutex> g(mu);
+        uint64_t h = tag | next++;
+        map[h] = std::move(p);
+        return h;
+    }
+    T *get(uint64_t h) {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = map.find(h);
+        return it == map.end() ? nullptr : it->second.get();
+    }
+    std::unique_ptr<T> take(uint64_t h) {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = map.find(h);
+        if (it == map.end()) return nullptr;
+        std::unique_ptr<T> p = std::move(it->second);
+        map.erase(it);
+        return p;
+    }
+};
+static Table<Schema> g_schemas(1);
+static Table<Spec> g_specs(2);
+static Table<Run> g_runs(3);
+static Table<Merge> g_merges(4);
+static int g_device = -1;
+
+static pg_status ensure_device() {
+    if (g_device < 0) return fail(PG_ERR_INVALID, "pg_init has not been called");
+    PG_CUDA(cudaSetDevice(g_device));
+    return PG_OK;
+}
+
+static void free_outputs(Merge *m) {
+    for (void *p : m->out_allocs) cudaFreeAsync(p, m->stream);
+    m->out_allocs.clear();
+    m->out_cols.clear();
+    m->has_batch = false;
+}
+
+static void destroy_merge(Merge *m) {
+    if (!m) return;
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    free_outputs(m);
+    if (m->d_desc) cudaFree(m->d_desc);
+    if (m->h_totals) cudaFreeHost(m->h_totals);
+    for (auto &e : m->ev) if (e) cudaEventDestroy(e);
+    if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
+}
+
+// ------------------------------------------------------------------ plan-time validation
+
+static bool agg_supports_retract(int agg) {
+    return agg == PG_AGG_SUM || agg == PG_AGG_PRODUCT || agg == PG_AGG_LAST_VALUE ||
+           agg == PG_AGG_LAST_NON_NULL_VALUE || agg == PG_AGG_PRIMARY_KEY;
+}
+
+static pg_status build_descriptors(Merge *m) {
+    const Schema *s = m->schema;
+    const Spec *sp = m->spec;
+    // key normalisation into one uint64
+    int bits = 0;
+    for (int f = 0; f < s->n_key; f++) {
+        int t = s->key_fields[f].type;
+        if (!(t == PG_INT8 || t == PG_INT16 || t == PG_INT32 || t == PG_INT64 || t == PG_BOOL))
+            return fail(PG_ERR_UNSUPPORTED, "primary-key type not implemented on the device merge path "
+                                            "(integer / date / time / timestamp / boolean keys only)");
+        bits += type_width(t) * 8;
+    }
+    if (s->n_key < 1 || s->n_key > PG_MAX_KEY_FIELDS || bits > 64)
+        return fail(PG_ERR_UNSUPPORTED, "composite primary key wider than 64 bits is not implemented");
+    m->key.n_fields = s->n_key;
+    int used = 0;
+    for (int f = 0; f < s->n_key; f++) {
+        int w = type_width(s->key_fields[f].type) * 8;
+        used += w;
+        m->key.type[f] = s->key_fields[f].type;
+        m->key.shift[f] = bits - used;
+    }
+    if (!sp->seq_fields.empty())
+        return fail(PG_ERR_UNSUPPORTED, "'sequence.field' (user defined sequence comparator) is not "
+                                        "implemented on the device merge path yet");
+    m->flags = MergeFlags{sp->engine, sp->ignore_delete, sp->remove_record_on_delete, sp->drop_delete};
+
+    const int nc = s->n_cols();
+    m->cols.assign(nc, ColDesc{});
+    m->varlen_cols.clear();
+    for (int c = 0; c < nc; c++) {
+        pg_field f = s->field(c);
+        ColDesc &cd = m->cols[c];
+        cd.type = f.type;
+        cd.width = type_width(f.type);
+        cd.nullable = f.nullable;
+        cd.agg = PG_AGG_NONE;
+        cd.retract = RT_OK;
+        cd.varlen_index = -1;
+        if (is_varlen(f.type)) {
+            cd.varlen_index = (int)m->varlen_cols.size();
+            m->varlen_cols.push_back(c);
+        }
+        if (c < s->n_key) { cd.mode = CM_KEY; cd.nullable = 0; }
+        else if (c == s->n_key) { cd.mode = CM_SEQ; cd.nullable = 0; }
+        else if (c == s->n_key + 1) { cd.mode = CM_KIND; cd.nullable = 0; }
+        else {
+            int vi = c - s->n_key - 2;
+            int agg = sp->agg.empty() ? PG_AGG_NONE : sp->agg[vi];
+            bool ign = !sp->ignore_retract.empty() && sp->ignore_retract[vi];
+            if (sp->engine == PG_ENGINE_AGGREGATE) {
+                if (agg == PG_AGG_NONE) agg = PG_AGG_LAST_NON_NULL_VALUE;   // AggregateMergeFunction.java:199-202
+                bool numeric = f.type == PG_INT8 || f.type == PG_INT16 || f.type == PG_INT32 ||
+                               f.type == PG_INT64 || f.type == PG_FLOAT || f.type == PG_DOUBLE;
+                if ((agg == PG_AGG_SUM || agg == PG_AGG_PRODUCT) && !numeric)
+                    return fail(PG_ERR_INVALID, "sum/product need a numeric column");
+                if ((agg == PG_AGG_BOOL_AND || agg == PG_AGG_BOOL_OR) && f.type != PG_BOOL)
+                    return fail(PG_ERR_INVALID, "bool_and/bool_or need a BOOLEAN column");
+                if ((agg == PG_AGG_MAX || agg == PG_AGG_MIN) && f.type == PG_BOOL)
+                    return fail(PG_ERR_INVALID, "Incomparable type: BOOLEAN");
+                if (agg < PG_AGG_SUM || agg > PG_AGG_PRIMARY_KEY)
+                    return fail(PG_ERR_UNSUPPORTED, "aggregate function not implemented on the device");
+                cd.mode = CM_FOLD;
+                cd.agg = agg;
+                cd.retract = ign ? RT_IGNORE : (agg_supports_retract(agg) ? RT_OK : RT_ERROR);
+            } else {
+                if (sp->engine == PG_ENGINE_PARTIAL_UPDATE && agg != PG_AGG_NONE &&
+                    agg != PG_AGG_LAST_NON_NULL_VALUE && agg != PG_AGG_PRIMARY_KEY)
+                    return fail(PG_ERR_INVALID, "Must use sequence group for aggregation functions");
+                cd.mode = CM_SELECT;
+            }
+        }
+    }
+
+    // one device allocation for all descriptor arrays
+    const int k = m->k, nk = s->n_key, nv = (int)m->varlen_cols.size();
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t o_key = 0;
+    size_t o_seq = o_key + align(sizeof(void *) * k * nk);
+    size_t o_kind = o_seq + align(sizeof(void *) * k);
+    size_t o_rc = o_kind + align(sizeof(void *) * k);
+    size_t o_cols = o_rc + align(sizeof(DevColumn) * (size_t)k * nc);
+    size_t o_vl = o_cols + align(sizeof(ColDesc) * nc);
+    size_t o_out = o_vl + align(sizeof(int32_t) * (nv + 1));
+    size_t o_tot = o_out + align(sizeof(pg_out_column) * nc);
+    size_t o_err = o_tot + align(sizeof(int64_t) * (nv + 1));
+    size_t total = o_err + 256;
+    std::vector<unsigned char> host(total, 0);
+    for (int r = 0; r < k; r++) {
+        const Run *run = m->runs[r];
+        for (int f = 0; f < nk; f++) ((const void **)(host.data() + o_key))[r * nk + f] = run->cols[f].data;
+        ((const void **)(host.data() + o_seq))[r] = run->cols[nk].data;
+        ((const void **)(host.data() + o_kind))[r] = run->cols[nk + 1].data;
+        for (int c = 0; c < nc; c++) ((DevColumn *)(host.data() + o_rc))[(size_t)r * nc + c] = run->cols[c];
+    }
+    memcpy(host.data() + o_cols, m->cols.data(), sizeof(ColDesc) * nc);
+    if (nv) memcpy(host.data() + o_vl, m->varlen_cols.data(), sizeof(int32_t) * nv);
+    PG_CUDA(cudaMalloc(&m->d_desc, total));
+    PG_CUDA(cudaMemcpy(m->d_desc, host.data(), total, cudaMemcpyHostToDevice));
+    unsigned char *d = (unsigned char *)m->d_desc;
+    m->d_key_ptrs = (const void **)(d + o_key);
+    m->d_seq_ptrs = (const int64_t **)(d + o_seq);
+    m->d_kind_ptrs = (const int8_t **)(d + o_kind);
+    m->d_run_cols = (DevColumn *)(d + o_rc);
+    m->d_cols = (ColDesc *)(d + o_cols);
+    m->d_varlen_cols = (int32_t *)(d + o_vl);
+    m->d_out_cols = (pg_out_column *)(d + o_out);
+    m->d_totals = (int64_t *)(d + o_tot);
+    m->d_err = (int32_t *)(d + o_err);
+    PG_CUDA(cudaMallocHost((void **)&m->h_totals, sizeof(int64_t) * (nv + 1) + 16));
+    m->h_err = (int32_t *)(m->h_totals + nv + 1);
+    return PG_OK;
+}
+
+static const char *kernel_error_message(int code) {
+    switch (code) {
+        case KERR_TILE_OVERFLOW:
+            return "internal: a merge tile overflowed (does a run contain duplicate keys? "
+                   "SortMergeReader.java:37 requires unique keys per reader)";
+        case KERR_PU_DELETE:
+            return "By default, Partial update can not accept delete records, you can choose one of the "
+                   "following solutions:\n1. Configure 'ignore-delete' to ignore delete records.\n"
+                   "2. Configure 'partial-update.remove-record-on-delete' to remove the whole row when "
+                   "receiving delete records.\n3. Configure 'sequence-group's to retract partial columns. "
+                   "Also configure 'partial-update.remove-record-on-sequence-group' to remove the whole "
+                   "row when receiving deleted records of `specified sequence group`.";
+        case KERR_FIRST_ROW_RETRACT:
+            return "By default, First row merge engine can not accept DELETE/UPDATE_BEFORE records.\n"
+                   "You can config 'ignore-delete' to ignore the DELETE/UPDATE_BEFORE records.";
+        case KERR_AGG_RETRACT:
+            return "Aggregate function does not support retraction, If you allow this function to ignore "
+                   "retraction messages, you can configure 'fields.${field_name}.ignore-retract'='true'.";
+        case KERR_OFFSET_OVERFLOW:
+            return "a var-len output column exceeds 2 GiB (int32 offsets); merge fewer rows per call";
+        case KERR_DIV_ZERO:
+            return "ArithmeticException: / by zero";
+        default:
+            return "unknown kernel error";
+    }
+}
+
+// ------------------------------------------------------------------ one merge
+
+static pg_status execute(Merge *m) {
+    pg_status st = ensure_device();
+    if (st) return st;
+    cudaStream_t sm = m->stream;
+    free_outputs(m);
+    const Schema *s = m->schema;
+    const int k = m->k, nc = s->n_cols(), nv = (int)m->varlen_cols.size();
+    m->stats = pg_stats{};
+    m->stats.rows_in = m->n_in;
+    int launches = 0;
+
+    // ---- level sizes
+    const int S = kSampleStride;
+    const int q = kTileMax / S - 2 * k;
+    if (q < 1) return fail(PG_ERR_UNSUPPORTED, "too many runs for one merge call");
+    std::vector<LevelView> views;
+    std::vector<int64_t> level_total;
+    {
+        int64_t stride = 1;
+        while (true) {
+            LevelView lv{};
+            lv.stride = stride;
+            int64_t tot = 0;
+            for (int r = 0; r < k; r++) { lv.count[r] = m->runs[r]->n_rows / stride; tot += lv.count[r]; }
+            views.push_back(lv);
+            level_total.push_back(tot);
+            if (tot <= kTileMax) break;
+            stride *= S;
+        }
+    }
+    const int top = (int)views.size() - 1;
+    std::vector<int> n_tiles(top + 1);
+    n_tiles[top] = 1;
+    for (int l = top - 1; l >= 0; l--) n_tiles[l] = (int)((level_total[l + 1] + q - 1) / q);
+    m->stats.n_levels = top;
+    m->stats.n_tiles = n_tiles[0];
+
+    PG_CUDA(cudaMemsetAsync(m->d_err, 0, sizeof(int32_t), sm));
+    PG_CUDA(cudaEventRecord(m->ev[0], sm));
+
+    MergeLaunch ml{k, m->key, m->d_key_ptrs, sm, m->d_err};
+    std::vector<void *> temps;
+    auto talloc = [&](size_t bytes, void **out) -> cudaError_t {
+        cudaError_t e = cudaMallocAsync(out, bytes ? bytes : 16, sm);
+        if (e == cudaSuccess) temps.push_back(*out);
+        return e;
+    };
+    auto free_temps = [&]() { for (void *p : temps) cudaFreeAsync(p, sm); temps.clear(); };
+
+    int64_t *bounds0 = nullptr;
+    uint64_t *sk_above = nullptr;         // sorted sample keys of the level above the current one
+    for (int l = top; l >= 0; l--) {
+        int64_t *bounds = nullptr;
+        PG_CUDA(talloc(sizeof(int64_t) * (size_t)(n_tiles[l] + 1) * k, (void **)&bounds));
+        launch_partition(ml, views[l], sk_above, l == top ? 0 : level_total[l + 1], q, n_tiles[l], bounds);
+        launches++;
+        if (l > 0) {
+            uint64_t *sk = nullptr;
+            PG_CUDA(talloc(sizeof(uint64_t) * (size_t)std::max<int64_t>(level_total[l], 1), (void **)&sk));
+            launch_merge_keys(ml, views[l], bounds, n_tiles[l], sk);
+            launches++;
+            sk_above = sk;
+        } else {
+            bounds0 = bounds;
+        }
+    }
+    PG_CUDA(cudaEventRecord(m->ev[1], sm));
+
+    // ---- plan + scan
+    const int T = n_tiles[0];
+    const int64_t N = m->n_in;
+    uint16_t *plan = nullptr;
+    int32_t *tile_rows = nullptr, *tile_bytes = nullptr;
+    int64_t *tmp_seq = nullptr, *row_base = nullptr, *byte_base = nullptr;
+    int8_t *tmp_kind = nullptr;
+    PG_CUDA(talloc(sizeof(uint16_t) * (size_t)N + 16, (void **)&plan));
+    PG_CUDA(talloc(sizeof(int32_t) * (size_t)T, (void **)&tile_rows));
+    PG_CUDA(talloc(sizeof(int32_t) * (size_t)T * std::max(nv, 1), (void **)&tile_bytes));
+    PG_CUDA(talloc(sizeof(int64_t) * (size_t)N + 16, (void **)&tmp_seq));
+    PG_CUDA(talloc((size_t)N + 16, (void **)&tmp_kind));
+    PG_CUDA(talloc(sizeof(int64_t) * (size_t)T, (void **)&row_base));
+    PG_CUDA(talloc(sizeof(int64_t) * (size_t)T * std::max(nv, 1), (void **)&byte_base));
+
+    PlanArgs pa{};
+    pa.bounds = bounds0;
+    pa.n_tiles = T;
+    pa.seq_ptrs = m->d_seq_ptrs;
+    pa.kind_ptrs = m->d_kind_ptrs;
+    pa.flags = m->flags;
+    pa.n_varlen = nv;
+    pa.varlen_cols = m->d_varlen_cols;
+    pa.cols = m->d_cols;
+    pa.run_cols = m->d_run_cols;
+    pa.n_cols = nc;
+    pa.plan = plan;
+    pa.tile_rows = tile_rows;
+    pa.tile_bytes = tile_bytes;
+    pa.tmp_seq = tmp_seq;
+    pa.tmp_kind = tmp_kind;
+    launch_plan(ml, pa);
+    launch_scan(sm, tile_rows, tile_bytes, T, nv, row_base, byte_base, m->d_totals, m->d_err);
+    launches += 2;
+    PG_CUDA(cudaEventRecord(m->ev[2], sm));
+    PG_CUDA(cudaMemcpyAsync(m->h_totals, m->d_totals, sizeof(int64_t) * (nv + 1), cudaMemcpyDeviceToHost, sm));
+    PG_CUDA(cudaMemcpyAsync(m->h_err, m->d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, sm));
+    PG_CUDA(cudaStreamSynchronize(sm));      // the one size read-back: output buffers are sized exactly
+    if (*m->h_err != KERR_NONE) {
+        free_temps();
+        return fail(*m->h_err == KERR_TILE_OVERFLOW || *m->h_err == KERR_OFFSET_OVERFLOW ? PG_ERR_INTERNAL
+                                                                                        : PG_ERR_MERGE_FUNCTION,
+                    kernel_error_message(*m->h_err));
+    }
+
+    // ---- output buffers
+    const int64_t n_out = m->h_totals[0];
+    m->n_out = n_out;
+    m->out_cols.assign(nc, pg_out_column{});
+    int64_t bytes_out = 0;
+    auto oalloc = [&](size_t bytes, void **out) -> cudaError_t {
+        cudaError_t e = cudaMallocAsync(out, bytes, sm);
+        if (e == cudaSuccess) m->out_allocs.push_back(*out);
+        return e;
+    };
+    for (int c = 0; c < nc; c++) {
+        const ColDesc &cd = m->cols[c];
+        pg_out_column &oc = m->out_cols[c];
+        if (cd.width > 0) {
+            oc.data_bytes = n_out * cd.width;
+            PG_CUDA(oalloc((size_t)oc.data_bytes + 64, &oc.data));
+        } else {
+            oc.data_bytes = m->h_totals[1 + cd.varlen_index];
+            PG_CUDA(oalloc((size_t)oc.data_bytes + 64, &oc.data));
+            PG_CUDA(oalloc(sizeof(int32_t) * (size_t)(n_out + 1) + 64, (void **)&oc.offsets));
+            bytes_out += 4 * (n_out + 1);
+        }
+        bytes_out += oc.data_bytes;
+        if (cd.nullable) {
+            size_t vb = (size_t)((n_out + 31) / 32) * 4 + 64;
+            PG_CUDA(oalloc(vb, (void **)&oc.validity));
+            PG_CUDA(cudaMemsetAsync(oc.validity, 0, vb, sm));
+            bytes_out += (n_out + 7) / 8;
+        }
+    }
+    m->stats.bytes_out = bytes_out;
+    PG_CUDA(cudaMemcpyAsync(m->d_out_cols, m->out_cols.data(), sizeof(pg_out_column) * nc,
+                            cudaMemcpyHostToDevice, sm));
+
+    // ---- emit
+    EmitArgs ea{};
+    ea.bounds = bounds0;
+    ea.n_tiles = T;
+    ea.k = k;
+    ea.n_key = s->n_key;
+    ea.plan = plan;
+    ea.row_base = row_base;
+    ea.byte_base = byte_base;
+    ea.tmp_seq = tmp_seq;
+    ea.tmp_kind = tmp_kind;
+    ea.cols = m->d_cols;
+    ea.run_cols = m->d_run_cols;
+    ea.n_cols = nc;
+    ea.out_cols = m->d_out_cols;
+    ea.totals = m->d_totals;
+    ea.err = m->d_err;
+    ea.stream = sm;
+    launch_emit(ea);
+    launches++;
+    PG_CUDA(cudaEventRecord(m->ev[3], sm));
+    PG_CUDA(cudaMemcpyAsync(m->h_err, m->d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, sm));
+    free_temps();
+    PG_CUDA(cudaStreamSynchronize(sm));
+    PG_CUDA(cudaGetLastError());
+    m->has_batch = true;
+    if (*m->h_err != KERR_NONE) {
+        free_outputs(m);
+        return fail(PG_ERR_MERGE_FUNCTION, kernel_error_message(*m->h_err));
+    }
+    m->stats.rows_out = n_out;
+    m->stats.launches = launches;
+    cudaEventElapsedTime(&m->stats.ms_partition, m->ev[0], m->ev[1]);
+    cudaEventElapsedTime(&m->stats.ms_plan, m->ev[1], m->ev[2]);
+    cudaEventElapsedTime(&m->stats.ms_emit, m->ev[2], m->ev[3]);
+    cudaEventElapsedTime(&m->stats.ms_total, m->ev[0], m->ev[3]);
+    return PG_OK;
+}
+
+}  // namespace pg
+
+// ====================================================================== C ABI
+
+using namespace pg;
+
+extern "C" {
+
+const char *pg_last_error(void) { return g_last_error.c_str(); }
+int32_t pg_abi_version(void) { return PG_ABI_VERSION; }
+
+pg_status pg_init(int32_t device_ordinal) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(PG_ERR_CUDA, std::string("no CUDA device: libpaimon_gpu has no CPU fallback (") +
+                                     cudaGetErrorString(e) + ")");
+    if (device_ordinal < 0 || device_ordinal >= n) return fail(PG_ERR_INVALID, "bad device ordinal");
+    PG_CUDA(cudaSetDevice(device_ordinal));
+    g_device = device_ordinal;
+    cudaMemPool_t pool;
+    PG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device_ordinal));
+    uint64_t thr = UINT64_MAX;                 // keep freed blocks cached: steady-state merges do not hit the driver
+    PG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    return PG_OK;
+}
+
+pg_status pg_shutdown(void) {
+    if (g_device >= 0) {
+        cudaSetDevice(g_device);
+        cudaDeviceSynchronize();
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, g_device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    }
+    return PG_OK;
+}
+
+pg_status pg_schema_create(const pg_schema_desc *desc, uint64_t *out_schema) {
+    if (!desc || !out_schema) return fail(PG_ERR_INVALID, "null argument");
+    if (desc->n_key < 1 || desc->n_val < 0 || desc->n_key + 2 + desc->n_val > kMaxCols)
+        return fail(PG_ERR_INVALID, "bad field counts");
+    auto s = std::make_unique<Schema>();
+    s->n_key = desc->n_key;
+    s->n_val = desc->n_val;
+    for (int i = 0; i < desc->n_key; i++) {
+        if (!type_ok(desc->key_fields[i].type)) return fail(PG_ERR_INVALID, "bad key field type");
+        s->key_fields.push_back(pg_field{desc->key_fields[i].type, 0});
+    }
+    for (int i = 0; i < desc->n_val; i++) {
+        if (!type_ok(desc->val_fields[i].type)) return fail(PG_ERR_INVALID, "bad value field type");
+        s->val_fields.push_back(desc->val_fields[i]);
+    }
+    *out_schema = g_schemas.put(std::move(s));
+    return PG_OK;
+}
+
+pg_status pg_schema_free(uint64_t schema) {
+    return g_schemas.take(schema) ? PG_OK : fail(PG_ERR_INVALID, "unknown schema handle");
+}
+
+pg_status pg_merge_spec_create(uint64_t schema, const pg_merge_spec *spec, uint64_t *out_spec) {
+    Schema *s = g_schemas.get(schema);
+    if (!s || !spec || !out_spec) return fail(PG_ERR_INVALID, "bad schema handle or null argument");
+    if (spec->engine < PG_ENGINE_DEDUPLICATE || spec->engine > PG_ENGINE_FIRST_ROW)
+        return fail(PG_ERR_INVALID, "Unsupported merge engine");
+    if (spec->n_sequence_groups != 0)
+        return fail(PG_ERR_UNSUPPORTED, "partial-update sequence groups are not implemented on the device "
+                                        "merge path yet");
+    auto sp = std::make_unique<Spec>();
+    sp->schema_h = schema;
+    sp->schema = s;
+    sp->engine = spec->engine;
+    sp->ignore_delete = spec->ignore_delete != 0;
+    sp->remove_record_on_delete = spec->remove_record_on_delete != 0;
+    sp->drop_delete = spec->drop_delete != 0;
+    sp->seq_ascending = spec->seq_ascending;
+    for (int i = 0; i < spec->n_seq_fields; i++) sp->seq_fields.push_back(spec->seq_fields[i]);
+    if (spec->agg) sp->agg.assign(spec->agg, spec->agg + s->n_val);
+    if (spec->ignore_retract) sp->ignore_retract.assign(spec->ignore_retract, spec->ignore_retract + s->n_val);
+    if (sp->engine == PG_ENGINE_PARTIAL_UPDATE && sp->ignore_delete && sp->remove_record_on_delete)
+        return fail(PG_ERR_INVALID, "ignore-delete and partial-update.remove-record-on-delete have conflicting "
+                                    "behavior so should not be enabled at the same time.");
+    *out_spec = g_specs.put(std::move(sp));
+    return PG_OK;
+}
+
+pg_status pg_merge_spec_free(uint64_t spec) {
+    return g_specs.take(spec) ? PG_OK : fail(PG_ERR_INVALID, "unknown spec handle");
+}
+
+pg_status pg_run_open(uint64_t schema, const pg_run_desc *desc, int32_t mem, uint64_t *out_run) {
+    Schema *s = g_schemas.get(schema);
+    if (!s || !desc || !out_run) return fail(PG_ERR_INVALID, "bad schema handle or null argument");
+    if (desc->n_rows < 0 || desc->n_rows > 0x7fffffffLL) return fail(PG_ERR_INVALID, "bad row count");
+    pg_status st = ensure_device();
+    if (st) return st;
+    auto run = std::make_unique<Run>();
+    run->schema = s;
+    run->n_rows = desc->n_rows;
+    const int nc = s->n_cols();
+    const int64_t n = desc->n_rows;
+    run->cols.resize(nc);
+    if (mem == PG_MEM_DEVICE) {
+        for (int c = 0; c < nc; c++)
+            run->cols[c] = DevColumn{desc->cols[c].data, desc->cols[c].offsets, desc->cols[c].validity};
+    } else if (mem == PG_MEM_HOST) {
+        // one device allocation per run, columns sub-allocated at 256-byte boundaries
+        auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        std::vector<size_t> o_data(nc), o_off(nc), o_val(nc), b_data(nc), b_off(nc), b_val(nc);
+        size_t total = 0;
+        for (int c = 0; c < nc; c++) {
+            pg_field f = s->field(c);
+            const pg_column &pc = desc->cols[c];
+            if (is_varlen(f.type)) {
+                if (n > 0 && !pc.offsets) return fail(PG_ERR_INVALID, "var-len column without offsets");
+                b_off[c] = sizeof(int32_t) * (size_t)(n + 1);
+                b_data[c] = n > 0 ? (size_t)pc.offsets[n] : 0;
+            } else {
+                b_off[c] = 0;
+                b_data[c] = (size_t)n * type_width(f.type);
+            }
+            b_val[c] = pc.validity ? (size_t)((n + 7) / 8) : 0;
+            o_data[c] = total; total += align(b_data[c] + 16);
+            o_off[c] = total; total += align(b_off[c]);
+            o_val[c] = total; total += align(b_val[c] + 8);
+        }
+        void *base = nullptr;
+        PG_CUDA(cudaMalloc(&base, total + 256));
+        run->owned.push_back(base);
+        unsigned char *d = (unsigned char *)base;
+        for (int c = 0; c < nc; c++) {
+            const pg_column &pc = desc->cols[c];
+            DevColumn dc;
+            dc.data = d + o_data[c];
+            if (b_data[c]) PG_CUDA(cudaMemcpyAsync(d + o_data[c], pc.data, b_data[c], cudaMemcpyHostToDevice, 0));
+            if (b_off[c]) {
+                dc.offsets = (const int32_t *)(d + o_off[c]);
+                if (n >= 0 && pc.offsets)
+                    PG_CUDA(cudaMemcpyAsync(d + o_off[c], pc.offsets, b_off[c], cudaMemcpyHostToDevice, 0));
+            }
+            if (b_val[c]) {
+                dc.validity = d + o_val[c];
+                PG_CUDA(cudaMemcpyAsync(d + o_val[c], pc.validity, b_val[c], cudaMemcpyHostToDevice, 0));
+            }
+            run->bytes_h2d += (int64_t)(b_data[c] + b_off[c] + b_val[c]);
+            run->cols[c] = dc;
+        }
+        PG_CUDA(cudaStreamSynchronize(0));
+    } else {
+        return fail(PG_ERR_INVALID, "bad memory kind");
+    }
+    *out_run = g_runs.put(std::move(run));
+    return PG_OK;
+}
+
+pg_status pg_run_free(uint64_t run) {
+    auto r = g_runs.take(run);
+    if (!r) return fail(PG_ERR_INVALID, "unknown run handle");
+    for (void *p : r->owned) cudaFree(p);
+    return PG_OK;
+}
+
+pg_status pg_merge_open(uint64_t spec, const uint64_t *runs, int32_t k, uint64_t *out_merge) {
+    Spec *sp = g_specs.get(spec);
+    if (!sp || !out_merge || (k > 0 && !runs)) return fail(PG_ERR_INVALID, "bad spec handle or null argument");
+    if (k < 0) return fail(PG_ERR_INVALID, "negative run count");
+    if (k > PG_MAX_RUNS)
+        return fail(PG_ERR_UNSUPPORTED, "more than PG_MAX_RUNS runs in one merge call");
+    pg_status st = ensure_device();
+    if (st) return st;
+    std::unique_ptr<Merge> m(new Merge());
+    m->spec = sp;
+    m->schema = sp->schema;
+    for (int i = 0; i < k; i++) {
+        Run *r = g_runs.get(runs[i]);
+        if (!r) return fail(PG_ERR_INVALID, "unknown run handle");
+        if (r->schema != sp->schema) return fail(PG_ERR_INVALID, "run and spec use different schemas");
+        if (r->n_rows == 0) continue;            // exhausted readers are legal (SortMergeReaderTestBase.java:53-56)
+        m->runs.push_back(r);
+        m->n_in += r->n_rows;
+        m->stats.bytes_h2d += r->bytes_h2d;
+    }
+    m->k = (int)m->runs.size();
+    PG_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    for (auto &e : m->ev) PG_CUDA(cudaEventCreate(&e));
+    if (m->k > 0) {
+        st = build_descriptors(m.get());
+        if (st) { destroy_merge(m.get()); return st; }
+    } else {
+        // still validate the spec so that unsupported specs are refused even for empty inputs
+        m->k = 0;
+    }
+    *out_merge = g_merges.put(std::move(m));
+    return PG_OK;
+}
+
+pg_status pg_merge_execute(uint64_t merge) {
+    Merge *m = g_merges.get(merge);
+    if (!m) return fail(PG_ERR_INVALID, "unknown merge handle");
+    if (m->k == 0 || m->n_in == 0) {
+        // no input rows: one empty batch
+        free_outputs(m);
+        m->n_out = 0;
+        m->out_cols.assign(m->schema->n_cols(), pg_out_column{});
+        m->has_batch = true;
+        m->stats = pg_stats{};
+        return PG_OK;
+    }
+    int64_t h2d = m->stats.bytes_h2d;
+    pg_status st = execute(m);
+    m->stats.bytes_h2d = h2d;
+    return st;
+}
+
+pg_status pg_merge_device_batch(uint64_t merge, pg_batch *out) {
+    Merge *m = g_merges.get(merge);
+    if (!m || !out) return fail(PG_ERR_INVALID, "unknown merge handle");
+    if (!m->has_batch) return fail(PG_ERR_INVALID, "no batch: call pg_merge_execute first");
+    out->n_rows = m->n_out;
+    out->n_cols = (int32_t)m->out_cols.size();
+    out->cols = m->out_cols.data();
+    return PG_OK;
+}
+
+pg_status pg_merge_fetch(uint64_t merge, const pg_out_column *host_cols, int32_t n_cols) {
+    Merge *m = g_merges.get(merge);
+    if (!m || !host_cols) return fail(PG_ERR_INVALID, "unknown merge handle");
+    if (!m->has_batch) return fail(PG_ERR_INVALID, "no batch: call pg_merge_execute first");
+    if (n_cols != (int32_t)m->out_cols.size()) return fail(PG_ERR_INVALID, "column count mismatch");
+    pg_status st = ensure_device();
+    if (st) return st;
+    const int64_t n = m->n_out;
+    int64_t bytes = 0;
+    for (int c = 0; c < n_cols && n > 0; c++) {
+        const pg_out_column &oc = m->out_cols[c];
+        const pg_out_column &hc = host_cols[c];
+        if (oc.data_bytes && hc.data) {
+            PG_CUDA(cudaMemcpyAsync(hc.data, oc.data, (size_t)oc.data_bytes, cudaMemcpyDeviceToHost, m->stream));
+            bytes += oc.data_bytes;
+        }
+        if (oc.offsets && hc.offsets) {
+            PG_CUDA(cudaMemcpyAsync(hc.offsets, oc.offsets, sizeof(int32_t) * (size_t)(n + 1),
+                                    cudaMemcpyDeviceToHost, m->stream));
+            bytes += 4 * (n + 1);
+        }
+        if (oc.validity && hc.validity) {
+            PG_CUDA(cudaMemcpyAsync(hc.validity, oc.validity, (size_t)((n + 7) / 8), cudaMemcpyDeviceToHost,
+                                    m->stream));
+            bytes += (n + 7) / 8;
+        }
+    }
+    PG_CUDA(cudaStreamSynchronize(m->stream));
+    m->stats.bytes_d2h = bytes;
+    return PG_OK;
+}
+
+pg_status pg_merge_release(uint64_t merge) {
+    Merge *m = g_merges.get(merge);
+    if (!m) return fail(PG_ERR_INVALID, "unknown merge handle");
+    if (ensure_device() == PG_OK) free_outputs(m);
+    return PG_OK;
+}
+
+pg_status pg_merge_stats(uint64_t merge, pg_stats *out) {
+    Merge *m = g_merges.get(merge);
+    if (!m || !out) return fail(PG_ERR_INVALID, "unknown merge handle");
+    *out = m->stats;
+    return PG_OK;
+}
+
+pg_status pg_merge_stream(uint64_t merge, void **out_cuda_stream) {
+    Merge *m = g_merges.get(merge);
+    if (!m || !out_cuda_stream) return fail(PG_ERR_INVALID, "unknown merge handle");
+    *out_cuda_stream = (void *)m->stream;
+    return PG_OK;
+}
+
+pg_status pg_merge_free(uint64_t merge) {
+    auto m = g_merges.take(merge);
+    if (!m) return fail(PG_ERR_INVALID, "unknown merge handle");
+    if (g_device >= 0) cudaSetDevice(g_device);
+    destroy_merge(m.get());
+    return PG_OK;
+}
+
+// IntervalPartition.partition(), paimon-core/.../mergetree/compact/IntervalPartition.java:67-125.
+// Host logic: it only looks at file key bounds ("negligible; stays on host").
+pg_status pg_interval_partition(int32_t n_files, const int64_t *min_key, const int64_t *max_key,
+                                int32_t *section_of, int32_t *run_of, int32_t *n_sections) {
+    if (n_files < 0 || (n_files > 0 && (!min_key || !max_key || !section_of || !run_of)) || !n_sections)
+        return fail(PG_ERR_INVALID, "null argument");
+    std::vector<int> order(n_files);
+    for (int i = 0; i < n_files; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        if (min_key[a] != min_key[b]) return min_key[a] < min_key[b];
+        return max_key[a] < max_key[b];
+    });
+    int sections = 0;
+    size_t begin = 0;
+    auto close_section = [&](size_t b, size_t e) {
+        // runs ordered by the max key of their last file; the smallest takes the next file if it fits
+        using Item = std::pair<int64_t, int>;                 // (last max key, run id)
+        std::priority_queue<Item, std::vector<Item>, std::greater<Item>> heap;
+        int n_runs = 0;
+        for (size_t i = b; i < e; i++) {
+            int f = order[i];
+            if (!heap.empty() && min_key[f] > heap.top().first) {
+                Item top = heap.top();
+                heap.pop();
+                run_of[f] = top.second;
+                heap.push(Item(max_key[f], top.second));
+            } else {
+                run_of[f] = n_runs;
+                heap.push(Item(max_key[f], n_runs++));
+            }
+            section_of[f] = sections;
+        }
+        sections++;
+    };
+    int64_t bound = 0;
+    for (size_t i = 0; i < (size_t)n_files; i++) {
+        int f = order[i];
+        if (i > begin && min_key[f] > bound) {
+            close_section(begin, i);
+            begin = i;
+        }
+        if (i == begin || max_key[f] > bound) bound = max_key[f];
+    }
+    if ((size_t)n_files > begin) close_section(begin, n_files);
+    *n_sections = sections;
+    return PG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,178 @@
+// Internal declarations shared by the translation units of libpaimon_gpu.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "paimon_gpu.h"
+
+namespace pg {
+
+constexpr int kTileMax = 4096;       // rows merged by one CTA (shared-memory tile)
+constexpr int kSampleStride = 32;    // S: every S-th key of a level is a sample of the next level
+constexpr int kThreads = 256;
+constexpr int kMaxCols = 256;
+
+// ---- plan entry (one uint16 per merged input position) ----
+// bits 0..11 slot inside the tile (source order: run-major), bits 12..13 member op,
+// bit 14 group emits an output row (on the head), bit 15 first member of a key group
+constexpr uint16_t kPlanSlotMask = 0x0FFF;
+constexpr int kPlanOpShift = 12;
+constexpr uint16_t kPlanEmit = 0x4000;
+constexpr uint16_t kPlanHead = 0x8000;
+enum : int { OP_NOOP = 0, OP_UPD = 1, OP_SET = 2, OP_RETRACT = 3 };
+
+// error codes raised by kernels (first one wins), decoded in api.cu
+enum : int {
+    KERR_NONE = 0,
+    KERR_TILE_OVERFLOW = 1,          // internal: a tile exceeded kTileMax (duplicate keys inside a run?)
+    KERR_PU_DELETE = 2,              // PartialUpdateMergeFunction.java:155-164
+    KERR_FIRST_ROW_RETRACT = 3,      // FirstRowMergeFunction.java:56-60
+    KERR_AGG_RETRACT = 4,            // FieldAggregator.java:47-54
+    KERR_OFFSET_OVERFLOW = 5,        // a var-len output column exceeds int32 offsets
+    KERR_DIV_ZERO = 6                // FieldProductAgg retract: integer division by zero
+};
+
+struct Schema {
+    int n_key = 0, n_val = 0;
+    std::vector<pg_field> key_fields, val_fields;
+    int n_cols() const { return n_key + 2 + n_val; }
+    pg_field field(int c) const {
+        if (c < n_key) return key_fields[c];
+        if (c == n_key) return pg_field{PG_INT64, 0};
+        if (c == n_key + 1) return pg_field{PG_INT8, 0};
+        return val_fields[c - n_key - 2];
+    }
+};
+
+struct Spec {
+    uint64_t schema_h = 0;
+    const Schema *schema = nullptr;
+    int engine = 0, ignore_delete = 0, remove_record_on_delete = 0, drop_delete = 0;
+    std::vector<int32_t> seq_fields;
+    int seq_ascending = 1;
+    std::vector<int32_t> agg;            // per value field
+    std::vector<uint8_t> ignore_retract;
+};
+
+struct DevColumn {
+    const void *data = nullptr;
+    const int32_t *offsets = nullptr;
+    const uint8_t *validity = nullptr;
+};
+
+struct Run {
+    const Schema *schema = nullptr;
+    int64_t n_rows = 0;
+    std::vector<DevColumn> cols;
+    std::vector<void *> owned;           // device allocations made by pg_run_open(PG_MEM_HOST)
+    int64_t bytes_h2d = 0;
+};
+
+// ---- device-side descriptors (copied to device memory once per merge handle) ----
+
+// column descriptor used by the emit kernel
+struct ColDesc {
+    int32_t type;        // pg_type
+    int32_t width;       // bytes, 0 for var-len
+    int32_t nullable;    // output carries a validity bitmap
+    int32_t mode;        // CM_*
+    int32_t agg;         // PG_AGG_* for CM_FOLD
+    int32_t retract;     // RT_*
+    int32_t varlen_index;// index among var-len columns, -1 otherwise
+    int32_t pad;
+};
+enum : int { CM_SELECT = 0, CM_FOLD = 1, CM_KEY = 2, CM_SEQ = 3, CM_KIND = 4 };
+enum : int { RT_OK = 0, RT_IGNORE = 1, RT_ERROR = 2 };
+
+struct MergeFlags {
+    int32_t engine, ignore_delete, remove_record_on_delete, drop_delete;
+};
+
+// key normalisation: how to build the order-preserving uint64 of a row
+struct KeyDesc {
+    int32_t n_fields;
+    int32_t type[PG_MAX_KEY_FIELDS];
+    int32_t shift[PG_MAX_KEY_FIELDS];   // left shift of the field inside the uint64
+};
+
+void set_error(const std::string &msg);
+pg_status fail(pg_status code, const std::string &msg);
+
+#define PG_CUDA(expr)                                                                      \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess)                                                             \
+            return pg::fail(PG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+// ---- kernel launchers (merge.cu) ----
+
+struct LevelView {             // keys of level l of run r: key(row = (j + 1) * stride - 1), j < count
+    int64_t count[PG_MAX_RUNS];
+    int64_t stride;
+};
+
+struct MergeLaunch {
+    int k;
+    KeyDesc key;
+    const void *const *key_ptrs;       // device: [k][n_key] key column data pointers
+    cudaStream_t stream;
+    int32_t *err;                      // device error word
+};
+
+// B[(t) * k + r] for t in [0, n_tiles]: tile boundaries per run at this level.
+void launch_partition(const MergeLaunch &ml, const LevelView &lv, const uint64_t *splitter_keys,
+                      int64_t n_splitter_keys, int q, int n_tiles, int64_t *bounds);
+void launch_merge_keys(const MergeLaunch &ml, const LevelView &lv, const int64_t *bounds, int n_tiles,
+                       uint64_t *sorted_keys);
+
+struct PlanArgs {
+    const int64_t *bounds;             // level-0 tile bounds [(n_tiles+1) * k]
+    int n_tiles;
+    const int64_t *const *seq_ptrs;    // device [k]
+    const int8_t *const *kind_ptrs;    // device [k]
+    MergeFlags flags;
+    // var-len bookkeeping
+    int n_varlen;
+    const int32_t *varlen_cols;        // device [n_varlen] file column index
+    const ColDesc *cols;               // device [n_cols]
+    const DevColumn *run_cols;         // device [k * n_cols]
+    int n_cols;
+    // outputs
+    uint16_t *plan;                    // [N]
+    int32_t *tile_rows;                // [n_tiles]
+    int32_t *tile_bytes;               // [n_varlen * n_tiles]
+    int64_t *tmp_seq;                  // [N]  result sequence number per (tile in_base + out idx)
+    int8_t *tmp_kind;                  // [N]
+};
+void launch_plan(const MergeLaunch &ml, const PlanArgs &pa);
+
+// exclusive scan of tile_rows / tile_bytes into int64 offsets; totals[0] = rows, totals[1+v] = bytes
+void launch_scan(cudaStream_t stream, const int32_t *tile_rows, const int32_t *tile_bytes, int n_tiles,
+                 int n_varlen, int64_t *row_base, int64_t *byte_base, int64_t *totals, int32_t *err);
+
+struct EmitArgs {
+    const int64_t *bounds;
+    int n_tiles;
+    int k;
+    int n_key;
+    const uint16_t *plan;
+    const int64_t *row_base;           // [n_tiles]
+    const int64_t *byte_base;          // [n_varlen * n_tiles]
+    const int64_t *tmp_seq;
+    const int8_t *tmp_kind;
+    const ColDesc *cols;
+    const DevColumn *run_cols;         // [k * n_cols]
+    int n_cols;
+    const pg_out_column *out_cols;     // device [n_cols]
+    const int64_t *totals;             // device
+    int32_t *err;
+    cudaStream_t stream;
+};
+void launch_emit(const EmitArgs &ea);
+
+}  // namespace pg

@@ -1,0 +1,276 @@
+"""Host-side mirror of the reference's reader interfaces for the merge path.
+
+  RecordReader            paimon-common/src/main/java/org/apache/paimon/reader/RecordReader.java:40-72
+  SortMergeReader         paimon-core/.../mergetree/compact/SortMergeReader.java:41-57
+  ReducerMergeFunctionWrapper  …/compact/ReducerMergeFunctionWrapper.java:45-73 (semantics live in the plan kernel)
+  DropDeleteReader        paimon-core/.../mergetree/DropDeleteReader.java:50-68
+  MergeTreeReaders.readerForSection  paimon-core/.../mergetree/MergeTreeReaders.java:67-92
+
+Same names, same argument meaning, same error behaviour (the exceptions carry the reference's
+messages), but batches are columnar (``KeyValueBatch``) instead of row iterators, and all work
+happens in libpaimon_gpu.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+from .columnar import Column, KeyValueBatch
+from .merge_function import MergeSpec, SortEngine
+from .types import KeyValueSchema, PhysicalType, is_varlen, numpy_dtype
+
+
+def _np_ptr(a: Optional[np.ndarray]) -> Optional[int]:
+    return None if a is None else a.ctypes.data
+
+
+class _SchemaHandle:
+    def __init__(self, schema: KeyValueSchema, device: int):
+        self.schema = schema
+        lib = N.init(device)
+        kf = (N.PgField * schema.n_key)(*[N.PgField(int(f.physical), 0) for f in schema.key_type.fields])
+        vf = (N.PgField * max(schema.n_val, 1))(
+            *[N.PgField(int(f.physical), int(f.nullable)) for f in schema.value_type.fields])
+        desc = N.PgSchemaDesc(schema.n_key, schema.n_val, kf, vf)
+        h = C.c_uint64(0)
+        N.check(lib.pg_schema_create(C.byref(desc), C.byref(h)))
+        self.handle = h.value
+
+    def close(self):
+        if self.handle:
+            N.load().pg_schema_free(self.handle)
+            self.handle = 0
+
+
+class RecordReader:
+    """RecordReader<KeyValue>: read_batch() returns a columnar batch or None at end of input."""
+
+    def read_batch(self) -> Optional[KeyValueBatch]:
+        raise NotImplementedError
+
+    def close(self) -> None:
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+@dataclass
+class DeviceColumn:
+    data: int
+    offsets: int = 0
+    validity: int = 0
+
+
+class SortedRunReader(RecordReader):
+    """One sorted run (keys strictly increasing) — what MergeTreeReaders.readerForRun yields
+    (MergeTreeReaders.java:94-101).  Either host columns (copied to the device when the merge opens
+    it) or device-resident columns (pointers borrowed; `keepalive` pins their owner)."""
+
+    def __init__(self, schema: KeyValueSchema, batch: Optional[KeyValueBatch] = None, *,
+                 n_rows: Optional[int] = None, device_columns: Optional[Sequence[DeviceColumn]] = None,
+                 keepalive=None):
+        self.schema = schema
+        self.batch = batch
+        self.device_columns = list(device_columns) if device_columns is not None else None
+        self.n_rows = batch.n_rows if batch is not None else int(n_rows or 0)
+        self.keepalive = keepalive
+        self._consumed = False
+        self._handle = 0
+
+    @staticmethod
+    def from_device(schema: KeyValueSchema, n_rows: int, columns: Sequence[DeviceColumn], keepalive=None):
+        return SortedRunReader(schema, None, n_rows=n_rows, device_columns=columns, keepalive=keepalive)
+
+    def read_batch(self) -> Optional[KeyValueBatch]:
+        if self._consumed or self.batch is None:
+            return None
+        self._consumed = True
+        return self.batch
+
+    # -- native registration (used by SortMergeReader) --
+    def _open(self, schema_handle: int) -> int:
+        lib = N.load()
+        nc = self.schema.n_cols
+        cols = (N.PgColumn * nc)()
+        keep = []
+        if self.device_columns is not None:
+            for i, dc in enumerate(self.device_columns):
+                cols[i] = N.PgColumn(dc.data or None, dc.offsets or None, dc.validity or None)
+            mem = N.PG_MEM_DEVICE
+        else:
+            for i, col in enumerate(self.batch.columns):
+                data = np.ascontiguousarray(col.data)
+                offs = None if col.offsets is None else np.ascontiguousarray(col.offsets, np.int32)
+                val = None if col.valid is None else np.ascontiguousarray(col.valid, np.uint8)
+                keep += [data, offs, val]
+                cols[i] = N.PgColumn(_np_ptr(data), _np_ptr(offs), _np_ptr(val))
+            mem = N.PG_MEM_HOST
+        desc = N.PgRunDesc(self.n_rows, cols)
+        h = C.c_uint64(0)
+        N.check(lib.pg_run_open(schema_handle, C.byref(desc), mem, C.byref(h)))
+        self._handle = h.value
+        return self._handle
+
+    def close(self) -> None:
+        if self._handle:
+            N.load().pg_run_free(self._handle)
+            self._handle = 0
+
+
+@dataclass
+class DeviceBatch:
+    """The merged batch left on the device: (data, offsets, validity, data_bytes) pointers per column."""
+    n_rows: int
+    columns: List[N.PgOutColumn]
+
+
+class SortMergeReader(RecordReader):
+    """k-way merge of sorted runs + per-key merge function (+ optional DropDeleteReader).
+
+    Like SortMergeReaderWithLoserTree (SortMergeReaderWithLoserTree.java:67-73) the reader produces
+    exactly one batch."""
+
+    @staticmethod
+    def create_sort_merge_reader(readers: Sequence[SortedRunReader], user_key_comparator=None,
+                                 user_defined_seq_comparator=None,
+                                 merge_function_wrapper: Optional[MergeSpec] = None,
+                                 sort_engine: SortEngine = SortEngine.LOSER_TREE,
+                                 device: int = 0) -> "SortMergeReader":
+        """SortMergeReader.createSortMergeReader (SortMergeReader.java:41-57).
+
+        `user_key_comparator` must be None (the key order is the schema's natural order, which is what
+        the reference's generated comparator implements); `user_defined_seq_comparator` is a list of
+        value-field indexes or None; `merge_function_wrapper` is the MergeSpec built by a
+        MergeFunctionFactory.  `sort_engine` is accepted for signature parity: both engines produce the
+        same rows and the device implements one algorithm."""
+        if user_key_comparator is not None:
+            raise N.UnsupportedOnDevice(2, "custom key comparators cannot run on the device")
+        if merge_function_wrapper is None:
+            raise ValueError("merge_function_wrapper (MergeSpec) is required")
+        return SortMergeReader(list(readers), merge_function_wrapper, user_defined_seq_comparator, device)
+
+    def __init__(self, readers: List[SortedRunReader], spec: MergeSpec, seq_fields=None, device: int = 0):
+        self.readers = readers
+        self.lib = N.init(device)
+        schema = readers[0].schema if readers else None
+        self.schema = schema
+        self._done = False
+        self._schema_h = None
+        self._spec_h = 0
+        self._merge_h = 0
+        self._keep = []
+        if schema is None:
+            return
+        self._schema_h = _SchemaHandle(schema, device)
+        sp = spec.normalised(schema.n_val)
+        seq = list(seq_fields) if seq_fields else list(sp.seq_fields)
+        seq_arr = np.array(seq, np.int32)
+        agg = np.array([int(a) for a in sp.agg], np.int32)
+        ign = np.array([1 if b else 0 for b in sp.ignore_retract], np.uint8)
+        self._keep += [seq_arr, agg, ign]
+        cs = N.PgMergeSpec(int(sp.engine), int(sp.ignore_delete), int(sp.remove_record_on_delete),
+                           int(sp.drop_delete), len(seq), _np_ptr(seq_arr) if len(seq) else None,
+                           int(sp.seq_ascending), _np_ptr(agg), _np_ptr(ign), len(sp.groups))
+        h = C.c_uint64(0)
+        try:
+            N.check(self.lib.pg_merge_spec_create(self._schema_h.handle, C.byref(cs), C.byref(h)))
+            self._spec_h = h.value
+            run_handles = (C.c_uint64 * max(len(readers), 1))()
+            for i, r in enumerate(readers):
+                run_handles[i] = r._open(self._schema_h.handle)
+            mh = C.c_uint64(0)
+            N.check(self.lib.pg_merge_open(self._spec_h, run_handles, len(readers), C.byref(mh)))
+            self._merge_h = mh.value
+        except Exception:
+            self.close()
+            raise
+
+    # -- execution --
+    def execute(self) -> None:
+        N.check(self.lib.pg_merge_execute(self._merge_h))
+
+    def stats(self) -> N.PgStats:
+        st = N.PgStats()
+        N.check(self.lib.pg_merge_stats(self._merge_h, C.byref(st)))
+        return st
+
+    def cuda_stream(self) -> int:
+        p = C.c_void_p(0)
+        N.check(self.lib.pg_merge_stream(self._merge_h, C.byref(p)))
+        return p.value or 0
+
+    def device_batch(self) -> DeviceBatch:
+        b = N.PgBatch()
+        N.check(self.lib.pg_merge_device_batch(self._merge_h, C.byref(b)))
+        return DeviceBatch(b.n_rows, [b.cols[i] for i in range(b.n_cols)])
+
+    def fetch(self) -> KeyValueBatch:
+        """Device batch -> host columns (D2H)."""
+        db = self.device_batch()
+        n = db.n_rows
+        types = self.schema.physical_types()
+        fields = self.schema.file_fields()
+        host = (N.PgOutColumn * len(types))()
+        cols: List[Column] = []
+        for i, t in enumerate(types):
+            oc = db.columns[i]
+            nullable = fields[i].nullable
+            valid = np.zeros((n + 7) // 8 + 8, np.uint8) if nullable else None
+            if is_varlen(t):
+                data = np.zeros(max(int(oc.data_bytes), 1), np.uint8)
+                offs = np.zeros(n + 1, np.int32)
+                host[i] = N.PgOutColumn(_np_ptr(data), _np_ptr(offs), _np_ptr(valid), oc.data_bytes)
+                cols.append(Column(t, data[: int(oc.data_bytes)], offs, valid))
+            else:
+                data = np.zeros(max(n, 1), numpy_dtype(t))
+                host[i] = N.PgOutColumn(_np_ptr(data), None, _np_ptr(valid), oc.data_bytes)
+                cols.append(Column(t, data[:n], None, valid))
+        N.check(self.lib.pg_merge_fetch(self._merge_h, host, len(types)))
+        return KeyValueBatch(self.schema, cols)
+
+    def read_batch(self) -> Optional[KeyValueBatch]:
+        if self._done or self.schema is None:
+            return None
+        self._done = True
+        self.execute()
+        batch = self.fetch()
+        return batch if batch.n_rows > 0 else None
+
+    def release_batch(self) -> None:
+        if self._merge_h:
+            self.lib.pg_merge_release(self._merge_h)
+
+    def close(self) -> None:
+        lib = N.load()
+        if self._merge_h:
+            lib.pg_merge_free(self._merge_h)
+            self._merge_h = 0
+        for r in self.readers:
+            r.close()
+        if self._spec_h:
+            lib.pg_merge_spec_free(self._spec_h)
+            self._spec_h = 0
+        if self._schema_h is not None:
+            self._schema_h.close()
+            self._schema_h = None
+
+
+def merge_runs(schema: KeyValueSchema, spec: MergeSpec, runs: Sequence[KeyValueBatch], device: int = 0) -> KeyValueBatch:
+    """Convenience: merge host batches and return the (possibly empty) merged batch."""
+    readers = [SortedRunReader(schema, b) for b in runs]
+    if not readers:
+        return KeyValueBatch.from_rows(schema, [])
+    rd = SortMergeReader.create_sort_merge_reader(readers, None, None, spec, device=device)
+    try:
+        rd.execute()
+        return rd.fetch()
+    finally:
+        rd.close()

@@ -1,0 +1,242 @@
+"""Parity of the CUDA merge path (through the C ABI) against the CPU oracle.  Needs a B200."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle
+from paimon_b200 import _native as N
+from paimon_b200 import datagen
+from paimon_b200.columnar import KeyValueBatch
+from paimon_b200.merge_function import (AggregateMergeFunction, DeduplicateMergeFunction,
+                                        FirstRowMergeFunction, PartialUpdateMergeFunction)
+from paimon_b200.sort_merge_reader import SortedRunReader, SortMergeReader, merge_runs
+from paimon_b200.types import DataField, KeyValueSchema, RowKind, RowType
+
+from reusing_test_data import SCHEMA, VALUE_TYPE, generate_random_readers, parse, to_batch
+from test_oracle_golden import FIXED_VECTORS
+
+pytestmark = pytest.mark.gpu
+
+
+def assert_same(schema, spec, runs):
+    want = pyoracle.merge(schema, spec, runs, pyoracle.SORT_LOSER_TREE)
+    got = merge_runs(schema, spec, runs)
+    assert got.equals(want), got.first_difference(want)
+    return got
+
+
+SPECS = {
+    "dedup": DeduplicateMergeFunction.factory().create(),
+    "dedup_ignore_delete": DeduplicateMergeFunction.factory({"ignore-delete": "true"}).create(),
+    "dedup_drop_delete": DeduplicateMergeFunction.factory().create().with_drop_delete(),
+    "first_row_ignore_delete": FirstRowMergeFunction.factory({"ignore-delete": "true"}).create(),
+    "pu_ignore_delete": PartialUpdateMergeFunction.factory({"ignore-delete": "true"}, VALUE_TYPE, ["f0"]).create(),
+    "pu_remove_on_delete": PartialUpdateMergeFunction.factory(
+        {"partial-update.remove-record-on-delete": "true"}, VALUE_TYPE, ["f0"]).create(),
+    "agg_sum": AggregateMergeFunction.factory({"fields.f1.aggregate-function": "sum"}, VALUE_TYPE, ["f0"]).create(),
+    "agg_sum_remove_on_delete": AggregateMergeFunction.factory(
+        {"fields.f1.aggregate-function": "sum", "aggregation.remove-record-on-delete": "true"},
+        VALUE_TYPE, ["f0"]).create(),
+    "agg_default": AggregateMergeFunction.factory({}, VALUE_TYPE, ["f0"]).create(),
+    "agg_max_ignore_retract": AggregateMergeFunction.factory(
+        {"fields.f1.aggregate-function": "max", "fields.f1.ignore-retract": "true"}, VALUE_TYPE, ["f0"]).create(),
+    "agg_product_drop_delete": AggregateMergeFunction.factory(
+        {"fields.f1.aggregate-function": "product"}, VALUE_TYPE, ["f0"]).create().with_drop_delete(),
+}
+
+
+@pytest.mark.parametrize("spec_name", sorted(SPECS))
+@pytest.mark.parametrize("name", sorted(FIXED_VECTORS))
+def test_fixed_vectors(name, spec_name):
+    readers = [to_batch(parse(s)) for s in FIXED_VECTORS[name]]
+    assert_same(SCHEMA, SPECS[spec_name], readers)
+
+
+@pytest.mark.parametrize("spec_name", sorted(SPECS))
+def test_random_rounds(spec_name):
+    """CombiningRecordReaderTestBase.testRandom (1-20 readers x 1-100 rows), every engine."""
+    rng = random.Random(hash(spec_name) & 0xffff)
+    for _ in range(25):
+        readers = [to_batch(r) for r in generate_random_readers(rng, only_add=False)]
+        assert_same(SCHEMA, SPECS[spec_name], readers)
+
+
+def test_first_row_add_only_and_error():
+    rng = random.Random(3)
+    spec = FirstRowMergeFunction.factory().create()
+    for _ in range(10):
+        readers = [to_batch(r) for r in generate_random_readers(rng, only_add=True)]
+        assert_same(SCHEMA, spec, readers)
+    readers = [to_batch(parse("1, 1, +, 10")), to_batch(parse("1, 3, -, 11"))]
+    with pytest.raises(N.MergeFunctionError, match="First row merge engine can not accept"):
+        merge_runs(SCHEMA, spec, readers)
+
+
+def test_partial_update_delete_error_message():
+    spec = PartialUpdateMergeFunction.factory({}, VALUE_TYPE, ["f0"]).create()
+    readers = [to_batch(parse("1, 1, +, 10")), to_batch(parse("1, 3, -, 11"))]
+    with pytest.raises(N.MergeFunctionError, match="Partial update can not accept delete records"):
+        merge_runs(SCHEMA, spec, readers)
+    # a lone DELETE passes through untouched (ReducerMergeFunctionWrapper)
+    got = merge_runs(SCHEMA, spec, [to_batch(parse("1, 3, -, 11"))])
+    assert got.to_rows() == [(1, 3, 3, 1, 11)]
+
+
+def test_agg_retract_unsupported_error():
+    spec = AggregateMergeFunction.factory({"fields.f1.aggregate-function": "max"}, VALUE_TYPE, ["f0"]).create()
+    readers = [to_batch(parse("1, 1, +, 10")), to_batch(parse("1, 3, -, 11"))]
+    with pytest.raises(N.MergeFunctionError, match="does not support retraction"):
+        merge_runs(SCHEMA, spec, readers)
+
+
+def test_unsupported_specs_are_refused():
+    # string primary key: refused at plan time, no CPU fallback
+    vt = RowType((DataField("k", "STRING", False), DataField("v", "BIGINT", True)))
+    schema = KeyValueSchema.of(vt, ["k"])
+    run = KeyValueBatch.from_rows(schema, [("a", 1, 0, "a", 5)])
+    with pytest.raises(N.UnsupportedOnDevice):
+        merge_runs(schema, DeduplicateMergeFunction.factory().create(), [run, run])
+
+
+def test_empty_and_single_inputs():
+    spec = DeduplicateMergeFunction.factory().create()
+    assert merge_runs(SCHEMA, spec, []).n_rows == 0
+    assert merge_runs(SCHEMA, spec, [to_batch([])]).n_rows == 0
+    assert merge_runs(SCHEMA, spec, [to_batch([]), to_batch([]), to_batch([])]).n_rows == 0
+    one = to_batch(parse("1, 1, +, 100 | 2, 500, -, 200"))
+    assert_same(SCHEMA, spec, [one])
+    rd = SortMergeReader.create_sort_merge_reader([SortedRunReader(SCHEMA, to_batch([]))], None, None, spec)
+    assert rd.read_batch() is None
+    rd.close()
+
+
+def all_types_schema():
+    vt = RowType((DataField("pk", "INT", False), DataField("t", "TINYINT", True), DataField("s", "SMALLINT", True),
+                  DataField("i", "INT", True), DataField("l", "BIGINT", True), DataField("f", "FLOAT", True),
+                  DataField("d", "DOUBLE", True), DataField("b", "BOOLEAN", True), DataField("str", "STRING", True),
+                  DataField("bin", "BINARY", True), DataField("nn", "BIGINT", False)))
+    return KeyValueSchema.of(vt, ["pk"]), vt
+
+
+def random_all_types_runs(rng, n_runs, max_rows, key_space, kinds):
+    schema, _ = all_types_schema()
+    runs, seq = [], 0
+    for r in range(n_runs):
+        n = rng.randrange(0, max_rows + 1)
+        keys = sorted(rng.sample(range(key_space), min(n, key_space)))
+        rows = []
+        for k in keys:
+            seq += rng.randrange(1, 5)
+            def opt(v):
+                return None if rng.random() < 0.3 else v
+            rows.append((k, seq * 7919 % 100003 + seq, rng.choice(kinds), k,
+                         opt(rng.randrange(-128, 128)), opt(rng.randrange(-32768, 32768)),
+                         opt(rng.randrange(-2 ** 31, 2 ** 31)), opt(rng.randrange(-2 ** 63, 2 ** 63)),
+                         opt(rng.uniform(-1e3, 1e3)), opt(rng.uniform(-1e6, 1e6)), opt(rng.randrange(2)),
+                         opt("".join(rng.choice("abcxyz") for _ in range(rng.randrange(0, 12)))),
+                         opt(bytes(rng.randrange(256) for _ in range(rng.randrange(0, 9)))),
+                         rng.randrange(-1000, 1000)))
+        runs.append(KeyValueBatch.from_rows(schema, rows))
+    return schema, runs
+
+
+ALL_TYPES_SPECS = {
+    "dedup": lambda vt: DeduplicateMergeFunction.factory().create(),
+    "pu": lambda vt: PartialUpdateMergeFunction.factory({"ignore-delete": "true"}, vt, ["pk"]).create(),
+    "pu_rod": lambda vt: PartialUpdateMergeFunction.factory({"partial-update.remove-record-on-delete": "true"}, vt, ["pk"]).create(),
+    "agg_mixed": lambda vt: AggregateMergeFunction.factory({
+        "fields.t.aggregate-function": "sum", "fields.s.aggregate-function": "product",
+        "fields.i.aggregate-function": "max", "fields.l.aggregate-function": "sum",
+        "fields.f.aggregate-function": "sum", "fields.d.aggregate-function": "sum",
+        "fields.b.aggregate-function": "bool_or", "fields.str.aggregate-function": "max",
+        "fields.bin.aggregate-function": "first_non_null_value", "fields.nn.aggregate-function": "min",
+        "fields.i.ignore-retract": "true", "fields.b.ignore-retract": "true", "fields.str.ignore-retract": "true",
+        "fields.bin.ignore-retract": "true", "fields.nn.ignore-retract": "true"}, vt, ["pk"]).create(),
+    "agg_first_last": lambda vt: AggregateMergeFunction.factory({
+        "fields.default-aggregate-function": "first_value", "fields.l.aggregate-function": "last_value",
+        "fields.d.aggregate-function": "product", "fields.str.aggregate-function": "min",
+        "fields.f.aggregate-function": "min", "fields.b.aggregate-function": "bool_and"}, vt, ["pk"]).create(),
+}
+
+
+@pytest.mark.parametrize("spec_name", sorted(ALL_TYPES_SPECS))
+def test_all_types_nulls_varlen(spec_name):
+    """35-type-row spirit of ParquetReadWriteTest / FieldAggregatorTest: every physical type, 30 % nulls,
+    var-len columns, retract rows where the spec tolerates them."""
+    rng = random.Random(17)
+    _, vt = all_types_schema()
+    spec = ALL_TYPES_SPECS[spec_name](vt)
+    kinds = [0, 0, 0, 2] if spec_name == "agg_first_last" else [0, 0, 2, 3, 1]
+    for _ in range(12):
+        schema, runs = random_all_types_runs(rng, rng.randrange(1, 9), 60, 90, kinds)
+        assert_same(schema, spec, runs)
+
+
+@pytest.mark.parametrize("n_runs,total", [(2, 20000), (8, 100000), (16, 300000), (32, 200000)])
+def test_multi_tile_deduplicate(n_runs, total):
+    """Large enough for several partition levels (tiles of <= 4096 rows, stride-32 sampling)."""
+    schema = datagen.schema_c2()
+    runs = datagen.make_runs(schema, n_runs, total, seed=3, null_prob=0.2, delete_prob=0.05)
+    got = assert_same(schema, DeduplicateMergeFunction.factory().create(), runs)
+    keys = got.columns[0].data
+    assert np.all(keys[1:] > keys[:-1])          # strictly increasing keys: sorted and deduplicated
+
+
+def test_multi_tile_partial_update_wide_row():
+    schema = datagen.schema_c3(n_i64=4, n_f64=3, n_str=3)
+    runs = datagen.make_runs(schema, 16, 120000, seed=5, null_prob=0.5)
+    spec = PartialUpdateMergeFunction.factory({}, schema.value_type, ["pk"]).create()
+    assert_same(schema, spec, runs)
+
+
+def test_multi_tile_aggregate_double_sum_is_bit_exact():
+    schema = datagen.schema_c3(n_i64=2, n_f64=4, n_str=1)
+    runs = datagen.make_runs(schema, 16, 100000, seed=9, null_prob=0.3)
+    opts = {f"fields.d{i}.aggregate-function": "sum" for i in range(4)}
+    opts["fields.i0.aggregate-function"] = "sum"
+    spec = AggregateMergeFunction.factory(opts, schema.value_type, ["pk"]).create()
+    assert_same(schema, spec, runs)
+
+
+def test_skewed_run_lengths_and_tiny_runs():
+    schema = datagen.schema_c1()
+    rng = np.random.default_rng(0)
+    sizes = [50000, 3, 0, 17000, 1, 31, 33, 4097]
+    runs = [datagen.make_run(schema, r, datagen.run_keys(rng, 40000, n), seed=2) for r, n in enumerate(sizes)]
+    assert_same(schema, DeduplicateMergeFunction.factory().create(), runs)
+
+
+def test_composite_and_narrow_keys():
+    vt = RowType((DataField("a", "INT", False), DataField("b", "SMALLINT", False), DataField("v", "BIGINT", True)))
+    schema = KeyValueSchema.of(vt, ["a", "b"])
+    rng = random.Random(8)
+    runs, seq = [], 0
+    for r in range(5):
+        keys = sorted({(rng.randrange(-50, 50), rng.randrange(-3, 3)) for _ in range(300)})
+        rows = []
+        for (a, b) in keys:
+            seq += 1
+            rows.append((a, b, seq, 0, a, b, rng.randrange(100)))
+        runs.append(KeyValueBatch.from_rows(schema, rows))
+    assert_same(schema, DeduplicateMergeFunction.factory().create(), runs)
+
+
+def test_size_independent_properties_at_scale():
+    """C1-shaped 2M rows: checks that do not need the oracle — sortedness, idempotence, row conservation."""
+    schema = datagen.schema_c1()
+    runs = datagen.make_runs(schema, 4, 2_000_000, seed=11)
+    spec = DeduplicateMergeFunction.factory().create()
+    got = merge_runs(schema, spec, runs)
+    keys = got.columns[0].data
+    assert np.all(keys[1:] > keys[:-1])
+    all_keys = np.concatenate([r.columns[0].data for r in runs])
+    assert got.n_rows == len(np.unique(all_keys))
+    # the winner of every key is the row with the highest sequence number
+    all_seq = np.concatenate([r.sequence_numbers for r in runs])
+    order = np.lexsort((all_seq, all_keys))
+    last = np.r_[all_keys[order][1:] != all_keys[order][:-1], True]
+    assert np.array_equal(got.sequence_numbers, all_seq[order][last])
+    # merging the merged result with nothing changes nothing
+    again = merge_runs(schema, spec, [got])
+    assert again.equals(got)
