@@ -1,0 +1,447 @@
+#!/usr/bin/env python
+"""bench.py — merged rows/s of the LSM merge hot path on B200 (BASELINE.json metric).
+
+One "step" = one pass of the hot path (sampled partition -> plan -> scan -> emit) over one bucket of
+synthetic sorted runs.  Workloads (BASELINE.json configs):
+  c3 (default, the configuration the metric is quoted on): 16 runs x 6.25 M rows = 100 M rows,
+      partial-update merge engine, 50-column wide row (pk + 20 BIGINT + 15 DOUBLE + 14 VARCHAR(8..24)),
+      every non-pk cell NULL with p = 0.5
+  c2: 8 runs x 12.5 M rows = 100 M rows, deduplicate, BIGINT pk + 10 BIGINT columns
+  c1: 2 runs x 500 K rows, deduplicate, BIGINT pk + BIGINT value
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c1] [--rows R]
+    python bench.py --impl reference ...     # the reference algorithm on the host cores (CPU)
+
+`value`     whole-job merged (= input) rows/s with the runs already resident in HBM.
+`e2e`       same metric through the public reader API with HOST buffers: every step copies the runs
+            host->device (pinned memory) and the merged batch device->host.
+`roofline`  achieved HBM GB/s of the dominant kernel (emit) on the algorithmic bytes
+            N_in*B + N_out*B, against MEASURED_PEAKS.json.
+`cpu_baseline`  the oracle (C restatement of LoserTree + MergeFunction) timed on this box's host cores.
+Multi-GPU: one process per GPU (torchrun); buckets are independent, so every rank merges its own
+bucket and there is no data-path collective ("weak" scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    "c3": dict(n_runs=16, rows=100_000_000, engine="partial-update", null_prob=0.5,
+               desc="16-run partial-update, 50-col wide row (pk+20 i64+15 f64+14 varchar), 100M rows"),
+    "c2": dict(n_runs=8, rows=100_000_000, engine="deduplicate", null_prob=0.0,
+               desc="8-run deduplicate, int64 pk + 10 int64 cols, 100M rows"),
+    "c1": dict(n_runs=2, rows=1_000_000, engine="deduplicate", null_prob=0.0,
+               desc="2-run deduplicate, int64 pk + int64 val, 1M rows"),
+}
+
+
+def make_schema(workload):
+    from paimon_b200 import datagen
+    return {"c1": datagen.schema_c1, "c2": datagen.schema_c2, "c3": datagen.schema_c3}[workload]()
+
+
+def make_spec(workload, schema):
+    from paimon_b200.merge_function import DeduplicateMergeFunction, PartialUpdateMergeFunction
+    if WORKLOADS[workload]["engine"] == "partial-update":
+        return PartialUpdateMergeFunction.factory({}, schema.value_type, ["pk"]).create()
+    return DeduplicateMergeFunction.factory().create()
+
+
+# ------------------------------------------------------------------ device-side synthetic runs
+
+def _splitmix64(x):
+    import torch
+    x = x + (-7046029254386353131)                       # 0x9E3779B97F4A7C15 as int64
+    x = (x ^ ((x >> 30) & ((1 << 34) - 1))) * (-4658895280553007687)   # 0xBF58476D1CE4E5B9
+    x = (x ^ ((x >> 27) & ((1 << 37) - 1))) * (-7723592293110705685)   # 0x94D049BB133111EB
+    return x ^ ((x >> 31) & ((1 << 33) - 1))
+
+
+def gen_device_run(schema, run_index, n, key_space, null_prob, seed, dev):
+    """One sorted run generated directly in HBM.  Returns (columns, keepalive tensors, key tensor)."""
+    import torch
+    from paimon_b200.sort_merge_reader import DeviceColumn
+    from paimon_b200.types import PhysicalType
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed * 1000003 + run_index)
+    keys = torch.randperm(key_space, device=dev, generator=g)[:n].sort().values.contiguous()
+    keep = [keys]
+    cols = []
+    for _ in schema.key_type.fields:
+        cols.append(DeviceColumn(keys.data_ptr()))
+    seq = (torch.arange(n, device=dev, dtype=torch.int64) + (run_index << 32)).contiguous()
+    kind = torch.zeros(n, device=dev, dtype=torch.int8)
+    keep += [seq, kind]
+    cols += [DeviceColumn(seq.data_ptr()), DeviceColumn(kind.data_ptr())]
+    nbytes = keys.numel() * 8 + seq.numel() * 8 + kind.numel()
+    pk_names = {f.name[len("_KEY_"):] for f in schema.key_type.fields}
+    for ci, f in enumerate(schema.value_type.fields):
+        t = f.physical
+        if f.name in pk_names:
+            cols.append(DeviceColumn(keys.data_ptr()))
+            nbytes += keys.numel() * 8
+            continue
+        h = _splitmix64(keys ^ ((run_index + 1) * 0x100 + ci << 40))
+        valid_ptr = 0
+        bits = None
+        if f.nullable and null_prob > 0:
+            assert null_prob == 0.5, "device generator draws validity bits with p = 0.5"
+            vbytes = torch.randint(0, 256, ((n + 7) // 8 + 8,), device=dev, dtype=torch.uint8, generator=g)
+            keep.append(vbytes)
+            valid_ptr = vbytes.data_ptr()
+            nbytes += (n + 7) // 8
+            if t in (PhysicalType.STRING, PhysicalType.BINARY):
+                sh = torch.arange(8, device=dev, dtype=torch.uint8)
+                bits = ((vbytes[:, None] >> sh) & 1).flatten()[:n].to(torch.int64)
+        if t == PhysicalType.INT64:
+            keep.append(h)
+            cols.append(DeviceColumn(h.data_ptr(), 0, valid_ptr))
+            nbytes += n * 8
+        elif t == PhysicalType.DOUBLE:
+            d = ((h >> 11) & ((1 << 53) - 1)).to(torch.float64) * (2000.0 / (1 << 53)) - 1000.0
+            keep.append(d)
+            cols.append(DeviceColumn(d.data_ptr(), 0, valid_ptr))
+            nbytes += n * 8
+        elif t in (PhysicalType.STRING, PhysicalType.BINARY):
+            lens = 8 + ((h >> 3) & 0xffff) % 17                       # U[8, 24]
+            if bits is not None:
+                lens = lens * bits                                     # NULL cells carry no payload
+            offs = torch.zeros(n + 1, device=dev, dtype=torch.int64)
+            torch.cumsum(lens, 0, out=offs[1:])
+            total = int(offs[-1].item())
+            offs32 = offs.to(torch.int32)
+            data = torch.randint(48, 112, (max(total, 1) + 16,), device=dev, dtype=torch.uint8, generator=g)
+            keep += [offs32, data]
+            cols.append(DeviceColumn(data.data_ptr(), offs32.data_ptr(), valid_ptr))
+            nbytes += total + 4 * (n + 1)
+            del lens, offs, bits
+        else:
+            raise ValueError(f"bench generator: unsupported type {t}")
+    return cols, keep, keys, nbytes
+
+
+def device_runs(workload, schema, rows, dev, seed):
+    import torch
+    from paimon_b200.sort_merge_reader import SortedRunReader
+    w = WORKLOADS[workload]
+    n_runs = w["n_runs"]
+    per_run = rows // n_runs
+    key_space = max(rows // 2, per_run)
+    readers, all_keys, in_bytes = [], [], 0
+    for r in range(n_runs):
+        cols, keep, keys, nb = gen_device_run(schema, r, per_run, key_space, w["null_prob"], seed, dev)
+        readers.append(SortedRunReader.from_device(schema, per_run, cols, keepalive=keep))
+        all_keys.append(keys)
+        in_bytes += nb
+    torch.cuda.synchronize()
+    return readers, all_keys, in_bytes
+
+
+# ------------------------------------------------------------------ clocks sampling
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            p = [x.strip() for x in s.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU baseline (oracle)
+
+def cpu_baseline(workload, total_sample_rows, threads, steps=1, seed=7):
+    """The reference algorithm (oracle port) on the host cores: `threads` independent buckets, one thread
+    per bucket exactly like the reference's one-thread-per-split readers."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle
+    from paimon_b200 import datagen
+    schema = make_schema(workload)
+    spec = make_spec(workload, schema)
+    w = WORKLOADS[workload]
+    per_bucket = max(total_sample_rows // threads, w["n_runs"] * 64)
+    buckets = [datagen.make_runs(schema, w["n_runs"], per_bucket, seed=seed + b, null_prob=w["null_prob"])
+               for b in range(threads)]
+    pyoracle.lib()
+
+    def work(b):
+        out = pyoracle.merge(schema, spec, buckets[b], pyoracle.SORT_LOSER_TREE)
+        return out.n_rows
+
+    times = []
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            outs = list(ex.map(work, range(threads)))
+            times.append(time.perf_counter() - t0)
+    rows = per_bucket // w["n_runs"] * w["n_runs"] * threads
+    return rows, times, sum(outs)
+
+
+# ------------------------------------------------------------------ main
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=None, help="override total input rows per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-rows", type=int, default=None)
+    ap.add_argument("--cpu-threads", type=int, default=None)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    w = WORKLOADS[args.workload]
+    rows = args.rows or w["rows"]
+    metric = "merged rows/sec at 16 runs x 100M rows" if args.workload == "c3" else f"merged rows/sec ({args.workload})"
+    config = {"workload": f"{args.workload}: {w['desc']}", "rows_per_gpu": rows, "n_runs": w["n_runs"],
+              "merge_engine": w["engine"], "buckets_per_gpu": 1, "parallelism": f"bucket-per-gpu x{world}",
+              "l2": "inputs (>50 GB) far exceed the 126 MB L2; no explicit flush" if rows >= 10_000_000
+                    else "small input: L2-resident (not a headline configuration)"}
+
+    # ---------------- reference arm: the reference's CPU algorithm on the host cores
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        threads = args.cpu_threads or min(os.cpu_count() or 1, 64)
+        sample = args.cpu_sample_rows or (2_000_000 if args.workload == "c3" else 8_000_000)
+        sample = min(sample, rows)
+        cpu_baseline(args.workload, min(sample, 200_000), threads, steps=max(args.warmup, 1) if args.warmup else 0)
+        nrows, times, _ = cpu_baseline(args.workload, sample, threads, steps=args.steps)
+        total = sum(times)
+        val = nrows * len(times) / total
+        line = {"impl": "reference", "metric": metric, "value": val, "unit": "rows/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "rows/s", "cores": threads, "kind": "port",
+                                 "sample": f"{threads} buckets x {nrows // threads} rows of the same shape, one "
+                                           f"thread per bucket (C restatement of LoserTree+MergeFunction; no JVM in the image)"},
+                "e2e": {"value": val, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ---------------- B200 arm
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: the merge path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from paimon_b200 import _native as N
+    from paimon_b200.columnar import Column, KeyValueBatch
+    from paimon_b200.sort_merge_reader import SortedRunReader, SortMergeReader
+
+    schema = make_schema(args.workload)
+    spec = make_spec(args.workload, schema)
+    N.init(local_rank)
+    readers, all_keys, in_bytes = device_runs(args.workload, schema, rows, dev, seed=100 + rank)
+    n_in = sum(r.n_rows for r in readers)
+    rd = SortMergeReader.create_sort_merge_reader(readers, None, None, spec, device=local_rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        rd.execute()
+    st = rd.stats()
+    n_out = st.rows_out
+    # sanity at full size (size-independent properties): row conservation + strictly increasing keys
+    uniq = torch.unique(torch.cat(all_keys)).numel()
+    assert n_out == uniq, f"merged rows {n_out} != distinct keys {uniq}"
+    out_bytes = st.bytes_out
+
+    ext = torch.cuda.ExternalStream(rd.cuda_stream(), device=dev)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms_emit = ms_plan = ms_part = ms_tot = ms_alloc = 0.0
+    launches = 0
+    t0 = time.perf_counter()
+    e0.record(ext)
+    for _ in range(args.steps):
+        rd.execute()
+        s = rd.stats()
+        ms_emit += s.ms_emit; ms_plan += s.ms_plan; ms_part += s.ms_partition; ms_tot += s.ms_total
+        ms_alloc += s.ms_alloc
+        launches += s.launches
+    e1.record(ext)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    dev_ms = e0.elapsed_time(e1)
+    t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms = float(t.item()) / args.steps
+    value = world * n_in / (step_ms * 1e-3)
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_kind = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    alg_bytes = in_bytes + out_bytes
+    emit_ms = ms_emit / args.steps
+    achieved = alg_bytes / (emit_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_emit", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_kind, "traffic": None,
+                "algorithmic_bytes": alg_bytes, "kernel_ms": emit_ms,
+                "step_frac": alg_bytes / (step_ms * 1e-3) / 1e9 / peak,
+                "phase_ms": {"partition": ms_part / args.steps, "plan+scan": ms_plan / args.steps,
+                             "size_readback+alloc": ms_alloc / args.steps, "emit": emit_ms,
+                             "device_total": ms_tot / args.steps}}
+
+    # ---------------- e2e: host buffers in, host batch out, through the public reader API
+    e2e = None
+    if not args.no_e2e:
+        ftypes = schema.physical_types()
+        # device -> pinned host copies of every input buffer (the step's inputs live in page-locked memory)
+        host_runs = []
+        for r in readers:
+            cols = []
+            byptr = {tt.data_ptr(): tt for tt in r.keepalive}
+            cache = {}
+
+            def to_host(ptr, byptr=byptr, cache=cache):
+                if not ptr:
+                    return None
+                if ptr not in cache:
+                    tt = byptr[ptr]
+                    hb = torch.empty(tt.shape, dtype=tt.dtype, pin_memory=True)
+                    hb.copy_(tt)
+                    cache[ptr] = hb.numpy()
+                return cache[ptr]
+            for ci, dc in enumerate(r.device_columns):
+                t_ = ftypes[ci]
+                data, offs, val = to_host(dc.data), to_host(dc.offsets), to_host(dc.validity)
+                if offs is not None:
+                    data = data.view(np.uint8)
+                cols.append(Column(t_, data, offs, val))
+            host_runs.append(KeyValueBatch(schema, cols))
+        torch.cuda.synchronize()
+        rd.close()
+        del readers, all_keys
+        torch.cuda.empty_cache()
+        arena = torch.empty(int(out_bytes * 1.02) + (64 << 20), dtype=torch.uint8, pin_memory=True)
+        arena_np = arena.numpy()
+        e2e_times, h2d_b, d2h_b = [], 0, 0
+        for it_ in range(args.e2e_steps + 1):
+            top = [0]
+
+            def alloc(nbytes):
+                a = (top[0] + 63) & ~63
+                top[0] = a + nbytes
+                return arena_np[a:a + nbytes]
+            barrier()
+            t0 = time.perf_counter()
+            hr = [SortedRunReader(schema, b) for b in host_runs]
+            mr = SortMergeReader.create_sort_merge_reader(hr, None, None, spec, device=local_rank)   # H2D
+            mr.execute()
+            out = mr.fetch(allocator=alloc)                                                           # D2H
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            s = mr.stats()
+            h2d_b, d2h_b = s.bytes_h2d, s.bytes_d2h
+            assert out.n_rows == n_out
+            mr.close()
+            if it_ > 0:
+                e2e_times.append(dt)
+        tt = torch.tensor([sum(e2e_times) / len(e2e_times)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n_in / float(tt.item()), "unit": "rows/s", "h2d_bytes_per_step": int(h2d_b),
+               "d2h_bytes_per_step": int(d2h_b), "ms_per_step": 1e3 * float(tt.item()), "steps": len(e2e_times),
+               "api": "SortMergeReader.create_sort_merge_reader(host runs).execute()+fetch() over the C ABI"}
+    else:
+        rd.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = args.cpu_threads or min(os.cpu_count() or 1, 64)
+        sample = args.cpu_sample_rows or (2_000_000 if args.workload == "c3" else 8_000_000)
+        sample = min(sample, rows)
+        nrows, times, _ = cpu_baseline(args.workload, sample, threads, steps=2)
+        cpu = {"value": nrows / min(times), "unit": "rows/s", "cores": threads, "kind": "port",
+               "sample": f"{threads} buckets x {nrows // threads} rows of the same shape, one thread per bucket; "
+                         f"oracle = C restatement of LoserTree+MergeFunction (no JVM in the image)"}
+
+    if rank == 0:
+        line = {"metric": metric, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config,
+                "rows_in_per_gpu": int(n_in), "rows_out_per_gpu": int(n_out), "wall_ms_per_step": 1e3 * wall / args.steps,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -142,8 +142,9 @@ typedef struct {
     int32_t n_tiles;
     int32_t n_levels;              /* sampled partition levels above level 0 */
     float ms_partition;            /* CUDA-event times of the last execute, on the handle's stream */
-    float ms_plan;
-    float ms_emit;
+    float ms_plan;                 /* plan kernel + row-count scan */
+    float ms_alloc;                /* size read-back + output allocation (host-paced gap on the stream) */
+    float ms_emit;                 /* emit kernel only */
     float ms_total;
     int32_t launches;              /* kernels launched by the last execute */
 } pg_stats;
@@ -163,7 +164,9 @@ pg_status pg_merge_spec_free(uint64_t spec);
 
 /* Register one sorted run.  PG_MEM_HOST: the buffers are copied to the device now (they may be
  * freed after the call).  PG_MEM_DEVICE: the pointers are device pointers that the caller keeps
- * alive until pg_run_free. */
+ * alive until pg_run_free; every buffer must be 16-byte aligned and readable up to the next multiple
+ * of 16 bytes (true for any cudaMalloc'ed / framework-allocated buffer): the kernels stage column
+ * segments with 16-byte bulk async copies. */
 pg_status pg_run_open(uint64_t schema, const pg_run_desc *run, int32_t mem, uint64_t *out_run);
 pg_status pg_run_free(uint64_t run);
 

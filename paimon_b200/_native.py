@@ -54,7 +54,7 @@ class PgStats(C.Structure):
     _fields_ = [("rows_in", C.c_int64), ("rows_out", C.c_int64), ("bytes_h2d", C.c_int64),
                 ("bytes_d2h", C.c_int64), ("bytes_out", C.c_int64), ("n_tiles", C.c_int32),
                 ("n_levels", C.c_int32), ("ms_partition", C.c_float), ("ms_plan", C.c_float),
-                ("ms_emit", C.c_float), ("ms_total", C.c_float), ("launches", C.c_int32)]
+                ("ms_alloc", C.c_float), ("ms_emit", C.c_float), ("ms_total", C.c_float), ("launches", C.c_int32)]
 
 
 class PaimonGpuError(RuntimeError):

@@ -40,7 +40,8 @@ struct Merge {
     int k = 0;
     int64_t n_in = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::vector<int64_t> varlen_bound;     // per var-len column: sum of the runs' payload bytes
     KeyDesc key{};
     MergeFlags flags{};
     std::vector<ColDesc> cols;
@@ -50,9 +51,10 @@ struct Merge {
     const void **d_key_ptrs = nullptr;
     const int64_t **d_seq_ptrs = nullptr;
     const int8_t **d_kind_ptrs = nullptr;
-    DevColumn *d_run_cols = nullptr;
+    ColPtrs d_ptrs{};                   // [col * k + run]
+    int64_t *d_run_rows = nullptr;
     ColDesc *d_cols = nullptr;
-    int32_t *d_varlen_cols = nullptr;
+    int32_t *d_tile_counter = nullptr;
     pg_out_column *d_out_cols = nullptr;
     int64_t *d_totals = nullptr;       // [1 + n_varlen]
     int32_t *d_err = nullptr;
@@ -196,6 +198,10 @@ static pg_status build_descriptors(Merge *m) {
                     return fail(PG_ERR_UNSUPPORTED, "aggregate function not implemented on the device");
                 cd.mode = CM_FOLD;
                 cd.agg = agg;
+                // an aggregator can produce NULL from non-null inputs (retract of last_value, ignored
+                // retracts only, ...) and AggregateMergeFunction does not re-check NOT NULL: the output of a
+                // folded column always carries a validity bitmap
+                cd.nullable = 1;
                 cd.retract = ign ? RT_IGNORE : (agg_supports_retract(agg) ? RT_OK : RT_ERROR);
             } else {
                 if (sp->engine == PG_ENGINE_PARTIAL_UPDATE && agg != PG_AGG_NONE &&
@@ -212,35 +218,47 @@ static pg_status build_descriptors(Merge *m) {
     size_t o_key = 0;
     size_t o_seq = o_key + align(sizeof(void *) * k * nk);
     size_t o_kind = o_seq + align(sizeof(void *) * k);
-    size_t o_rc = o_kind + align(sizeof(void *) * k);
-    size_t o_cols = o_rc + align(sizeof(DevColumn) * (size_t)k * nc);
-    size_t o_vl = o_cols + align(sizeof(ColDesc) * nc);
-    size_t o_out = o_vl + align(sizeof(int32_t) * (nv + 1));
+    size_t o_pd = o_kind + align(sizeof(void *) * k);
+    size_t o_po = o_pd + align(sizeof(void *) * (size_t)k * nc);
+    size_t o_pv = o_po + align(sizeof(void *) * (size_t)k * nc);
+    size_t o_rows = o_pv + align(sizeof(void *) * (size_t)k * nc);
+    size_t o_cols = o_rows + align(sizeof(int64_t) * k);
+    size_t o_out = o_cols + align(sizeof(ColDesc) * nc);
     size_t o_tot = o_out + align(sizeof(pg_out_column) * nc);
     size_t o_err = o_tot + align(sizeof(int64_t) * (nv + 1));
-    size_t total = o_err + 256;
+    size_t o_cnt = o_err + 256;
+    size_t total = o_cnt + 256;
     std::vector<unsigned char> host(total, 0);
+    m->varlen_bound.assign(nv, 0);
     for (int r = 0; r < k; r++) {
         const Run *run = m->runs[r];
         for (int f = 0; f < nk; f++) ((const void **)(host.data() + o_key))[r * nk + f] = run->cols[f].data;
         ((const void **)(host.data() + o_seq))[r] = run->cols[nk].data;
         ((const void **)(host.data() + o_kind))[r] = run->cols[nk + 1].data;
-        for (int c = 0; c < nc; c++) ((DevColumn *)(host.data() + o_rc))[(size_t)r * nc + c] = run->cols[c];
+        for (int c = 0; c < nc; c++) {
+            ((const void **)(host.data() + o_pd))[(size_t)c * k + r] = run->cols[c].data;
+            ((const void **)(host.data() + o_po))[(size_t)c * k + r] = run->cols[c].offsets;
+            ((const void **)(host.data() + o_pv))[(size_t)c * k + r] = run->cols[c].validity;
+            if (m->cols[c].varlen_index >= 0) m->varlen_bound[m->cols[c].varlen_index] += run->varlen_bytes[c];
+        }
+        ((int64_t *)(host.data() + o_rows))[r] = run->n_rows;
     }
     memcpy(host.data() + o_cols, m->cols.data(), sizeof(ColDesc) * nc);
-    if (nv) memcpy(host.data() + o_vl, m->varlen_cols.data(), sizeof(int32_t) * nv);
     PG_CUDA(cudaMalloc(&m->d_desc, total));
     PG_CUDA(cudaMemcpy(m->d_desc, host.data(), total, cudaMemcpyHostToDevice));
     unsigned char *d = (unsigned char *)m->d_desc;
     m->d_key_ptrs = (const void **)(d + o_key);
     m->d_seq_ptrs = (const int64_t **)(d + o_seq);
     m->d_kind_ptrs = (const int8_t **)(d + o_kind);
-    m->d_run_cols = (DevColumn *)(d + o_rc);
+    m->d_ptrs.data = (const void *const *)(d + o_pd);
+    m->d_ptrs.offsets = (const int32_t *const *)(d + o_po);
+    m->d_ptrs.validity = (const uint32_t *const *)(d + o_pv);
+    m->d_run_rows = (int64_t *)(d + o_rows);
     m->d_cols = (ColDesc *)(d + o_cols);
-    m->d_varlen_cols = (int32_t *)(d + o_vl);
     m->d_out_cols = (pg_out_column *)(d + o_out);
     m->d_totals = (int64_t *)(d + o_tot);
     m->d_err = (int32_t *)(d + o_err);
+    m->d_tile_counter = (int32_t *)(d + o_cnt);
     PG_CUDA(cudaMallocHost((void **)&m->h_totals, sizeof(int64_t) * (nv + 1) + 16));
     m->h_err = (int32_t *)(m->h_totals + nv + 1);
     return PG_OK;
@@ -347,16 +365,18 @@ static pg_status execute(Merge *m) {
     const int T = n_tiles[0];
     const int64_t N = m->n_in;
     uint16_t *plan = nullptr;
-    int32_t *tile_rows = nullptr, *tile_bytes = nullptr;
-    int64_t *tmp_seq = nullptr, *row_base = nullptr, *byte_base = nullptr;
+    int32_t *tile_rows = nullptr;
+    int64_t *tmp_seq = nullptr, *row_base = nullptr;
+    uint64_t *vl_state = nullptr;
     int8_t *tmp_kind = nullptr;
     PG_CUDA(talloc(sizeof(uint16_t) * (size_t)N + 16, (void **)&plan));
     PG_CUDA(talloc(sizeof(int32_t) * (size_t)T, (void **)&tile_rows));
-    PG_CUDA(talloc(sizeof(int32_t) * (size_t)T * std::max(nv, 1), (void **)&tile_bytes));
     PG_CUDA(talloc(sizeof(int64_t) * (size_t)N + 16, (void **)&tmp_seq));
     PG_CUDA(talloc((size_t)N + 16, (void **)&tmp_kind));
     PG_CUDA(talloc(sizeof(int64_t) * (size_t)T, (void **)&row_base));
-    PG_CUDA(talloc(sizeof(int64_t) * (size_t)T * std::max(nv, 1), (void **)&byte_base));
+    PG_CUDA(talloc(sizeof(uint64_t) * (size_t)T * std::max(nv, 1), (void **)&vl_state));
+    PG_CUDA(cudaMemsetAsync(vl_state, 0, sizeof(uint64_t) * (size_t)T * std::max(nv, 1), sm));
+    PG_CUDA(cudaMemsetAsync(m->d_tile_counter, 0, sizeof(int32_t), sm));
 
     PlanArgs pa{};
     pa.bounds = bounds0;
@@ -364,21 +384,15 @@ static pg_status execute(Merge *m) {
     pa.seq_ptrs = m->d_seq_ptrs;
     pa.kind_ptrs = m->d_kind_ptrs;
     pa.flags = m->flags;
-    pa.n_varlen = nv;
-    pa.varlen_cols = m->d_varlen_cols;
-    pa.cols = m->d_cols;
-    pa.run_cols = m->d_run_cols;
-    pa.n_cols = nc;
     pa.plan = plan;
     pa.tile_rows = tile_rows;
-    pa.tile_bytes = tile_bytes;
     pa.tmp_seq = tmp_seq;
     pa.tmp_kind = tmp_kind;
     launch_plan(ml, pa);
-    launch_scan(sm, tile_rows, tile_bytes, T, nv, row_base, byte_base, m->d_totals, m->d_err);
+    launch_scan(sm, tile_rows, T, row_base, m->d_totals);
     launches += 2;
     PG_CUDA(cudaEventRecord(m->ev[2], sm));
-    PG_CUDA(cudaMemcpyAsync(m->h_totals, m->d_totals, sizeof(int64_t) * (nv + 1), cudaMemcpyDeviceToHost, sm));
+    PG_CUDA(cudaMemcpyAsync(m->h_totals, m->d_totals, sizeof(int64_t), cudaMemcpyDeviceToHost, sm));
     PG_CUDA(cudaMemcpyAsync(m->h_err, m->d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, sm));
     PG_CUDA(cudaStreamSynchronize(sm));      // the one size read-back: output buffers are sized exactly
     if (*m->h_err != KERR_NONE) {
@@ -405,12 +419,14 @@ static pg_status execute(Merge *m) {
             oc.data_bytes = n_out * cd.width;
             PG_CUDA(oalloc((size_t)oc.data_bytes + 64, &oc.data));
         } else {
-            oc.data_bytes = m->h_totals[1 + cd.varlen_index];
+            // exact size is only known after the emit kernel's look-back; every output cell is one input
+            // cell, so the runs' payload bytes bound it
+            oc.data_bytes = m->varlen_bound[cd.varlen_index];
             PG_CUDA(oalloc((size_t)oc.data_bytes + 64, &oc.data));
             PG_CUDA(oalloc(sizeof(int32_t) * (size_t)(n_out + 1) + 64, (void **)&oc.offsets));
             bytes_out += 4 * (n_out + 1);
         }
-        bytes_out += oc.data_bytes;
+        if (cd.width > 0) bytes_out += oc.data_bytes;
         if (cd.nullable) {
             size_t vb = (size_t)((n_out + 31) / 32) * 4 + 64;
             PG_CUDA(oalloc(vb, (void **)&oc.validity));
@@ -427,23 +443,27 @@ static pg_status execute(Merge *m) {
     ea.bounds = bounds0;
     ea.n_tiles = T;
     ea.k = k;
-    ea.n_key = s->n_key;
     ea.plan = plan;
     ea.row_base = row_base;
-    ea.byte_base = byte_base;
     ea.tmp_seq = tmp_seq;
     ea.tmp_kind = tmp_kind;
     ea.cols = m->d_cols;
-    ea.run_cols = m->d_run_cols;
+    ea.ptrs = m->d_ptrs;
+    ea.run_rows = m->d_run_rows;
     ea.n_cols = nc;
+    ea.n_varlen = nv;
     ea.out_cols = m->d_out_cols;
     ea.totals = m->d_totals;
+    ea.vl_state = vl_state;
+    ea.tile_counter = m->d_tile_counter;
     ea.err = m->d_err;
     ea.stream = sm;
+    PG_CUDA(cudaEventRecord(m->ev[4], sm));
     launch_emit(ea);
     launches++;
     PG_CUDA(cudaEventRecord(m->ev[3], sm));
     PG_CUDA(cudaMemcpyAsync(m->h_err, m->d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, sm));
+    PG_CUDA(cudaMemcpyAsync(m->h_totals, m->d_totals, sizeof(int64_t) * (nv + 1), cudaMemcpyDeviceToHost, sm));
     free_temps();
     PG_CUDA(cudaStreamSynchronize(sm));
     PG_CUDA(cudaGetLastError());
@@ -452,11 +472,17 @@ static pg_status execute(Merge *m) {
         free_outputs(m);
         return fail(PG_ERR_MERGE_FUNCTION, kernel_error_message(*m->h_err));
     }
+    for (int c = 0; c < nc; c++)
+        if (m->cols[c].width == 0) {
+            m->out_cols[c].data_bytes = m->h_totals[1 + m->cols[c].varlen_index];
+            m->stats.bytes_out += m->out_cols[c].data_bytes;
+        }
     m->stats.rows_out = n_out;
     m->stats.launches = launches;
     cudaEventElapsedTime(&m->stats.ms_partition, m->ev[0], m->ev[1]);
     cudaEventElapsedTime(&m->stats.ms_plan, m->ev[1], m->ev[2]);
-    cudaEventElapsedTime(&m->stats.ms_emit, m->ev[2], m->ev[3]);
+    cudaEventElapsedTime(&m->stats.ms_alloc, m->ev[2], m->ev[4]);
+    cudaEventElapsedTime(&m->stats.ms_emit, m->ev[4], m->ev[3]);
     cudaEventElapsedTime(&m->stats.ms_total, m->ev[0], m->ev[3]);
     return PG_OK;
 }
@@ -563,9 +589,20 @@ pg_status pg_run_open(uint64_t schema, const pg_run_desc *desc, int32_t mem, uin
     const int nc = s->n_cols();
     const int64_t n = desc->n_rows;
     run->cols.resize(nc);
+    run->varlen_bytes.assign(nc, 0);
     if (mem == PG_MEM_DEVICE) {
-        for (int c = 0; c < nc; c++)
-            run->cols[c] = DevColumn{desc->cols[c].data, desc->cols[c].offsets, desc->cols[c].validity};
+        for (int c = 0; c < nc; c++) {
+            const pg_column &pc = desc->cols[c];
+            if ((((uintptr_t)pc.data) | ((uintptr_t)pc.offsets) | ((uintptr_t)pc.validity)) & 15)
+                return fail(PG_ERR_INVALID, "device column buffers must be 16-byte aligned");
+            run->cols[c] = DevColumn{pc.data, pc.offsets, pc.validity};
+            if (is_varlen(s->field(c).type) && n > 0) {
+                if (!pc.offsets) return fail(PG_ERR_INVALID, "var-len column without offsets");
+                int32_t last = 0;
+                PG_CUDA(cudaMemcpy(&last, pc.offsets + n, sizeof(int32_t), cudaMemcpyDeviceToHost));
+                run->varlen_bytes[c] = last;
+            }
+        }
     } else if (mem == PG_MEM_HOST) {
         // one device allocation per run, columns sub-allocated at 256-byte boundaries
         auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -606,6 +643,7 @@ pg_status pg_run_open(uint64_t schema, const pg_run_desc *desc, int32_t mem, uin
                 PG_CUDA(cudaMemcpyAsync(d + o_val[c], pc.validity, b_val[c], cudaMemcpyHostToDevice, 0));
             }
             run->bytes_h2d += (int64_t)(b_data[c] + b_off[c] + b_val[c]);
+            if (is_varlen(s->field(c).type)) run->varlen_bytes[c] = (int64_t)b_data[c];
             run->cols[c] = dc;
         }
         PG_CUDA(cudaStreamSynchronize(0));

@@ -1,0 +1,537 @@
+// emit.cu — the dominant kernel of the merge: per tile and column, stage the k run segments into
+// shared memory with 1-D bulk async copies (TMA, cp.async.bulk + mbarrier), resolve every output row
+// from its key group's members (select / fold per the plan's op codes), and store the result column
+// coalesced.  All random access happens in shared memory; global memory only sees contiguous streams.
+//
+// Replaces, per output row and column, MergeFunction.add()/getResult() of the reference:
+//   DeduplicateMergeFunction.java:47-60, PartialUpdateMergeFunction.java:177-188 (updateNonNullFields),
+//   aggregate/AggregateMergeFunction.java:91-101 + FieldAggregator implementations.
+//
+// Pipeline per CTA (one tile): column c+1's segments are in flight (async proxy) while column c is being
+// resolved from the other stage; validity words of column c+1 are prefetched into registers.
+// Var-len columns get their output byte offsets from a decoupled look-back over tiles (tiles are taken
+// in ticket order), so no second pass over the data is needed to size them.
+#include "device_utils.cuh"
+
+namespace pg {
+
+constexpr int kStages = 2;
+constexpr int kEmitThreads = 512;
+constexpr int kEmitWarps = kEmitThreads / 32;
+#define kFlagAgg (1ull << 62)
+#define kFlagPrefix (2ull << 62)
+#define kValMask ((1ull << 62) - 1)
+
+// per merged position: staged row position (13 bits) | op (2 bits) | first-member-of-group (1 bit)
+constexpr uint32_t kPmPosMask = 0x1FFF;
+constexpr int kPmOpShift = 13;
+constexpr uint32_t kPmHead = 0x8000;
+
+struct EmitLayout {
+    int rt;              // staged rows capacity per stage (multiple of 32)
+    size_t stage_bytes;
+    size_t total;
+};
+__host__ __device__ inline EmitLayout emit_layout(int k) {
+    EmitLayout L;
+    L.rt = kTileMax + 64 * k;
+    L.stage_bytes = (((size_t)L.rt * 8 + (size_t)L.rt / 32 * 4) + 127) & ~(size_t)127;
+    L.total = kStages * L.stage_bytes + (size_t)kTileMax * (2 + 2 + 1) + (PG_MAX_RUNS + 1) * 4 * 2 +
+              PG_MAX_RUNS * 8 + kStages * PG_MAX_RUNS * 8 + kStages * 8 + 34 * 4 + 64;
+    return L;
+}
+
+__device__ __forceinline__ bool staged_valid(const uint32_t *vw, int p) { return (vw[p >> 5] >> (p & 31)) & 1; }
+
+template <int W> __device__ __forceinline__ uint64_t lds_fixed(const unsigned char *vals, int p);
+template <> __device__ __forceinline__ uint64_t lds_fixed<1>(const unsigned char *v, int p) { return v[p]; }
+template <> __device__ __forceinline__ uint64_t lds_fixed<2>(const unsigned char *v, int p) { return ((const uint16_t *)v)[p]; }
+template <> __device__ __forceinline__ uint64_t lds_fixed<4>(const unsigned char *v, int p) { return ((const uint32_t *)v)[p]; }
+template <> __device__ __forceinline__ uint64_t lds_fixed<8>(const unsigned char *v, int p) { return ((const uint64_t *)v)[p]; }
+template <int W> __device__ __forceinline__ void stg_fixed(void *d, int64_t row, uint64_t v);
+template <> __device__ __forceinline__ void stg_fixed<1>(void *d, int64_t r, uint64_t v) { ((uint8_t *)d)[r] = (uint8_t)v; }
+template <> __device__ __forceinline__ void stg_fixed<2>(void *d, int64_t r, uint64_t v) { ((uint16_t *)d)[r] = (uint16_t)v; }
+template <> __device__ __forceinline__ void stg_fixed<4>(void *d, int64_t r, uint64_t v) { ((uint32_t *)d)[r] = (uint32_t)v; }
+template <> __device__ __forceinline__ void stg_fixed<8>(void *d, int64_t r, uint64_t v) { ((uint64_t *)d)[r] = v; }
+
+// ops-based select, newest member first: the newest UPD member with a non-null cell wins; a SET member
+// ends the scan (its cell, null or not, is the result).  Returns the staged position or -1 (NULL).
+__device__ __forceinline__ int select_pos(const uint16_t *pm, const uint32_t *vw, int last) {
+    int j = last;
+    while (true) {
+        uint32_t e = pm[j];
+        uint32_t op = (e >> kPmOpShift) & 3;
+        if (op != OP_NOOP) {
+            int pj = e & kPmPosMask;
+            if (staged_valid(vw, pj)) return pj;
+            if (op == OP_SET) return -1;
+        }
+        if (e & kPmHead) return -1;
+        --j;
+    }
+}
+// same, but returns the member's merged position (needed for its run id)
+__device__ __forceinline__ int select_member_idx(const uint16_t *pm, const uint32_t *vw, int last) {
+    int j = last;
+    while (true) {
+        uint32_t e = pm[j];
+        uint32_t op = (e >> kPmOpShift) & 3;
+        if (op != OP_NOOP) {
+            if (staged_valid(vw, e & kPmPosMask)) return j;
+            if (op == OP_SET) return -1;
+        }
+        if (e & kPmHead) return -1;
+        --j;
+    }
+}
+
+__device__ __forceinline__ int group_first(const uint16_t *pm, int last) {
+    int j = last;
+    while (!(pm[j] & kPmHead)) --j;
+    return j;
+}
+
+// aggregate engine on a var-len column: fold with the member index as accumulator
+__device__ int fold_member_idx(const ColDesc &cd, const uint16_t *pm, const uint8_t *mrun, const uint32_t *vw,
+                               const int32_t *offs, const uint8_t *const *cdata, int last, int32_t *err) {
+    int acc = -1;
+    bool initialized = false;
+    for (int j = group_first(pm, last); j <= last; j++) {
+        uint32_t e = pm[j];
+        int op = (e >> kPmOpShift) & 3;
+        if (op == OP_NOOP) continue;
+        bool v = staged_valid(vw, e & kPmPosMask);
+        int in = v ? j : -1;
+        if (op == OP_SET) { acc = in; continue; }
+        if (op == OP_RETRACT) {
+            if (cd.retract == RT_IGNORE) continue;
+            switch (cd.agg) {
+                case PG_AGG_LAST_VALUE: acc = -1; break;
+                case PG_AGG_LAST_NON_NULL_VALUE: if (v) acc = -1; break;
+                case PG_AGG_PRIMARY_KEY: acc = in; break;
+                default: atomicCAS(err, KERR_NONE, KERR_AGG_RETRACT); break;
+            }
+            continue;
+        }
+        switch (cd.agg) {
+            case PG_AGG_LAST_VALUE: case PG_AGG_PRIMARY_KEY: acc = in; break;
+            case PG_AGG_LAST_NON_NULL_VALUE: if (v) acc = in; break;
+            case PG_AGG_FIRST_VALUE: if (!initialized) { initialized = true; acc = in; } break;
+            case PG_AGG_FIRST_NON_NULL_VALUE: if (!initialized && v) { initialized = true; acc = in; } break;
+            case PG_AGG_MAX: case PG_AGG_MIN:
+                if (acc < 0 || in < 0) { if (acc < 0) acc = in; break; }
+                {
+                    int pa = pm[acc] & kPmPosMask, pb = e & kPmPosMask;
+                    int d = bytes_compare(cdata[mrun[acc]] + offs[pa], offs[pa + 1] - offs[pa],
+                                          cdata[mrun[j]] + offs[pb], offs[pb + 1] - offs[pb]);
+                    if (cd.agg == PG_AGG_MAX) { if (d < 0) acc = in; }
+                    else { if (!(d < 0)) acc = in; }
+                }
+                break;
+            default: break;
+        }
+    }
+    return acc;
+}
+
+// strict left fold of a fixed-width column in sequence order (AggregateMergeFunction.java:91-101)
+__device__ void fold_fixed(const ColDesc &cd, const uint16_t *pm, const uint32_t *vw, const unsigned char *vals,
+                           int last, uint64_t *out_val, bool *out_valid, int32_t *err) {
+    const int w = cd.width;
+    uint64_t val = 0;
+    bool is_valid = false, initialized = false;
+    for (int j = group_first(pm, last); j <= last; j++) {
+        uint32_t e = pm[j];
+        int op = (e >> kPmOpShift) & 3;
+        if (op == OP_NOOP) continue;
+        int pj = e & kPmPosMask;
+        bool v = staged_valid(vw, pj);
+        uint64_t in = v ? load_fixed(vals, w, pj) : 0;
+        if (op == OP_SET) { val = in; is_valid = v; continue; }
+        if (op == OP_RETRACT) {
+            if (cd.retract == RT_IGNORE) continue;
+            switch (cd.agg) {
+                case PG_AGG_SUM:       // FieldSumAgg.retract :87-131, negative :133-163
+                    if (!is_valid) { if (v) { val = negate_fixed(cd.type, w, in); is_valid = true; } }
+                    else if (v) val = arith(cd.type, w, 1, val, in, err);
+                    break;
+                case PG_AGG_PRODUCT:
+                    if (is_valid && v) val = arith(cd.type, w, 3, val, in, err);
+                    break;
+                case PG_AGG_LAST_VALUE: is_valid = false; val = 0; break;
+                case PG_AGG_LAST_NON_NULL_VALUE: if (v) { is_valid = false; val = 0; } break;
+                case PG_AGG_PRIMARY_KEY: val = in; is_valid = v; break;
+                default: atomicCAS(err, KERR_NONE, KERR_AGG_RETRACT); break;
+            }
+            continue;
+        }
+        switch (cd.agg) {
+            case PG_AGG_SUM: case PG_AGG_PRODUCT:
+                if (!is_valid || !v) { if (!is_valid) { val = in; is_valid = v; } }
+                else val = arith(cd.type, w, cd.agg == PG_AGG_SUM ? 0 : 2, val, in, err);
+                break;
+            case PG_AGG_MAX: case PG_AGG_MIN:
+                if (!is_valid || !v) { if (!is_valid) { val = in; is_valid = v; } }
+                else {
+                    int d = compare_fixed(cd.type, w, val, in);
+                    if (cd.agg == PG_AGG_MAX) { if (d < 0) val = in; }
+                    else { if (!(d < 0)) val = in; }
+                }
+                break;
+            case PG_AGG_BOOL_AND: case PG_AGG_BOOL_OR:
+                if (!is_valid || !v) { if (!is_valid) { val = in; is_valid = v; } }
+                else val = cd.agg == PG_AGG_BOOL_AND ? ((val != 0) && (in != 0)) : ((val != 0) || (in != 0));
+                break;
+            case PG_AGG_LAST_VALUE: case PG_AGG_PRIMARY_KEY: val = in; is_valid = v; break;
+            case PG_AGG_LAST_NON_NULL_VALUE: if (v) { val = in; is_valid = true; } break;
+            case PG_AGG_FIRST_VALUE:
+                if (!initialized) { initialized = true; val = in; is_valid = v; }
+                break;
+            case PG_AGG_FIRST_NON_NULL_VALUE:
+                if (!initialized && v) { initialized = true; val = in; is_valid = true; }
+                break;
+            default: break;
+        }
+    }
+    *out_val = val;
+    *out_valid = is_valid;
+}
+
+struct TileView {
+    const uint16_t *pm;
+    const uint16_t *glast;
+    int n_out;
+    int o_shift;
+    int64_t out_base;
+    int64_t in_base;
+};
+
+// one output validity word per warp iteration: interior words are plain stores, tile-boundary words OR
+__device__ __forceinline__ void put_validity_word(uint8_t *validity, int64_t out_base, int wb, int n_out,
+                                                  bool bit) {
+    unsigned mask = __ballot_sync(0xffffffffu, bit);
+    if ((threadIdx.x & 31) == 0) {
+        int64_t word = (out_base + wb) >> 5;
+        bool full = wb >= 0 && wb + 32 <= n_out;
+        uint32_t *bm = (uint32_t *)validity;
+        if (full) bm[word] = mask;
+        else if (mask) atomicOr(&bm[word], mask);
+    }
+}
+
+template <int W>
+__device__ __forceinline__ void emit_fixed_column(const EmitArgs &ea, const ColDesc &cd, const pg_out_column &oc,
+                                                  const TileView &tv, const unsigned char *vals, const uint32_t *vw) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int wb = (tid & ~31) - tv.o_shift; wb < tv.n_out; wb += kEmitThreads) {   // warp-uniform trip count
+        const int ob = wb + lane;
+        const bool active = ob >= 0 && ob < tv.n_out;
+        bool is_valid = false;
+        if (active) {
+            uint64_t val = 0;
+            const int last = tv.glast[ob];
+            if (cd.mode == CM_SELECT) {
+                int pj = select_pos(tv.pm, vw, last);
+                if (pj >= 0) { val = lds_fixed<W>(vals, pj); is_valid = true; }
+            } else if (cd.mode == CM_KEY) {
+                val = lds_fixed<W>(vals, tv.pm[last] & kPmPosMask); is_valid = true;
+            } else if (cd.mode == CM_SEQ) {
+                val = (uint64_t)ea.tmp_seq[tv.in_base + ob]; is_valid = true;
+            } else if (cd.mode == CM_KIND) {
+                val = (uint8_t)ea.tmp_kind[tv.in_base + ob]; is_valid = true;
+            } else {
+                fold_fixed(cd, tv.pm, vw, vals, last, &val, &is_valid, ea.err);
+                if (!is_valid) val = 0;
+            }
+            stg_fixed<W>(oc.data, tv.out_base + ob, val);
+        }
+        if (oc.validity != nullptr) put_validity_word(oc.validity, tv.out_base, wb, tv.n_out, is_valid);
+    }
+}
+
+__global__ void __launch_bounds__(kEmitThreads, 2)
+k_emit(EmitArgs ea) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int k = ea.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const EmitLayout L = emit_layout(k);
+    unsigned char *stage_vals[kStages];
+    uint32_t *stage_vw[kStages];
+    for (int s = 0; s < kStages; s++) {
+        stage_vals[s] = smem + s * L.stage_bytes;
+        stage_vw[s] = (uint32_t *)(stage_vals[s] + (size_t)L.rt * 8);
+    }
+    unsigned char *p = smem + kStages * L.stage_bytes;
+    uint16_t *pm = (uint16_t *)p;              p += kTileMax * 2;
+    uint16_t *glast = (uint16_t *)p;           p += kTileMax * 2;   // per output row: last member position
+    uint8_t *mrun = (uint8_t *)p;              p += kTileMax;
+    int64_t *rstart = (int64_t *)p;            p += PG_MAX_RUNS * 8;
+    const uint8_t **cdata = (const uint8_t **)p; p += kStages * PG_MAX_RUNS * 8;   // payload base per run (var-len)
+    uint64_t *mbar = (uint64_t *)p;            p += kStages * 8;
+    int64_t *s_i64 = (int64_t *)p;             p += 16;
+    int *seg = (int *)p;                       p += (PG_MAX_RUNS + 1) * 4;
+    int *rr = (int *)p;                        p += (PG_MAX_RUNS + 1) * 4;         // staged row base per run
+    int *ws = (int *)p;                        p += 34 * 4;
+    int *s_i32 = (int *)p;                     p += 16;
+
+    // ---- tile ticket (tiles are started in order => look-back never waits on an unscheduled tile)
+    if (tid == 0) {
+        s_i32[0] = atomicAdd(ea.tile_counter, 1);
+        for (int s = 0; s < kStages; s++) mbar_init(&mbar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int tile = s_i32[0];
+    if (tid == 0) {
+        int acc = 0, racc = 0;
+        for (int r = 0; r < k; r++) {
+            int64_t b0 = ea.bounds[(int64_t)tile * k + r], b1 = ea.bounds[(int64_t)(tile + 1) * k + r];
+            rstart[r] = b0;
+            seg[r] = acc;
+            rr[r] = racc;
+            int len = (int)(b1 - b0);
+            acc += len;
+            racc += (((int)(b0 & 31) + len + 1) + 31) & ~31;
+        }
+        seg[k] = acc;
+        rr[k] = racc;
+    }
+    __syncthreads();
+    const int n = seg[k];
+    const int n_vw = rr[k] >> 5;                       // staged validity words
+    int64_t in_base = 0;
+    for (int r = 0; r < k; r++) in_base += rstart[r];
+
+    // ---- plan -> (staged position | op | head), output rows
+    constexpr int VT = kTileMax / kEmitThreads;
+    const int p0 = tid * VT, p1 = min(p0 + VT, n);
+    int my = 0;
+    uint32_t emit_bits = 0;
+    for (int i = p0; i < p1; i++) {
+        uint16_t e = ea.plan[in_base + i];
+        int slot = e & kPlanSlotMask;
+        int r = run_of_slot(seg, k, slot);
+        mrun[i] = (uint8_t)r;
+        uint32_t pos = (uint32_t)(rr[r] + (int)(rstart[r] & 31) + (slot - seg[r]));
+        uint32_t op = (e >> kPlanOpShift) & 3;
+        pm[i] = (uint16_t)(pos | (op << kPmOpShift) | ((e & kPlanHead) ? kPmHead : 0));
+        if ((e & kPlanHead) && (e & kPlanEmit)) { my++; emit_bits |= 1u << (i - p0); }
+    }
+    int n_out = 0;
+    int o = block_scan_excl(my, ws, &n_out);          // (syncs: pm is complete afterwards)
+    for (int i = p0; i < p1; i++) {
+        if (emit_bits & (1u << (i - p0))) {
+            int e = i + 1;
+            while (e < n && !(pm[e] & kPmHead)) e++;
+            glast[o++] = (uint16_t)(e - 1);
+        }
+    }
+    // validity word owned by this thread: (run, global word index), fixed for the whole tile
+    int vw_run = -1;
+    int64_t vw_gword = 0;
+    if (tid < n_vw) {
+        int r = 0;
+        while (r + 1 < k && (rr[r + 1] >> 5) <= tid) r++;
+        vw_run = r;
+        vw_gword = (rstart[r] >> 5) + (tid - (rr[r] >> 5));
+        if (vw_gword > ((ea.run_rows[r] - 1) >> 5)) vw_run = -1;      // beyond the run's bitmap: never used
+    }
+    __syncthreads();
+
+    TileView tv;
+    tv.pm = pm;
+    tv.glast = glast;
+    tv.n_out = n_out;
+    tv.out_base = ea.row_base[tile];
+    tv.o_shift = (int)(tv.out_base & 31);
+    tv.in_base = in_base;
+    const int ncols = ea.n_cols;
+    uint32_t phase = 0;                                // bit s = parity to wait for on stage s
+
+    auto col_staged = [&](const ColDesc &cd) { return cd.mode != CM_SEQ && cd.mode != CM_KIND; };
+
+    // issue the bulk copies of column c into stage s (warp 0; lane r = run r)
+    auto issue = [&](int c, int s) {
+        const ColDesc cd = ea.cols[c];
+        if (!col_staged(cd)) return;
+        // the stage was last touched through the generic proxy (scratch + validity words)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        uint32_t bytes = 0;
+        const unsigned char *src = nullptr;
+        unsigned char *dst = nullptr;
+        if (lane < k) {
+            const int r = lane;
+            const int len = seg[r + 1] - seg[r];
+            const int64_t row0 = rstart[r] & ~(int64_t)31;
+            const int head = (int)(rstart[r] & 31);
+            if (cd.width > 0) {
+                if (len > 0) {
+                    bytes = (uint32_t)(((head + len) * cd.width + 15) & ~15);
+                    src = (const unsigned char *)ea.ptrs.data[(int64_t)c * k + r] + row0 * cd.width;
+                    dst = stage_vals[s] + (size_t)rr[r] * cd.width;
+                }
+            } else {
+                if (len > 0) {
+                    bytes = (uint32_t)(((head + len + 1) * 4 + 15) & ~15);
+                    src = (const unsigned char *)(ea.ptrs.offsets[(int64_t)c * k + r] + row0);
+                    dst = stage_vals[s] + (size_t)rr[r] * 4;
+                }
+                cdata[s * PG_MAX_RUNS + r] = (const uint8_t *)ea.ptrs.data[(int64_t)c * k + r];
+            }
+        }
+        uint32_t total = bytes;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+        if (lane == 0) mbar_arrive_expect_tx(&mbar[s], total);
+        __syncwarp();
+        if (bytes) bulk_g2s(dst, src, bytes, &mbar[s]);
+    };
+    auto load_vw = [&](int c) -> uint32_t {
+        if (vw_run < 0) return 0xffffffffu;
+        const uint32_t *vp = ea.ptrs.validity[(int64_t)c * k + vw_run];
+        return vp ? vp[vw_gword] : 0xffffffffu;
+    };
+
+    // ---- prologue: column 0
+    if (warp == 0 && ncols > 0) issue(0, 0);
+    if (tid < n_vw && ncols > 0) stage_vw[0][tid] = load_vw(0);
+    __syncthreads();
+
+    for (int c = 0; c < ncols; c++) {
+        const int s = c & 1;
+        const ColDesc cd = ea.cols[c];
+        const pg_out_column oc = ea.out_cols[c];
+        if (warp == 0 && c + 1 < ncols) issue(c + 1, s ^ 1);
+        uint32_t next_vw = (c + 1 < ncols && tid < n_vw) ? load_vw(c + 1) : 0;
+        if (col_staged(cd)) {
+            mbar_wait(&mbar[s], (phase >> s) & 1);
+            phase ^= 1u << s;
+        }
+        const unsigned char *vals = stage_vals[s];
+        const uint32_t *vw = stage_vw[s];
+
+        if (cd.width == 8) emit_fixed_column<8>(ea, cd, oc, tv, vals, vw);
+        else if (cd.width == 4) emit_fixed_column<4>(ea, cd, oc, tv, vals, vw);
+        else if (cd.width == 1) emit_fixed_column<1>(ea, cd, oc, tv, vals, vw);
+        else if (cd.width == 2) emit_fixed_column<2>(ea, cd, oc, tv, vals, vw);
+        else {
+            // ---- var-len column: offsets staged as int32 at the staged row positions; the upper half of the
+            // stage is free (offsets are 4 bytes per row) and holds the per-row source + per-warp scratch
+            const int32_t *offs = (const int32_t *)vals;
+            uint16_t *vsrc = (uint16_t *)(vals + (size_t)L.rt * 4);
+            int *wpre = (int *)(vsrc + kTileMax);                                   // per warp: 33 ints
+            const uint8_t **wsrc = (const uint8_t **)(wpre + ((kEmitWarps * 33 + 1) & ~1));   // 8-byte aligned
+            const uint8_t *const *cd_data = cdata + s * PG_MAX_RUNS;
+            // pass 1: source member per output row, tile byte total
+            int my_bytes = 0;
+            for (int ob = tid; ob < n_out; ob += kEmitThreads) {
+                const int last = glast[ob];
+                int src = cd.mode == CM_KEY ? last
+                          : cd.mode == CM_FOLD ? fold_member_idx(cd, pm, mrun, vw, offs, cd_data, last, ea.err)
+                                               : select_member_idx(pm, vw, last);
+                vsrc[ob] = src < 0 ? (uint16_t)0xFFFF : (uint16_t)src;
+                if (src >= 0) { int ps = pm[src] & kPmPosMask; my_bytes += offs[ps + 1] - offs[ps]; }
+            }
+            int tile_bytes = 0;
+            block_scan_excl(my_bytes, ws, &tile_bytes);
+            // decoupled look-back: exclusive byte prefix of this tile for this column
+            uint64_t *state = ea.vl_state + (int64_t)cd.varlen_index * ea.n_tiles;
+            if (warp == 0) {
+                uint64_t excl = 0;
+                if (lane == 0 && tile > 0) {
+                    __threadfence();
+                    atomicExch((unsigned long long *)&state[tile], kFlagAgg | (uint64_t)tile_bytes);
+                }
+                int t = tile - 1;
+                while (t >= 0) {
+                    int idx = t - lane;
+                    uint64_t sv = idx >= 0 ? *((volatile uint64_t *)&state[idx]) : kFlagPrefix;
+                    unsigned flag = (unsigned)(sv >> 62);
+                    unsigned inval = __ballot_sync(0xffffffffu, flag == 0);
+                    unsigned pref = __ballot_sync(0xffffffffu, flag == 2);
+                    int first = pref ? __ffs(pref) - 1 : 32;
+                    unsigned need = first >= 31 ? 0xffffffffu : ((1u << (first + 1)) - 1);
+                    if (inval & need) continue;                      // a needed predecessor has not published yet
+                    uint64_t contrib = lane <= first ? (sv & kValMask) : 0;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+                    excl += contrib;
+                    if (first < 32) break;
+                    t -= 32;
+                }
+                if (lane == 0) {
+                    __threadfence();
+                    atomicExch((unsigned long long *)&state[tile], kFlagPrefix | (excl + (uint64_t)tile_bytes));
+                    s_i64[0] = (int64_t)excl;
+                    if (tile == ea.n_tiles - 1) {
+                        uint64_t tot = excl + (uint64_t)tile_bytes;
+                        ea.totals[1 + cd.varlen_index] = (int64_t)tot;
+                        if (tot > 0x7fffffffull) atomicCAS(ea.err, KERR_NONE, KERR_OFFSET_OVERFLOW);
+                        oc.offsets[ea.totals[0]] = (int32_t)tot;
+                    }
+                }
+            }
+            __syncthreads();
+            const int64_t byte_base = s_i64[0];
+            uint8_t *dbase = (uint8_t *)oc.data + byte_base;
+            // pass 2: offsets, validity, payload copy
+            int carry = 0;
+            int *my_pre = wpre + warp * 33;
+            const uint8_t **my_src = wsrc + warp * 32;
+            for (int ob0 = -tv.o_shift; ob0 < n_out; ob0 += kEmitThreads) {
+                const int ob = ob0 + tid;
+                const bool active = ob >= 0 && ob < n_out;
+                int len = 0;
+                const uint8_t *sp = nullptr;
+                bool has = false;
+                if (active) {
+                    int src = vsrc[ob];
+                    if (src != 0xFFFF) {
+                        int ps = pm[src] & kPmPosMask;
+                        int st = offs[ps];
+                        len = offs[ps + 1] - st;
+                        sp = cd_data[mrun[src]] + st;
+                        has = true;
+                    }
+                }
+                int tot = 0;
+                int off = block_scan_excl(len, ws, &tot) + carry;
+                carry += tot;
+                if (active) oc.offsets[tv.out_base + ob] = (int32_t)(byte_base + off);
+                if (oc.validity != nullptr)
+                    put_validity_word(oc.validity, tv.out_base, ob0 + (tid & ~31), n_out, has);
+                // warp-cooperative payload copy: the warp's 32 rows form one contiguous destination range;
+                // 8 lanes serve one row, so stores coalesce and short strings do not idle a whole warp
+                my_pre[lane] = off;
+                my_src[lane] = sp;
+                if (lane == 31) my_pre[32] = off + len;
+                __syncwarp();
+#pragma unroll
+                for (int rg = 0; rg < 32; rg += 4) {
+                    const int row = rg + (lane >> 3);
+                    const int o0 = my_pre[row], o1 = my_pre[row + 1];
+                    const uint8_t *rp = my_src[row] - o0;
+                    int b = o0 + (lane & 7);
+                    if (b < o1) { dbase[b] = rp[b]; b += 8;
+                        if (b < o1) { dbase[b] = rp[b]; b += 8;
+                            if (b < o1) { dbase[b] = rp[b]; b += 8;
+                                for (; b < o1; b += 8) dbase[b] = rp[b]; } } }
+                }
+                __syncwarp();
+            }
+        }
+        if (c + 1 < ncols && tid < n_vw) stage_vw[s ^ 1][tid] = next_vw;
+        __syncthreads();
+    }
+}
+
+static bool g_emit_attr = false;
+void launch_emit(const EmitArgs &ea) {
+    EmitLayout L = emit_layout(ea.k);
+    if (!g_emit_attr) {
+        cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        g_emit_attr = true;
+    }
+    k_emit<<<ea.n_tiles, kEmitThreads, L.total, ea.stream>>>(ea);
+}
+
+}  // namespace pg

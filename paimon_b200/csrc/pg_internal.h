@@ -68,6 +68,7 @@ struct Run {
     const Schema *schema = nullptr;
     int64_t n_rows = 0;
     std::vector<DevColumn> cols;
+    std::vector<int64_t> varlen_bytes;   // per column: payload bytes of a var-len column (offsets[n_rows])
     std::vector<void *> owned;           // device allocations made by pg_run_open(PG_MEM_HOST)
     int64_t bytes_h2d = 0;
 };
@@ -136,40 +137,41 @@ struct PlanArgs {
     const int64_t *const *seq_ptrs;    // device [k]
     const int8_t *const *kind_ptrs;    // device [k]
     MergeFlags flags;
-    // var-len bookkeeping
-    int n_varlen;
-    const int32_t *varlen_cols;        // device [n_varlen] file column index
-    const ColDesc *cols;               // device [n_cols]
-    const DevColumn *run_cols;         // device [k * n_cols]
-    int n_cols;
     // outputs
     uint16_t *plan;                    // [N]
     int32_t *tile_rows;                // [n_tiles]
-    int32_t *tile_bytes;               // [n_varlen * n_tiles]
     int64_t *tmp_seq;                  // [N]  result sequence number per (tile in_base + out idx)
     int8_t *tmp_kind;                  // [N]
 };
 void launch_plan(const MergeLaunch &ml, const PlanArgs &pa);
 
-// exclusive scan of tile_rows / tile_bytes into int64 offsets; totals[0] = rows, totals[1+v] = bytes
-void launch_scan(cudaStream_t stream, const int32_t *tile_rows, const int32_t *tile_bytes, int n_tiles,
-                 int n_varlen, int64_t *row_base, int64_t *byte_base, int64_t *totals, int32_t *err);
+// exclusive scan of tile_rows into int64 row offsets; totals[0] = output rows
+void launch_scan(cudaStream_t stream, const int32_t *tile_rows, int n_tiles, int64_t *row_base, int64_t *totals);
+
+// per-column, per-run input pointers, transposed for coalesced access: [col * k + run]
+struct ColPtrs {
+    const void *const *data;
+    const int32_t *const *offsets;
+    const uint32_t *const *validity;   // bitmaps read as 32-bit words
+};
 
 struct EmitArgs {
     const int64_t *bounds;
     int n_tiles;
     int k;
-    int n_key;
     const uint16_t *plan;
     const int64_t *row_base;           // [n_tiles]
-    const int64_t *byte_base;          // [n_varlen * n_tiles]
     const int64_t *tmp_seq;
     const int8_t *tmp_kind;
     const ColDesc *cols;
-    const DevColumn *run_cols;         // [k * n_cols]
+    ColPtrs ptrs;
+    const int64_t *run_rows;           // device [k] rows per run
     int n_cols;
+    int n_varlen;
     const pg_out_column *out_cols;     // device [n_cols]
-    const int64_t *totals;             // device
+    int64_t *totals;                   // device [1 + n_varlen]: [0] rows (in), [1+v] var-len bytes (out)
+    uint64_t *vl_state;                // [n_varlen * n_tiles] decoupled look-back state, zeroed per launch
+    int32_t *tile_counter;             // ticket counter, zeroed per launch
     int32_t *err;
     cudaStream_t stream;
 };

@@ -212,25 +212,26 @@ class SortMergeReader(RecordReader):
         N.check(self.lib.pg_merge_device_batch(self._merge_h, C.byref(b)))
         return DeviceBatch(b.n_rows, [b.cols[i] for i in range(b.n_cols)])
 
-    def fetch(self) -> KeyValueBatch:
-        """Device batch -> host columns (D2H)."""
+    def fetch(self, allocator=None) -> KeyValueBatch:
+        """Device batch -> host columns (D2H).  `allocator(nbytes) -> np.uint8 array` lets the caller supply
+        page-locked memory (the Java side passes direct buffers); default is ordinary numpy memory."""
+        alloc = allocator or (lambda nbytes: np.zeros(nbytes, np.uint8))
         db = self.device_batch()
         n = db.n_rows
         types = self.schema.physical_types()
-        fields = self.schema.file_fields()
         host = (N.PgOutColumn * len(types))()
         cols: List[Column] = []
         for i, t in enumerate(types):
             oc = db.columns[i]
-            nullable = fields[i].nullable
-            valid = np.zeros((n + 7) // 8 + 8, np.uint8) if nullable else None
+            valid = alloc((n + 7) // 8 + 8) if oc.validity else None
             if is_varlen(t):
-                data = np.zeros(max(int(oc.data_bytes), 1), np.uint8)
-                offs = np.zeros(n + 1, np.int32)
+                data = alloc(max(int(oc.data_bytes), 1))
+                offs = alloc(4 * (n + 1)).view(np.int32)
                 host[i] = N.PgOutColumn(_np_ptr(data), _np_ptr(offs), _np_ptr(valid), oc.data_bytes)
                 cols.append(Column(t, data[: int(oc.data_bytes)], offs, valid))
             else:
-                data = np.zeros(max(n, 1), numpy_dtype(t))
+                dt = np.dtype(numpy_dtype(t))
+                data = alloc(max(n, 1) * dt.itemsize).view(dt)
                 host[i] = N.PgOutColumn(_np_ptr(data), None, _np_ptr(valid), oc.data_bytes)
                 cols.append(Column(t, data[:n], None, valid))
         N.check(self.lib.pg_merge_fetch(self._merge_h, host, len(types)))
