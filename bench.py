@@ -211,13 +211,13 @@ def cpu_baseline(workload, total_sample_rows, threads, steps=1, seed=7):
     spec = make_spec(workload, schema)
     w = WORKLOADS[workload]
     per_bucket = max(total_sample_rows // threads, w["n_runs"] * 64)
+    n_distinct = min(threads, 8)        # distinct synthetic buckets; threads beyond that re-merge a copy's inputs
     buckets = [datagen.make_runs(schema, w["n_runs"], per_bucket, seed=seed + b, null_prob=w["null_prob"])
-               for b in range(threads)]
-    pyoracle.lib()
+               for b in range(n_distinct)]
+    prepared = [pyoracle.prepare(schema, spec, buckets[b % n_distinct]) for b in range(threads)]
 
     def work(b):
-        out = pyoracle.merge(schema, spec, buckets[b], pyoracle.SORT_LOSER_TREE)
-        return out.n_rows
+        return pyoracle.run_prepared(prepared[b])          # C call only; the GIL is released
 
     times = []
     with ThreadPoolExecutor(max_workers=threads) as ex:
@@ -262,7 +262,7 @@ def main():
         if rank != 0:
             return
         threads = args.cpu_threads or min(os.cpu_count() or 1, 64)
-        sample = args.cpu_sample_rows or (2_000_000 if args.workload == "c3" else 8_000_000)
+        sample = args.cpu_sample_rows or threads * (250_000 if args.workload == "c3" else 1_000_000)
         sample = min(sample, rows)
         cpu_baseline(args.workload, min(sample, 200_000), threads, steps=max(args.warmup, 1) if args.warmup else 0)
         nrows, times, _ = cpu_baseline(args.workload, sample, threads, steps=args.steps)
@@ -425,7 +425,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = args.cpu_threads or min(os.cpu_count() or 1, 64)
-        sample = args.cpu_sample_rows or (2_000_000 if args.workload == "c3" else 8_000_000)
+        sample = args.cpu_sample_rows or threads * (250_000 if args.workload == "c3" else 1_000_000)
         sample = min(sample, rows)
         nrows, times, _ = cpu_baseline(args.workload, sample, threads, steps=2)
         cpu = {"value": nrows / min(times), "unit": "rows/s", "cores": threads, "kind": "port",

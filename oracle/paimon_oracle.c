@@ -870,8 +870,12 @@ static void buf_reserve(buf_t *b, int64_t extra) {
     if (b->len + extra > b->cap) {
         int64_t nc = b->cap ? b->cap * 2 : 4096;
         while (nc < b->len + extra) nc *= 2;
-        b->p = (uint8_t *)realloc(b->p, (size_t)nc);
-        memset(b->p + b->cap, 0, (size_t)(nc - b->cap));
+        if (b->p == NULL) {
+            b->p = (uint8_t *)calloc(1, (size_t)nc);          /* lazily zeroed pages */
+        } else {
+            b->p = (uint8_t *)realloc(b->p, (size_t)nc);
+            memset(b->p + b->cap, 0, (size_t)(nc - b->cap));
+        }
         b->cap = nc;
     }
 }
@@ -902,6 +906,24 @@ static writer_t *wr_new(const ctx_t *c) {
     w->data = (buf_t *)calloc(w->ncols, sizeof(buf_t));
     w->offsets = (buf_t *)calloc(w->ncols, sizeof(buf_t));
     w->valid = (buf_t *)calloc(w->ncols, sizeof(buf_t));
+    /* size every output buffer for the worst case (all input rows survive) up front: a growing realloc
+     * per column makes many-thread runs serialise in the kernel's mmap path, which would understate the
+     * CPU baseline */
+    int64_t n_in = 0;
+    for (int r = 0; r < c->k; r++) n_in += c->runs[r].n_rows;
+    for (int i = 0; i < w->ncols; i++) {
+        int t = col_type(c, i);
+        if (is_varlen(t)) {
+            int64_t bytes = 0;
+            for (int r = 0; r < c->k; r++)
+                if (c->runs[r].n_rows > 0) bytes += c->runs[r].cols[i].offsets[c->runs[r].n_rows];
+            buf_reserve(&w->data[i], bytes + 16);
+            buf_reserve(&w->offsets[i], 4 * (n_in + 1) + 16);
+        } else {
+            buf_reserve(&w->data[i], n_in * type_width(t) + 16);
+        }
+        buf_reserve(&w->valid[i], n_in / 8 + 16);
+    }
     int32_t zero = 0;
     for (int i = 0; i < w->ncols; i++)
         if (is_varlen(col_type(c, i))) buf_append(&w->offsets[i], &zero, 4);

@@ -193,3 +193,22 @@ def interval_partition(min_keys: Sequence[int], max_keys: Sequence[int]):
     ns = C.c_int32(0)
     lib().po_interval_partition(n, _ptr(mn), _ptr(mx), _ptr(sec), _ptr(run), C.byref(ns))
     return sec[:n], run[:n], ns.value
+
+
+def prepare(schema: KeyValueSchema, spec: MergeSpec, runs: Sequence[KeyValueBatch],
+            sort_engine: int = SORT_LOSER_TREE):
+    """Marshal once (outside any timed region); see run_prepared."""
+    lib()
+    return _Marshalled(schema, spec, runs, sort_engine)
+
+
+def run_prepared(m) -> int:
+    """Only the C call (ctypes drops the GIL for its duration): merge and discard, returning the row count.
+    Used by bench.py's cpu_baseline so that Python marshalling is not billed to the reference algorithm."""
+    out = C.POINTER(_Result)()
+    rc = lib().po_merge(C.byref(m.schema), C.byref(m.spec), m.k, m.runs, C.byref(out))
+    if rc != 0:
+        raise OracleError(lib().po_last_error().decode())
+    n = out.contents.n_rows
+    lib().po_result_free(out)
+    return n

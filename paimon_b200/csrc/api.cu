@@ -33,6 +33,33 @@ static int type_width(int t) {
 static bool type_ok(int t) { return t >= PG_INT8 && t <= PG_BINARY; }
 static bool is_varlen(int t) { return t == PG_STRING || t == PG_BINARY; }
 
+// grow-only device arena with a bump pointer
+struct Arena {
+    unsigned char *base = nullptr;
+    size_t cap = 0, top = 0;
+    cudaError_t reserve(size_t bytes) {
+        top = 0;
+        if (bytes <= cap) return cudaSuccess;
+        if (base) cudaFree(base);
+        base = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc((void **)&base, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void *take(size_t bytes) {
+        size_t a = (top + 255) & ~(size_t)255;
+        if (a + bytes > cap) return nullptr;
+        top = a + bytes;
+        return base + a;
+    }
+    void release() {
+        if (base) cudaFree(base);
+        base = nullptr;
+        cap = top = 0;
+    }
+};
+
 struct Merge {
     const Spec *spec = nullptr;
     const Schema *schema = nullptr;
@@ -63,7 +90,8 @@ struct Merge {
     int32_t *h_err = nullptr;
     // output of the last execute
     std::vector<pg_out_column> out_cols;
-    std::vector<void *> out_allocs;
+    Arena work;                        // temporaries of one execute (bounds, sample keys, plan, ...)
+    Arena outbuf;                      // the output batch
     int64_t n_out = 0;
     bool has_batch = false;
     pg_stats stats{};
@@ -110,17 +138,21 @@ static pg_status ensure_device() {
     return PG_OK;
 }
 
-static void free_outputs(Merge *m) {
-    for (void *p : m->out_allocs) cudaFreeAsync(p, m->stream);
-    m->out_allocs.clear();
+// drop the current batch; the arena itself is kept for the next execute unless `release_memory`
+static void free_outputs(Merge *m, bool release_memory = false) {
     m->out_cols.clear();
     m->has_batch = false;
+    if (release_memory) {
+        if (m->stream) cudaStreamSynchronize(m->stream);
+        m->outbuf.release();
+    }
 }
 
 static void destroy_merge(Merge *m) {
     if (!m) return;
     if (m->stream) cudaStreamSynchronize(m->stream);
-    free_outputs(m);
+    free_outputs(m, true);
+    m->work.release();
     if (m->d_desc) cudaFree(m->d_desc);
     if (m->h_totals) cudaFreeHost(m->h_totals);
     for (auto &e : m->ev) if (e) cudaEventDestroy(e);
@@ -334,13 +366,25 @@ static pg_status execute(Merge *m) {
     PG_CUDA(cudaEventRecord(m->ev[0], sm));
 
     MergeLaunch ml{k, m->key, m->d_key_ptrs, sm, m->d_err};
-    std::vector<void *> temps;
+    // Workspace: one grow-only device allocation per merge handle, carved with a bump pointer.  Its size
+    // depends only on the input shapes, so a reader that is executed repeatedly (or a pool of readers of
+    // one bucket layout) never goes back to the driver allocator.
+    {
+        size_t need = 4096;
+        auto add = [&](size_t b) { need += ((b ? b : 16) + 255) & ~(size_t)255; };
+        for (int l = top; l >= 0; l--) {
+            add(sizeof(int64_t) * (size_t)(n_tiles[l] + 1) * k);
+            if (l > 0) add(sizeof(uint64_t) * (size_t)std::max<int64_t>(level_total[l], 1));
+        }
+        const size_t N_ = (size_t)m->n_in, T_ = (size_t)n_tiles[0];
+        add(2 * N_ + 16); add(4 * T_); add(8 * N_ + 16); add(N_ + 16); add(8 * T_); add(8 * T_ * std::max(nv, 1));
+        PG_CUDA(m->work.reserve(need));
+    }
     auto talloc = [&](size_t bytes, void **out) -> cudaError_t {
-        cudaError_t e = cudaMallocAsync(out, bytes ? bytes : 16, sm);
-        if (e == cudaSuccess) temps.push_back(*out);
-        return e;
+        *out = m->work.take(bytes ? bytes : 16);
+        return *out ? cudaSuccess : cudaErrorMemoryAllocation;
     };
-    auto free_temps = [&]() { for (void *p : temps) cudaFreeAsync(p, sm); temps.clear(); };
+    auto free_temps = [&]() {};
 
     int64_t *bounds0 = nullptr;
     uint64_t *sk_above = nullptr;         // sorted sample keys of the level above the current one
@@ -407,11 +451,38 @@ static pg_status execute(Merge *m) {
     m->n_out = n_out;
     m->out_cols.assign(nc, pg_out_column{});
     int64_t bytes_out = 0;
+    {
+        // output arena (grow-only, reused until pg_merge_release): validity bitmaps first and contiguous,
+        // so that one memset clears them all
+        size_t need = 4096, vbytes = 0;
+        auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        for (int c = 0; c < nc; c++) {
+            const ColDesc &cd = m->cols[c];
+            if (cd.nullable) vbytes += pad((size_t)((n_out + 31) / 32) * 4 + 64);
+            if (cd.width > 0) need += pad((size_t)n_out * cd.width + 64);
+            else need += pad((size_t)m->varlen_bound[cd.varlen_index] + 64) + pad(4 * (size_t)(n_out + 1) + 64);
+        }
+        PG_CUDA(m->outbuf.reserve(need + vbytes));
+        if (vbytes) {
+            void *v0 = m->outbuf.take(vbytes);
+            PG_CUDA(cudaMemsetAsync(v0, 0, vbytes, sm));
+            m->outbuf.top = 0;                       // validity buffers are taken again, one by one, below
+        }
+    }
+    bool validity_phase = true;
     auto oalloc = [&](size_t bytes, void **out) -> cudaError_t {
-        cudaError_t e = cudaMallocAsync(out, bytes, sm);
-        if (e == cudaSuccess) m->out_allocs.push_back(*out);
-        return e;
+        (void)validity_phase;
+        *out = m->outbuf.take(bytes);
+        return *out ? cudaSuccess : cudaErrorMemoryAllocation;
     };
+    // pass 1: validity bitmaps (the zeroed region), pass 2: data + offsets
+    for (int c = 0; c < nc; c++) {
+        if (m->cols[c].nullable) {
+            size_t vb = (size_t)((n_out + 31) / 32) * 4 + 64;
+            PG_CUDA(oalloc(vb, (void **)&m->out_cols[c].validity));
+            bytes_out += (n_out + 7) / 8;
+        }
+    }
     for (int c = 0; c < nc; c++) {
         const ColDesc &cd = m->cols[c];
         pg_out_column &oc = m->out_cols[c];
@@ -427,12 +498,6 @@ static pg_status execute(Merge *m) {
             bytes_out += 4 * (n_out + 1);
         }
         if (cd.width > 0) bytes_out += oc.data_bytes;
-        if (cd.nullable) {
-            size_t vb = (size_t)((n_out + 31) / 32) * 4 + 64;
-            PG_CUDA(oalloc(vb, (void **)&oc.validity));
-            PG_CUDA(cudaMemsetAsync(oc.validity, 0, vb, sm));
-            bytes_out += (n_out + 7) / 8;
-        }
     }
     m->stats.bytes_out = bytes_out;
     PG_CUDA(cudaMemcpyAsync(m->d_out_cols, m->out_cols.data(), sizeof(pg_out_column) * nc,
@@ -758,7 +823,7 @@ pg_status pg_merge_fetch(uint64_t merge, const pg_out_column *host_cols, int32_t
 pg_status pg_merge_release(uint64_t merge) {
     Merge *m = g_merges.get(merge);
     if (!m) return fail(PG_ERR_INVALID, "unknown merge handle");
-    if (ensure_device() == PG_OK) free_outputs(m);
+    if (ensure_device() == PG_OK) free_outputs(m, true);
     return PG_OK;
 }
 

@@ -306,12 +306,24 @@ k_emit(EmitArgs ea) {
     const int p0 = tid * VT, p1 = min(p0 + VT, n);
     int my = 0;
     uint32_t emit_bits = 0;
+    // slot -> (staged position, run) tables, built per run segment (no searches); they live in memory that
+    // is not in use yet (glast, stage 1)
+    uint16_t *spos = glast;
+    uint8_t *srun = stage_vals[1];
+    for (int r = 0; r < k; r++) {
+        const int s0 = seg[r], s1 = seg[r + 1];
+        const int delta = rr[r] + (int)(rstart[r] & 31) - s0;
+        for (int sl = s0 + tid; sl < s1; sl += kEmitThreads) {
+            spos[sl] = (uint16_t)(sl + delta);
+            srun[sl] = (uint8_t)r;
+        }
+    }
+    __syncthreads();
     for (int i = p0; i < p1; i++) {
         uint16_t e = ea.plan[in_base + i];
         int slot = e & kPlanSlotMask;
-        int r = run_of_slot(seg, k, slot);
-        mrun[i] = (uint8_t)r;
-        uint32_t pos = (uint32_t)(rr[r] + (int)(rstart[r] & 31) + (slot - seg[r]));
+        mrun[i] = srun[slot];
+        uint32_t pos = spos[slot];
         uint32_t op = (e >> kPlanOpShift) & 3;
         pm[i] = (uint16_t)(pos | (op << kPmOpShift) | ((e & kPlanHead) ? kPmHead : 0));
         if ((e & kPlanHead) && (e & kPlanEmit)) { my++; emit_bits |= 1u << (i - p0); }
@@ -421,21 +433,36 @@ k_emit(EmitArgs ea) {
             int *wpre = (int *)(vsrc + kTileMax);                                   // per warp: 33 ints
             const uint8_t **wsrc = (const uint8_t **)(wpre + ((kEmitWarps * 33 + 1) & ~1));   // 8-byte aligned
             const uint8_t *const *cd_data = cdata + s * PG_MAX_RUNS;
-            // pass 1: source member per output row, tile byte total
+            // Rows are dealt to warps in contiguous chunks of RW rows (RW a multiple of 32, aligned to the
+            // output's 32-row validity words), so that offsets come from warp-level scans and the only
+            // block-level steps are one 16-entry scan and the look-back.
+            const int span = tv.o_shift + n_out;
+            const int RW = (((span + kEmitWarps - 1) / kEmitWarps) + 31) & ~31;
+            const int wbeg = -tv.o_shift + warp * RW;
+            // pass 1: source member per output row, byte total of this warp's rows
             int my_bytes = 0;
-            for (int ob = tid; ob < n_out; ob += kEmitThreads) {
-                const int last = glast[ob];
-                int src = cd.mode == CM_KEY ? last
-                          : cd.mode == CM_FOLD ? fold_member_idx(cd, pm, mrun, vw, offs, cd_data, last, ea.err)
-                                               : select_member_idx(pm, vw, last);
-                vsrc[ob] = src < 0 ? (uint16_t)0xFFFF : (uint16_t)src;
-                if (src >= 0) { int ps = pm[src] & kPmPosMask; my_bytes += offs[ps + 1] - offs[ps]; }
+            for (int ob0 = wbeg; ob0 < wbeg + RW && ob0 < n_out; ob0 += 32) {
+                const int ob = ob0 + lane;
+                if (ob >= 0 && ob < n_out) {
+                    const int last = glast[ob];
+                    int src = cd.mode == CM_KEY ? last
+                              : cd.mode == CM_FOLD ? fold_member_idx(cd, pm, mrun, vw, offs, cd_data, last, ea.err)
+                                                   : select_member_idx(pm, vw, last);
+                    vsrc[ob] = src < 0 ? (uint16_t)0xFFFF : (uint16_t)src;
+                    if (src >= 0) { int ps = pm[src] & kPmPosMask; my_bytes += offs[ps + 1] - offs[ps]; }
+                }
             }
-            int tile_bytes = 0;
-            block_scan_excl(my_bytes, ws, &tile_bytes);
-            // decoupled look-back: exclusive byte prefix of this tile for this column
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) my_bytes += __shfl_xor_sync(0xffffffffu, my_bytes, d);
+            if (lane == 0) ws[warp] = my_bytes;
+            __syncthreads();
+            // warp 0: exclusive scan of the 16 warp totals + decoupled look-back over earlier tiles
             uint64_t *state = ea.vl_state + (int64_t)cd.varlen_index * ea.n_tiles;
             if (warp == 0) {
+                int x = lane < kEmitWarps ? ws[lane] : 0;
+                int xi = warp_scan_incl(x);
+                const int tile_bytes = __shfl_sync(0xffffffffu, xi, 31);
+                if (lane < kEmitWarps) ws[lane] = xi - x;
                 uint64_t excl = 0;
                 if (lane == 0 && tile > 0) {
                     __threadfence();
@@ -473,12 +500,12 @@ k_emit(EmitArgs ea) {
             __syncthreads();
             const int64_t byte_base = s_i64[0];
             uint8_t *dbase = (uint8_t *)oc.data + byte_base;
-            // pass 2: offsets, validity, payload copy
-            int carry = 0;
+            // pass 2: offsets, validity, payload copy — warp-local
+            int carry = ws[warp];
             int *my_pre = wpre + warp * 33;
             const uint8_t **my_src = wsrc + warp * 32;
-            for (int ob0 = -tv.o_shift; ob0 < n_out; ob0 += kEmitThreads) {
-                const int ob = ob0 + tid;
+            for (int ob0 = wbeg; ob0 < wbeg + RW && ob0 < n_out; ob0 += 32) {
+                const int ob = ob0 + lane;
                 const bool active = ob >= 0 && ob < n_out;
                 int len = 0;
                 const uint8_t *sp = nullptr;
@@ -493,28 +520,39 @@ k_emit(EmitArgs ea) {
                         has = true;
                     }
                 }
-                int tot = 0;
-                int off = block_scan_excl(len, ws, &tot) + carry;
-                carry += tot;
+                const int incl = warp_scan_incl(len);
+                const int off = carry + incl - len;
+                carry += __shfl_sync(0xffffffffu, incl, 31);
                 if (active) oc.offsets[tv.out_base + ob] = (int32_t)(byte_base + off);
-                if (oc.validity != nullptr)
-                    put_validity_word(oc.validity, tv.out_base, ob0 + (tid & ~31), n_out, has);
+                if (oc.validity != nullptr) put_validity_word(oc.validity, tv.out_base, ob0, n_out, has);
                 // warp-cooperative payload copy: the warp's 32 rows form one contiguous destination range;
-                // 8 lanes serve one row, so stores coalesce and short strings do not idle a whole warp
+                // 8 lanes serve one row (so stores coalesce and short strings do not idle a whole warp), two
+                // row groups are in flight at a time and all loads are issued before the stores
                 my_pre[lane] = off;
                 my_src[lane] = sp;
                 if (lane == 31) my_pre[32] = off + len;
                 __syncwarp();
 #pragma unroll
-                for (int rg = 0; rg < 32; rg += 4) {
-                    const int row = rg + (lane >> 3);
-                    const int o0 = my_pre[row], o1 = my_pre[row + 1];
-                    const uint8_t *rp = my_src[row] - o0;
-                    int b = o0 + (lane & 7);
-                    if (b < o1) { dbase[b] = rp[b]; b += 8;
-                        if (b < o1) { dbase[b] = rp[b]; b += 8;
-                            if (b < o1) { dbase[b] = rp[b]; b += 8;
-                                for (; b < o1; b += 8) dbase[b] = rp[b]; } } }
+                for (int rg = 0; rg < 32; rg += 8) {
+                    const int ra = rg + (lane >> 3), rb = ra + 4;
+                    const int a0 = my_pre[ra], a1 = my_pre[ra + 1], b0 = my_pre[rb], b1 = my_pre[rb + 1];
+                    const uint8_t *pa = my_src[ra] - a0, *pb = my_src[rb] - b0;
+                    const int ia = a0 + (lane & 7), ib = b0 + (lane & 7);
+                    uint8_t xa0 = 0, xa1 = 0, xa2 = 0, xb0 = 0, xb1 = 0, xb2 = 0;
+                    if (ia < a1) xa0 = pa[ia];
+                    if (ia + 8 < a1) xa1 = pa[ia + 8];
+                    if (ia + 16 < a1) xa2 = pa[ia + 16];
+                    if (ib < b1) xb0 = pb[ib];
+                    if (ib + 8 < b1) xb1 = pb[ib + 8];
+                    if (ib + 16 < b1) xb2 = pb[ib + 16];
+                    if (ia < a1) dbase[ia] = xa0;
+                    if (ia + 8 < a1) dbase[ia + 8] = xa1;
+                    if (ia + 16 < a1) dbase[ia + 16] = xa2;
+                    if (ib < b1) dbase[ib] = xb0;
+                    if (ib + 8 < b1) dbase[ib + 8] = xb1;
+                    if (ib + 16 < b1) dbase[ib + 16] = xb2;
+                    for (int b = ia + 24; b < a1; b += 8) dbase[b] = pa[b];
+                    for (int b = ib + 24; b < b1; b += 8) dbase[b] = pb[b];
                 }
                 __syncwarp();
             }

@@ -66,6 +66,11 @@ __global__ void k_partition(int k, KeyDesc kd, const void *const *key_ptrs, Leve
 
 // ------------------------------------------------------------------ in-tile merge
 
+// shared-memory index padding: one extra slot per 16 elements, so that the merge-path threads (which start
+// 16 elements apart) fall into different banks instead of all hitting the same one
+#define PADI(i) ((i) + ((i) >> 4))
+constexpr int kTilePad = kTileMax + kTileMax / 16;
+
 struct TileCtx {
     uint64_t *key[2];
     uint16_t *idx[2];
@@ -101,11 +106,13 @@ __device__ bool merge_tile(TileCtx &tc, int k, const KeyDesc &kd, const void *co
         return false;
     }
     const int n = tc.n;
-    for (int i = tid; i < n; i += blockDim.x) {
-        int r = run_of_slot(tc.seg, k, i);
-        int64_t j = tc.rstart[r] + (i - tc.seg[r]);
-        tc.key[0][i] = load_key(key_ptrs, kd, r, (j + 1) * stride - 1);
-        tc.idx[0][i] = (uint16_t)i;
+    for (int r = 0; r < k; r++) {                    // coalesced per run segment
+        const int s0 = tc.seg[r], s1 = tc.seg[r + 1];
+        const int64_t j0 = tc.rstart[r] - s0;
+        for (int i = s0 + tid; i < s1; i += blockDim.x) {
+            tc.key[0][PADI(i)] = load_key(key_ptrs, kd, r, (j0 + i + 1) * stride - 1);
+            tc.idx[0][PADI(i)] = (uint16_t)i;
+        }
     }
     __syncthreads();
 
@@ -129,18 +136,18 @@ __device__ bool merge_tile(TileCtx &tc, int k, const KeyDesc &kd, const void *co
             int lo = max(0, d - nb), hi = min(d, na);
             while (lo < hi) {                    // merge path: #elements taken from A among the first d
                 int mid = (lo + hi) >> 1;
-                if (sk[a0 + mid] <= sk[a1 + d - 1 - mid]) lo = mid + 1; else hi = mid;
+                if (sk[PADI(a0 + mid)] <= sk[PADI(a1 + d - 1 - mid)]) lo = mid + 1; else hi = mid;
             }
             int ai = lo, bi = d - lo;
-            uint64_t ka = ai < na ? sk[a0 + ai] : 0, kb = bi < nb ? sk[a1 + bi] : 0;
+            uint64_t ka = ai < na ? sk[PADI(a0 + ai)] : 0, kb = bi < nb ? sk[PADI(a1 + bi)] : 0;
             for (int s = 0; s < cnt; s++) {
                 bool take_a = (bi >= nb) || (ai < na && ka <= kb);   // stable: lower run first on ties
                 if (take_a) {
-                    dk[pos + s] = ka; di[pos + s] = si[a0 + ai];
-                    ai++; ka = ai < na ? sk[a0 + ai] : 0;
+                    dk[PADI(pos + s)] = ka; di[PADI(pos + s)] = si[PADI(a0 + ai)];
+                    ai++; ka = ai < na ? sk[PADI(a0 + ai)] : 0;
                 } else {
-                    dk[pos + s] = kb; di[pos + s] = si[a1 + bi];
-                    bi++; kb = bi < nb ? sk[a1 + bi] : 0;
+                    dk[PADI(pos + s)] = kb; di[PADI(pos + s)] = si[PADI(a1 + bi)];
+                    bi++; kb = bi < nb ? sk[PADI(a1 + bi)] : 0;
                 }
             }
             pos += cnt;
@@ -157,15 +164,15 @@ __device__ bool merge_tile(TileCtx &tc, int k, const KeyDesc &kd, const void *co
 
 __device__ __forceinline__ void carve_tile(TileCtx &tc, unsigned char *smem, int k) {
     tc.key[0] = (uint64_t *)smem;
-    tc.key[1] = tc.key[0] + kTileMax;
-    tc.idx[0] = (uint16_t *)(tc.key[1] + kTileMax);
-    tc.idx[1] = tc.idx[0] + kTileMax;
-    tc.rstart = (int64_t *)(tc.idx[1] + kTileMax);
+    tc.key[1] = tc.key[0] + kTilePad;
+    tc.idx[0] = (uint16_t *)(tc.key[1] + kTilePad);
+    tc.idx[1] = tc.idx[0] + kTilePad;
+    tc.rstart = (int64_t *)(tc.idx[1] + kTilePad);
     tc.lb[0] = (int *)(tc.rstart + PG_MAX_RUNS);
     tc.lb[1] = tc.lb[0] + PG_MAX_RUNS + 1;
     tc.seg = tc.lb[1] + PG_MAX_RUNS + 1;
 }
-constexpr size_t kTileSmem = (size_t)kTileMax * (8 + 8 + 2 + 2) + PG_MAX_RUNS * 8 + 3 * (PG_MAX_RUNS + 1) * 4;
+constexpr size_t kTileSmem = (size_t)kTilePad * (8 + 8 + 2 + 2) + PG_MAX_RUNS * 8 + 3 * (PG_MAX_RUNS + 1) * 4;
 
 __global__ void __launch_bounds__(kThreads)
 k_merge_keys(int k, KeyDesc kd, const void *const *key_ptrs, LevelView lv, const int64_t *bounds,
@@ -178,7 +185,7 @@ k_merge_keys(int k, KeyDesc kd, const void *const *key_ptrs, LevelView lv, const
     int64_t base = 0;
     for (int r = 0; r < k; r++) base += tc.rstart[r];
     const uint64_t *fk = tc.key[tc.fin];
-    for (int i = threadIdx.x; i < tc.n; i += blockDim.x) sorted_keys[base + i] = fk[i];
+    for (int i = threadIdx.x; i < tc.n; i += blockDim.x) sorted_keys[base + i] = fk[PADI(i)];
 }
 
 // ------------------------------------------------------------------ plan kernel
@@ -216,11 +223,14 @@ k_plan(int k, KeyDesc kd, const void *const *key_ptrs, PlanArgs pa, int32_t *err
     for (int r = 0; r < k; r++) in_base += tc.rstart[r];
 
     // stage sequence numbers and kinds (coalesced per run segment)
-    for (int s = tid; s < n; s += blockDim.x) {
-        int r = run_of_slot(tc.seg, k, s);
-        int64_t row = tc.rstart[r] + (s - tc.seg[r]);
-        seq_s[s] = pa.seq_ptrs[r][row];
-        kind_s[s] = (uint8_t)pa.kind_ptrs[r][row];
+    for (int r = 0; r < k; r++) {
+        const int s0 = tc.seg[r], s1 = tc.seg[r + 1];
+        const int64_t *sq = pa.seq_ptrs[r] + (tc.rstart[r] - s0);
+        const int8_t *kd8 = pa.kind_ptrs[r] + (tc.rstart[r] - s0);
+        for (int s = s0 + tid; s < s1; s += blockDim.x) {
+            seq_s[s] = sq[s];
+            kind_s[s] = (uint8_t)kd8[s];
+        }
     }
     __syncthreads();
 
@@ -230,25 +240,25 @@ k_plan(int k, KeyDesc kd, const void *const *key_ptrs, PlanArgs pa, int32_t *err
     int my_emit = 0;
 
     for (int i = p0; i < p1; i++) {
-        bool head = (i == 0) || (fk[i] != fk[i - 1]);
+        bool head = (i == 0) || (fk[PADI(i)] != fk[PADI(i - 1)]);
         if (!head) continue;
         int e = i + 1;
-        while (e < n && fk[e] == fk[i]) e++;
+        while (e < n && fk[PADI(e)] == fk[PADI(i)]) e++;
         const int g = e - i;
         // members in ascending sequence order (SortMergeReaderWithLoserTree.java:52-65); ties (which the
         // reference leaves unspecified) resolve by run order = slot order
         for (int a = i + 1; a < e; a++) {
-            uint16_t sa = fi[a];
+            uint16_t sa = fi[PADI(a)];
             int64_t qa = seq_s[sa];
             int b = a - 1;
             while (b >= i) {
-                uint16_t sb = fi[b];
+                uint16_t sb = fi[PADI(b)];
                 int64_t qb = seq_s[sb];
                 if (qb < qa || (qb == qa && sb < sa)) break;
-                fi[b + 1] = sb;
+                fi[PADI(b + 1)] = sb;
                 b--;
             }
-            fi[b + 1] = sa;
+            fi[PADI(b + 1)] = sa;
         }
         // row-level semantics of the merge function
         bool emit = true;
@@ -257,43 +267,43 @@ k_plan(int k, KeyDesc kd, const void *const *key_ptrs, PlanArgs pa, int32_t *err
         if (g == 1) {
             // ReducerMergeFunctionWrapper.java:53-73: a lone record is returned untouched
             ops[i] = OP_SET;
-            res_slot = fi[i];
-            res_kind = kind_s[fi[i]];
+            res_slot = fi[PADI(i)];
+            res_kind = kind_s[fi[PADI(i)]];
         } else if (fl.engine == PG_ENGINE_DEDUPLICATE) {
             // DeduplicateMergeFunction.java:47-60
             int win = -1;
             for (int j = e - 1; j >= i; j--) {
-                if (fl.ignore_delete && kind_is_retract(kind_s[fi[j]])) continue;
+                if (fl.ignore_delete && kind_is_retract(kind_s[fi[PADI(j)]])) continue;
                 win = j;
                 break;
             }
             for (int j = i; j < e; j++) ops[j] = (j == win) ? OP_SET : OP_NOOP;
             if (win < 0) emit = false;
-            else { res_slot = fi[win]; res_kind = kind_s[fi[win]]; }
+            else { res_slot = fi[PADI(win)]; res_kind = kind_s[fi[PADI(win)]]; }
         } else if (fl.engine == PG_ENGINE_FIRST_ROW) {
             // FirstRowMergeFunction.java:50-73
             int win = -1;
             for (int j = i; j < e; j++) {
                 ops[j] = OP_NOOP;
-                if (kind_is_retract(kind_s[fi[j]])) {
+                if (kind_is_retract(kind_s[fi[PADI(j)]])) {
                     if (!fl.ignore_delete) atomicCAS(err, KERR_NONE, KERR_FIRST_ROW_RETRACT);
                     continue;
                 }
                 if (win < 0) win = j;
             }
             if (win < 0) emit = false;
-            else { ops[win] = OP_SET; res_slot = fi[win]; res_kind = kind_s[fi[win]]; }
+            else { ops[win] = OP_SET; res_slot = fi[PADI(win)]; res_kind = kind_s[fi[PADI(win)]]; }
         } else if (fl.engine == PG_ENGINE_PARTIAL_UPDATE) {
             // PartialUpdateMergeFunction.java:121-175 (no sequence groups), getResult :354-362
             bool filled = false, meet = false, cur_del = false;
             for (int j = i; j < e; j++) {
-                int kind = kind_s[fi[j]];
+                int kind = kind_s[fi[PADI(j)]];
                 int op = OP_NOOP;
                 cur_del = false;
                 if (kind_is_retract(kind)) {
                     if (!filled) { op = OP_SET; filled = true; }          // initRow
                     if (!fl.ignore_delete) {
-                        res_slot = fi[j];                                  // latestSequenceNumber
+                        res_slot = fi[PADI(j)];                                  // latestSequenceNumber
                         if (fl.remove_record_on_delete) {
                             if (kind == PG_DELETE) { cur_del = true; op = OP_SET; }
                         } else {
@@ -301,7 +311,7 @@ k_plan(int k, KeyDesc kd, const void *const *key_ptrs, PlanArgs pa, int32_t *err
                         }
                     }
                 } else {
-                    res_slot = fi[j];
+                    res_slot = fi[PADI(j)];
                     op = OP_UPD;
                     meet = true;
                     filled = true;
@@ -313,11 +323,11 @@ k_plan(int k, KeyDesc kd, const void *const *key_ptrs, PlanArgs pa, int32_t *err
             // AggregateMergeFunction.java:80-125
             bool cur_del = false;
             for (int j = i; j < e; j++) {
-                int kind = kind_s[fi[j]];
+                int kind = kind_s[fi[PADI(j)]];
                 cur_del = fl.remove_record_on_delete && kind == PG_DELETE;
                 ops[j] = cur_del ? OP_SET : (kind_is_retract(kind) ? OP_RETRACT : OP_UPD);
             }
-            res_slot = fi[e - 1];
+            res_slot = fi[PADI(e - 1)];
             res_kind = cur_del ? PG_DELETE : PG_INSERT;
         }
         // DropDeleteReader.java:58: only kv.isAdd() survives
@@ -332,8 +342,8 @@ k_plan(int k, KeyDesc kd, const void *const *key_ptrs, PlanArgs pa, int32_t *err
     int total = 0;
     int o = block_scan_excl(my_emit, px.ws, &total);
     for (int i = p0; i < p1; i++) {
-        bool head = (i == 0) || (fk[i] != fk[i - 1]);
-        uint16_t entry = (uint16_t)(fi[i] | (ops[i] << kPlanOpShift));
+        bool head = (i == 0) || (fk[PADI(i)] != fk[PADI(i - 1)]);
+        uint16_t entry = (uint16_t)(fi[PADI(i)] | (ops[i] << kPlanOpShift));
         if (head) {
             entry |= kPlanHead;
             if (px.res_kind[i] & 0x80) {
