@@ -183,6 +183,33 @@ pg_status pg_merge_stats(uint64_t merge, pg_stats *out);
 pg_status pg_merge_stream(uint64_t merge, void **out_cuda_stream);
 pg_status pg_merge_free(uint64_t merge);
 
+/* A registered run's shape, and a device->host copy of its columns (sizes from pg_run_layout). */
+pg_status pg_run_layout(uint64_t run, int64_t *n_rows, int64_t *data_bytes, int32_t *has_validity, int32_t n_cols);
+pg_status pg_run_fetch(uint64_t run, const pg_out_column *host_cols, int32_t n_cols);
+
+/* ---- format seam: Parquet data file -> device-resident sorted run -------------------------------------
+ * Replaces FormatReaderFactory.createReader(context) + FileRecordReader.readBatch()
+ * (paimon-common/.../format/FormatReaderFactory.java:33-57, paimon-format/.../parquet/ParquetReaderFactory.java:
+ * 113-148, reader/VectorizedParquetRecordReader.java:178-241) for KeyValue data files: the file bytes (read by the
+ * Java FileIO) are parsed on the host for footer + page headers and decoded on the device straight into the
+ * columnar run the merge consumes.  ABI v1 decodes flat schemas, INT32/INT64/FLOAT/DOUBLE/BYTE_ARRAY, PLAIN and
+ * dictionary encodings, data pages V1/V2, uncompressed pages; anything else returns PG_ERR_UNSUPPORTED. */
+typedef struct {
+    int64_t n_rows;
+    int32_t n_row_groups;
+    int32_t n_columns;
+    int32_t n_data_pages;
+    int32_t n_dictionary_pages;
+    float ms_decode;               /* CUDA-event time of the last pg_parquet_read_run */
+    int32_t launches;
+} pg_parquet_info;
+
+pg_status pg_parquet_open(uint64_t schema, const uint8_t *file_bytes, int64_t size, uint64_t *out_reader);
+pg_status pg_parquet_describe(uint64_t reader, pg_parquet_info *out);
+/* decode the whole file into a run handle (free it with pg_run_free); usable directly in pg_merge_open */
+pg_status pg_parquet_read_run(uint64_t reader, uint64_t *out_run);
+pg_status pg_parquet_free(uint64_t reader);
+
 /* IntervalPartition over int64 (min,max) key bounds of data files: section and run id per file */
 pg_status pg_interval_partition(int32_t n_files, const int64_t *min_key, const int64_t *max_key,
                                 int32_t *section_of, int32_t *run_of, int32_t *n_sections);

@@ -57,6 +57,12 @@ class PgStats(C.Structure):
                 ("ms_alloc", C.c_float), ("ms_emit", C.c_float), ("ms_total", C.c_float), ("launches", C.c_int32)]
 
 
+class PgParquetInfo(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("n_row_groups", C.c_int32), ("n_columns", C.c_int32),
+                ("n_data_pages", C.c_int32), ("n_dictionary_pages", C.c_int32), ("ms_decode", C.c_float),
+                ("launches", C.c_int32)]
+
+
 class PaimonGpuError(RuntimeError):
     """A non-zero pg_status.  `.status` holds the code (PG_ERR_*)."""
 
@@ -95,6 +101,12 @@ _SIGNATURES = {
     "pg_merge_free": (C.c_int32, [C.c_uint64]),
     "pg_interval_partition": (C.c_int32, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.POINTER(C.c_int32)]),
+    "pg_run_layout": (C.c_int32, [C.c_uint64, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p, C.c_int32]),
+    "pg_run_fetch": (C.c_int32, [C.c_uint64, C.POINTER(PgOutColumn), C.c_int32]),
+    "pg_parquet_open": (C.c_int32, [C.c_uint64, C.c_void_p, C.c_int64, C.POINTER(C.c_uint64)]),
+    "pg_parquet_describe": (C.c_int32, [C.c_uint64, C.POINTER(PgParquetInfo)]),
+    "pg_parquet_read_run": (C.c_int32, [C.c_uint64, C.POINTER(C.c_uint64)]),
+    "pg_parquet_free": (C.c_int32, [C.c_uint64]),
 }
 
 _lib: Optional[C.CDLL] = None

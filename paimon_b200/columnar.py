@@ -80,8 +80,16 @@ class Column:
         n = len(self)
         mask = unpack_validity(self.valid, n)
         if is_varlen(self.type):
-            return Column(self.type, self.data[: int(self.offsets[n])], self.offsets[: n + 1],
-                          pack_validity(mask))
+            offs = np.asarray(self.offsets[: n + 1], np.int64)
+            lens = (offs[1:] - offs[:-1]) * mask                     # payload under a NULL slot does not count
+            new_offs = np.zeros(n + 1, np.int64)
+            np.cumsum(lens, out=new_offs[1:])
+            if n and int(new_offs[-1]) != int(offs[-1]) - int(offs[0]) or (n and offs[0] != 0):
+                idx = np.repeat(offs[:-1] - new_offs[:-1], lens) + np.arange(int(new_offs[-1]))
+                data = np.asarray(self.data)[idx] if len(idx) else np.zeros(0, np.uint8)
+            else:
+                data = np.asarray(self.data[: int(offs[-1]) if n else 0])
+            return Column(self.type, data, new_offs.astype(np.int32), pack_validity(mask))
         d = np.array(self.data[:n], copy=True)
         d[~mask] = 0
         return Column(self.type, d, None, pack_validity(mask))

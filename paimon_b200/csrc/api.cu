@@ -138,6 +138,11 @@ static pg_status ensure_device() {
     return PG_OK;
 }
 
+// hooks for the other translation units (parquet_decode.cu)
+Schema *schema_from_handle(uint64_t h) { return g_schemas.get(h); }
+uint64_t register_run(std::unique_ptr<Run> run) { return g_runs.put(std::move(run)); }
+pg_status require_device() { return ensure_device(); }
+
 // drop the current batch; the arena itself is kept for the next execute unless `release_memory`
 static void free_outputs(Merge *m, bool release_memory = false) {
     m->out_cols.clear();
@@ -723,6 +728,42 @@ pg_status pg_run_free(uint64_t run) {
     auto r = g_runs.take(run);
     if (!r) return fail(PG_ERR_INVALID, "unknown run handle");
     for (void *p : r->owned) cudaFree(p);
+    return PG_OK;
+}
+
+pg_status pg_run_layout(uint64_t run, int64_t *n_rows, int64_t *data_bytes, int32_t *has_validity, int32_t n_cols) {
+    Run *r = g_runs.get(run);
+    if (!r || !n_rows) return fail(PG_ERR_INVALID, "unknown run handle");
+    const int nc = r->schema->n_cols();
+    if (n_cols != nc) return fail(PG_ERR_INVALID, "column count mismatch");
+    *n_rows = r->n_rows;
+    for (int c = 0; c < nc; c++) {
+        pg_field f = r->schema->field(c);
+        if (data_bytes) data_bytes[c] = is_varlen(f.type) ? r->varlen_bytes[c] : r->n_rows * type_width(f.type);
+        if (has_validity) has_validity[c] = r->cols[c].validity != nullptr;
+    }
+    return PG_OK;
+}
+
+pg_status pg_run_fetch(uint64_t run, const pg_out_column *host_cols, int32_t n_cols) {
+    Run *r = g_runs.get(run);
+    if (!r || !host_cols) return fail(PG_ERR_INVALID, "unknown run handle");
+    const int nc = r->schema->n_cols();
+    if (n_cols != nc) return fail(PG_ERR_INVALID, "column count mismatch");
+    pg_status st = ensure_device();
+    if (st) return st;
+    const int64_t n = r->n_rows;
+    for (int c = 0; c < nc && n > 0; c++) {
+        pg_field f = r->schema->field(c);
+        const DevColumn &dc = r->cols[c];
+        const pg_out_column &hc = host_cols[c];
+        size_t db = is_varlen(f.type) ? (size_t)r->varlen_bytes[c] : (size_t)n * type_width(f.type);
+        if (db && hc.data) PG_CUDA(cudaMemcpy(hc.data, dc.data, db, cudaMemcpyDeviceToHost));
+        if (dc.offsets && hc.offsets)
+            PG_CUDA(cudaMemcpy(hc.offsets, dc.offsets, sizeof(int32_t) * (size_t)(n + 1), cudaMemcpyDeviceToHost));
+        if (dc.validity && hc.validity)
+            PG_CUDA(cudaMemcpy(hc.validity, dc.validity, (size_t)((n + 7) / 8), cudaMemcpyDeviceToHost));
+    }
     return PG_OK;
 }
 

@@ -1,0 +1,156 @@
+"""Host-side mirror of the reference's file-format plugin SPI for the Parquet decode path.
+
+  FileFormat / FileFormatFactory    paimon-common/src/main/java/org/apache/paimon/format/FileFormat.java:43-93,
+                                    FileFormatFactory.java:28-32 (ServiceLoader lookup by identifier)
+  FormatReaderFactory.createReader  paimon-common/.../format/FormatReaderFactory.java:33-57
+  FormatReaderContext               paimon-common/.../format/FormatReaderContext.java:29-68
+  ParquetFileFormat / ParquetReaderFactory   paimon-format/.../parquet/ParquetFileFormat.java:67-73,
+                                    ParquetReaderFactory.java:113-148
+  FileRecordReader.readBatch        paimon-common/.../reader/FileRecordReader.java
+
+Same names and call order; the reader decodes the whole file on the device (libpaimon_gpu.so,
+pg_parquet_*) and either hands the batch to the host (`read_batch`) or keeps it in HBM as the sorted run
+of a merge (`as_sorted_run_reader`) — the fused decode -> merge path of KeyValueFileReaderFactory
+(paimon-core/.../io/KeyValueFileReaderFactory.java:119-172).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _native as N
+from .columnar import KeyValueBatch
+from .sort_merge_reader import RecordReader, SortedRunReader, _SchemaHandle, fetch_run
+from .types import KeyValueSchema
+
+
+class LocalFileIO:
+    """Stand-in for org.apache.paimon.fs.FileIO: supplies the file's bytes (the Java side reads them with its
+    own FileIO and passes a direct buffer)."""
+
+    def read_bytes(self, path: str) -> bytes:
+        with open(path, "rb") as f:
+            return f.read()
+
+    def get_file_size(self, path: str) -> int:
+        import os
+        return os.path.getsize(path)
+
+
+@dataclass
+class FormatReaderContext:
+    file_io: LocalFileIO
+    file_path: str
+    file_size: Optional[int] = None
+    selection: Optional[object] = None      # RoaringBitmap32 row selection: not supported on device yet
+
+
+class FileRecordReader(RecordReader):
+    pass
+
+
+class ParquetFileRecordReader(FileRecordReader):
+    """One KeyValue data file, decoded on the device."""
+
+    def __init__(self, schema: KeyValueSchema, file_bytes: bytes, device: int = 0):
+        self.schema = schema
+        self.lib = N.init(device)
+        self._schema_h = _SchemaHandle(schema, device)
+        self._buf = np.frombuffer(file_bytes, dtype=np.uint8)
+        h = C.c_uint64(0)
+        try:
+            N.check(self.lib.pg_parquet_open(self._schema_h.handle, self._buf.ctypes.data, len(self._buf), C.byref(h)))
+        except Exception:
+            self._schema_h.close()
+            raise
+        self._reader = h.value
+        self._run = 0
+        self._done = False
+
+    def info(self) -> N.PgParquetInfo:
+        info = N.PgParquetInfo()
+        N.check(self.lib.pg_parquet_describe(self._reader, C.byref(info)))
+        return info
+
+    def _decode(self) -> int:
+        if not self._run:
+            h = C.c_uint64(0)
+            N.check(self.lib.pg_parquet_read_run(self._reader, C.byref(h)))
+            self._run = h.value
+        return self._run
+
+    def read_batch(self) -> Optional[KeyValueBatch]:
+        """FileRecordReader.readBatch(): the whole file as one batch, then None (end of input)."""
+        if self._done:
+            return None
+        self._done = True
+        batch = fetch_run(self.schema, self._decode())
+        return batch if batch.n_rows > 0 else None
+
+    def as_sorted_run_reader(self) -> SortedRunReader:
+        """Keep the decoded columns in HBM and hand them to a SortMergeReader (no host round trip).  The
+        returned reader owns the run handle."""
+        run = self._decode()
+        self._run = 0
+        return SortedRunReader.from_native_run(self.schema, self.info().n_rows, run)
+
+    def close(self) -> None:
+        lib = N.load()
+        if self._run:
+            lib.pg_run_free(self._run)
+            self._run = 0
+        if self._reader:
+            lib.pg_parquet_free(self._reader)
+            self._reader = 0
+        if self._schema_h is not None:
+            self._schema_h.close()
+            self._schema_h = None
+
+
+class FormatReaderFactory:
+    def create_reader(self, context: FormatReaderContext) -> FileRecordReader:
+        raise NotImplementedError
+
+
+class ParquetReaderFactory(FormatReaderFactory):
+    def __init__(self, data_schema: KeyValueSchema, device: int = 0):
+        self.data_schema = data_schema
+        self.device = device
+
+    def create_reader(self, context: FormatReaderContext) -> ParquetFileRecordReader:
+        if context.selection is not None:
+            raise N.UnsupportedOnDevice(2, "row selections (deletion-vector pushdown) are not decoded on device yet")
+        return ParquetFileRecordReader(self.data_schema, context.file_io.read_bytes(context.file_path), self.device)
+
+
+class FileFormat:
+    """FileFormat.fromIdentifier / createReaderFactory."""
+
+    identifier = ""
+
+    @staticmethod
+    def from_identifier(identifier: str, device: int = 0) -> "FileFormat":
+        if identifier.lower() == "parquet":
+            return ParquetFileFormat(device)
+        raise N.UnsupportedOnDevice(2, f"file format '{identifier}' is not decoded on device (parquet only; "
+                                       f"ORC is a later row of SURVEY §8f)")
+
+    def create_reader_factory(self, data_schema: KeyValueSchema, projected=None, filters=None) -> FormatReaderFactory:
+        raise NotImplementedError
+
+
+class ParquetFileFormat(FileFormat):
+    identifier = "parquet"
+
+    def __init__(self, device: int = 0):
+        self.device = device
+
+    def create_reader_factory(self, data_schema: KeyValueSchema, projected=None, filters=None) -> ParquetReaderFactory:
+        # keys are never projected before a merge and only key filters may be pushed into overlapping
+        # sections (MergeFileSplitRead.java:204-213, 276-277): the merge path reads full files
+        if projected is not None and projected != data_schema:
+            raise N.UnsupportedOnDevice(2, "projection push-down is not applied on the merge path")
+        return ParquetReaderFactory(data_schema, self.device)

@@ -89,14 +89,28 @@ class SortedRunReader(RecordReader):
     def from_device(schema: KeyValueSchema, n_rows: int, columns: Sequence[DeviceColumn], keepalive=None):
         return SortedRunReader(schema, None, n_rows=n_rows, device_columns=columns, keepalive=keepalive)
 
+    @staticmethod
+    def from_native_run(schema: KeyValueSchema, n_rows: int, run_handle: int, keepalive=None):
+        """A run that already lives in the library (e.g. decoded from a Parquet file on the device)."""
+        r = SortedRunReader(schema, None, n_rows=n_rows, keepalive=keepalive)
+        r._handle = run_handle
+        r._native = True
+        return r
+
     def read_batch(self) -> Optional[KeyValueBatch]:
-        if self._consumed or self.batch is None:
+        if self._consumed:
             return None
         self._consumed = True
-        return self.batch
+        if self.batch is not None:
+            return self.batch
+        if getattr(self, "_native", False) and self._handle:
+            return fetch_run(self.schema, self._handle)
+        return None
 
     # -- native registration (used by SortMergeReader) --
     def _open(self, schema_handle: int) -> int:
+        if getattr(self, "_native", False):
+            return self._handle
         lib = N.load()
         nc = self.schema.n_cols
         cols = (N.PgColumn * nc)()
@@ -123,6 +137,32 @@ class SortedRunReader(RecordReader):
         if self._handle:
             N.load().pg_run_free(self._handle)
             self._handle = 0
+
+
+def fetch_run(schema: KeyValueSchema, run_handle: int) -> KeyValueBatch:
+    """Device-resident run -> host columns (pg_run_layout + pg_run_fetch)."""
+    lib = N.load()
+    nc = schema.n_cols
+    n_rows = C.c_int64(0)
+    data_bytes = np.zeros(nc, np.int64)
+    has_valid = np.zeros(nc, np.int32)
+    N.check(lib.pg_run_layout(run_handle, C.byref(n_rows), data_bytes.ctypes.data, has_valid.ctypes.data, nc))
+    n = n_rows.value
+    host = (N.PgOutColumn * nc)()
+    cols: List[Column] = []
+    for i, t in enumerate(schema.physical_types()):
+        valid = np.zeros((n + 7) // 8 + 8, np.uint8) if has_valid[i] else None
+        if is_varlen(t):
+            data = np.zeros(max(int(data_bytes[i]), 1), np.uint8)
+            offs = np.zeros(n + 1, np.int32)
+            host[i] = N.PgOutColumn(_np_ptr(data), _np_ptr(offs), _np_ptr(valid), int(data_bytes[i]))
+            cols.append(Column(t, data[: int(data_bytes[i])], offs, valid))
+        else:
+            data = np.zeros(max(n, 1), numpy_dtype(t))
+            host[i] = N.PgOutColumn(_np_ptr(data), None, _np_ptr(valid), int(data_bytes[i]))
+            cols.append(Column(t, data[:n], None, valid))
+    N.check(lib.pg_run_fetch(run_handle, host, nc))
+    return KeyValueBatch(schema, cols)
 
 
 @dataclass
