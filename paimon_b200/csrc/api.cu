@@ -654,7 +654,8 @@ pg_status pg_run_open(uint64_t schema, const pg_run_desc *desc, int32_t mem, uin
     pg_status st = ensure_device();
     if (st) return st;
     auto run = std::make_unique<Run>();
-    run->schema = s;
+    run->own_schema = *s;
+    run->schema = &run->own_schema;   // the run outlives the schema handle it was opened with
     run->n_rows = desc->n_rows;
     const int nc = s->n_cols();
     const int64_t n = desc->n_rows;
@@ -781,7 +782,13 @@ pg_status pg_merge_open(uint64_t spec, const uint64_t *runs, int32_t k, uint64_t
     for (int i = 0; i < k; i++) {
         Run *r = g_runs.get(runs[i]);
         if (!r) return fail(PG_ERR_INVALID, "unknown run handle");
-        if (r->schema != sp->schema) return fail(PG_ERR_INVALID, "run and spec use different schemas");
+        if (r->schema != sp->schema) {           // different handles are fine as long as the schemas are equal
+            const Schema *a = r->schema, *b = sp->schema;
+            bool same = a->n_key == b->n_key && a->n_val == b->n_val;
+            for (int c = 0; same && c < a->n_cols(); c++)
+                same = a->field(c).type == b->field(c).type && a->field(c).nullable == b->field(c).nullable;
+            if (!same) return fail(PG_ERR_INVALID, "run and spec use different schemas");
+        }
         if (r->n_rows == 0) continue;            // exhausted readers are legal (SortMergeReaderTestBase.java:53-56)
         m->runs.push_back(r);
         m->n_in += r->n_rows;

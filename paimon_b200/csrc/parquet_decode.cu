@@ -440,7 +440,8 @@ static pg_status pq_read_run(PqReader *rd, uint64_t *out_run) {
     const int nc = s->n_cols();
     const int64_t n = rd->n_rows;
     auto run = std::make_unique<Run>();
-    run->schema = s;
+    run->own_schema = *s;
+    run->schema = &run->own_schema;
     run->n_rows = n;
     run->cols.resize(nc);
     run->varlen_bytes.assign(nc, 0);

@@ -66,6 +66,7 @@ struct DevColumn {
 
 struct Run {
     const Schema *schema = nullptr;
+    Schema own_schema;                   // copy: a run may outlive the schema handle it was opened with
     int64_t n_rows = 0;
     std::vector<DevColumn> cols;
     std::vector<int64_t> varlen_bytes;   // per column: payload bytes of a var-len column (offsets[n_rows])
