@@ -82,6 +82,7 @@ struct Merge {
     int64_t *d_run_rows = nullptr;
     ColDesc *d_cols = nullptr;
     int32_t *d_tile_counter = nullptr;
+    int32_t *d_col_order = nullptr;
     pg_out_column *d_out_cols = nullptr;
     int64_t *d_totals = nullptr;       // [1 + n_varlen]
     int32_t *d_err = nullptr;
@@ -264,7 +265,8 @@ static pg_status build_descriptors(Merge *m) {
     size_t o_tot = o_out + align(sizeof(pg_out_column) * nc);
     size_t o_err = o_tot + align(sizeof(int64_t) * (nv + 1));
     size_t o_cnt = o_err + 256;
-    size_t total = o_cnt + 256;
+    size_t o_ord = o_cnt + 256;
+    size_t total = o_ord + align(sizeof(int32_t) * nc);
     std::vector<unsigned char> host(total, 0);
     m->varlen_bound.assign(nv, 0);
     for (int r = 0; r < k; r++) {
@@ -281,6 +283,13 @@ static pg_status build_descriptors(Merge *m) {
         ((int64_t *)(host.data() + o_rows))[r] = run->n_rows;
     }
     memcpy(host.data() + o_cols, m->cols.data(), sizeof(ColDesc) * nc);
+    {
+        // var-len columns first (see k_emit), then the fixed-width ones in schema order
+        int32_t *ord = (int32_t *)(host.data() + o_ord);
+        int n = 0;
+        for (int c = 0; c < nc; c++) if (m->cols[c].width == 0) ord[n++] = c;
+        for (int c = 0; c < nc; c++) if (m->cols[c].width != 0) ord[n++] = c;
+    }
     PG_CUDA(cudaMalloc(&m->d_desc, total));
     PG_CUDA(cudaMemcpy(m->d_desc, host.data(), total, cudaMemcpyHostToDevice));
     unsigned char *d = (unsigned char *)m->d_desc;
@@ -296,6 +305,7 @@ static pg_status build_descriptors(Merge *m) {
     m->d_totals = (int64_t *)(d + o_tot);
     m->d_err = (int32_t *)(d + o_err);
     m->d_tile_counter = (int32_t *)(d + o_cnt);
+    m->d_col_order = (int32_t *)(d + o_ord);
     PG_CUDA(cudaMallocHost((void **)&m->h_totals, sizeof(int64_t) * (nv + 1) + 16));
     m->h_err = (int32_t *)(m->h_totals + nv + 1);
     return PG_OK;
@@ -518,6 +528,7 @@ static pg_status execute(Merge *m) {
     ea.tmp_seq = tmp_seq;
     ea.tmp_kind = tmp_kind;
     ea.cols = m->d_cols;
+    ea.col_order = m->d_col_order;
     ea.ptrs = m->d_ptrs;
     ea.run_rows = m->d_run_rows;
     ea.n_cols = nc;

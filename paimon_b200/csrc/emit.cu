@@ -404,16 +404,20 @@ k_emit(EmitArgs ea) {
     };
 
     // ---- prologue: column 0
-    if (warp == 0 && ncols > 0) issue(0, 0);
-    if (tid < n_vw && ncols > 0) stage_vw[0][tid] = load_vw(0);
+    // columns are walked in ea.col_order (var-len columns first: their look-back then happens while the
+    // CTAs of a wave are still close together in time)
+    if (warp == 0 && ncols > 0) issue(ea.col_order[0], 0);
+    if (tid < n_vw && ncols > 0) stage_vw[0][tid] = load_vw(ea.col_order[0]);
     __syncthreads();
 
-    for (int c = 0; c < ncols; c++) {
-        const int s = c & 1;
+    for (int ci = 0; ci < ncols; ci++) {
+        const int s = ci & 1;
+        const int c = ea.col_order[ci];
+        const int cn = ci + 1 < ncols ? ea.col_order[ci + 1] : -1;
         const ColDesc cd = ea.cols[c];
         const pg_out_column oc = ea.out_cols[c];
-        if (warp == 0 && c + 1 < ncols) issue(c + 1, s ^ 1);
-        uint32_t next_vw = (c + 1 < ncols && tid < n_vw) ? load_vw(c + 1) : 0;
+        if (warp == 0 && cn >= 0) issue(cn, s ^ 1);
+        uint32_t next_vw = (cn >= 0 && tid < n_vw) ? load_vw(cn) : 0;
         if (col_staged(cd)) {
             mbar_wait(&mbar[s], (phase >> s) & 1);
             phase ^= 1u << s;
@@ -557,7 +561,7 @@ k_emit(EmitArgs ea) {
                 __syncwarp();
             }
         }
-        if (c + 1 < ncols && tid < n_vw) stage_vw[s ^ 1][tid] = next_vw;
+        if (cn >= 0 && tid < n_vw) stage_vw[s ^ 1][tid] = next_vw;
         __syncthreads();
     }
 }

@@ -13,7 +13,7 @@ namespace pg {
 
 constexpr int kTileMax = 4096;       // rows merged by one CTA (shared-memory tile)
 constexpr int kSampleStride = 32;    // S: every S-th key of a level is a sample of the next level
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;         // plan / merge-keys CTAs (2 per SM: shared memory bound)
 constexpr int kMaxCols = 256;
 
 // ---- plan entry (one uint16 per merged input position) ----
@@ -165,6 +165,7 @@ struct EmitArgs {
     const int64_t *tmp_seq;
     const int8_t *tmp_kind;
     const ColDesc *cols;
+    const int32_t *col_order;          // device [n_cols]: order in which the emit kernel walks the columns
     ColPtrs ptrs;
     const int64_t *run_rows;           // device [k] rows per run
     int n_cols;
