@@ -155,35 +155,69 @@ __global__ void k_pq_hybrid(const PqPageJob *jobs, int n_jobs, const PqCol *cols
     if ((threadIdx.x & 31) == 0) state[j] = PqPageState{values_off, n_nonnull};
 }
 
-// one thread per PLAIN BYTE_ARRAY page (data or dictionary): walk the [len][bytes] stream
-// (VectorizedPlainValuesReader.java:275-288)
-__global__ void k_pq_walk_bytes(const PqPageJob *jobs, int n_jobs, const PqDictJob *dicts, int n_dicts,
-                                const PqCol *cols, const PqPageState *state, const uint8_t **dict_ptr,
-                                int32_t *dict_len) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per PLAIN BYTE_ARRAY page (data or dictionary): walk the [len:4][bytes] stream
+// (VectorizedPlainValuesReader.java:275-288).  The lengths are embedded in the stream, so the walk itself is
+// sequential; the warp stages the page through shared memory in 2 KiB windows (coalesced 16-byte loads), lane 0
+// walks the window at shared-memory latency, and the (pointer, length) pairs go out coalesced.
+constexpr int kWalkWindow = 2048;
+constexpr int kWalkWarps = 8;
+
+__device__ void pq_walk_stream(const uint8_t *p, const uint8_t *end, int count, const uint8_t **out_ptr,
+                               int32_t *out_len, uint8_t *win, uint32_t *w_off, int32_t *w_len) {
+    const int lane = threadIdx.x & 31;
+    int done = 0;
+    while (done < count && p + 4 <= end) {
+        // window = [base, base + kWalkWindow + 16) clipped to the page, base 16-byte aligned
+        const uint8_t *base = (const uint8_t *)((uintptr_t)p & ~(uintptr_t)15);
+        const int skip = (int)(p - base);
+        const int avail = (int)min((int64_t)(end - base), (int64_t)(kWalkWindow + 16));
+        for (int o = lane * 16; o < avail; o += 32 * 16) *(uint4 *)(win + o) = *(const uint4 *)(base + o);
+        __syncwarp();
+        int nfound = 0, q = skip;
+        if (lane == 0) {
+            while (done + nfound < count && q + 4 <= avail && nfound < 256) {
+                int32_t len = (int32_t)((uint32_t)win[q] | ((uint32_t)win[q + 1] << 8) | ((uint32_t)win[q + 2] << 16) |
+                                        ((uint32_t)win[q + 3] << 24));
+                w_off[nfound] = (uint32_t)(q + 4);
+                w_len[nfound] = len;
+                nfound++;
+                q += 4 + len;
+                if (len < 0) { q = avail; break; }            // corrupt length: stop
+            }
+        }
+        nfound = __shfl_sync(0xffffffffu, nfound, 0);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        __syncwarp();
+        for (int i = lane; i < nfound; i += 32) {
+            out_ptr[done + i] = base + w_off[i];
+            out_len[done + i] = w_len[i];
+        }
+        __syncwarp();
+        if (nfound == 0) break;                               // a length word straddles the page end: malformed
+        done += nfound;
+        p = base + q;
+    }
+}
+
+__global__ void __launch_bounds__(kWalkWarps * 32)
+k_pq_walk_bytes(const PqPageJob *jobs, int n_jobs, const PqDictJob *dicts, int n_dicts, const PqCol *cols,
+                const PqPageState *state, const uint8_t **dict_ptr, int32_t *dict_len) {
+    __shared__ __align__(16) uint8_t s_win[kWalkWarps][kWalkWindow + 32];
+    __shared__ uint32_t s_off[kWalkWarps][256];
+    __shared__ int32_t s_len[kWalkWarps][256];
+    const int w = threadIdx.x >> 5;
+    const int t = blockIdx.x * kWalkWarps + w;
     if (t < n_jobs) {
         const PqPageJob job = jobs[t];
         const PqCol col = cols[job.col];
         if (col.phys != pq::T_BYTE_ARRAY || job.is_dict) return;
-        const uint8_t *p = job.body + state[t].values_off, *end = job.body + job.body_len;
-        const uint8_t **vptr = col.vptr + job.row0;
-        int32_t *vlen = col.vlen + job.row0;
-        for (int i = 0; i < state[t].n_nonnull && p + 4 <= end; i++) {
-            int32_t len = (int32_t)((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24));
-            vptr[i] = p + 4;
-            vlen[i] = len;
-            p += 4 + (int64_t)len;
-        }
+        pq_walk_stream(job.body + state[t].values_off, job.body + job.body_len, state[t].n_nonnull,
+                       col.vptr + job.row0, col.vlen + job.row0, s_win[w], s_off[w], s_len[w]);
     } else if (t < n_jobs + n_dicts) {
         const PqDictJob dj = dicts[t - n_jobs];
         if (cols[dj.col].phys != pq::T_BYTE_ARRAY) return;
-        const uint8_t *p = dj.body, *end = dj.body + dj.body_len;
-        for (int i = 0; i < dj.num_values && p + 4 <= end; i++) {
-            int32_t len = (int32_t)((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24));
-            dict_ptr[dj.entry_base + i] = p + 4;
-            dict_len[dj.entry_base + i] = len;
-            p += 4 + (int64_t)len;
-        }
+        pq_walk_stream(dj.body, dj.body + dj.body_len, dj.num_values, dict_ptr + dj.entry_base,
+                       dict_len + dj.entry_base, s_win[w], s_off[w], s_len[w]);
     }
 }
 
@@ -532,8 +566,8 @@ static pg_status pq_read_run(PqReader *rd, uint64_t *out_run) {
     int launches = 0;
     if (nj > 0) {
         k_pq_hybrid<<<(nj * 32 + 127) / 128, 128, 0, sm>>>(d_jobs, nj, d_cols, d_state);
-        k_pq_walk_bytes<<<(nj + nd + 127) / 128, 128, 0, sm>>>(d_jobs, nj, d_dicts, nd, d_cols, d_state, d_dict_ptr,
-                                                                d_dict_len);
+        k_pq_walk_bytes<<<(nj + nd + kWalkWarps - 1) / kWalkWarps, kWalkWarps * 32, 0, sm>>>(
+            d_jobs, nj, d_dicts, nd, d_cols, d_state, d_dict_ptr, d_dict_len);
         k_pq_assemble<<<nj, 256, 0, sm>>>(d_jobs, d_dicts, d_cols, d_state, d_dict_ptr, d_dict_len);
         launches += 3;
     }
@@ -547,19 +581,31 @@ static pg_status pq_read_run(PqReader *rd, uint64_t *out_run) {
         k_scan_apply<<<(int)nb, 256, 0, sm>>>(cols[c].out_offsets + 1, n, block_sums[c]);
         launches += 3;
     }
-    for (int c = 0; c < nc && n > 0; c++) {
-        if (cols[c].phys != pq::T_BYTE_ARRAY) continue;
-        int32_t total = 0;
-        PG_CUDA(cudaMemcpyAsync(&total, cols[c].out_offsets + n, 4, cudaMemcpyDeviceToHost, sm));
+    {
+        // one read-back for all var-len columns (their exact payload sizes), one allocation, then the copies
+        std::vector<int32_t> totals(nc, 0);
+        for (int c = 0; c < nc && n > 0; c++)
+            if (cols[c].phys == pq::T_BYTE_ARRAY)
+                PG_CUDA(cudaMemcpyAsync(&totals[c], cols[c].out_offsets + n, 4, cudaMemcpyDeviceToHost, sm));
         PG_CUDA(cudaStreamSynchronize(sm));
+        size_t sum = 256;
+        for (int c = 0; c < nc; c++) if (cols[c].phys == pq::T_BYTE_ARRAY) sum += pad((size_t)totals[c] + 64);
         unsigned char *pl = nullptr;
-        PG_CUDA(cudaMalloc((void **)&pl, (size_t)total + 256));
-        run->owned.push_back(pl);
-        payload[c] = pl;
-        run->varlen_bytes[c] = total;
-        int64_t threads = n * 8;
-        k_pq_copy_bytes<<<(int)((threads + 255) / 256), 256, 0, sm>>>(cols[c].rowsrc, cols[c].out_offsets, pl, n);
-        launches++;
+        if (n > 0 && sum > 256) {
+            PG_CUDA(cudaMalloc((void **)&pl, sum));
+            run->owned.push_back(pl);
+        }
+        size_t pt = 0;
+        for (int c = 0; c < nc && n > 0; c++) {
+            if (cols[c].phys != pq::T_BYTE_ARRAY) continue;
+            payload[c] = pl + pt;
+            pt += pad((size_t)totals[c] + 64);
+            run->varlen_bytes[c] = totals[c];
+            int64_t threads = n * 8;
+            k_pq_copy_bytes<<<(int)((threads + 255) / 256), 256, 0, sm>>>(cols[c].rowsrc, cols[c].out_offsets,
+                                                                        payload[c], n);
+            launches++;
+        }
     }
     PG_CUDA(cudaEventRecord(e1, sm));
     int32_t herr = 0;
