@@ -70,6 +70,7 @@ struct Merge {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     std::vector<int64_t> varlen_bound;     // per var-len column: sum of the runs' payload bytes
     KeyDesc key{};
+    SeqFields seq{};
     MergeFlags flags{};
     std::vector<ColDesc> cols;
     std::vector<int32_t> varlen_cols;
@@ -194,9 +195,22 @@ static pg_status build_descriptors(Merge *m) {
         m->key.type[f] = s->key_fields[f].type;
         m->key.shift[f] = bits - used;
     }
-    if (!sp->seq_fields.empty())
-        return fail(PG_ERR_UNSUPPORTED, "'sequence.field' (user defined sequence comparator) is not "
-                                        "implemented on the device merge path yet");
+    // 'sequence.field': fixed-width value fields compared before _SEQUENCE_NUMBER
+    m->seq = SeqFields{};
+    if (sp->seq_fields.size() > 4)
+        return fail(PG_ERR_UNSUPPORTED, "more than 4 'sequence.field' columns are not implemented on the device");
+    for (size_t i = 0; i < sp->seq_fields.size(); i++) {
+        int vf = sp->seq_fields[i];
+        if (vf < 0 || vf >= s->n_val) return fail(PG_ERR_INVALID, "sequence.field index out of range");
+        int t = s->val_fields[vf].type;
+        if (is_varlen(t))
+            return fail(PG_ERR_UNSUPPORTED, "var-len 'sequence.field' columns are not implemented on the device");
+        m->seq.col[i] = s->n_key + 2 + vf;
+        m->seq.type[i] = t;
+        m->seq.width[i] = type_width(t);
+    }
+    m->seq.n = (int32_t)sp->seq_fields.size();
+    m->seq.ascending = sp->seq_ascending ? 1 : 0;
     m->flags = MergeFlags{sp->engine, sp->ignore_delete, sp->remove_record_on_delete, sp->drop_delete};
 
     const int nc = s->n_cols();
@@ -443,6 +457,8 @@ static pg_status execute(Merge *m) {
     pa.seq_ptrs = m->d_seq_ptrs;
     pa.kind_ptrs = m->d_kind_ptrs;
     pa.flags = m->flags;
+    pa.seq = m->seq;
+    pa.ptrs = m->d_ptrs;
     pa.plan = plan;
     pa.tile_rows = tile_rows;
     pa.tmp_seq = tmp_seq;

@@ -188,6 +188,49 @@ k_merge_keys(int k, KeyDesc kd, const void *const *key_ptrs, LevelView lv, const
     for (int i = threadIdx.x; i < tc.n; i += blockDim.x) sorted_keys[base + i] = fk[PADI(i)];
 }
 
+// ------------------------------------------------------------------ 'sequence.field' comparator
+
+// userDefinedSeqComparator.compare(a.value(), b.value()) for two members given by their tile slots.
+// Generated-comparator rules (paimon-codegen GenerateUtils.scala:113-126, 305-345; nullIsLast = false):
+// both null -> next field; one null -> that side is smaller, decided BEFORE the descending sign flip;
+// numbers compare with > / < (NaN is "equal" to everything); BOOLEAN false < true.
+__device__ int compare_seq_fields(const SeqFields &sf, const ColPtrs &ptrs, int k, const int *seg,
+                                  const int64_t *rstart, int slot_a, int slot_b) {
+    const int ra = run_of_slot(seg, k, slot_a), rb = run_of_slot(seg, k, slot_b);
+    const int64_t row_a = rstart[ra] + (slot_a - seg[ra]), row_b = rstart[rb] + (slot_b - seg[rb]);
+    for (int f = 0; f < sf.n; f++) {
+        const int col = sf.col[f];
+        const uint8_t *va = (const uint8_t *)ptrs.validity[(int64_t)col * k + ra];
+        const uint8_t *vb = (const uint8_t *)ptrs.validity[(int64_t)col * k + rb];
+        const bool na = !valid_bit(va, row_a), nb = !valid_bit(vb, row_b);
+        if (na && nb) continue;
+        if (na) return -1;
+        if (nb) return 1;
+        const void *da = ptrs.data[(int64_t)col * k + ra], *db = ptrs.data[(int64_t)col * k + rb];
+        int d;
+        switch (sf.type[f]) {
+            case PG_FLOAT: {
+                float x = ((const float *)da)[row_a], y = ((const float *)db)[row_b];
+                d = x > y ? 1 : x < y ? -1 : 0;
+                break;
+            }
+            case PG_DOUBLE: {
+                double x = ((const double *)da)[row_a], y = ((const double *)db)[row_b];
+                d = x > y ? 1 : x < y ? -1 : 0;
+                break;
+            }
+            default: {
+                const int w = sf.width[f];
+                int64_t x = sext(load_fixed(da, w, row_a), w), y = sext(load_fixed(db, w, row_b), w);
+                if (sf.type[f] == PG_BOOL) { x = x != 0; y = y != 0; }
+                d = x > y ? 1 : x < y ? -1 : 0;
+            }
+        }
+        if (d != 0) return sf.ascending ? d : -d;
+    }
+    return 0;
+}
+
 // ------------------------------------------------------------------ plan kernel
 
 struct PlanSmemExtra {
@@ -254,7 +297,10 @@ k_plan(int k, KeyDesc kd, const void *const *key_ptrs, PlanArgs pa, int32_t *err
             while (b >= i) {
                 uint16_t sb = fi[PADI(b)];
                 int64_t qb = seq_s[sb];
-                if (qb < qa || (qb == qa && sb < sa)) break;
+                // 'sequence.field': the user defined sequence fields order the members first
+                // (SortMergeReaderWithLoserTree.java:58-64), then the sequence number
+                int ud = pa.seq.n ? compare_seq_fields(pa.seq, pa.ptrs, k, tc.seg, tc.rstart, sb, sa) : 0;
+                if (ud < 0 || (ud == 0 && (qb < qa || (qb == qa && sb < sa)))) break;
                 fi[PADI(b + 1)] = sb;
                 b--;
             }

@@ -132,9 +132,27 @@ void launch_partition(const MergeLaunch &ml, const LevelView &lv, const uint64_t
 void launch_merge_keys(const MergeLaunch &ml, const LevelView &lv, const int64_t *bounds, int n_tiles,
                        uint64_t *sorted_keys);
 
+// per-column, per-run input pointers, transposed for coalesced access: [col * k + run]
+struct ColPtrs {
+    const void *const *data;
+    const int32_t *const *offsets;
+    const uint32_t *const *validity;   // bitmaps read as 32-bit words
+};
+
+// 'sequence.field': user defined sequence fields (file column indexes), compared before _SEQUENCE_NUMBER
+struct SeqFields {
+    int32_t n;
+    int32_t ascending;
+    int32_t col[4];
+    int32_t type[4];
+    int32_t width[4];
+};
+
 struct PlanArgs {
     const int64_t *bounds;             // level-0 tile bounds [(n_tiles+1) * k]
     int n_tiles;
+    SeqFields seq;
+    ColPtrs ptrs;
     const int64_t *const *seq_ptrs;    // device [k]
     const int8_t *const *kind_ptrs;    // device [k]
     MergeFlags flags;
@@ -148,13 +166,6 @@ void launch_plan(const MergeLaunch &ml, const PlanArgs &pa);
 
 // exclusive scan of tile_rows into int64 row offsets; totals[0] = output rows
 void launch_scan(cudaStream_t stream, const int32_t *tile_rows, int n_tiles, int64_t *row_base, int64_t *totals);
-
-// per-column, per-run input pointers, transposed for coalesced access: [col * k + run]
-struct ColPtrs {
-    const void *const *data;
-    const int32_t *const *offsets;
-    const uint32_t *const *validity;   // bitmaps read as 32-bit words
-};
 
 struct EmitArgs {
     const int64_t *bounds;

@@ -283,3 +283,35 @@ def merge_function_factory(options: Dict[str, str], row_type: RowType, primary_k
     if engine == "first-row":
         return FirstRowMergeFunction.factory(options)
     raise ValueError(f"Unsupported merge engine: {engine}")
+
+
+class UserDefinedSeqComparator:
+    """Mirror of paimon-core/.../utils/UserDefinedSeqComparator.java:30-96: the 'sequence.field' columns and their
+    sort order.  On the device it is data (field indexes + order), not code."""
+
+    def __init__(self, fields: Sequence[int], ascending: bool = True):
+        self.fields = list(fields)
+        self.ascending = bool(ascending)
+
+    def compare_fields(self) -> List[int]:
+        return list(self.fields)
+
+    def is_ascending_order(self) -> bool:
+        return self.ascending
+
+    @staticmethod
+    def create(row_type: RowType, options: Dict[str, str]) -> Optional["UserDefinedSeqComparator"]:
+        """UserDefinedSeqComparator.create(rowType, CoreOptions): None when 'sequence.field' is not set."""
+        raw = (options or {}).get("sequence.field")
+        if not raw:
+            return None
+        fields = [row_type.index_of(n.strip()) for n in raw.split(",")]
+        asc = (options or {}).get("sequence.field.sort-order", "ascending").lower() == "ascending"
+        return UserDefinedSeqComparator(fields, asc)
+
+    def apply(self, spec: "MergeSpec") -> "MergeSpec":
+        import copy
+        s = copy.deepcopy(spec)
+        s.seq_fields = list(self.fields)
+        s.seq_ascending = self.ascending
+        return s

@@ -195,7 +195,14 @@ class SortMergeReader(RecordReader):
             raise N.UnsupportedOnDevice(2, "custom key comparators cannot run on the device")
         if merge_function_wrapper is None:
             raise ValueError("merge_function_wrapper (MergeSpec) is required")
-        return SortMergeReader(list(readers), merge_function_wrapper, user_defined_seq_comparator, device)
+        spec = merge_function_wrapper
+        if user_defined_seq_comparator is not None:
+            if hasattr(user_defined_seq_comparator, "apply"):           # UserDefinedSeqComparator
+                spec = user_defined_seq_comparator.apply(spec)
+            else:                                                       # plain list of value-field indexes
+                spec = spec.normalised(readers[0].schema.n_val) if readers else spec
+                spec.seq_fields = list(user_defined_seq_comparator)
+        return SortMergeReader(list(readers), spec, None, device)
 
     def __init__(self, readers: List[SortedRunReader], spec: MergeSpec, seq_fields=None, device: int = 0):
         self.readers = readers

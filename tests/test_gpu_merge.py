@@ -240,3 +240,46 @@ def test_size_independent_properties_at_scale():
     # merging the merged result with nothing changes nothing
     again = merge_runs(schema, spec, [got])
     assert again.equals(got)
+
+
+@pytest.mark.parametrize("ascending", [True, False])
+@pytest.mark.parametrize("engine", ["dedup", "partial-update", "aggregation"])
+def test_user_defined_sequence_fields(engine, ascending):
+    """'sequence.field': members are ordered by the user fields (nulls first, before the descending flip;
+    GenerateUtils.scala:305-345), then by _SEQUENCE_NUMBER (SortMergeReaderWithLoserTree.java:58-64)."""
+    from paimon_b200.merge_function import UserDefinedSeqComparator
+    vt = RowType((DataField("pk", "INT", False), DataField("ts", "INT", True), DataField("score", "DOUBLE", True),
+                  DataField("v", "BIGINT", True), DataField("s", "STRING", True)))
+    schema = KeyValueSchema.of(vt, ["pk"])
+    opts = {"sequence.field": "ts,score", "sequence.field.sort-order": "ascending" if ascending else "descending"}
+    if engine == "dedup":
+        spec = DeduplicateMergeFunction.factory(opts).create()
+    elif engine == "partial-update":
+        spec = PartialUpdateMergeFunction.factory(opts, vt, ["pk"]).create()
+    else:
+        spec = AggregateMergeFunction.factory(dict(opts, **{"fields.v.aggregate-function": "sum"}), vt, ["pk"]).create()
+    udsc = UserDefinedSeqComparator.create(vt, opts)
+    assert udsc.compare_fields() == [1, 2] and udsc.is_ascending_order() == ascending
+    rng = random.Random(77 + ascending)
+    for _ in range(10):
+        runs, seq = [], 0
+        for r in range(rng.randrange(2, 9)):
+            keys = sorted(rng.sample(range(60), rng.randrange(1, 50)))
+            rows = []
+            for kx in keys:
+                seq += 1
+                rows.append((kx, seq, 0, kx,
+                             None if rng.random() < 0.3 else rng.randrange(0, 4),          # many ties and nulls
+                             None if rng.random() < 0.3 else rng.choice([1.5, 2.5, float("nan"), -0.0, 0.0]),
+                             None if rng.random() < 0.2 else rng.randrange(-1000, 1000),
+                             None if rng.random() < 0.3 else rng.choice(["a", "bb", "ccc"])))
+            runs.append(KeyValueBatch.from_rows(schema, rows))
+        want = pyoracle.merge(schema, udsc.apply(spec), runs, pyoracle.SORT_LOSER_TREE)
+        readers = [SortedRunReader(schema, b) for b in runs]
+        rd = SortMergeReader.create_sort_merge_reader(readers, None, udsc, spec)
+        try:
+            rd.execute()
+            got = rd.fetch()
+        finally:
+            rd.close()
+        assert got.equals(want), got.first_difference(want)
