@@ -349,9 +349,18 @@ def main():
     peak_kind = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     alg_bytes = in_bytes + out_bytes
     emit_ms = ms_emit / args.steps
+    # DRAM traffic of the dominant kernel from the committed ncu capture of this workload at its full size
+    # (profiles/traffic.json; only meaningful for the default row count)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if args.workload in tj and rows == w["rows"]:
+            traffic = tj[args.workload]["traffic"]
+    except Exception:
+        pass
     achieved = alg_bytes / (emit_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_emit", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_kind, "traffic": None,
+                "frac": achieved / peak, "peak_source": peak_kind, "traffic": traffic,
                 "algorithmic_bytes": alg_bytes, "kernel_ms": emit_ms,
                 "step_frac": alg_bytes / (step_ms * 1e-3) / 1e9 / peak,
                 "phase_ms": {"partition": ms_part / args.steps, "plan+scan": ms_plan / args.steps,
