@@ -77,6 +77,7 @@ struct Merge {
     // persistent device descriptors
     void *d_desc = nullptr;            // one allocation holding all descriptor arrays
     const void **d_key_ptrs = nullptr;
+    const int32_t **d_key_offs = nullptr;
     const int64_t **d_seq_ptrs = nullptr;
     const int8_t **d_kind_ptrs = nullptr;
     ColPtrs d_ptrs{};                   // [col * k + run]
@@ -176,25 +177,25 @@ static bool agg_supports_retract(int agg) {
 static pg_status build_descriptors(Merge *m) {
     const Schema *s = m->schema;
     const Spec *sp = m->spec;
-    // key normalisation into one uint64
-    int bits = 0;
+    // primary key: a 64-bit order-preserving prefix lives in shared memory; keys that do not fit it exactly
+    // (strings, binaries, composites wider than 8 bytes) fall back to a full comparison on prefix ties
+    if (s->n_key < 1 || s->n_key > PG_MAX_KEY_FIELDS)
+        return fail(PG_ERR_UNSUPPORTED, "more than 4 primary-key fields are not implemented on the device");
+    m->key = KeyDesc{};
+    m->key.n_fields = s->n_key;
+    int key_bytes = 0;
+    bool all_fixed = true;
     for (int f = 0; f < s->n_key; f++) {
         int t = s->key_fields[f].type;
-        if (!(t == PG_INT8 || t == PG_INT16 || t == PG_INT32 || t == PG_INT64 || t == PG_BOOL))
-            return fail(PG_ERR_UNSUPPORTED, "primary-key type not implemented on the device merge path "
-                                            "(integer / date / time / timestamp / boolean keys only)");
-        bits += type_width(t) * 8;
+        if (t == PG_FLOAT || t == PG_DOUBLE)
+            return fail(PG_ERR_UNSUPPORTED, "FLOAT / DOUBLE primary keys are not implemented on the device "
+                                            "(the reference's comparator treats NaN as equal to everything)");
+        m->key.type[f] = t;
+        m->key.width[f] = type_width(t);
+        if (is_varlen(t)) all_fixed = false;
+        key_bytes += type_width(t);
     }
-    if (s->n_key < 1 || s->n_key > PG_MAX_KEY_FIELDS || bits > 64)
-        return fail(PG_ERR_UNSUPPORTED, "composite primary key wider than 64 bits is not implemented");
-    m->key.n_fields = s->n_key;
-    int used = 0;
-    for (int f = 0; f < s->n_key; f++) {
-        int w = type_width(s->key_fields[f].type) * 8;
-        used += w;
-        m->key.type[f] = s->key_fields[f].type;
-        m->key.shift[f] = bits - used;
-    }
+    m->key.exact = all_fixed && key_bytes <= 8;
     // 'sequence.field': fixed-width value fields compared before _SEQUENCE_NUMBER
     m->seq = SeqFields{};
     if (sp->seq_fields.size() > 4)
@@ -268,7 +269,8 @@ static pg_status build_descriptors(Merge *m) {
     const int k = m->k, nk = s->n_key, nv = (int)m->varlen_cols.size();
     auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t o_key = 0;
-    size_t o_seq = o_key + align(sizeof(void *) * k * nk);
+    size_t o_koff = o_key + align(sizeof(void *) * k * nk);
+    size_t o_seq = o_koff + align(sizeof(void *) * k * nk);
     size_t o_kind = o_seq + align(sizeof(void *) * k);
     size_t o_pd = o_kind + align(sizeof(void *) * k);
     size_t o_po = o_pd + align(sizeof(void *) * (size_t)k * nc);
@@ -285,7 +287,10 @@ static pg_status build_descriptors(Merge *m) {
     m->varlen_bound.assign(nv, 0);
     for (int r = 0; r < k; r++) {
         const Run *run = m->runs[r];
-        for (int f = 0; f < nk; f++) ((const void **)(host.data() + o_key))[r * nk + f] = run->cols[f].data;
+        for (int f = 0; f < nk; f++) {
+            ((const void **)(host.data() + o_key))[r * nk + f] = run->cols[f].data;
+            ((const void **)(host.data() + o_koff))[r * nk + f] = run->cols[f].offsets;
+        }
         ((const void **)(host.data() + o_seq))[r] = run->cols[nk].data;
         ((const void **)(host.data() + o_kind))[r] = run->cols[nk + 1].data;
         for (int c = 0; c < nc; c++) {
@@ -308,6 +313,7 @@ static pg_status build_descriptors(Merge *m) {
     PG_CUDA(cudaMemcpy(m->d_desc, host.data(), total, cudaMemcpyHostToDevice));
     unsigned char *d = (unsigned char *)m->d_desc;
     m->d_key_ptrs = (const void **)(d + o_key);
+    m->d_key_offs = (const int32_t **)(d + o_koff);
     m->d_seq_ptrs = (const int64_t **)(d + o_seq);
     m->d_kind_ptrs = (const int8_t **)(d + o_kind);
     m->d_ptrs.data = (const void *const *)(d + o_pd);
@@ -394,7 +400,7 @@ static pg_status execute(Merge *m) {
     PG_CUDA(cudaMemsetAsync(m->d_err, 0, sizeof(int32_t), sm));
     PG_CUDA(cudaEventRecord(m->ev[0], sm));
 
-    MergeLaunch ml{k, m->key, m->d_key_ptrs, sm, m->d_err};
+    MergeLaunch ml{k, m->key, KeySrc{m->d_key_ptrs, m->d_key_offs}, sm, m->d_err};
     // Workspace: one grow-only device allocation per merge handle, carved with a bump pointer.  Its size
     // depends only on the input shapes, so a reader that is executed repeatedly (or a pool of readers of
     // one bucket layout) never goes back to the driver allocator.
@@ -403,7 +409,7 @@ static pg_status execute(Merge *m) {
         auto add = [&](size_t b) { need += ((b ? b : 16) + 255) & ~(size_t)255; };
         for (int l = top; l >= 0; l--) {
             add(sizeof(int64_t) * (size_t)(n_tiles[l] + 1) * k);
-            if (l > 0) add(sizeof(uint64_t) * (size_t)std::max<int64_t>(level_total[l], 1));
+            if (l > 0) { add(sizeof(uint64_t) * (size_t)std::max<int64_t>(level_total[l], 1)); add(sizeof(uint64_t) * (size_t)std::max<int64_t>(level_total[l], 1)); }
         }
         const size_t N_ = (size_t)m->n_in, T_ = (size_t)n_tiles[0];
         add(2 * N_ + 16); add(4 * T_); add(8 * N_ + 16); add(N_ + 16); add(8 * T_); add(8 * T_ * std::max(nv, 1));
@@ -417,15 +423,19 @@ static pg_status execute(Merge *m) {
 
     int64_t *bounds0 = nullptr;
     uint64_t *sk_above = nullptr;         // sorted sample keys of the level above the current one
+    uint64_t *sref_above = nullptr;       // ... and the rows they came from (non-exact keys)
     for (int l = top; l >= 0; l--) {
         int64_t *bounds = nullptr;
         PG_CUDA(talloc(sizeof(int64_t) * (size_t)(n_tiles[l] + 1) * k, (void **)&bounds));
-        launch_partition(ml, views[l], sk_above, l == top ? 0 : level_total[l + 1], q, n_tiles[l], bounds);
+        launch_partition(ml, views[l], sk_above, sref_above, q, n_tiles[l], bounds);
         launches++;
         if (l > 0) {
             uint64_t *sk = nullptr;
             PG_CUDA(talloc(sizeof(uint64_t) * (size_t)std::max<int64_t>(level_total[l], 1), (void **)&sk));
-            launch_merge_keys(ml, views[l], bounds, n_tiles[l], sk);
+            uint64_t *sref = nullptr;
+            PG_CUDA(talloc(sizeof(uint64_t) * (size_t)std::max<int64_t>(level_total[l], 1), (void **)&sref));
+            launch_merge_keys(ml, views[l], bounds, n_tiles[l], sk, sref);
+            sref_above = sref;
             launches++;
             sk_above = sk;
         } else {

@@ -32,19 +32,58 @@ __device__ __forceinline__ uint64_t norm_field(const void *base, int type, int64
     }
 }
 
-__device__ __forceinline__ uint64_t load_key(const void *const *key_ptrs, const KeyDesc &kd, int run,
-                                             int64_t row) {
-    if (kd.n_fields == 1) return norm_field(key_ptrs[run], kd.type[0], row);
+// Order-preserving 64-bit prefix of a row's primary key: the key fields laid out big-endian, most
+// significant first, cut after 8 bytes.  prefix(a) < prefix(b) implies a < b; equal prefixes decide nothing
+// unless kd.exact (all fields fixed-width and together <= 8 bytes).  A var-len field contributes its first
+// bytes (zero padded) and ends the prefix.
+__device__ __forceinline__ uint64_t load_key(const KeySrc &ks, const KeyDesc &kd, int run, int64_t row) {
+    if (kd.n_fields == 1 && kd.width[0] == 8) return norm_field(ks.data[run], kd.type[0], row);
     uint64_t k = 0;
-    for (int f = 0; f < kd.n_fields; f++)
-        k |= norm_field(key_ptrs[run * kd.n_fields + f], kd.type[f], row) << kd.shift[f];
+    int pos = 0;                                         // bytes of the prefix already filled
+    for (int f = 0; f < kd.n_fields && pos < 8; f++) {
+        const void *base = ks.data[run * kd.n_fields + f];
+        const int w = kd.width[f];
+        if (w > 0) {
+            uint64_t v = norm_field(base, kd.type[f], row);
+            int room = 8 - pos;
+            if (w <= room) k |= v << ((room - w) * 8);
+            else k |= v >> ((w - room) * 8);
+            pos += w;
+        } else {
+            const int32_t *offs = ks.offsets[run * kd.n_fields + f];
+            const uint8_t *bytes = (const uint8_t *)base + offs[row];
+            int len = offs[row + 1] - offs[row];
+            for (int b = 0; b < len && pos < 8; b++, pos++) k |= (uint64_t)bytes[b] << ((7 - pos) * 8);
+            pos = 8;
+        }
+    }
     return k;
+}
+
+// Full comparison of two rows' keys, field by field, with the generated comparator's rules
+// (GenerateUtils.scala:113-126): integers signed, BOOLEAN false < true, CHAR/VARCHAR/BINARY unsigned bytewise
+// then length (BinaryString.java:109-126, SortUtil.java:212-241).
+__device__ int full_key_compare(const KeySrc &ks, const KeyDesc &kd, int ra, int64_t row_a, int rb, int64_t row_b) {
+    for (int f = 0; f < kd.n_fields; f++) {
+        const void *da = ks.data[ra * kd.n_fields + f], *db = ks.data[rb * kd.n_fields + f];
+        const int w = kd.width[f];
+        if (w > 0) {
+            uint64_t x = norm_field(da, kd.type[f], row_a), y = norm_field(db, kd.type[f], row_b);
+            if (x != y) return x < y ? -1 : 1;
+        } else {
+            const int32_t *oa = ks.offsets[ra * kd.n_fields + f], *ob = ks.offsets[rb * kd.n_fields + f];
+            int la = oa[row_a + 1] - oa[row_a], lb = ob[row_b + 1] - ob[row_b];
+            int d = bytes_compare((const uint8_t *)da + oa[row_a], la, (const uint8_t *)db + ob[row_b], lb);
+            if (d != 0) return d < 0 ? -1 : 1;
+        }
+    }
+    return 0;
 }
 
 // ------------------------------------------------------------------ partition
 
-__global__ void k_partition(int k, KeyDesc kd, const void *const *key_ptrs, LevelView lv,
-                            const uint64_t *__restrict__ sk, int q, int n_tiles, int64_t *bounds) {
+__global__ void k_partition(int k, KeyDesc kd, KeySrc ks, LevelView lv, const uint64_t *__restrict__ sk,
+                            const uint64_t *__restrict__ sref, int q, int n_tiles, int64_t *bounds) {
     int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (idx >= (int64_t)(n_tiles + 1) * k) return;
     int t = (int)(idx / k), r = (int)(idx % k);
@@ -52,12 +91,18 @@ __global__ void k_partition(int k, KeyDesc kd, const void *const *key_ptrs, Leve
     if (t == 0) res = 0;
     else if (t == n_tiles) res = lv.count[r];
     else {
-        uint64_t x = sk[(int64_t)t * q];
+        const uint64_t x = sk[(int64_t)t * q];
+        const uint64_t xr = kd.exact ? 0 : sref[(int64_t)t * q];      // splitter row: run << 40 | row
+        const int s_run = (int)(xr >> 40);
+        const int64_t s_row = (int64_t)(xr & ((1ull << 40) - 1));
         int64_t lo = 0, hi = lv.count[r];
-        while (lo < hi) {                      // lower_bound: first j with key(j) >= x
+        while (lo < hi) {                      // lower_bound: first j with key(j) >= splitter key
             int64_t mid = (lo + hi) >> 1;
-            uint64_t km = load_key(key_ptrs, kd, r, (mid + 1) * lv.stride - 1);
-            if (km < x) lo = mid + 1; else hi = mid;
+            const int64_t row = (mid + 1) * lv.stride - 1;
+            uint64_t km = load_key(ks, kd, r, row);
+            bool less = km < x;
+            if (!less && km == x && !kd.exact) less = full_key_compare(ks, kd, r, row, s_run, s_row) < 0;
+            if (less) lo = mid + 1; else hi = mid;
         }
         res = lo;
     }
@@ -82,7 +127,7 @@ struct TileCtx {
 };
 
 // Loads the tile's k segments and merges them.  Returns false when the tile overflows.
-__device__ bool merge_tile(TileCtx &tc, int k, const KeyDesc &kd, const void *const *key_ptrs,
+__device__ bool merge_tile(TileCtx &tc, int k, const KeyDesc &kd, const KeySrc &ks,
                            const int64_t *bounds, int tile, int64_t stride, int32_t *err) {
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -110,11 +155,21 @@ __device__ bool merge_tile(TileCtx &tc, int k, const KeyDesc &kd, const void *co
         const int s0 = tc.seg[r], s1 = tc.seg[r + 1];
         const int64_t j0 = tc.rstart[r] - s0;
         for (int i = s0 + tid; i < s1; i += blockDim.x) {
-            tc.key[0][PADI(i)] = load_key(key_ptrs, kd, r, (j0 + i + 1) * stride - 1);
+            tc.key[0][PADI(i)] = load_key(ks, kd, r, (j0 + i + 1) * stride - 1);
             tc.idx[0][PADI(i)] = (uint16_t)i;
         }
     }
     __syncthreads();
+
+    // a <= b on (prefix, slot) pairs; equal prefixes of a non-exact key fall back to the full comparison
+    auto le = [&](uint64_t ka, int sa, uint64_t kb, int sb) -> bool {
+        if (ka != kb) return ka < kb;
+        if (kd.exact) return true;
+        const int ra = run_of_slot(tc.seg, k, sa), rb = run_of_slot(tc.seg, k, sb);
+        const int64_t row_a = (tc.rstart[ra] + (sa - tc.seg[ra]) + 1) * stride - 1;
+        const int64_t row_b = (tc.rstart[rb] + (sb - tc.seg[rb]) + 1) * stride - 1;
+        return full_key_compare(ks, kd, ra, row_a, rb, row_b) <= 0;
+    };
 
     int L = k, cur = 0;
     constexpr int VT = kTileMax / kThreads;
@@ -136,18 +191,24 @@ __device__ bool merge_tile(TileCtx &tc, int k, const KeyDesc &kd, const void *co
             int lo = max(0, d - nb), hi = min(d, na);
             while (lo < hi) {                    // merge path: #elements taken from A among the first d
                 int mid = (lo + hi) >> 1;
-                if (sk[PADI(a0 + mid)] <= sk[PADI(a1 + d - 1 - mid)]) lo = mid + 1; else hi = mid;
+                if (le(sk[PADI(a0 + mid)], si[PADI(a0 + mid)], sk[PADI(a1 + d - 1 - mid)], si[PADI(a1 + d - 1 - mid)]))
+                    lo = mid + 1;
+                else
+                    hi = mid;
             }
             int ai = lo, bi = d - lo;
             uint64_t ka = ai < na ? sk[PADI(a0 + ai)] : 0, kb = bi < nb ? sk[PADI(a1 + bi)] : 0;
+            uint16_t ia = ai < na ? si[PADI(a0 + ai)] : 0, ib = bi < nb ? si[PADI(a1 + bi)] : 0;
             for (int s = 0; s < cnt; s++) {
-                bool take_a = (bi >= nb) || (ai < na && ka <= kb);   // stable: lower run first on ties
+                bool take_a = (bi >= nb) || (ai < na && le(ka, ia, kb, ib));   // stable: lower run first on ties
                 if (take_a) {
-                    dk[PADI(pos + s)] = ka; di[PADI(pos + s)] = si[PADI(a0 + ai)];
-                    ai++; ka = ai < na ? sk[PADI(a0 + ai)] : 0;
+                    dk[PADI(pos + s)] = ka; di[PADI(pos + s)] = ia;
+                    ai++;
+                    if (ai < na) { ka = sk[PADI(a0 + ai)]; ia = si[PADI(a0 + ai)]; }
                 } else {
-                    dk[PADI(pos + s)] = kb; di[PADI(pos + s)] = si[PADI(a1 + bi)];
-                    bi++; kb = bi < nb ? sk[PADI(a1 + bi)] : 0;
+                    dk[PADI(pos + s)] = kb; di[PADI(pos + s)] = ib;
+                    bi++;
+                    if (bi < nb) { kb = sk[PADI(a1 + bi)]; ib = si[PADI(a1 + bi)]; }
                 }
             }
             pos += cnt;
@@ -175,17 +236,26 @@ __device__ __forceinline__ void carve_tile(TileCtx &tc, unsigned char *smem, int
 constexpr size_t kTileSmem = (size_t)kTilePad * (8 + 8 + 2 + 2) + PG_MAX_RUNS * 8 + 3 * (PG_MAX_RUNS + 1) * 4;
 
 __global__ void __launch_bounds__(kThreads)
-k_merge_keys(int k, KeyDesc kd, const void *const *key_ptrs, LevelView lv, const int64_t *bounds,
-             uint64_t *sorted_keys, int32_t *err) {
+k_merge_keys(int k, KeyDesc kd, KeySrc ks, LevelView lv, const int64_t *bounds, uint64_t *sorted_keys,
+             uint64_t *sorted_refs, int32_t *err) {
     extern __shared__ __align__(16) unsigned char smem[];
     TileCtx tc;
     carve_tile(tc, smem, k);
     int tile = blockIdx.x;
-    if (!merge_tile(tc, k, kd, key_ptrs, bounds, tile, lv.stride, err)) return;
+    if (!merge_tile(tc, k, kd, ks, bounds, tile, lv.stride, err)) return;
     int64_t base = 0;
     for (int r = 0; r < k; r++) base += tc.rstart[r];
     const uint64_t *fk = tc.key[tc.fin];
-    for (int i = threadIdx.x; i < tc.n; i += blockDim.x) sorted_keys[base + i] = fk[PADI(i)];
+    const uint16_t *fi = tc.idx[tc.fin];
+    for (int i = threadIdx.x; i < tc.n; i += blockDim.x) {
+        sorted_keys[base + i] = fk[PADI(i)];
+        if (!kd.exact) {                       // the sample's row, for full comparisons against it
+            const int slot = fi[PADI(i)];
+            const int r = run_of_slot(tc.seg, k, slot);
+            const int64_t row = (tc.rstart[r] + (slot - tc.seg[r]) + 1) * lv.stride - 1;
+            sorted_refs[base + i] = ((uint64_t)r << 40) | (uint64_t)row;
+        }
+    }
 }
 
 // ------------------------------------------------------------------ 'sequence.field' comparator
@@ -241,7 +311,7 @@ struct PlanSmemExtra {
 constexpr size_t kPlanSmem = kTileSmem + (size_t)kTileMax * 3 + 34 * 4 + 16;
 
 __global__ void __launch_bounds__(kThreads, 2)
-k_plan(int k, KeyDesc kd, const void *const *key_ptrs, PlanArgs pa, int32_t *err) {
+k_plan(int k, KeyDesc kd, KeySrc ks, PlanArgs pa, int32_t *err) {
     extern __shared__ __align__(16) unsigned char smem[];
     TileCtx tc;
     carve_tile(tc, smem, k);
@@ -251,7 +321,7 @@ k_plan(int k, KeyDesc kd, const void *const *key_ptrs, PlanArgs pa, int32_t *err
     px.ws = (int *)(px.res_kind + kTileMax);
 
     const int tile = blockIdx.x, tid = threadIdx.x;
-    if (!merge_tile(tc, k, kd, key_ptrs, pa.bounds, tile, 1, err)) {
+    if (!merge_tile(tc, k, kd, ks, pa.bounds, tile, 1, err)) {
         if (tid == 0) pa.tile_rows[tile] = 0;
         return;
     }
@@ -264,6 +334,15 @@ k_plan(int k, KeyDesc kd, const void *const *key_ptrs, PlanArgs pa, int32_t *err
 
     int64_t in_base = 0;
     for (int r = 0; r < k; r++) in_base += tc.rstart[r];
+
+    // do the merged positions a and b hold the same key?  (equal prefixes decide only for exact keys)
+    auto same_key = [&](int a, int b) -> bool {
+        if (fk[PADI(a)] != fk[PADI(b)]) return false;
+        if (kd.exact) return true;
+        const int sa = fi[PADI(a)], sb = fi[PADI(b)];
+        const int ra = run_of_slot(tc.seg, k, sa), rb = run_of_slot(tc.seg, k, sb);
+        return full_key_compare(ks, kd, ra, tc.rstart[ra] + (sa - tc.seg[ra]), rb, tc.rstart[rb] + (sb - tc.seg[rb])) == 0;
+    };
 
     // stage sequence numbers and kinds (coalesced per run segment)
     for (int r = 0; r < k; r++) {
@@ -283,10 +362,10 @@ k_plan(int k, KeyDesc kd, const void *const *key_ptrs, PlanArgs pa, int32_t *err
     int my_emit = 0;
 
     for (int i = p0; i < p1; i++) {
-        bool head = (i == 0) || (fk[PADI(i)] != fk[PADI(i - 1)]);
+        bool head = (i == 0) || !same_key(i - 1, i);
         if (!head) continue;
         int e = i + 1;
-        while (e < n && fk[PADI(e)] == fk[PADI(i)]) e++;
+        while (e < n && same_key(i, e)) e++;
         const int g = e - i;
         // members in ascending sequence order (SortMergeReaderWithLoserTree.java:52-65); ties (which the
         // reference leaves unspecified) resolve by run order = slot order
@@ -388,7 +467,7 @@ k_plan(int k, KeyDesc kd, const void *const *key_ptrs, PlanArgs pa, int32_t *err
     int total = 0;
     int o = block_scan_excl(my_emit, px.ws, &total);
     for (int i = p0; i < p1; i++) {
-        bool head = (i == 0) || (fk[PADI(i)] != fk[PADI(i - 1)]);
+        bool head = (i == 0) || !same_key(i - 1, i);
         uint16_t entry = (uint16_t)(fi[PADI(i)] | (ops[i] << kPlanOpShift));
         if (head) {
             entry |= kPlanHead;
@@ -436,23 +515,23 @@ static void set_attrs() {
 }
 
 void launch_partition(const MergeLaunch &ml, const LevelView &lv, const uint64_t *splitter_keys,
-                      int64_t n_splitter_keys, int q, int n_tiles, int64_t *bounds) {
-    (void)n_splitter_keys;
+                      const uint64_t *splitter_refs, int q, int n_tiles, int64_t *bounds) {
     int64_t total = (int64_t)(n_tiles + 1) * ml.k;
     int blocks = (int)((total + 127) / 128);
-    k_partition<<<blocks, 128, 0, ml.stream>>>(ml.k, ml.key, ml.key_ptrs, lv, splitter_keys, q, n_tiles, bounds);
+    k_partition<<<blocks, 128, 0, ml.stream>>>(ml.k, ml.key, ml.ks, lv, splitter_keys, splitter_refs, q, n_tiles,
+                                                 bounds);
 }
 
 void launch_merge_keys(const MergeLaunch &ml, const LevelView &lv, const int64_t *bounds, int n_tiles,
-                       uint64_t *sorted_keys) {
+                       uint64_t *sorted_keys, uint64_t *sorted_refs) {
     set_attrs();
-    k_merge_keys<<<n_tiles, kThreads, kTileSmem, ml.stream>>>(ml.k, ml.key, ml.key_ptrs, lv, bounds, sorted_keys,
-                                                                ml.err);
+    k_merge_keys<<<n_tiles, kThreads, kTileSmem, ml.stream>>>(ml.k, ml.key, ml.ks, lv, bounds, sorted_keys,
+                                                                sorted_refs, ml.err);
 }
 
 void launch_plan(const MergeLaunch &ml, const PlanArgs &pa) {
     set_attrs();
-    k_plan<<<pa.n_tiles, kThreads, kPlanSmem, ml.stream>>>(ml.k, ml.key, ml.key_ptrs, pa, ml.err);
+    k_plan<<<pa.n_tiles, kThreads, kPlanSmem, ml.stream>>>(ml.k, ml.key, ml.ks, pa, ml.err);
 }
 
 void launch_scan(cudaStream_t stream, const int32_t *tile_rows, int n_tiles, int64_t *row_base, int64_t *totals) {

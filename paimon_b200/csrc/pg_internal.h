@@ -97,8 +97,15 @@ struct MergeFlags {
 // key normalisation: how to build the order-preserving uint64 of a row
 struct KeyDesc {
     int32_t n_fields;
+    int32_t exact;                      // the 64-bit prefix IS the key (fixed-width fields, <= 8 bytes in total)
     int32_t type[PG_MAX_KEY_FIELDS];
-    int32_t shift[PG_MAX_KEY_FIELDS];   // left shift of the field inside the uint64
+    int32_t width[PG_MAX_KEY_FIELDS];   // bytes; 0 = var-len (CHAR / VARCHAR / BINARY)
+};
+
+// key columns of the runs: [run * n_fields + field]
+struct KeySrc {
+    const void *const *data;
+    const int32_t *const *offsets;      // var-len fields, else NULL entries
 };
 
 void set_error(const std::string &msg);
@@ -121,16 +128,16 @@ struct LevelView {             // keys of level l of run r: key(row = (j + 1) * 
 struct MergeLaunch {
     int k;
     KeyDesc key;
-    const void *const *key_ptrs;       // device: [k][n_key] key column data pointers
+    KeySrc ks;                         // device: [k][n_key] key column data / offsets pointers
     cudaStream_t stream;
     int32_t *err;                      // device error word
 };
 
 // B[(t) * k + r] for t in [0, n_tiles]: tile boundaries per run at this level.
 void launch_partition(const MergeLaunch &ml, const LevelView &lv, const uint64_t *splitter_keys,
-                      int64_t n_splitter_keys, int q, int n_tiles, int64_t *bounds);
+                      const uint64_t *splitter_refs, int q, int n_tiles, int64_t *bounds);
 void launch_merge_keys(const MergeLaunch &ml, const LevelView &lv, const int64_t *bounds, int n_tiles,
-                       uint64_t *sorted_keys);
+                       uint64_t *sorted_keys, uint64_t *sorted_refs);
 
 // per-column, per-run input pointers, transposed for coalesced access: [col * k + run]
 struct ColPtrs {

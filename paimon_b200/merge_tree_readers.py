@@ -1,0 +1,224 @@
+"""Host orchestration of the merge path: files -> sections -> runs -> device merges -> one reader.
+
+Mirrors (same names, same argument meaning):
+  IntervalPartition.partition           paimon-core/.../mergetree/compact/IntervalPartition.java:67-125
+  SortedRun                             paimon-core/.../mergetree/SortedRun.java:40-116
+  MergeTreeReaders.readerForMergeTree / readerForSection / readerForRun
+                                        paimon-core/.../mergetree/MergeTreeReaders.java:44-101
+  ConcatRecordReader                    paimon-core/.../mergetree/compact/ConcatRecordReader.java:35-86
+  MergeFileSplitRead.createMergeReader  paimon-core/.../operation/MergeFileSplitRead.java:269-316
+  DataFileMeta (the fields the path needs)   paimon-core/.../io/DataFileMeta.java:66-89
+
+The control flow stays on the host exactly where the reference has it (it only touches file *metadata*);
+every section is merged by one SortMergeReader on the device, sections are key-disjoint so their outputs
+concatenate.  Files of one run inside a section are key-disjoint and ordered, so a run is the concatenation of
+its files (SortedRun.fromSorted): the device gets them as one run made of several decoded files.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+from .columnar import Column, KeyValueBatch
+from .format import FileFormat, FormatReaderContext, LocalFileIO
+from .merge_function import MergeFunctionFactory, MergeSpec
+from .sort_merge_reader import RecordReader, SortedRunReader, SortMergeReader
+from .types import KeyValueSchema, is_varlen
+
+
+@dataclass
+class DataFileMeta:
+    """Input descriptor at the seam (DataFileMeta.java:66-89): what scan planning hands to the reader."""
+    file_name: str
+    file_size: int
+    row_count: int
+    min_key: int                 # single integer key column: the key bounds as integers
+    max_key: int
+    min_sequence_number: int = 0
+    max_sequence_number: int = 0
+    level: int = 0
+    delete_row_count: int = 0
+
+
+@dataclass
+class SortedRun:
+    files: List[DataFileMeta] = field(default_factory=list)
+
+    @staticmethod
+    def from_sorted(files: Sequence[DataFileMeta]) -> "SortedRun":
+        run = SortedRun(list(files))
+        run.validate()
+        return run
+
+    def validate(self) -> None:                       # SortedRun.java:85-95
+        for a, b in zip(self.files, self.files[1:]):
+            if not a.max_key < b.min_key:
+                raise ValueError("SortedRun is not sorted and may contain overlapping key intervals")
+
+    def total_size(self) -> int:
+        return sum(f.file_size for f in self.files)
+
+
+class IntervalPartition:
+    """Sections (key-disjoint) of runs (fewest non-overlapping file chains).  The algorithm runs in
+    libpaimon_gpu.so's host code (pg_interval_partition) so that Java and Python share one implementation."""
+
+    def __init__(self, input_files: Sequence[DataFileMeta]):
+        self.files = list(input_files)
+
+    def partition(self) -> List[List[SortedRun]]:
+        n = len(self.files)
+        if n == 0:
+            return []
+        lib = N.load()
+        mn = np.array([f.min_key for f in self.files], np.int64)
+        mx = np.array([f.max_key for f in self.files], np.int64)
+        sec = np.zeros(n, np.int32)
+        run = np.zeros(n, np.int32)
+        ns = C.c_int32(0)
+        N.check(lib.pg_interval_partition(n, mn.ctypes.data, mx.ctypes.data, sec.ctypes.data, run.ctypes.data,
+                                          C.byref(ns)))
+        sections: List[dict] = [dict() for _ in range(ns.value)]
+        for i, f in enumerate(self.files):
+            sections[sec[i]].setdefault(int(run[i]), []).append(f)
+        out = []
+        for s in sections:
+            runs = []
+            for rid in sorted(s):
+                files = sorted(s[rid], key=lambda f: (f.min_key, f.max_key))
+                runs.append(SortedRun.from_sorted(files))
+            out.append(runs)
+        return out
+
+
+class ConcatRecordReader(RecordReader):
+    """Readers are opened lazily one after the other (ConcatRecordReader.java:52-75)."""
+
+    def __init__(self, suppliers: Sequence[Callable[[], RecordReader]]):
+        self.queue = list(suppliers)
+        self.current: Optional[RecordReader] = None
+
+    def read_batch(self) -> Optional[KeyValueBatch]:
+        while True:
+            if self.current is not None:
+                batch = self.current.read_batch()
+                if batch is not None:
+                    return batch
+                self.current.close()
+                self.current = None
+            if not self.queue:
+                return None
+            self.current = self.queue.pop(0)()
+
+    def close(self) -> None:
+        if self.current is not None:
+            self.current.close()
+            self.current = None
+
+
+def concat_batches(schema: KeyValueSchema, batches: Sequence[KeyValueBatch]) -> KeyValueBatch:
+    """Concatenate key-disjoint, ordered batches (host helper for tests / small results)."""
+    if not batches:
+        return KeyValueBatch.from_rows(schema, [])
+    cols = []
+    for ci, t in enumerate(schema.physical_types()):
+        parts = [b.columns[ci].canonical() for b in batches]
+        from .columnar import pack_validity, unpack_validity
+        valid = np.concatenate([unpack_validity(p.valid, len(p)) for p in parts])
+        if is_varlen(t):
+            data = np.concatenate([p.data for p in parts]) if parts else np.zeros(0, np.uint8)
+            offs = [np.zeros(1, np.int64)]
+            base = 0
+            for p in parts:
+                offs.append(p.offsets[1:].astype(np.int64) + base)
+                base += int(p.offsets[-1])
+            cols.append(Column(t, data, np.concatenate(offs).astype(np.int32), pack_validity(valid)))
+        else:
+            cols.append(Column(t, np.concatenate([p.data for p in parts]), None, pack_validity(valid)))
+    return KeyValueBatch(schema, cols)
+
+
+class KeyValueFileReaderFactory:
+    """createRecordReader(file) — KeyValueFileReaderFactory.java:119-172: format by file suffix, decode on the
+    device.  (Schema evolution mappings and deletion vectors are applied on the Java side today.)"""
+
+    def __init__(self, schema: KeyValueSchema, file_io: Optional[LocalFileIO] = None, device: int = 0):
+        self.schema = schema
+        self.file_io = file_io or LocalFileIO()
+        self.device = device
+
+    def create_record_reader(self, meta: DataFileMeta):
+        suffix = meta.file_name.rsplit(".", 1)[-1]
+        fmt = FileFormat.from_identifier(suffix, self.device)
+        return fmt.create_reader_factory(self.schema).create_reader(
+            FormatReaderContext(self.file_io, meta.file_name, meta.file_size))
+
+
+class MergeTreeReaders:
+    @staticmethod
+    def reader_for_run(run: SortedRun, reader_factory: KeyValueFileReaderFactory) -> List[SortedRunReader]:
+        """A run = its files in key order.  Each decoded file is handed to the merge as its own sorted input:
+        files of one run never share keys, so giving them to the k-way merge separately yields the same rows as
+        concatenating them first (MergeTreeReaders.java:94-101)."""
+        out = []
+        for meta in run.files:
+            fr = reader_factory.create_record_reader(meta)
+            out.append((fr, fr.as_sorted_run_reader()))
+        return out
+
+    @staticmethod
+    def reader_for_section(section: Sequence[SortedRun], reader_factory: KeyValueFileReaderFactory,
+                           user_defined_seq_comparator, merge_function_wrapper: MergeSpec) -> RecordReader:
+        opened = []
+        for run in section:
+            opened += MergeTreeReaders.reader_for_run(run, reader_factory)
+        if len(opened) > 32:
+            raise N.UnsupportedOnDevice(2, "more than 32 files in one section: merge in rounds is not implemented yet")
+        merge = SortMergeReader.create_sort_merge_reader([r for _, r in opened], None, user_defined_seq_comparator,
+                                                         merge_function_wrapper, device=reader_factory.device)
+
+        class _Section(RecordReader):
+            def read_batch(self_inner):
+                return merge.read_batch()
+
+            def close(self_inner):
+                merge.close()
+                for fr, _ in opened:
+                    fr.close()
+        return _Section()
+
+    @staticmethod
+    def reader_for_merge_tree(sections: Sequence[Sequence[SortedRun]], reader_factory: KeyValueFileReaderFactory,
+                              user_defined_seq_comparator, merge_function_wrapper: MergeSpec) -> RecordReader:
+        """MergeTreeReaders.readerForMergeTree (:44-65): ConcatRecordReader over lazily opened section readers."""
+        return ConcatRecordReader([
+            (lambda s=s: MergeTreeReaders.reader_for_section(s, reader_factory, user_defined_seq_comparator,
+                                                             merge_function_wrapper))
+            for s in sections])
+
+
+class MergeFileSplitRead:
+    """createMergeReader(partition, bucket, files, deletionVectors, keepDelete) — MergeFileSplitRead.java:269-316:
+    sections from IntervalPartition, one merge per section, DropDeleteReader unless forceKeepDelete."""
+
+    def __init__(self, schema: KeyValueSchema, mf_factory: MergeFunctionFactory, user_defined_seq_comparator=None,
+                 file_io: Optional[LocalFileIO] = None, device: int = 0):
+        self.schema = schema
+        self.mf_factory = mf_factory
+        self.udsc = user_defined_seq_comparator
+        self.reader_factory = KeyValueFileReaderFactory(schema, file_io, device)
+        self.force_keep_delete = False
+
+    def force_keep_delete_(self) -> "MergeFileSplitRead":      # forceKeepDelete()
+        self.force_keep_delete = True
+        return self
+
+    def create_merge_reader(self, files: Sequence[DataFileMeta], keep_delete: Optional[bool] = None) -> RecordReader:
+        keep = self.force_keep_delete if keep_delete is None else keep_delete
+        spec = self.mf_factory.create().with_drop_delete(not keep)      # DropDeleteReader fused into the merge
+        sections = IntervalPartition(files).partition()
+        return MergeTreeReaders.reader_for_merge_tree(sections, self.reader_factory, self.udsc, spec)

@@ -91,10 +91,10 @@ def test_agg_retract_unsupported_error():
 
 
 def test_unsupported_specs_are_refused():
-    # string primary key: refused at plan time, no CPU fallback
-    vt = RowType((DataField("k", "STRING", False), DataField("v", "BIGINT", True)))
+    # DOUBLE primary key (NaN compares equal to everything in the reference): refused at plan time, no CPU fallback
+    vt = RowType((DataField("k", "DOUBLE", False), DataField("v", "BIGINT", True)))
     schema = KeyValueSchema.of(vt, ["k"])
-    run = KeyValueBatch.from_rows(schema, [("a", 1, 0, "a", 5)])
+    run = KeyValueBatch.from_rows(schema, [(1.0, 1, 0, 1.0, 5)])
     with pytest.raises(N.UnsupportedOnDevice):
         merge_runs(schema, DeduplicateMergeFunction.factory().create(), [run, run])
 
@@ -283,3 +283,61 @@ def test_user_defined_sequence_fields(engine, ascending):
         finally:
             rd.close()
         assert got.equals(want), got.first_difference(want)
+
+
+def _utf8_sort_key(x):
+    return x.encode() if isinstance(x, str) else x
+
+
+@pytest.mark.parametrize("case", ["short_strings", "long_common_prefix", "prefix_of_each_other", "binary_high_bytes",
+                                  "string_then_int", "bigint_then_int", "int_then_string"])
+def test_general_primary_keys(case):
+    """Keys that do not fit the 64-bit prefix exactly: strings / binaries (unsigned bytewise, then length —
+    BinaryString.java:109-126, SortUtil.java:212-241) and wide composites; ties on the prefix are resolved by the
+    full comparison."""
+    rng = random.Random(hash(case) & 0xffff)
+    if case in ("short_strings", "long_common_prefix", "prefix_of_each_other"):
+        vt = RowType((DataField("k", "STRING", False), DataField("v", "BIGINT", True)))
+        pk = ["k"]
+        if case == "short_strings":
+            mk = lambda rng: "".join(rng.choice("abc") for _ in range(rng.randrange(0, 6)))
+        elif case == "long_common_prefix":
+            mk = lambda rng: "customer_id_000000_" + "%06d" % rng.randrange(3000)
+        else:
+            mk = lambda rng: "ab" * rng.randrange(0, 9) + rng.choice(["", "\x00", "\x01", "a"])
+        sort = lambda u: sorted(u, key=_utf8_sort_key)
+    elif case == "binary_high_bytes":
+        vt = RowType((DataField("k", "BINARY", False), DataField("v", "BIGINT", True)))
+        pk = ["k"]
+        mk = lambda rng: bytes(rng.choice([0, 1, 127, 128, 255]) for _ in range(rng.randrange(0, 12)))
+        sort = sorted
+    elif case == "string_then_int":
+        vt = RowType((DataField("s", "STRING", False), DataField("i", "INT", False), DataField("v", "BIGINT", True)))
+        pk = ["s", "i"]
+        mk = lambda rng: (rng.choice(["", "a", "ab", "abcdefgh", "abcdefghi", "b"]), rng.randrange(-3, 3))
+        sort = lambda u: sorted(u, key=lambda t: (t[0].encode(), t[1]))
+    elif case == "bigint_then_int":
+        vt = RowType((DataField("o", "BIGINT", False), DataField("l", "INT", False), DataField("v", "BIGINT", True)))
+        pk = ["o", "l"]
+        mk = lambda rng: (rng.choice([-2 ** 63, -5, 0, 7, 2 ** 40, 2 ** 63 - 1]) + rng.randrange(0, 3) * 0, rng.randrange(-4, 4))
+        sort = sorted
+    else:
+        vt = RowType((DataField("i", "INT", False), DataField("s", "STRING", False), DataField("v", "BIGINT", True)))
+        pk = ["i", "s"]
+        mk = lambda rng: (rng.randrange(-2, 3), "".join(rng.choice("xyz") for _ in range(rng.randrange(0, 10))))
+        sort = lambda u: sorted(u, key=lambda t: (t[0], t[1].encode()))
+    schema = KeyValueSchema.of(vt, pk)
+    for n_runs, n_keys in ((2, 40), (7, 300), (16, 6000)):
+        universe = sort({mk(rng) for _ in range(n_keys)})
+        runs, seq = [], 0
+        for r in range(n_runs):
+            rows = []
+            for key in universe:
+                if rng.random() < 0.4:
+                    seq += 1
+                    kt = key if isinstance(key, tuple) else (key,)
+                    rows.append(kt + (seq, rng.choice([0, 0, 0, 3])) + kt + (rng.randrange(1000),))
+            runs.append(KeyValueBatch.from_rows(schema, rows))
+        assert_same(schema, DeduplicateMergeFunction.factory().create(), runs)
+        assert_same(schema, AggregateMergeFunction.factory({"fields.v.aggregate-function": "sum",
+                                                           "fields.v.ignore-retract": "true"}, vt, pk).create(), runs)

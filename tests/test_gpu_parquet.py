@@ -132,3 +132,44 @@ def test_fused_decode_then_merge_matches_oracle(tmp_path, engine):
 def test_unsupported_format_is_refused():
     with pytest.raises(N.UnsupportedOnDevice):
         FileFormat.from_identifier("orc")
+
+
+def test_merge_file_split_read_end_to_end(tmp_path):
+    """MergeFileSplitRead.createMergeReader over Parquet data files: IntervalPartition -> sections ->
+    per-section device merge -> concat -> drop delete, against the oracle merging every file as its own run
+    (CORE-T/operation/MergeFileSplitReadTest: scan result == model of the table)."""
+    from paimon_b200.merge_tree_readers import DataFileMeta, IntervalPartition, MergeFileSplitRead, concat_batches
+    schema = datagen.schema_c3(n_i64=2, n_f64=1, n_str=2)
+    rng = np.random.default_rng(42)
+    metas, file_runs = [], []
+    # three key ranges; inside each, several overlapping files (level 0) and one chain of disjoint files (level 1)
+    for sec, (lo, hi) in enumerate([(0, 3000), (5000, 9000), (20000, 20500)]):
+        for f in range(4):
+            keys = np.sort(rng.choice(np.arange(lo, hi), size=int((hi - lo) * 0.3), replace=False)).astype(np.int64)
+            file_runs.append(datagen.make_run(schema, len(file_runs), keys, seed=9, null_prob=0.4, delete_prob=0.1))
+        step = (hi - lo) // 3
+        for j in range(3):                                   # a sorted run made of three key-disjoint files
+            keys = np.arange(lo + j * step, lo + (j + 1) * step - 5, 2, dtype=np.int64)
+            file_runs.append(datagen.make_run(schema, len(file_runs), keys, seed=9, null_prob=0.4))
+    for i, run in enumerate(file_runs):
+        path = str(tmp_path / f"data-{i}.parquet")
+        write_kv_parquet(run, path, use_dictionary=(i % 2 == 0))
+        k = run.columns[0].data
+        metas.append(DataFileMeta(path, 0, run.n_rows, int(k[0]), int(k[-1]), level=0))
+    sections = IntervalPartition(metas).partition()
+    assert len(sections) == 3 and all(len(s) == 5 for s in sections)       # 4 overlapping files + 1 chain each
+    assert sorted(len(r.files) for r in sections[0]) == [1, 1, 1, 1, 3]
+    for keep_delete in (False, True):
+        spec = PartialUpdateMergeFunction.factory({"ignore-delete": "true"}, schema.value_type, ["pk"])
+        read = MergeFileSplitRead(schema, spec)
+        rd = read.create_merge_reader(metas, keep_delete=keep_delete)
+        batches = []
+        while True:
+            b = rd.read_batch()
+            if b is None:
+                break
+            batches.append(b)
+        rd.close()
+        got = concat_batches(schema, batches)
+        want = pyoracle.merge(schema, spec.create().with_drop_delete(not keep_delete), file_runs)
+        assert got.equals(want), got.first_difference(want)
