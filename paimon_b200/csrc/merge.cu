@@ -127,6 +127,7 @@ struct TileCtx {
 };
 
 // Loads the tile's k segments and merges them.  Returns false when the tile overflows.
+template <bool EXACT>
 __device__ bool merge_tile(TileCtx &tc, int k, const KeyDesc &kd, const KeySrc &ks,
                            const int64_t *bounds, int tile, int64_t stride, int32_t *err) {
     const int tid = threadIdx.x;
@@ -164,7 +165,7 @@ __device__ bool merge_tile(TileCtx &tc, int k, const KeyDesc &kd, const KeySrc &
     // a <= b on (prefix, slot) pairs; equal prefixes of a non-exact key fall back to the full comparison
     auto le = [&](uint64_t ka, int sa, uint64_t kb, int sb) -> bool {
         if (ka != kb) return ka < kb;
-        if (kd.exact) return true;
+        if (EXACT) return true;
         const int ra = run_of_slot(tc.seg, k, sa), rb = run_of_slot(tc.seg, k, sb);
         const int64_t row_a = (tc.rstart[ra] + (sa - tc.seg[ra]) + 1) * stride - 1;
         const int64_t row_b = (tc.rstart[rb] + (sb - tc.seg[rb]) + 1) * stride - 1;
@@ -235,6 +236,7 @@ __device__ __forceinline__ void carve_tile(TileCtx &tc, unsigned char *smem, int
 }
 constexpr size_t kTileSmem = (size_t)kTilePad * (8 + 8 + 2 + 2) + PG_MAX_RUNS * 8 + 3 * (PG_MAX_RUNS + 1) * 4;
 
+template <bool EXACT>
 __global__ void __launch_bounds__(kThreads)
 k_merge_keys(int k, KeyDesc kd, KeySrc ks, LevelView lv, const int64_t *bounds, uint64_t *sorted_keys,
              uint64_t *sorted_refs, int32_t *err) {
@@ -242,14 +244,14 @@ k_merge_keys(int k, KeyDesc kd, KeySrc ks, LevelView lv, const int64_t *bounds, 
     TileCtx tc;
     carve_tile(tc, smem, k);
     int tile = blockIdx.x;
-    if (!merge_tile(tc, k, kd, ks, bounds, tile, lv.stride, err)) return;
+    if (!merge_tile<EXACT>(tc, k, kd, ks, bounds, tile, lv.stride, err)) return;
     int64_t base = 0;
     for (int r = 0; r < k; r++) base += tc.rstart[r];
     const uint64_t *fk = tc.key[tc.fin];
     const uint16_t *fi = tc.idx[tc.fin];
     for (int i = threadIdx.x; i < tc.n; i += blockDim.x) {
         sorted_keys[base + i] = fk[PADI(i)];
-        if (!kd.exact) {                       // the sample's row, for full comparisons against it
+        if (!EXACT) {                          // the sample's row, for full comparisons against it
             const int slot = fi[PADI(i)];
             const int r = run_of_slot(tc.seg, k, slot);
             const int64_t row = (tc.rstart[r] + (slot - tc.seg[r]) + 1) * lv.stride - 1;
@@ -310,6 +312,7 @@ struct PlanSmemExtra {
 };
 constexpr size_t kPlanSmem = kTileSmem + (size_t)kTileMax * 3 + 34 * 4 + 16;
 
+template <bool EXACT>
 __global__ void __launch_bounds__(kThreads, 2)
 k_plan(int k, KeyDesc kd, KeySrc ks, PlanArgs pa, int32_t *err) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -321,7 +324,7 @@ k_plan(int k, KeyDesc kd, KeySrc ks, PlanArgs pa, int32_t *err) {
     px.ws = (int *)(px.res_kind + kTileMax);
 
     const int tile = blockIdx.x, tid = threadIdx.x;
-    if (!merge_tile(tc, k, kd, ks, pa.bounds, tile, 1, err)) {
+    if (!merge_tile<EXACT>(tc, k, kd, ks, pa.bounds, tile, 1, err)) {
         if (tid == 0) pa.tile_rows[tile] = 0;
         return;
     }
@@ -338,7 +341,7 @@ k_plan(int k, KeyDesc kd, KeySrc ks, PlanArgs pa, int32_t *err) {
     // do the merged positions a and b hold the same key?  (equal prefixes decide only for exact keys)
     auto same_key = [&](int a, int b) -> bool {
         if (fk[PADI(a)] != fk[PADI(b)]) return false;
-        if (kd.exact) return true;
+        if (EXACT) return true;
         const int sa = fi[PADI(a)], sb = fi[PADI(b)];
         const int ra = run_of_slot(tc.seg, k, sa), rb = run_of_slot(tc.seg, k, sb);
         return full_key_compare(ks, kd, ra, tc.rstart[ra] + (sa - tc.seg[ra]), rb, tc.rstart[rb] + (sb - tc.seg[rb])) == 0;
@@ -509,8 +512,10 @@ __global__ void k_scan(const int32_t *tile_rows, int n_tiles, int64_t *row_base,
 static bool g_attr_done = false;
 static void set_attrs() {
     if (g_attr_done) return;
-    cudaFuncSetAttribute(k_merge_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem);
-    cudaFuncSetAttribute(k_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPlanSmem);
+    cudaFuncSetAttribute(k_merge_keys<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem);
+    cudaFuncSetAttribute(k_merge_keys<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem);
+    cudaFuncSetAttribute(k_plan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPlanSmem);
+    cudaFuncSetAttribute(k_plan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPlanSmem);
     g_attr_done = true;
 }
 
@@ -525,13 +530,18 @@ void launch_partition(const MergeLaunch &ml, const LevelView &lv, const uint64_t
 void launch_merge_keys(const MergeLaunch &ml, const LevelView &lv, const int64_t *bounds, int n_tiles,
                        uint64_t *sorted_keys, uint64_t *sorted_refs) {
     set_attrs();
-    k_merge_keys<<<n_tiles, kThreads, kTileSmem, ml.stream>>>(ml.k, ml.key, ml.ks, lv, bounds, sorted_keys,
-                                                                sorted_refs, ml.err);
+    if (ml.key.exact)
+        k_merge_keys<true><<<n_tiles, kThreads, kTileSmem, ml.stream>>>(ml.k, ml.key, ml.ks, lv, bounds, sorted_keys,
+                                                                          sorted_refs, ml.err);
+    else
+        k_merge_keys<false><<<n_tiles, kThreads, kTileSmem, ml.stream>>>(ml.k, ml.key, ml.ks, lv, bounds,
+                                                                           sorted_keys, sorted_refs, ml.err);
 }
 
 void launch_plan(const MergeLaunch &ml, const PlanArgs &pa) {
     set_attrs();
-    k_plan<<<pa.n_tiles, kThreads, kPlanSmem, ml.stream>>>(ml.k, ml.key, ml.ks, pa, ml.err);
+    if (ml.key.exact) k_plan<true><<<pa.n_tiles, kThreads, kPlanSmem, ml.stream>>>(ml.k, ml.key, ml.ks, pa, ml.err);
+    else k_plan<false><<<pa.n_tiles, kThreads, kPlanSmem, ml.stream>>>(ml.k, ml.key, ml.ks, pa, ml.err);
 }
 
 void launch_scan(cudaStream_t stream, const int32_t *tile_rows, int n_tiles, int64_t *row_base, int64_t *totals) {

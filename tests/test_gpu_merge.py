@@ -190,6 +190,19 @@ def test_multi_tile_partial_update_wide_row():
     assert_same(schema, spec, runs)
 
 
+@pytest.mark.parametrize("engine", ["partial-update", "deduplicate"])
+def test_more_than_64_select_columns(engine):
+    """The emit kernel resolves select columns through per-member take masks of 64 columns: a 100-column row
+    needs two passes over the column chunks."""
+    schema = datagen.schema_c3(n_i64=60, n_f64=25, n_str=14)
+    runs = datagen.make_runs(schema, 6, 30000, seed=11, null_prob=0.5, delete_prob=0.05 if engine == "deduplicate" else 0.0)
+    if engine == "partial-update":
+        spec = PartialUpdateMergeFunction.factory({}, schema.value_type, ["pk"]).create()
+    else:
+        spec = DeduplicateMergeFunction.factory().create()
+    assert_same(schema, spec, runs)
+
+
 def test_multi_tile_aggregate_double_sum_is_bit_exact():
     schema = datagen.schema_c3(n_i64=2, n_f64=4, n_str=1)
     runs = datagen.make_runs(schema, 16, 100000, seed=9, null_prob=0.3)
