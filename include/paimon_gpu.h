@@ -44,6 +44,7 @@ extern "C" {
 
 #define PG_ABI_VERSION 1
 #define PG_MAX_RUNS 32          /* runs merged by one call; more => merge in rounds on the host */
+#define PG_MAX_SEQ_GROUPS 16
 #define PG_MAX_KEY_FIELDS 4
 
 typedef int32_t pg_status;
@@ -105,7 +106,15 @@ typedef struct {
     int32_t seq_ascending;              /* 'sequence.field.sort-order' */
     const int32_t *agg;                 /* [n_val] PG_AGG_*; NULL = all NONE */
     const uint8_t *ignore_retract;      /* [n_val]; NULL = all false */
-    int32_t n_sequence_groups;          /* partial-update sequence groups; must be 0 in ABI v1 */
+    /* partial-update sequence groups ('fields.<seq,...>.sequence-group' = 'a,b'; PartialUpdateMergeFunction.java:
+     * 190-342, option parsing :389-489): a group's fields only move when the row's group sequence is >= the
+     * accumulated one */
+    int32_t n_sequence_groups;          /* 0 = none; at most PG_MAX_SEQ_GROUPS */
+    const int32_t *group_seq_start;     /* [n_sequence_groups + 1] CSR into group_seq_fields */
+    const int32_t *group_seq_fields;    /* value-field indexes of each group's sequence fields (<= 4 per group) */
+    const int32_t *field_group;         /* [n_val] group protecting the field (its sequence fields included), -1 */
+    const uint8_t *group_partial_delete;/* [n_val] sequence field listed in
+                                           'partial-update.remove-record-on-sequence-group'; NULL = none */
 } pg_merge_spec;
 
 /* one column, Arrow buffer layout */

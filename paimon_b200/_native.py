@@ -30,7 +30,9 @@ class PgMergeSpec(C.Structure):
     _fields_ = [("engine", C.c_int32), ("ignore_delete", C.c_int32), ("remove_record_on_delete", C.c_int32),
                 ("drop_delete", C.c_int32), ("n_seq_fields", C.c_int32), ("seq_fields", C.c_void_p),
                 ("seq_ascending", C.c_int32), ("agg", C.c_void_p), ("ignore_retract", C.c_void_p),
-                ("n_sequence_groups", C.c_int32)]
+                ("n_sequence_groups", C.c_int32), ("group_seq_start", C.c_void_p),
+                ("group_seq_fields", C.c_void_p), ("field_group", C.c_void_p),
+                ("group_partial_delete", C.c_void_p)]
 
 
 class PgColumn(C.Structure):

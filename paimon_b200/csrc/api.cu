@@ -85,6 +85,7 @@ struct Merge {
     ColDesc *d_cols = nullptr;
     int32_t *d_tile_counter = nullptr;
     int32_t *d_col_order = nullptr;
+    const SeqGroups *d_groups = nullptr;
     pg_out_column *d_out_cols = nullptr;
     int64_t *d_totals = nullptr;       // [1 + n_varlen]
     int32_t *d_err = nullptr;
@@ -261,6 +262,15 @@ static pg_status build_descriptors(Merge *m) {
                     agg != PG_AGG_LAST_NON_NULL_VALUE && agg != PG_AGG_PRIMARY_KEY)
                     return fail(PG_ERR_INVALID, "Must use sequence group for aggregation functions");
                 cd.mode = CM_SELECT;
+                if (sp->n_groups() > 0 && sp->field_group[vi] >= 0) {
+                    const int g = sp->field_group[vi];
+                    bool is_seq = false;
+                    for (int j = sp->group_seq_start[g]; j < sp->group_seq_start[g + 1]; j++)
+                        if (sp->group_seq_fields[j] == vi) is_seq = true;
+                    cd.mode = is_seq ? CM_GSEQ : CM_GVAL;
+                    cd.agg = g;
+                    cd.nullable = 1;                // a retract NULLs the group's fields whatever the schema says
+                }
             }
         }
     }
@@ -282,7 +292,8 @@ static pg_status build_descriptors(Merge *m) {
     size_t o_err = o_tot + align(sizeof(int64_t) * (nv + 1));
     size_t o_cnt = o_err + 256;
     size_t o_ord = o_cnt + 256;
-    size_t total = o_ord + align(sizeof(int32_t) * nc);
+    size_t o_sg = o_ord + align(sizeof(int32_t) * nc);
+    size_t total = o_sg + align(sizeof(SeqGroups));
     std::vector<unsigned char> host(total, 0);
     m->varlen_bound.assign(nv, 0);
     for (int r = 0; r < k; r++) {
@@ -309,6 +320,19 @@ static pg_status build_descriptors(Merge *m) {
         for (int c = 0; c < nc; c++) if (m->cols[c].width == 0) ord[n++] = c;
         for (int c = 0; c < nc; c++) if (m->cols[c].width != 0) ord[n++] = c;
     }
+    m->d_groups = nullptr;
+    if (sp->n_groups() > 0) {
+        SeqGroups *sg = (SeqGroups *)(host.data() + o_sg);
+        sg->n = sp->n_groups();
+        for (int g = 0; g <= sg->n; g++) sg->start[g] = sp->group_seq_start[g];
+        for (int j = 0; j < sp->group_seq_start[sg->n]; j++) {
+            const int vf = sp->group_seq_fields[j];
+            sg->col[j] = s->n_key + 2 + vf;
+            sg->type[j] = s->val_fields[vf].type;
+            sg->width[j] = type_width(s->val_fields[vf].type);
+        }
+        for (int g = 0; g < sg->n; g++) sg->partial_delete[g] = sp->group_partial_delete[g];
+    }
     PG_CUDA(cudaMalloc(&m->d_desc, total));
     PG_CUDA(cudaMemcpy(m->d_desc, host.data(), total, cudaMemcpyHostToDevice));
     unsigned char *d = (unsigned char *)m->d_desc;
@@ -326,6 +350,7 @@ static pg_status build_descriptors(Merge *m) {
     m->d_err = (int32_t *)(d + o_err);
     m->d_tile_counter = (int32_t *)(d + o_cnt);
     m->d_col_order = (int32_t *)(d + o_ord);
+    if (sp->n_groups() > 0) m->d_groups = (const SeqGroups *)(d + o_sg);
     PG_CUDA(cudaMallocHost((void **)&m->h_totals, sizeof(int64_t) * (nv + 1) + 16));
     m->h_err = (int32_t *)(m->h_totals + nv + 1);
     return PG_OK;
@@ -412,7 +437,7 @@ static pg_status execute(Merge *m) {
             if (l > 0) { add(sizeof(uint64_t) * (size_t)std::max<int64_t>(level_total[l], 1)); add(sizeof(uint64_t) * (size_t)std::max<int64_t>(level_total[l], 1)); }
         }
         const size_t N_ = (size_t)m->n_in, T_ = (size_t)n_tiles[0];
-        add(2 * N_ + 16); add(4 * T_); add(8 * N_ + 16); add(N_ + 16); add(8 * T_); add(8 * T_ * std::max(nv, 1));
+        add(2 * N_ + 16); add(m->d_groups ? 4 * N_ + 16 : 16); add(4 * T_); add(8 * N_ + 16); add(N_ + 16); add(8 * T_); add(8 * T_ * std::max(nv, 1));
         PG_CUDA(m->work.reserve(need));
     }
     auto talloc = [&](size_t bytes, void **out) -> cudaError_t {
@@ -453,6 +478,8 @@ static pg_status execute(Merge *m) {
     uint64_t *vl_state = nullptr;
     int8_t *tmp_kind = nullptr;
     PG_CUDA(talloc(sizeof(uint16_t) * (size_t)N + 16, (void **)&plan));
+    uint32_t *gplan = nullptr;
+    if (m->d_groups) PG_CUDA(talloc(sizeof(uint32_t) * (size_t)N + 16, (void **)&gplan));
     PG_CUDA(talloc(sizeof(int32_t) * (size_t)T, (void **)&tile_rows));
     PG_CUDA(talloc(sizeof(int64_t) * (size_t)N + 16, (void **)&tmp_seq));
     PG_CUDA(talloc((size_t)N + 16, (void **)&tmp_kind));
@@ -473,6 +500,8 @@ static pg_status execute(Merge *m) {
     pa.tile_rows = tile_rows;
     pa.tmp_seq = tmp_seq;
     pa.tmp_kind = tmp_kind;
+    pa.groups = m->d_groups;
+    pa.gplan = gplan;
     launch_plan(ml, pa);
     launch_scan(sm, tile_rows, T, row_base, m->d_totals);
     launches += 2;
@@ -553,6 +582,7 @@ static pg_status execute(Merge *m) {
     ea.row_base = row_base;
     ea.tmp_seq = tmp_seq;
     ea.tmp_kind = tmp_kind;
+    ea.gplan = gplan;
     ea.cols = m->d_cols;
     ea.col_order = m->d_col_order;
     ea.ptrs = m->d_ptrs;
@@ -659,9 +689,13 @@ pg_status pg_merge_spec_create(uint64_t schema, const pg_merge_spec *spec, uint6
     if (!s || !spec || !out_spec) return fail(PG_ERR_INVALID, "bad schema handle or null argument");
     if (spec->engine < PG_ENGINE_DEDUPLICATE || spec->engine > PG_ENGINE_FIRST_ROW)
         return fail(PG_ERR_INVALID, "Unsupported merge engine");
-    if (spec->n_sequence_groups != 0)
-        return fail(PG_ERR_UNSUPPORTED, "partial-update sequence groups are not implemented on the device "
-                                        "merge path yet");
+    if (spec->n_sequence_groups < 0 || (spec->n_sequence_groups > 0 && (!spec->group_seq_start ||
+                                                                         !spec->group_seq_fields || !spec->field_group)))
+        return fail(PG_ERR_INVALID, "bad sequence group description");
+    if (spec->n_sequence_groups > 0 && spec->engine != PG_ENGINE_PARTIAL_UPDATE)
+        return fail(PG_ERR_INVALID, "sequence groups belong to the partial-update merge engine");
+    if (spec->n_sequence_groups > PG_MAX_SEQ_GROUPS)
+        return fail(PG_ERR_UNSUPPORTED, "more than 16 sequence groups are not implemented on the device");
     auto sp = std::make_unique<Spec>();
     sp->schema_h = schema;
     sp->schema = s;
@@ -673,6 +707,34 @@ pg_status pg_merge_spec_create(uint64_t schema, const pg_merge_spec *spec, uint6
     for (int i = 0; i < spec->n_seq_fields; i++) sp->seq_fields.push_back(spec->seq_fields[i]);
     if (spec->agg) sp->agg.assign(spec->agg, spec->agg + s->n_val);
     if (spec->ignore_retract) sp->ignore_retract.assign(spec->ignore_retract, spec->ignore_retract + s->n_val);
+    if (spec->n_sequence_groups > 0) {
+        const int ng = spec->n_sequence_groups;
+        sp->group_seq_start.assign(spec->group_seq_start, spec->group_seq_start + ng + 1);
+        sp->group_seq_fields.assign(spec->group_seq_fields, spec->group_seq_fields + sp->group_seq_start[ng]);
+        sp->field_group.assign(spec->field_group, spec->field_group + s->n_val);
+        sp->group_partial_delete.assign(ng, 0);
+        for (int g = 0; g < ng; g++) {
+            const int n = sp->group_seq_start[g + 1] - sp->group_seq_start[g];
+            if (n < 1) return fail(PG_ERR_INVALID, "a sequence group needs a sequence field");
+            if (n > 4)
+                return fail(PG_ERR_UNSUPPORTED, "more than 4 sequence fields in one sequence group are not "
+                                                "implemented on the device");
+            for (int j = sp->group_seq_start[g]; j < sp->group_seq_start[g + 1]; j++) {
+                const int f = sp->group_seq_fields[j];
+                if (f < 0 || f >= s->n_val) return fail(PG_ERR_INVALID, "sequence group field out of range");
+                if (is_varlen(s->val_fields[f].type))
+                    return fail(PG_ERR_UNSUPPORTED, "var-len sequence-group fields are not implemented on the device");
+                if (spec->group_partial_delete && spec->group_partial_delete[f]) sp->group_partial_delete[g] = 1;
+            }
+        }
+        for (int f = 0; f < s->n_val; f++) {
+            if (sp->field_group[f] < -1 || sp->field_group[f] >= ng)
+                return fail(PG_ERR_INVALID, "field_group out of range");
+            if (sp->field_group[f] >= 0 && !sp->agg.empty() && sp->agg[f] != PG_AGG_NONE)
+                return fail(PG_ERR_UNSUPPORTED, "aggregate functions inside a sequence group are not implemented "
+                                                "on the device");
+        }
+    }
     if (sp->engine == PG_ENGINE_PARTIAL_UPDATE && sp->ignore_delete && sp->remove_record_on_delete)
         return fail(PG_ERR_INVALID, "ignore-delete and partial-update.remove-record-on-delete have conflicting "
                                     "behavior so should not be enabled at the same time.");

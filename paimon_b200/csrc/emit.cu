@@ -85,6 +85,16 @@ __device__ __forceinline__ int select_member_idx(const uint16_t *pm, const uint3
     }
 }
 
+// partial-update sequence group column: the member the plan kernel marked (merged position), or -1
+__device__ __forceinline__ int select_marked_idx(const uint16_t *pm, const uint32_t *gplan, uint32_t bit, int last) {
+    int j = last;
+    while (true) {
+        if (gplan[j] & bit) return j;
+        if (pm[j] & kPmHead) return -1;
+        --j;
+    }
+}
+
 __device__ __forceinline__ int group_first(const uint16_t *pm, int last) {
     int j = last;
     while (!(pm[j] & kPmHead)) --j;
@@ -233,6 +243,13 @@ __device__ __forceinline__ void emit_fixed_column(const EmitArgs &ea, const ColD
             if (cd.mode == CM_SELECT) {
                 int pj = select_pos(tv.pm, vw, last);
                 if (pj >= 0) { val = lds_fixed<W>(vals, pj); is_valid = true; }
+            } else if (cd.mode == CM_GVAL || cd.mode == CM_GSEQ) {
+                const uint32_t gbit = 1u << (cd.agg + (cd.mode == CM_GSEQ ? 16 : 0));
+                const int j = select_marked_idx(tv.pm, ea.gplan + tv.in_base, gbit, last);
+                if (j >= 0) {
+                    const int pj = tv.pm[j] & kPmPosMask;
+                    if (staged_valid(vw, pj)) { val = lds_fixed<W>(vals, pj); is_valid = true; }
+                }
             } else if (cd.mode == CM_KEY) {
                 val = lds_fixed<W>(vals, tv.pm[last] & kPmPosMask); is_valid = true;
             } else if (cd.mode == CM_SEQ) {
@@ -449,9 +466,14 @@ k_emit(EmitArgs ea) {
                 const int ob = ob0 + lane;
                 if (ob >= 0 && ob < n_out) {
                     const int last = glast[ob];
-                    int src = cd.mode == CM_KEY ? last
-                              : cd.mode == CM_FOLD ? fold_member_idx(cd, pm, mrun, vw, offs, cd_data, last, ea.err)
-                                                   : select_member_idx(pm, vw, last);
+                    int src;
+                    if (cd.mode == CM_KEY) src = last;
+                    else if (cd.mode == CM_FOLD) src = fold_member_idx(cd, pm, mrun, vw, offs, cd_data, last, ea.err);
+                    else if (cd.mode == CM_GVAL || cd.mode == CM_GSEQ) {
+                        src = select_marked_idx(pm, ea.gplan + in_base,
+                                                1u << (cd.agg + (cd.mode == CM_GSEQ ? 16 : 0)), last);
+                        if (src >= 0 && !staged_valid(vw, pm[src] & kPmPosMask)) src = -1;
+                    } else src = select_member_idx(pm, vw, last);
                     vsrc[ob] = src < 0 ? (uint16_t)0xFFFF : (uint16_t)src;
                     if (src >= 0) { int ps = pm[src] & kPmPosMask; my_bytes += offs[ps + 1] - offs[ps]; }
                 }

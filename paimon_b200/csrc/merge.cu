@@ -303,6 +303,70 @@ __device__ int compare_seq_fields(const SeqFields &sf, const ColPtrs &ptrs, int 
     return 0;
 }
 
+// ---- partial-update sequence groups (PartialUpdateMergeFunction.java:190-342)
+
+// one value cell of a member given by its tile slot
+struct CellRef { const void *data; const uint8_t *validity; int64_t row; };
+__device__ __forceinline__ CellRef cell_of(const ColPtrs &ptrs, int k, const int *seg, const int64_t *rstart, int col,
+                                           int slot) {
+    const int r = run_of_slot(seg, k, slot);
+    CellRef c;
+    c.data = ptrs.data[(int64_t)col * k + r];
+    c.validity = (const uint8_t *)ptrs.validity[(int64_t)col * k + r];
+    c.row = rstart[r] + (slot - seg[r]);
+    return c;
+}
+
+// isEmptySequenceGroup (:249-269): every sequence field of the group is NULL in this member
+__device__ bool group_is_empty(const SeqGroups &sg, int g, const ColPtrs &ptrs, int k, const int *seg,
+                               const int64_t *rstart, int slot) {
+    for (int f = sg.start[g]; f < sg.start[g + 1]; f++) {
+        CellRef c = cell_of(ptrs, k, seg, rstart, sg.col[f], slot);
+        if (valid_bit(c.validity, c.row)) return false;
+    }
+    return true;
+}
+
+// seqComparator.compare(kv.value(), row) for group g: member `slot_a` against the accumulated sequence fields,
+// which are those of member `slot_b` (slot_b < 0: all NULL).  Ascending, NULL first (a5).
+__device__ int compare_group_seq(const SeqGroups &sg, int g, const ColPtrs &ptrs, int k, const int *seg,
+                                 const int64_t *rstart, int slot_a, int slot_b) {
+    for (int f = sg.start[g]; f < sg.start[g + 1]; f++) {
+        CellRef a = cell_of(ptrs, k, seg, rstart, sg.col[f], slot_a);
+        const bool na = !valid_bit(a.validity, a.row);
+        bool nb = true;
+        CellRef b{};
+        if (slot_b >= 0) {
+            b = cell_of(ptrs, k, seg, rstart, sg.col[f], slot_b);
+            nb = !valid_bit(b.validity, b.row);
+        }
+        if (na && nb) continue;
+        if (na) return -1;
+        if (nb) return 1;
+        int d;
+        switch (sg.type[f]) {
+            case PG_FLOAT: {
+                float x = ((const float *)a.data)[a.row], y = ((const float *)b.data)[b.row];
+                d = x > y ? 1 : x < y ? -1 : 0;
+                break;
+            }
+            case PG_DOUBLE: {
+                double x = ((const double *)a.data)[a.row], y = ((const double *)b.data)[b.row];
+                d = x > y ? 1 : x < y ? -1 : 0;
+                break;
+            }
+            default: {
+                const int w = sg.width[f];
+                int64_t x = sext(load_fixed(a.data, w, a.row), w), y = sext(load_fixed(b.data, w, b.row), w);
+                if (sg.type[f] == PG_BOOL) { x = x != 0; y = y != 0; }
+                d = x > y ? 1 : x < y ? -1 : 0;
+            }
+        }
+        if (d != 0) return d;
+    }
+    return 0;
+}
+
 // ------------------------------------------------------------------ plan kernel
 
 struct PlanSmemExtra {
@@ -397,6 +461,7 @@ k_plan(int k, KeyDesc kd, KeySrc ks, PlanArgs pa, int32_t *err) {
             ops[i] = OP_SET;
             res_slot = fi[PADI(i)];
             res_kind = kind_s[fi[PADI(i)]];
+            if (pa.groups) pa.gplan[in_base + i] = 0xFFFFFFFFu;      // every group field from this record
         } else if (fl.engine == PG_ENGINE_DEDUPLICATE) {
             // DeduplicateMergeFunction.java:47-60
             int win = -1;
@@ -424,10 +489,55 @@ k_plan(int k, KeyDesc kd, KeySrc ks, PlanArgs pa, int32_t *err) {
         } else if (fl.engine == PG_ENGINE_PARTIAL_UPDATE) {
             // PartialUpdateMergeFunction.java:121-175 (no sequence groups), getResult :354-362
             bool filled = false, meet = false, cur_del = false;
+            // sequence groups: which member currently provides group g's sequence fields / its other fields
+            // (-1: NULL).  Groups only see inserts whose group sequence is >= the accumulated one (:190-247);
+            // a retract with a >= sequence takes the sequence fields and NULLs the group's fields (:271-342)
+            int8_t seq_src[PG_MAX_SEQ_GROUPS], val_src[PG_MAX_SEQ_GROUPS];
+            const SeqGroups *sg = pa.groups;
+            const int ng = sg ? sg->n : 0;
+            for (int g = 0; g < ng; g++) { seq_src[g] = -1; val_src[g] = -1; }
             for (int j = i; j < e; j++) {
                 int kind = kind_s[fi[PADI(j)]];
                 int op = OP_NOOP;
                 cur_del = false;
+                if (ng > 0) {
+                    const int slot = fi[PADI(j)];
+                    const int mj = j - i;
+                    if (kind_is_retract(kind)) {
+                        if (!filled) {                                           // initRow: every field verbatim
+                            op = OP_SET; filled = true;
+                            for (int g = 0; g < ng; g++) { seq_src[g] = (int8_t)mj; val_src[g] = (int8_t)mj; }
+                        }
+                        if (!fl.ignore_delete) {
+                            res_slot = (uint16_t)slot;
+                            for (int g = 0; g < ng; g++) {
+                                if (group_is_empty(*sg, g, pa.ptrs, k, tc.seg, tc.rstart, slot)) continue;
+                                const int sb = seq_src[g] < 0 ? -1 : fi[PADI(i + seq_src[g])];
+                                if (compare_group_seq(*sg, g, pa.ptrs, k, tc.seg, tc.rstart, slot, sb) < 0) continue;
+                                if (kind == PG_DELETE && sg->partial_delete[g]) {
+                                    // remove-record-on-sequence-group: the row restarts from this record
+                                    cur_del = true; op = OP_SET;
+                                    for (int h = 0; h < ng; h++) { seq_src[h] = (int8_t)mj; val_src[h] = (int8_t)mj; }
+                                    break;
+                                }
+                                seq_src[g] = (int8_t)mj;
+                                val_src[g] = -1;
+                            }
+                        }
+                    } else {
+                        res_slot = (uint16_t)slot;
+                        op = OP_UPD; meet = true; filled = true;
+                        for (int g = 0; g < ng; g++) {
+                            if (group_is_empty(*sg, g, pa.ptrs, k, tc.seg, tc.rstart, slot)) continue;
+                            const int sb = seq_src[g] < 0 ? -1 : fi[PADI(i + seq_src[g])];
+                            if (compare_group_seq(*sg, g, pa.ptrs, k, tc.seg, tc.rstart, slot, sb) >= 0) {
+                                seq_src[g] = (int8_t)mj; val_src[g] = (int8_t)mj;
+                            }
+                        }
+                    }
+                    ops[j] = (uint8_t)op;
+                    continue;
+                }
                 if (kind_is_retract(kind)) {
                     if (!filled) { op = OP_SET; filled = true; }          // initRow
                     if (!fl.ignore_delete) {
@@ -447,6 +557,16 @@ k_plan(int k, KeyDesc kd, KeySrc ks, PlanArgs pa, int32_t *err) {
                 ops[j] = (uint8_t)op;
             }
             res_kind = (cur_del || !meet) ? PG_DELETE : PG_INSERT;
+            if (ng > 0) {
+                for (int j = i; j < e; j++) {
+                    uint32_t mk = 0;
+                    for (int g = 0; g < ng; g++) {
+                        if (val_src[g] == j - i) mk |= 1u << g;
+                        if (seq_src[g] == j - i) mk |= 1u << (16 + g);
+                    }
+                    pa.gplan[in_base + j] = mk;
+                }
+            }
         } else {
             // AggregateMergeFunction.java:80-125
             bool cur_del = false;

@@ -56,6 +56,10 @@ struct Spec {
     int seq_ascending = 1;
     std::vector<int32_t> agg;            // per value field
     std::vector<uint8_t> ignore_retract;
+    // partial-update sequence groups
+    std::vector<int32_t> group_seq_start, group_seq_fields, field_group;
+    std::vector<uint8_t> group_partial_delete;      // per group
+    int n_groups() const { return group_seq_start.empty() ? 0 : (int)group_seq_start.size() - 1; }
 };
 
 struct DevColumn {
@@ -87,7 +91,9 @@ struct ColDesc {
     int32_t varlen_index;// index among var-len columns, -1 otherwise
     int32_t pad;
 };
-enum : int { CM_SELECT = 0, CM_FOLD = 1, CM_KEY = 2, CM_SEQ = 3, CM_KIND = 4 };
+// CM_GVAL / CM_GSEQ: field / sequence field of partial-update sequence group `agg`: the cell of the member the
+// plan kernel marked for the group (verbatim, NULL included), NULL when no member is marked
+enum : int { CM_SELECT = 0, CM_FOLD = 1, CM_KEY = 2, CM_SEQ = 3, CM_KIND = 4, CM_GVAL = 5, CM_GSEQ = 6 };
 enum : int { RT_OK = 0, RT_IGNORE = 1, RT_ERROR = 2 };
 
 struct MergeFlags {
@@ -155,6 +161,16 @@ struct SeqFields {
     int32_t width[4];
 };
 
+// partial-update sequence groups, as the plan kernel needs them (device memory)
+struct SeqGroups {
+    int32_t n;
+    int32_t start[PG_MAX_SEQ_GROUPS + 1];            // CSR into col / type / width
+    int32_t col[PG_MAX_SEQ_GROUPS * 4];              // file column of a group's sequence field
+    int32_t type[PG_MAX_SEQ_GROUPS * 4];
+    int32_t width[PG_MAX_SEQ_GROUPS * 4];
+    int32_t partial_delete[PG_MAX_SEQ_GROUPS];       // 'partial-update.remove-record-on-sequence-group'
+};
+
 struct PlanArgs {
     const int64_t *bounds;             // level-0 tile bounds [(n_tiles+1) * k]
     int n_tiles;
@@ -168,6 +184,9 @@ struct PlanArgs {
     int32_t *tile_rows;                // [n_tiles]
     int64_t *tmp_seq;                  // [N]  result sequence number per (tile in_base + out idx)
     int8_t *tmp_kind;                  // [N]
+    const SeqGroups *groups;           // device; NULL without sequence groups
+    uint32_t *gplan;                   // [N] per merged position: bit g = value source of group g, bit 16+g = its
+                                       // sequence-field source
 };
 void launch_plan(const MergeLaunch &ml, const PlanArgs &pa);
 
@@ -182,6 +201,7 @@ struct EmitArgs {
     const int64_t *row_base;           // [n_tiles]
     const int64_t *tmp_seq;
     const int8_t *tmp_kind;
+    const uint32_t *gplan;             // sequence-group marks (see PlanArgs), NULL without groups
     const ColDesc *cols;
     const int32_t *col_order;          // device [n_cols]: order in which the emit kernel walks the columns
     ColPtrs ptrs;

@@ -223,9 +223,19 @@ class SortMergeReader(RecordReader):
         agg = np.array([int(a) for a in sp.agg], np.int32)
         ign = np.array([1 if b else 0 for b in sp.ignore_retract], np.uint8)
         self._keep += [seq_arr, agg, ign]
+        gstart = np.zeros(len(sp.groups) + 1, np.int32)
+        gfields = np.array([f for g in sp.groups for f in g] or [0], np.int32)
+        for i, g in enumerate(sp.groups):
+            gstart[i + 1] = gstart[i] + len(g)
+        fgroup = np.array(sp.field_group, np.int32)
+        gpd = np.array([1 if b else 0 for b in sp.group_partial_delete], np.uint8)
+        self._keep += [gstart, gfields, fgroup, gpd]
+        has_groups = len(sp.groups) > 0
         cs = N.PgMergeSpec(int(sp.engine), int(sp.ignore_delete), int(sp.remove_record_on_delete),
                            int(sp.drop_delete), len(seq), _np_ptr(seq_arr) if len(seq) else None,
-                           int(sp.seq_ascending), _np_ptr(agg), _np_ptr(ign), len(sp.groups))
+                           int(sp.seq_ascending), _np_ptr(agg), _np_ptr(ign), len(sp.groups),
+                           _np_ptr(gstart) if has_groups else None, _np_ptr(gfields) if has_groups else None,
+                           _np_ptr(fgroup) if has_groups else None, _np_ptr(gpd) if has_groups else None)
         h = C.c_uint64(0)
         try:
             N.check(self.lib.pg_merge_spec_create(self._schema_h.handle, C.byref(cs), C.byref(h)))

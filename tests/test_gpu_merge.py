@@ -354,3 +354,147 @@ def test_general_primary_keys(case):
         assert_same(schema, DeduplicateMergeFunction.factory().create(), runs)
         assert_same(schema, AggregateMergeFunction.factory({"fields.v.aggregate-function": "sum",
                                                            "fields.v.ignore-retract": "true"}, vt, pk).create(), runs)
+
+
+# ---------------------------------------------------------------- partial-update sequence groups
+
+class GpuFuncDriver:
+    """PartialUpdateMergeFunctionTest-style driver on the device: after n >= 2 add()s the state of the merge
+    function equals the merge of n single-row runs of one key (sequence 0..n-1)."""
+
+    def __init__(self, factory, row_type):
+        self.schema = KeyValueSchema(RowType((DataField("_KEY_k", "INT", False),)), row_type)
+        self.spec = factory.create()
+        self.rows = []
+
+    def reset(self):
+        self.rows = []
+
+    def add(self, *f, kind=RowKind.INSERT):
+        self.rows.append((1, len(self.rows), int(kind)) + tuple(f))
+
+    def validate(self, *f):
+        assert len(self.rows) >= 2
+        runs = [KeyValueBatch.from_rows(self.schema, [r]) for r in self.rows]
+        got = assert_same(self.schema, self.spec, runs)
+        assert got.n_rows == 1 and got.to_rows()[0][3:] == tuple(f)
+
+
+def _int_row_type(n):
+    return RowType(tuple(DataField(f"f{i}", "INT", True) for i in range(n)))
+
+
+SEQ_GROUP_OPTS = {"fields.f3.sequence-group": "f1,f2", "fields.f6.sequence-group": "f4,f5"}
+MULTI_SEQ_OPTS = {"fields.f3,f4.sequence-group": "f1,f2", "fields.f7,f8.sequence-group": "f5,f6"}
+_D = RowKind.DELETE
+
+
+def test_sequence_group_known_answers():
+    """PartialUpdateMergeFunctionTest.java:64-97 (testSequenceGroup)."""
+    rt = _int_row_type(7)
+    d = GpuFuncDriver(PartialUpdateMergeFunction.factory(SEQ_GROUP_OPTS, rt, ["f0"]), rt)
+    d.add(1, 1, 1, 1, 1, 1, 1)
+    d.add(1, 2, 2, 2, 2, 2, None)
+    d.validate(1, 2, 2, 2, 1, 1, 1)
+    d.add(1, 3, 3, 1, 3, 3, 3)
+    d.validate(1, 2, 2, 2, 3, 3, 3)
+    d.add(1, 1, 1, 3, 1, 1, None, kind=_D)
+    d.validate(1, None, None, 3, 3, 3, 3)
+    d.add(1, 1, 1, 3, 1, 1, 4, kind=_D)
+    d.validate(1, None, None, 3, None, None, 4)
+    d.add(1, 4, 4, 4, 5, 5, 5)
+    d.validate(1, 4, 4, 4, 5, 5, 5)
+    d.add(1, 1, 1, 6, 1, 1, 6, kind=_D)
+    d.validate(1, None, None, 6, None, None, 6)
+
+
+def test_sequence_group_partial_delete_known_answers():
+    """PartialUpdateMergeFunctionTest.java:99-134 ('partial-update.remove-record-on-sequence-group')."""
+    rt = _int_row_type(7)
+    opts = dict(SEQ_GROUP_OPTS, **{"partial-update.remove-record-on-sequence-group": "f6"})
+    d = GpuFuncDriver(PartialUpdateMergeFunction.factory(opts, rt, ["f0"]), rt)
+    d.add(1, 1, 1, 1, 1, 1, 1)
+    d.add(1, 2, 2, 2, 2, 2, None)
+    d.validate(1, 2, 2, 2, 1, 1, 1)
+    d.add(1, 3, 3, 1, 3, 3, 3)
+    d.validate(1, 2, 2, 2, 3, 3, 3)
+    d.add(1, 1, 1, 3, 1, 1, None, kind=_D)
+    d.validate(1, None, None, 3, 3, 3, 3)
+    d.add(1, 1, 1, 3, 1, 1, 4, kind=_D)
+    d.validate(1, 1, 1, 3, 1, 1, 4)
+    d.add(1, 4, 4, 4, 5, 5, 5)
+    d.validate(1, 4, 4, 4, 5, 5, 5)
+    d.add(1, 1, 1, 6, 1, 1, 6, kind=_D)
+    d.validate(1, 1, 1, 6, 1, 1, 6)
+
+
+def test_multi_sequence_fields_known_answers():
+    """PartialUpdateMergeFunctionTest.java:175-217 (two sequence fields per group)."""
+    rt = _int_row_type(9)
+    d = GpuFuncDriver(PartialUpdateMergeFunction.factory(MULTI_SEQ_OPTS, rt, ["f0"]), rt)
+    d.add(1, None, None, None, None, 1, 1, 1, 3)
+    d.add(1, 2, 2, None, None, 2, 2, 1, 3)
+    d.validate(1, None, None, None, None, 2, 2, 1, 3)
+    d.reset()
+    d.add(1, 1, 1, 1, 1, 1, 1, 1, 3)
+    d.add(1, 2, 2, 2, 2, 2, 1, 1, None)
+    d.validate(1, 2, 2, 2, 2, 1, 1, 1, 3)
+    d.add(1, 1, 3, 1, 3, 3, 3, 3, 2)
+    d.validate(1, 2, 2, 2, 2, 3, 3, 3, 2)
+    d.add(1, 1, 1, 3, 3, 1, 1, None, None, kind=_D)
+    d.validate(1, None, None, 3, 3, 3, 3, 3, 2)
+    d.add(1, 1, 1, 3, 1, 1, 1, 4, 4, kind=_D)
+    d.validate(1, None, None, 3, 3, None, None, 4, 4)
+    d.add(1, 4, 4, 4, 4, 5, 5, 5, 5)
+    d.validate(1, 4, 4, 4, 4, 5, 5, 5, 5)
+    d.add(1, 1, 1, 6, 1, 1, 1, 6, 1, kind=_D)
+    d.validate(1, None, None, 6, 1, None, None, 6, 1)
+
+
+def _seq_group_schema():
+    vt = RowType((DataField("pk", "BIGINT", False),
+                  DataField("a", "BIGINT", True), DataField("b", "VARCHAR(24)", True), DataField("g1", "INT", True),
+                  DataField("c", "DOUBLE", True), DataField("d", "INT", True),
+                  DataField("g2a", "INT", True), DataField("g2b", "BIGINT", True),
+                  DataField("e", "BIGINT", True), DataField("s", "VARCHAR(24)", True)))
+    return KeyValueSchema.of(vt, ["pk"])
+
+
+def _coarsen_sequence_fields(schema, runs, names, modulo):
+    """Small value ranges for the sequence fields so that ties and reversals between runs are common."""
+    idx = [schema.n_key + 2 + [f.name for f in schema.value_type.fields].index(nm) for nm in names]
+    for run in runs:
+        for ci in idx:
+            col = run.columns[ci]
+            col.data = (np.abs(col.data) % modulo).astype(col.data.dtype)
+    return runs
+
+
+@pytest.mark.parametrize("mode", ["inserts_only", "ignore_delete", "retract", "partial_delete"])
+@pytest.mark.parametrize("n_runs,total", [(3, 4000), (16, 60000)])
+def test_sequence_groups_match_oracle(mode, n_runs, total):
+    """'fields.<seq>.sequence-group': a group's fields follow the record with the greatest group sequence
+    (PartialUpdateMergeFunction.java:190-247); retracts with sequence groups (:271-342)."""
+    schema = _seq_group_schema()
+    opts = {"fields.g1.sequence-group": "a,b", "fields.g2a,g2b.sequence-group": "c,d"}
+    if mode == "ignore_delete":
+        opts["ignore-delete"] = "true"
+    if mode == "partial_delete":
+        opts["partial-update.remove-record-on-sequence-group"] = "g2a,g2b"
+    runs = datagen.make_runs(schema, n_runs, total, seed=21, null_prob=0.3,
+                             delete_prob=0.0 if mode == "inserts_only" else 0.15)
+    runs = _coarsen_sequence_fields(schema, runs, ["g1", "g2a", "g2b"], 3)
+    spec = PartialUpdateMergeFunction.factory(opts, schema.value_type, ["pk"]).create()
+    assert_same(schema, spec, runs)
+    assert_same(schema, spec.with_drop_delete(), runs)
+
+
+def test_sequence_group_specs_the_device_refuses():
+    rt = _int_row_type(5)
+    schema = KeyValueSchema(RowType((DataField("_KEY_k", "INT", False),)), rt)
+    run = KeyValueBatch.from_rows(schema, [(1, 0, 0, 1, 1, 1, 1, 1)])
+    # an aggregate function inside a sequence group
+    spec = PartialUpdateMergeFunction.factory({"fields.f1.sequence-group": "f2,f3",
+                                               "fields.f2.aggregate-function": "sum"}, rt, ["f0"]).create()
+    with pytest.raises(N.UnsupportedOnDevice):
+        merge_runs(schema, spec, [run])
