@@ -164,6 +164,8 @@ int32_t pg_abi_version(void);
 /* bind the calling thread's library state to a device; idempotent */
 pg_status pg_init(int32_t device_ordinal);
 pg_status pg_shutdown(void);
+/* give the cached device buffers of freed host-opened runs back to the driver */
+pg_status pg_trim(void);
 
 pg_status pg_schema_create(const pg_schema_desc *desc, uint64_t *out_schema);
 pg_status pg_schema_free(uint64_t schema);
@@ -182,6 +184,11 @@ pg_status pg_run_free(uint64_t run);
 /* k-way merge of `k` runs (all of `schema`) with the merge function of `spec`. */
 pg_status pg_merge_open(uint64_t spec, const uint64_t *runs, int32_t k, uint64_t *out_merge);
 /* run the kernels; asynchronous on the handle's stream except for one size read-back */
+/* Re-use a merge handle (its stream, descriptors and arenas) for another set of runs of the same schema, and
+ * start each run at start_rows[i] (NULL = 0): rows before it do not take part.  This is what a reader uses that
+ * streams a bucket through the device in key ranges: range j of run i is copied from the 8-row boundary below
+ * its first row (validity bitmaps are byte-granular), and start_rows skips the rows that belong to range j-1. */
+pg_status pg_merge_rebind(uint64_t merge, const uint64_t *runs, int32_t k, const int64_t *start_rows);
 pg_status pg_merge_execute(uint64_t merge);
 /* the single output batch, device-resident (pointers are device pointers) */
 pg_status pg_merge_device_batch(uint64_t merge, pg_batch *out);

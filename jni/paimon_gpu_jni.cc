@@ -70,7 +70,8 @@ JNIEXPORT jint JNICALL Java_org_apache_paimon_gpu_NativeMerge_schemaFree(JNIEnv 
 // the declarative MergeFunction (what MergeFunctionFactory.create(readType) would have built)
 JNIEXPORT jlong JNICALL Java_org_apache_paimon_gpu_NativeMerge_mergeSpecCreate(
     JNIEnv *env, jclass, jlong schema, jint engine, jboolean ignoreDelete, jboolean removeRecordOnDelete,
-    jboolean dropDelete, jintArray seqFields, jboolean seqAscending, jintArray agg, jbooleanArray ignoreRetract) {
+    jboolean dropDelete, jintArray seqFields, jboolean seqAscending, jintArray agg, jbooleanArray ignoreRetract,
+    jintArray groupSeqStart, jintArray groupSeqFields, jintArray fieldGroup, jbooleanArray groupPartialDelete) {
     jsize ns = seqFields ? env->GetArrayLength(seqFields) : 0;
     jsize nv = agg ? env->GetArrayLength(agg) : 0;
     std::vector<jint> sf(ns), ag(nv);
@@ -89,6 +90,27 @@ JNIEXPORT jlong JNICALL Java_org_apache_paimon_gpu_NativeMerge_mergeSpecCreate(
     sp.seq_ascending = seqAscending;
     sp.agg = nv ? ag.data() : nullptr;
     sp.ignore_retract = nv ? ir8.data() : nullptr;
+    // partial-update sequence groups (PartialUpdateMergeFunction.Factory: fields.<seq>.sequence-group)
+    std::vector<jint> gs, gf, fg;
+    std::vector<uint8_t> gpd8;
+    if (groupSeqStart && env->GetArrayLength(groupSeqStart) > 1) {
+        gs.resize(env->GetArrayLength(groupSeqStart));
+        gf.resize(env->GetArrayLength(groupSeqFields));
+        fg.resize(nv);
+        env->GetIntArrayRegion(groupSeqStart, 0, (jsize)gs.size(), gs.data());
+        env->GetIntArrayRegion(groupSeqFields, 0, (jsize)gf.size(), gf.data());
+        env->GetIntArrayRegion(fieldGroup, 0, nv, fg.data());
+        if (groupPartialDelete) {
+            std::vector<jboolean> gpd(nv);
+            env->GetBooleanArrayRegion(groupPartialDelete, 0, nv, gpd.data());
+            gpd8.assign(gpd.begin(), gpd.end());
+        }
+        sp.n_sequence_groups = (int32_t)gs.size() - 1;
+        sp.group_seq_start = gs.data();
+        sp.group_seq_fields = gf.data();
+        sp.field_group = fg.data();
+        sp.group_partial_delete = gpd8.empty() ? nullptr : gpd8.data();
+    }
     uint64_t h = 0;
     PG_CHECK(pg_merge_spec_create((uint64_t)schema, &sp, &h));
     return (jlong)h;

@@ -94,6 +94,8 @@ _SIGNATURES = {
     "pg_run_open": (C.c_int32, [C.c_uint64, C.POINTER(PgRunDesc), C.c_int32, C.POINTER(C.c_uint64)]),
     "pg_run_free": (C.c_int32, [C.c_uint64]),
     "pg_merge_open": (C.c_int32, [C.c_uint64, C.POINTER(C.c_uint64), C.c_int32, C.POINTER(C.c_uint64)]),
+    "pg_merge_rebind": (C.c_int32, [C.c_uint64, C.POINTER(C.c_uint64), C.c_int32, C.c_void_p]),
+    "pg_trim": (C.c_int32, []),
     "pg_merge_execute": (C.c_int32, [C.c_uint64]),
     "pg_merge_device_batch": (C.c_int32, [C.c_uint64, C.POINTER(PgBatch)]),
     "pg_merge_fetch": (C.c_int32, [C.c_uint64, C.POINTER(PgOutColumn), C.c_int32]),

@@ -4,7 +4,9 @@
 // (include/paimon_gpu.h).  There is no CPU fallback anywhere in this file: a spec the kernels do not
 // implement is refused with PG_ERR_UNSUPPORTED.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <queue>
@@ -64,8 +66,10 @@ struct Merge {
     const Spec *spec = nullptr;
     const Schema *schema = nullptr;
     std::vector<const Run *> runs;
+    std::vector<int64_t> row0;          // per run: first row that takes part (pg_merge_rebind), else 0
     int k = 0;
     int64_t n_in = 0;
+    size_t desc_cap = 0;                // bytes allocated behind d_desc
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     std::vector<int64_t> varlen_bound;     // per var-len column: sum of the runs' payload bytes
@@ -141,6 +145,71 @@ static pg_status ensure_device() {
     PG_CUDA(cudaSetDevice(g_device));
     return PG_OK;
 }
+
+void buf_trim(size_t keep_bytes);
+// ---- device buffers of host-opened runs are recycled: a reader that streams a bucket through the device in
+// key ranges opens and frees runs at a high rate, and cudaMalloc / cudaFree would serialise the pipeline
+static std::mutex g_buf_mu;
+static std::multimap<size_t, void *> g_free_bufs;
+static size_t g_free_bytes = 0;
+static size_t buf_cache_limit() {
+    static size_t lim = [] {
+        const char *e = getenv("PG_RUN_CACHE_BYTES");
+        return e ? (size_t)strtoull(e, nullptr, 10) : ((size_t)16 << 30);
+    }();
+    return lim;
+}
+static void *buf_take(size_t bytes, size_t *got) {
+    {
+        std::lock_guard<std::mutex> g(g_buf_mu);
+        auto it = g_free_bufs.lower_bound(bytes);
+        if (it != g_free_bufs.end() && it->first <= bytes + bytes / 2 + (1 << 20)) {
+            void *p = it->second;
+            *got = it->first;
+            g_free_bytes -= it->first;
+            g_free_bufs.erase(it);
+            return p;
+        }
+    }
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        buf_trim(0);                                  // give the cached buffers back and retry once
+        if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+    }
+    *got = bytes;
+    return p;
+}
+static void buf_give(void *p, size_t bytes) {
+    {
+        std::lock_guard<std::mutex> g(g_buf_mu);
+        if (g_free_bytes + bytes <= buf_cache_limit()) {
+            g_free_bufs.emplace(bytes, p);
+            g_free_bytes += bytes;
+            return;
+        }
+    }
+    cudaFree(p);
+}
+void buf_trim(size_t keep_bytes) {
+    std::vector<void *> drop;
+    {
+        std::lock_guard<std::mutex> g(g_buf_mu);
+        while (g_free_bytes > keep_bytes && !g_free_bufs.empty()) {
+            auto it = std::prev(g_free_bufs.end());
+            drop.push_back(it->second);
+            g_free_bytes -= it->first;
+            g_free_bufs.erase(it);
+        }
+    }
+    for (void *p : drop) cudaFree(p);
+}
+static cudaStream_t copy_stream() {                   // one non-blocking copy stream per calling thread
+    static thread_local cudaStream_t st = nullptr;
+    if (!st) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    return st;
+}
+
 
 // hooks for the other translation units (parquet_decode.cu)
 Schema *schema_from_handle(uint64_t h) { return g_schemas.get(h); }
@@ -333,8 +402,14 @@ static pg_status build_descriptors(Merge *m) {
         }
         for (int g = 0; g < sg->n; g++) sg->partial_delete[g] = sp->group_partial_delete[g];
     }
-    PG_CUDA(cudaMalloc(&m->d_desc, total));
-    PG_CUDA(cudaMemcpy(m->d_desc, host.data(), total, cudaMemcpyHostToDevice));
+    if (!m->d_desc || total > m->desc_cap) {
+        if (m->d_desc) cudaFree(m->d_desc);
+        m->d_desc = nullptr;
+        PG_CUDA(cudaMalloc(&m->d_desc, total));
+        m->desc_cap = total;
+    }
+    PG_CUDA(cudaMemcpyAsync(m->d_desc, host.data(), total, cudaMemcpyHostToDevice, m->stream));
+    PG_CUDA(cudaStreamSynchronize(m->stream));
     unsigned char *d = (unsigned char *)m->d_desc;
     m->d_key_ptrs = (const void **)(d + o_key);
     m->d_key_offs = (const int32_t **)(d + o_koff);
@@ -351,7 +426,7 @@ static pg_status build_descriptors(Merge *m) {
     m->d_tile_counter = (int32_t *)(d + o_cnt);
     m->d_col_order = (int32_t *)(d + o_ord);
     if (sp->n_groups() > 0) m->d_groups = (const SeqGroups *)(d + o_sg);
-    PG_CUDA(cudaMallocHost((void **)&m->h_totals, sizeof(int64_t) * (nv + 1) + 16));
+    if (!m->h_totals) PG_CUDA(cudaMallocHost((void **)&m->h_totals, sizeof(int64_t) * (nv + 1) + 16));
     m->h_err = (int32_t *)(m->h_totals + nv + 1);
     return PG_OK;
 }
@@ -408,7 +483,11 @@ static pg_status execute(Merge *m) {
             LevelView lv{};
             lv.stride = stride;
             int64_t tot = 0;
-            for (int r = 0; r < k; r++) { lv.count[r] = m->runs[r]->n_rows / stride; tot += lv.count[r]; }
+            for (int r = 0; r < k; r++) {
+                lv.row0[r] = m->row0[r];
+                lv.count[r] = (m->runs[r]->n_rows - m->row0[r]) / stride;
+                tot += lv.count[r];
+            }
             views.push_back(lv);
             level_total.push_back(tot);
             if (tot <= kTileMax) break;
@@ -436,7 +515,9 @@ static pg_status execute(Merge *m) {
             add(sizeof(int64_t) * (size_t)(n_tiles[l] + 1) * k);
             if (l > 0) { add(sizeof(uint64_t) * (size_t)std::max<int64_t>(level_total[l], 1)); add(sizeof(uint64_t) * (size_t)std::max<int64_t>(level_total[l], 1)); }
         }
-        const size_t N_ = (size_t)m->n_in, T_ = (size_t)n_tiles[0];
+        int64_t skipped = 0;                      // plan-sized arrays are indexed by sums of absolute rows
+        for (int r = 0; r < k; r++) skipped += m->row0[r];
+        const size_t N_ = (size_t)(m->n_in + skipped), T_ = (size_t)n_tiles[0];
         add(2 * N_ + 16); add(m->d_groups ? 4 * N_ + 16 : 16); add(4 * T_); add(8 * N_ + 16); add(N_ + 16); add(8 * T_); add(8 * T_ * std::max(nv, 1));
         PG_CUDA(m->work.reserve(need));
     }
@@ -471,7 +552,8 @@ static pg_status execute(Merge *m) {
 
     // ---- plan + scan
     const int T = n_tiles[0];
-    const int64_t N = m->n_in;
+    int64_t N = m->n_in;
+    for (int r = 0; r < k; r++) N += m->row0[r];
     uint16_t *plan = nullptr;
     int32_t *tile_rows = nullptr;
     int64_t *tmp_seq = nullptr, *row_base = nullptr;
@@ -655,6 +737,7 @@ pg_status pg_shutdown(void) {
     if (g_device >= 0) {
         cudaSetDevice(g_device);
         cudaDeviceSynchronize();
+        buf_trim(0);
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, g_device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
     }
@@ -746,6 +829,11 @@ pg_status pg_merge_spec_free(uint64_t spec) {
     return g_specs.take(spec) ? PG_OK : fail(PG_ERR_INVALID, "unknown spec handle");
 }
 
+pg_status pg_trim(void) {
+    buf_trim(0);
+    return PG_OK;
+}
+
 pg_status pg_run_open(uint64_t schema, const pg_run_desc *desc, int32_t mem, uint64_t *out_run) {
     Schema *s = g_schemas.get(schema);
     if (!s || !desc || !out_run) return fail(PG_ERR_INVALID, "bad schema handle or null argument");
@@ -760,6 +848,7 @@ pg_status pg_run_open(uint64_t schema, const pg_run_desc *desc, int32_t mem, uin
     const int64_t n = desc->n_rows;
     run->cols.resize(nc);
     run->varlen_bytes.assign(nc, 0);
+    run->varlen_base.assign(nc, 0);
     if (mem == PG_MEM_DEVICE) {
         for (int c = 0; c < nc; c++) {
             const pg_column &pc = desc->cols[c];
@@ -784,7 +873,10 @@ pg_status pg_run_open(uint64_t schema, const pg_run_desc *desc, int32_t mem, uin
             if (is_varlen(f.type)) {
                 if (n > 0 && !pc.offsets) return fail(PG_ERR_INVALID, "var-len column without offsets");
                 b_off[c] = sizeof(int32_t) * (size_t)(n + 1);
-                b_data[c] = n > 0 ? (size_t)pc.offsets[n] : 0;
+                // offsets may start anywhere (a slice of a longer run): only [offsets[0], offsets[n]) is copied
+                if (n > 0 && pc.offsets[n] < pc.offsets[0]) return fail(PG_ERR_INVALID, "decreasing offsets");
+                b_data[c] = n > 0 ? (size_t)(pc.offsets[n] - pc.offsets[0]) : 0;
+                run->varlen_base[c] = n > 0 ? pc.offsets[0] : 0;
             } else {
                 b_off[c] = 0;
                 b_data[c] = (size_t)n * type_width(f.type);
@@ -794,29 +886,35 @@ pg_status pg_run_open(uint64_t schema, const pg_run_desc *desc, int32_t mem, uin
             o_off[c] = total; total += align(b_off[c]);
             o_val[c] = total; total += align(b_val[c] + 8);
         }
-        void *base = nullptr;
-        PG_CUDA(cudaMalloc(&base, total + 256));
+        size_t got = 0;
+        void *base = buf_take(total + 256, &got);
+        if (!base) return fail(PG_ERR_CUDA, "out of device memory for a run");
         run->owned.push_back(base);
+        run->owned_bytes.push_back(got);
         unsigned char *d = (unsigned char *)base;
+        cudaStream_t cs = copy_stream();
         for (int c = 0; c < nc; c++) {
             const pg_column &pc = desc->cols[c];
             DevColumn dc;
-            dc.data = d + o_data[c];
-            if (b_data[c]) PG_CUDA(cudaMemcpyAsync(d + o_data[c], pc.data, b_data[c], cudaMemcpyHostToDevice, 0));
+            // var-len: `data` stays the address of byte 0 of the offsets' space
+            dc.data = d + o_data[c] - run->varlen_base[c];
+            if (b_data[c])
+                PG_CUDA(cudaMemcpyAsync(d + o_data[c], (const unsigned char *)pc.data + run->varlen_base[c], b_data[c],
+                                        cudaMemcpyHostToDevice, cs));
             if (b_off[c]) {
                 dc.offsets = (const int32_t *)(d + o_off[c]);
                 if (n >= 0 && pc.offsets)
-                    PG_CUDA(cudaMemcpyAsync(d + o_off[c], pc.offsets, b_off[c], cudaMemcpyHostToDevice, 0));
+                    PG_CUDA(cudaMemcpyAsync(d + o_off[c], pc.offsets, b_off[c], cudaMemcpyHostToDevice, cs));
             }
             if (b_val[c]) {
                 dc.validity = d + o_val[c];
-                PG_CUDA(cudaMemcpyAsync(d + o_val[c], pc.validity, b_val[c], cudaMemcpyHostToDevice, 0));
+                PG_CUDA(cudaMemcpyAsync(d + o_val[c], pc.validity, b_val[c], cudaMemcpyHostToDevice, cs));
             }
             run->bytes_h2d += (int64_t)(b_data[c] + b_off[c] + b_val[c]);
             if (is_varlen(s->field(c).type)) run->varlen_bytes[c] = (int64_t)b_data[c];
             run->cols[c] = dc;
         }
-        PG_CUDA(cudaStreamSynchronize(0));
+        PG_CUDA(cudaStreamSynchronize(cs));
     } else {
         return fail(PG_ERR_INVALID, "bad memory kind");
     }
@@ -827,7 +925,10 @@ pg_status pg_run_open(uint64_t schema, const pg_run_desc *desc, int32_t mem, uin
 pg_status pg_run_free(uint64_t run) {
     auto r = g_runs.take(run);
     if (!r) return fail(PG_ERR_INVALID, "unknown run handle");
-    for (void *p : r->owned) cudaFree(p);
+    for (size_t i = 0; i < r->owned.size(); i++) {
+        if (i < r->owned_bytes.size()) buf_give(r->owned[i], r->owned_bytes[i]);
+        else cudaFree(r->owned[i]);
+    }
     return PG_OK;
 }
 
@@ -858,12 +959,45 @@ pg_status pg_run_fetch(uint64_t run, const pg_out_column *host_cols, int32_t n_c
         const DevColumn &dc = r->cols[c];
         const pg_out_column &hc = host_cols[c];
         size_t db = is_varlen(f.type) ? (size_t)r->varlen_bytes[c] : (size_t)n * type_width(f.type);
-        if (db && hc.data) PG_CUDA(cudaMemcpy(hc.data, dc.data, db, cudaMemcpyDeviceToHost));
+        if (db && hc.data)
+            PG_CUDA(cudaMemcpy(hc.data, (const unsigned char *)dc.data + (c < (int)r->varlen_base.size() ? r->varlen_base[c] : 0),
+                               db, cudaMemcpyDeviceToHost));
         if (dc.offsets && hc.offsets)
             PG_CUDA(cudaMemcpy(hc.offsets, dc.offsets, sizeof(int32_t) * (size_t)(n + 1), cudaMemcpyDeviceToHost));
         if (dc.validity && hc.validity)
             PG_CUDA(cudaMemcpy(hc.validity, dc.validity, (size_t)((n + 7) / 8), cudaMemcpyDeviceToHost));
     }
+    return PG_OK;
+}
+
+// (re)binds a merge handle to k runs; runs without rows to merge are dropped (exhausted readers are legal,
+// SortMergeReaderTestBase.java:53-56)
+static pg_status bind_runs(Merge *m, const uint64_t *runs, int32_t k, const int64_t *row0) {
+    const Spec *sp = m->spec;
+    m->runs.clear();
+    m->row0.clear();
+    m->n_in = 0;
+    m->stats = pg_stats{};
+    for (int i = 0; i < k; i++) {
+        Run *r = g_runs.get(runs[i]);
+        if (!r) return fail(PG_ERR_INVALID, "unknown run handle");
+        if (r->schema != sp->schema) {           // different handles are fine as long as the schemas are equal
+            const Schema *a = r->schema, *b = sp->schema;
+            bool same = a->n_key == b->n_key && a->n_val == b->n_val;
+            for (int c = 0; same && c < a->n_cols(); c++)
+                same = a->field(c).type == b->field(c).type && a->field(c).nullable == b->field(c).nullable;
+            if (!same) return fail(PG_ERR_INVALID, "run and spec use different schemas");
+        }
+        const int64_t skip = row0 ? row0[i] : 0;
+        if (skip < 0 || skip > r->n_rows) return fail(PG_ERR_INVALID, "start row outside the run");
+        m->stats.bytes_h2d += r->bytes_h2d;
+        if (r->n_rows - skip == 0) continue;
+        m->runs.push_back(r);
+        m->row0.push_back(skip);
+        m->n_in += r->n_rows - skip;
+    }
+    m->k = (int)m->runs.size();
+    if (m->k > 0) return build_descriptors(m);
     return PG_OK;
 }
 
@@ -878,33 +1012,23 @@ pg_status pg_merge_open(uint64_t spec, const uint64_t *runs, int32_t k, uint64_t
     std::unique_ptr<Merge> m(new Merge());
     m->spec = sp;
     m->schema = sp->schema;
-    for (int i = 0; i < k; i++) {
-        Run *r = g_runs.get(runs[i]);
-        if (!r) return fail(PG_ERR_INVALID, "unknown run handle");
-        if (r->schema != sp->schema) {           // different handles are fine as long as the schemas are equal
-            const Schema *a = r->schema, *b = sp->schema;
-            bool same = a->n_key == b->n_key && a->n_val == b->n_val;
-            for (int c = 0; same && c < a->n_cols(); c++)
-                same = a->field(c).type == b->field(c).type && a->field(c).nullable == b->field(c).nullable;
-            if (!same) return fail(PG_ERR_INVALID, "run and spec use different schemas");
-        }
-        if (r->n_rows == 0) continue;            // exhausted readers are legal (SortMergeReaderTestBase.java:53-56)
-        m->runs.push_back(r);
-        m->n_in += r->n_rows;
-        m->stats.bytes_h2d += r->bytes_h2d;
-    }
-    m->k = (int)m->runs.size();
     PG_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     for (auto &e : m->ev) PG_CUDA(cudaEventCreate(&e));
-    if (m->k > 0) {
-        st = build_descriptors(m.get());
-        if (st) { destroy_merge(m.get()); return st; }
-    } else {
-        // still validate the spec so that unsupported specs are refused even for empty inputs
-        m->k = 0;
-    }
+    st = bind_runs(m.get(), runs, k, nullptr);
+    if (st) { destroy_merge(m.get()); return st; }
     *out_merge = g_merges.put(std::move(m));
     return PG_OK;
+}
+
+pg_status pg_merge_rebind(uint64_t merge, const uint64_t *runs, int32_t k, const int64_t *start_rows) {
+    Merge *m = g_merges.get(merge);
+    if (!m || (k > 0 && !runs)) return fail(PG_ERR_INVALID, "unknown merge handle or null argument");
+    if (k < 0 || k > PG_MAX_RUNS) return fail(PG_ERR_INVALID, "bad run count");
+    pg_status st = ensure_device();
+    if (st) return st;
+    PG_CUDA(cudaStreamSynchronize(m->stream));
+    free_outputs(m);
+    return bind_runs(m, runs, k, start_rows);
 }
 
 pg_status pg_merge_execute(uint64_t merge) {

@@ -98,7 +98,7 @@ __global__ void k_partition(int k, KeyDesc kd, KeySrc ks, LevelView lv, const ui
         int64_t lo = 0, hi = lv.count[r];
         while (lo < hi) {                      // lower_bound: first j with key(j) >= splitter key
             int64_t mid = (lo + hi) >> 1;
-            const int64_t row = (mid + 1) * lv.stride - 1;
+            const int64_t row = lv.row0[r] + (mid + 1) * lv.stride - 1;
             uint64_t km = load_key(ks, kd, r, row);
             bool less = km < x;
             if (!less && km == x && !kd.exact) less = full_key_compare(ks, kd, r, row, s_run, s_row) < 0;
@@ -106,7 +106,8 @@ __global__ void k_partition(int k, KeyDesc kd, KeySrc ks, LevelView lv, const ui
         }
         res = lo;
     }
-    bounds[idx] = res;
+    // level 0 hands out absolute rows (plan / emit index the runs with them), upper levels level-local indexes
+    bounds[idx] = lv.stride == 1 ? res + lv.row0[r] : res;
 }
 
 // ------------------------------------------------------------------ in-tile merge
@@ -129,7 +130,7 @@ struct TileCtx {
 // Loads the tile's k segments and merges them.  Returns false when the tile overflows.
 template <bool EXACT>
 __device__ bool merge_tile(TileCtx &tc, int k, const KeyDesc &kd, const KeySrc &ks,
-                           const int64_t *bounds, int tile, int64_t stride, int32_t *err) {
+                           const int64_t *bounds, int tile, int64_t stride, const int64_t *row0, int32_t *err) {
     const int tid = threadIdx.x;
     if (tid == 0) {
         int acc = 0;
@@ -155,8 +156,9 @@ __device__ bool merge_tile(TileCtx &tc, int k, const KeyDesc &kd, const KeySrc &
     for (int r = 0; r < k; r++) {                    // coalesced per run segment
         const int s0 = tc.seg[r], s1 = tc.seg[r + 1];
         const int64_t j0 = tc.rstart[r] - s0;
+        const int64_t rb = row0 ? row0[r] : 0;           // (level 0 bounds are absolute rows already)
         for (int i = s0 + tid; i < s1; i += blockDim.x) {
-            tc.key[0][PADI(i)] = load_key(ks, kd, r, (j0 + i + 1) * stride - 1);
+            tc.key[0][PADI(i)] = load_key(ks, kd, r, rb + (j0 + i + 1) * stride - 1);
             tc.idx[0][PADI(i)] = (uint16_t)i;
         }
     }
@@ -167,8 +169,8 @@ __device__ bool merge_tile(TileCtx &tc, int k, const KeyDesc &kd, const KeySrc &
         if (ka != kb) return ka < kb;
         if (EXACT) return true;
         const int ra = run_of_slot(tc.seg, k, sa), rb = run_of_slot(tc.seg, k, sb);
-        const int64_t row_a = (tc.rstart[ra] + (sa - tc.seg[ra]) + 1) * stride - 1;
-        const int64_t row_b = (tc.rstart[rb] + (sb - tc.seg[rb]) + 1) * stride - 1;
+        const int64_t row_a = (row0 ? row0[ra] : 0) + (tc.rstart[ra] + (sa - tc.seg[ra]) + 1) * stride - 1;
+        const int64_t row_b = (row0 ? row0[rb] : 0) + (tc.rstart[rb] + (sb - tc.seg[rb]) + 1) * stride - 1;
         return full_key_compare(ks, kd, ra, row_a, rb, row_b) <= 0;
     };
 
@@ -244,7 +246,7 @@ k_merge_keys(int k, KeyDesc kd, KeySrc ks, LevelView lv, const int64_t *bounds, 
     TileCtx tc;
     carve_tile(tc, smem, k);
     int tile = blockIdx.x;
-    if (!merge_tile<EXACT>(tc, k, kd, ks, bounds, tile, lv.stride, err)) return;
+    if (!merge_tile<EXACT>(tc, k, kd, ks, bounds, tile, lv.stride, lv.row0, err)) return;
     int64_t base = 0;
     for (int r = 0; r < k; r++) base += tc.rstart[r];
     const uint64_t *fk = tc.key[tc.fin];
@@ -254,7 +256,7 @@ k_merge_keys(int k, KeyDesc kd, KeySrc ks, LevelView lv, const int64_t *bounds, 
         if (!EXACT) {                          // the sample's row, for full comparisons against it
             const int slot = fi[PADI(i)];
             const int r = run_of_slot(tc.seg, k, slot);
-            const int64_t row = (tc.rstart[r] + (slot - tc.seg[r]) + 1) * lv.stride - 1;
+            const int64_t row = lv.row0[r] + (tc.rstart[r] + (slot - tc.seg[r]) + 1) * lv.stride - 1;
             sorted_refs[base + i] = ((uint64_t)r << 40) | (uint64_t)row;
         }
     }
@@ -388,7 +390,7 @@ k_plan(int k, KeyDesc kd, KeySrc ks, PlanArgs pa, int32_t *err) {
     px.ws = (int *)(px.res_kind + kTileMax);
 
     const int tile = blockIdx.x, tid = threadIdx.x;
-    if (!merge_tile<EXACT>(tc, k, kd, ks, pa.bounds, tile, 1, err)) {
+    if (!merge_tile<EXACT>(tc, k, kd, ks, pa.bounds, tile, 1, nullptr, err)) {
         if (tid == 0) pa.tile_rows[tile] = 0;
         return;
     }

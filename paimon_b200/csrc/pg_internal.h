@@ -73,7 +73,9 @@ struct Run {
     Schema own_schema;                   // copy: a run may outlive the schema handle it was opened with
     int64_t n_rows = 0;
     std::vector<DevColumn> cols;
-    std::vector<int64_t> varlen_bytes;   // per column: payload bytes of a var-len column (offsets[n_rows])
+    std::vector<int64_t> varlen_bytes;   // per column: payload bytes of a var-len column (offsets[n_rows] - offsets[0])
+    std::vector<int64_t> varlen_base;    // per column: offsets[0] (data points at byte 0 of the offsets' space)
+    std::vector<size_t> owned_bytes;     // sizes of `owned`
     std::vector<void *> owned;           // device allocations made by pg_run_open(PG_MEM_HOST)
     int64_t bytes_h2d = 0;
 };
@@ -126,8 +128,9 @@ pg_status fail(pg_status code, const std::string &msg);
 
 // ---- kernel launchers (merge.cu) ----
 
-struct LevelView {             // keys of level l of run r: key(row = (j + 1) * stride - 1), j < count
+struct LevelView {             // keys of level l of run r: key(row = row0 + (j + 1) * stride - 1), j < count
     int64_t count[PG_MAX_RUNS];
+    int64_t row0[PG_MAX_RUNS]; // first row of the run that takes part in the merge (rows before it are skipped)
     int64_t stride;
 };
 

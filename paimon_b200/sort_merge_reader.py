@@ -204,7 +204,8 @@ class SortMergeReader(RecordReader):
                 spec.seq_fields = list(user_defined_seq_comparator)
         return SortMergeReader(list(readers), spec, None, device)
 
-    def __init__(self, readers: List[SortedRunReader], spec: MergeSpec, seq_fields=None, device: int = 0):
+    def __init__(self, readers: List[SortedRunReader], spec: MergeSpec, seq_fields=None, device: int = 0,
+                 start_rows: Optional[Sequence[int]] = None):
         self.readers = readers
         self.lib = N.init(device)
         schema = readers[0].schema if readers else None
@@ -246,9 +247,21 @@ class SortMergeReader(RecordReader):
             mh = C.c_uint64(0)
             N.check(self.lib.pg_merge_open(self._spec_h, run_handles, len(readers), C.byref(mh)))
             self._merge_h = mh.value
+            if start_rows is not None and any(start_rows):
+                sr = np.array(list(start_rows), np.int64)
+                N.check(self.lib.pg_merge_rebind(self._merge_h, run_handles, len(readers), _np_ptr(sr)))
         except Exception:
             self.close()
             raise
+
+    def rebind(self, readers: List[SortedRunReader], start_rows: Optional[Sequence[int]] = None) -> None:
+        """Same merge (schema, merge function, device arenas, stream) over other runs (pg_merge_rebind)."""
+        self.readers = readers
+        run_handles = (C.c_uint64 * max(len(readers), 1))()
+        for i, r in enumerate(readers):
+            run_handles[i] = r._open(self._schema_h.handle)
+        sr = np.array(list(start_rows) if start_rows is not None else [0] * len(readers), np.int64)
+        N.check(self.lib.pg_merge_rebind(self._merge_h, run_handles, len(readers), _np_ptr(sr)))
 
     # -- execution --
     def execute(self) -> None:
@@ -319,6 +332,138 @@ class SortMergeReader(RecordReader):
         if self._schema_h is not None:
             self._schema_h.close()
             self._schema_h = None
+
+
+class RangeStreamingMergeReader(RecordReader):
+    """Merge of HOST-resident sorted runs that flows through the device in key ranges.
+
+    The reference's readers hand out one batch after the other (RecordReader.readBatch,
+    paimon-common/.../reader/RecordReader.java:42-72; ConcatRecordReader.java:52-75 for key-disjoint pieces);
+    here every batch is the merge of one key range of all runs.  The ranges are key-disjoint and ascending, so
+    the concatenation of the batches equals the single batch SortMergeReader would produce.  `depth` ranges are
+    in flight at a time, each on its own worker thread and CUDA stream: the host->device copy of range i+1
+    overlaps the merge of range i and the device->host copy of range i-1 (PCIe is full duplex), and the device
+    holds `depth` ranges instead of the whole bucket.
+
+    Requires a single fixed-width integer primary-key column (the range cuts are binary searches on the host key
+    arrays); other schemas use SortMergeReader."""
+
+    def __init__(self, schema: KeyValueSchema, runs: Sequence[KeyValueBatch], spec: MergeSpec,
+                 target_rows: int = 8 << 20, depth: int = 3, device: int = 0, allocator_factory=None):
+        import threading
+        self.schema = schema
+        self.lib = N.init(device)
+        self.runs = list(runs)
+        self.spec = spec
+        self.depth = max(1, depth)
+        self.device = device
+        self.allocator_factory = allocator_factory     # () -> allocator(nbytes) for one output batch
+        if schema.n_key != 1 or is_varlen(schema.physical_types()[0]):
+            raise N.UnsupportedOnDevice(2, "range streaming needs a single fixed-width integer key column")
+        self.bytes_h2d = 0
+        self.bytes_d2h = 0
+        self.ranges = self._cut_ranges(max(1, int(target_rows)))
+        self._results = {}
+        self._errors = []
+        self._cv = threading.Condition()
+        self._next_out = 0
+        self._consumed = 0
+        self._closed = False
+        self._threads = [threading.Thread(target=self._worker, args=(w,), daemon=True) for w in range(self.depth)]
+        for t in self._threads:
+            t.start()
+
+    # -- range cuts: per run the row where each splitter key starts
+    def _cut_ranges(self, target_rows: int):
+        keys = [np.asarray(r.columns[0].data) for r in self.runs]
+        total = sum(len(k) for k in keys)
+        n_ranges = max(1, -(-total // target_rows))
+        if n_ranges == 1 or total == 0:
+            return [[(0, len(k)) for k in keys]]
+        stride = max(1, total // (n_ranges * 64 * max(len(keys), 1)))
+        sample = np.sort(np.concatenate([k[stride - 1::stride] for k in keys if len(k)]))
+        if len(sample) == 0:
+            return [[(0, len(k)) for k in keys]]
+        cut_keys = np.unique(sample[(np.arange(1, n_ranges) * len(sample)) // n_ranges])
+        cuts = [np.concatenate([[0], np.searchsorted(k, cut_keys, side="left"), [len(k)]]) for k in keys]
+        return [[(int(c[j]), int(c[j + 1])) for c in cuts] for j in range(len(cut_keys) + 1)]
+
+    def _sub_run(self, run: KeyValueBatch, lo: int, hi: int):
+        """Rows [lo, hi) as a host run that starts at the 8-row boundary below lo (validity bitmaps are
+        byte-granular); returns (batch, start_row)."""
+        lo8 = lo & ~7
+        cols = []
+        for col in run.columns:
+            valid = None if col.valid is None else col.valid[lo8 // 8:(hi + 7) // 8]
+            if col.offsets is not None:
+                # offsets stay absolute, data is the whole payload: pg_run_open copies [offsets[0], offsets[n])
+                cols.append(Column(col.type, col.data, col.offsets[lo8:hi + 1], valid))
+            else:
+                cols.append(Column(col.type, col.data[lo8:hi], None, valid))
+        return KeyValueBatch(self.schema, cols), lo - lo8
+
+    def _worker(self, w: int):
+        rd = None
+        try:
+            for j in range(w, len(self.ranges), self.depth):
+                with self._cv:                          # bounded look-ahead: at most `depth` batches not yet consumed
+                    while not self._closed and j >= self._consumed + self.depth:
+                        self._cv.wait()
+                    if self._closed:
+                        return
+                subs, starts = [], []
+                for run, (lo, hi) in zip(self.runs, self.ranges[j]):
+                    b, s0 = self._sub_run(run, lo, hi)
+                    subs.append(b)
+                    starts.append(s0)
+                readers = [SortedRunReader(self.schema, b) for b in subs]
+                if rd is None:
+                    rd = SortMergeReader(readers, self.spec, None, self.device, start_rows=starts)
+                else:
+                    rd.rebind(readers, starts)
+                rd.execute()
+                alloc = self.allocator_factory() if self.allocator_factory else None
+                out = rd.fetch(allocator=alloc)
+                st = rd.stats()
+                for r in readers:
+                    r.close()
+                with self._cv:
+                    self.bytes_h2d += st.bytes_h2d
+                    self.bytes_d2h += st.bytes_d2h
+                    self._results[j] = out
+                    self._cv.notify_all()
+        except BaseException as e:                      # surfaced by read_batch
+            with self._cv:
+                self._errors.append(e)
+                self._cv.notify_all()
+        finally:
+            if rd is not None:
+                rd.readers = []
+                rd.close()
+
+    def read_batch(self) -> Optional[KeyValueBatch]:
+        while True:
+            with self._cv:
+                j = self._next_out
+                if j >= len(self.ranges):
+                    return None
+                while j not in self._results and not self._errors:
+                    self._cv.wait()
+                if self._errors:
+                    raise self._errors[0]
+                out = self._results.pop(j)
+                self._next_out += 1
+                self._consumed += 1
+                self._cv.notify_all()
+            if out.n_rows > 0:
+                return out
+
+    def close(self) -> None:
+        with self._cv:
+            self._closed = True
+            self._cv.notify_all()
+        for t in self._threads:
+            t.join()
 
 
 def merge_runs(schema: KeyValueSchema, spec: MergeSpec, runs: Sequence[KeyValueBatch], device: int = 0) -> KeyValueBatch:
