@@ -241,6 +241,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-range-rows", type=int, default=8 << 20,
+                    help="e2e: input rows per key range of the streaming reader (0 = one batch, no overlap)")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="e2e: key ranges in flight")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-rows", type=int, default=None)
     ap.add_argument("--cpu-threads", type=int, default=None)
@@ -290,7 +293,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     from paimon_b200 import _native as N
     from paimon_b200.columnar import Column, KeyValueBatch
-    from paimon_b200.sort_merge_reader import SortedRunReader, SortMergeReader
+    from paimon_b200.sort_merge_reader import RangeStreamingMergeReader, SortedRunReader, SortMergeReader
 
     schema = make_schema(args.workload)
     spec = make_spec(args.workload, schema)
@@ -401,25 +404,46 @@ def main():
         arena = torch.empty(int(out_bytes * 1.02) + (64 << 20), dtype=torch.uint8, pin_memory=True)
         arena_np = arena.numpy()
         e2e_times, h2d_b, d2h_b = [], 0, 0
+        import threading
+        single_key = schema.n_key == 1
         for it_ in range(args.e2e_steps + 1):
             top = [0]
+            lock = threading.Lock()
 
             def alloc(nbytes):
-                a = (top[0] + 63) & ~63
-                top[0] = a + nbytes
+                with lock:
+                    a = (top[0] + 63) & ~63
+                    top[0] = a + nbytes
                 return arena_np[a:a + nbytes]
             barrier()
             t0 = time.perf_counter()
-            hr = [SortedRunReader(schema, b) for b in host_runs]
-            mr = SortMergeReader.create_sort_merge_reader(hr, None, None, spec, device=local_rank)   # H2D
-            mr.execute()
-            out = mr.fetch(allocator=alloc)                                                           # D2H
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-            s = mr.stats()
-            h2d_b, d2h_b = s.bytes_h2d, s.bytes_d2h
-            assert out.n_rows == n_out
-            mr.close()
+            rows_out = 0
+            if single_key and args.e2e_range_rows > 0:
+                # batches of key ranges: H2D of range i+1 | merge of range i | D2H of range i-1
+                mr = RangeStreamingMergeReader(schema, host_runs, spec, target_rows=args.e2e_range_rows,
+                                               depth=args.e2e_depth, device=local_rank,
+                                               allocator_factory=lambda: alloc)
+                while True:
+                    out = mr.read_batch()
+                    if out is None:
+                        break
+                    rows_out += out.n_rows
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                h2d_b, d2h_b = mr.bytes_h2d, mr.bytes_d2h
+                mr.close()
+            else:
+                hr = [SortedRunReader(schema, b) for b in host_runs]
+                mr = SortMergeReader.create_sort_merge_reader(hr, None, None, spec, device=local_rank)   # H2D
+                mr.execute()
+                out = mr.fetch(allocator=alloc)                                                           # D2H
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                s = mr.stats()
+                h2d_b, d2h_b = s.bytes_h2d, s.bytes_d2h
+                rows_out = out.n_rows
+                mr.close()
+            assert rows_out == n_out, (rows_out, n_out)
             if it_ > 0:
                 e2e_times.append(dt)
         tt = torch.tensor([sum(e2e_times) / len(e2e_times)], device=dev, dtype=torch.float64)
@@ -427,7 +451,10 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * n_in / float(tt.item()), "unit": "rows/s", "h2d_bytes_per_step": int(h2d_b),
                "d2h_bytes_per_step": int(d2h_b), "ms_per_step": 1e3 * float(tt.item()), "steps": len(e2e_times),
-               "api": "SortMergeReader.create_sort_merge_reader(host runs).execute()+fetch() over the C ABI"}
+               "api": ("RangeStreamingMergeReader(host runs).read_batch() loop over the C ABI: key ranges of "
+                       f"~{args.e2e_range_rows} rows, {args.e2e_depth} in flight (H2D | merge | D2H overlap)")
+               if single_key and args.e2e_range_rows > 0 else
+               "SortMergeReader.create_sort_merge_reader(host runs).execute()+fetch() over the C ABI"}
     else:
         rd.close()
 

@@ -147,6 +147,27 @@ static pg_status ensure_device() {
 }
 
 void buf_trim(size_t keep_bytes);
+
+// Many small copies (one per column buffer) in one driver call: cudaMemcpyBatchAsync where the driver has it,
+// else one cudaMemcpyAsync per buffer.  A wide table has hundreds of buffers per run and the per-call cost
+// of the copy API would otherwise bound a reader that streams small key ranges.
+static pg_status copy_batch(std::vector<void *> &dsts, std::vector<void *> &srcs, std::vector<size_t> &sizes,
+                            cudaMemcpyKind kind, cudaStream_t stream) {
+    if (dsts.empty()) return PG_OK;
+    static bool batch_ok = true;
+    if (batch_ok && dsts.size() > 1) {
+        cudaMemcpyAttributes attr{};
+        attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+        size_t attr_idx = 0, fail_idx = 0;
+        cudaError_t e = cudaMemcpyBatchAsync(dsts.data(), srcs.data(), sizes.data(), dsts.size(), &attr, &attr_idx, 1,
+                                             &fail_idx, stream);
+        if (e == cudaSuccess) return PG_OK;
+        cudaGetLastError();
+        batch_ok = false;                               // not supported here: fall back for good
+    }
+    for (size_t i = 0; i < dsts.size(); i++) PG_CUDA(cudaMemcpyAsync(dsts[i], srcs[i], sizes[i], kind, stream));
+    return PG_OK;
+}
 // ---- device buffers of host-opened runs are recycled: a reader that streams a bucket through the device in
 // key ranges opens and frees runs at a high rate, and cudaMalloc / cudaFree would serialise the pipeline
 static std::mutex g_buf_mu;
@@ -893,27 +914,31 @@ pg_status pg_run_open(uint64_t schema, const pg_run_desc *desc, int32_t mem, uin
         run->owned_bytes.push_back(got);
         unsigned char *d = (unsigned char *)base;
         cudaStream_t cs = copy_stream();
+        std::vector<void *> cp_dst, cp_src;
+        std::vector<size_t> cp_size;
+        auto add_copy = [&](void *dst, const void *src, size_t bytes) {
+            cp_dst.push_back(dst); cp_src.push_back(const_cast<void *>(src)); cp_size.push_back(bytes);
+        };
         for (int c = 0; c < nc; c++) {
             const pg_column &pc = desc->cols[c];
             DevColumn dc;
             // var-len: `data` stays the address of byte 0 of the offsets' space
             dc.data = d + o_data[c] - run->varlen_base[c];
-            if (b_data[c])
-                PG_CUDA(cudaMemcpyAsync(d + o_data[c], (const unsigned char *)pc.data + run->varlen_base[c], b_data[c],
-                                        cudaMemcpyHostToDevice, cs));
+            if (b_data[c]) add_copy(d + o_data[c], (const unsigned char *)pc.data + run->varlen_base[c], b_data[c]);
             if (b_off[c]) {
                 dc.offsets = (const int32_t *)(d + o_off[c]);
-                if (n >= 0 && pc.offsets)
-                    PG_CUDA(cudaMemcpyAsync(d + o_off[c], pc.offsets, b_off[c], cudaMemcpyHostToDevice, cs));
+                if (n >= 0 && pc.offsets) add_copy(d + o_off[c], pc.offsets, b_off[c]);
             }
             if (b_val[c]) {
                 dc.validity = d + o_val[c];
-                PG_CUDA(cudaMemcpyAsync(d + o_val[c], pc.validity, b_val[c], cudaMemcpyHostToDevice, cs));
+                add_copy(d + o_val[c], pc.validity, b_val[c]);
             }
             run->bytes_h2d += (int64_t)(b_data[c] + b_off[c] + b_val[c]);
             if (is_varlen(s->field(c).type)) run->varlen_bytes[c] = (int64_t)b_data[c];
             run->cols[c] = dc;
         }
+        pg_status cst = copy_batch(cp_dst, cp_src, cp_size, cudaMemcpyHostToDevice, cs);
+        if (cst) return cst;
         PG_CUDA(cudaStreamSynchronize(cs));
     } else {
         return fail(PG_ERR_INVALID, "bad memory kind");
@@ -1068,24 +1093,26 @@ pg_status pg_merge_fetch(uint64_t merge, const pg_out_column *host_cols, int32_t
     if (st) return st;
     const int64_t n = m->n_out;
     int64_t bytes = 0;
+    std::vector<void *> cp_dst, cp_src;
+    std::vector<size_t> cp_size;
     for (int c = 0; c < n_cols && n > 0; c++) {
         const pg_out_column &oc = m->out_cols[c];
         const pg_out_column &hc = host_cols[c];
         if (oc.data_bytes && hc.data) {
-            PG_CUDA(cudaMemcpyAsync(hc.data, oc.data, (size_t)oc.data_bytes, cudaMemcpyDeviceToHost, m->stream));
+            cp_dst.push_back(hc.data); cp_src.push_back(oc.data); cp_size.push_back((size_t)oc.data_bytes);
             bytes += oc.data_bytes;
         }
         if (oc.offsets && hc.offsets) {
-            PG_CUDA(cudaMemcpyAsync(hc.offsets, oc.offsets, sizeof(int32_t) * (size_t)(n + 1),
-                                    cudaMemcpyDeviceToHost, m->stream));
+            cp_dst.push_back(hc.offsets); cp_src.push_back(oc.offsets); cp_size.push_back(sizeof(int32_t) * (size_t)(n + 1));
             bytes += 4 * (n + 1);
         }
         if (oc.validity && hc.validity) {
-            PG_CUDA(cudaMemcpyAsync(hc.validity, oc.validity, (size_t)((n + 7) / 8), cudaMemcpyDeviceToHost,
-                                    m->stream));
+            cp_dst.push_back(hc.validity); cp_src.push_back(oc.validity); cp_size.push_back((size_t)((n + 7) / 8));
             bytes += (n + 7) / 8;
         }
     }
+    st = copy_batch(cp_dst, cp_src, cp_size, cudaMemcpyDeviceToHost, m->stream);
+    if (st) return st;
     PG_CUDA(cudaStreamSynchronize(m->stream));
     m->stats.bytes_d2h = bytes;
     return PG_OK;

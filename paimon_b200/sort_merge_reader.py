@@ -205,10 +205,10 @@ class SortMergeReader(RecordReader):
         return SortMergeReader(list(readers), spec, None, device)
 
     def __init__(self, readers: List[SortedRunReader], spec: MergeSpec, seq_fields=None, device: int = 0,
-                 start_rows: Optional[Sequence[int]] = None):
+                 start_rows: Optional[Sequence[int]] = None, schema: Optional[KeyValueSchema] = None):
         self.readers = readers
         self.lib = N.init(device)
-        schema = readers[0].schema if readers else None
+        schema = readers[0].schema if readers else schema
         self.schema = schema
         self._done = False
         self._schema_h = None
@@ -363,6 +363,7 @@ class RangeStreamingMergeReader(RecordReader):
         self.bytes_h2d = 0
         self.bytes_d2h = 0
         self.ranges = self._cut_ranges(max(1, int(target_rows)))
+        self._tables = self._pointer_tables()
         self._results = {}
         self._errors = []
         self._cv = threading.Condition()
@@ -388,22 +389,51 @@ class RangeStreamingMergeReader(RecordReader):
         cuts = [np.concatenate([[0], np.searchsorted(k, cut_keys, side="left"), [len(k)]]) for k in keys]
         return [[(int(c[j]), int(c[j + 1])) for c in cuts] for j in range(len(cut_keys) + 1)]
 
-    def _sub_run(self, run: KeyValueBatch, lo: int, hi: int):
-        """Rows [lo, hi) as a host run that starts at the 8-row boundary below lo (validity bitmaps are
-        byte-granular); returns (batch, start_row)."""
+    def _pointer_tables(self):
+        """Per run: base address / element width of every column buffer, so that a range's pg_run_desc is a few
+        vectorised operations (no per-column Python work on the hot path)."""
+        tables = []
+        for run in self.runs:
+            nc = len(run.columns)
+            data = np.zeros(nc, np.uint64); offs = np.zeros(nc, np.uint64); val = np.zeros(nc, np.uint64)
+            width = np.zeros(nc, np.uint64)
+            keep = []
+            for i, col in enumerate(run.columns):
+                d = np.ascontiguousarray(col.data)
+                keep.append(d)
+                data[i] = d.ctypes.data
+                if col.offsets is not None:
+                    o = np.ascontiguousarray(col.offsets, np.int32)
+                    keep.append(o)
+                    offs[i] = o.ctypes.data
+                else:
+                    width[i] = d.dtype.itemsize
+                if col.valid is not None:
+                    v = np.ascontiguousarray(col.valid, np.uint8)
+                    keep.append(v)
+                    val[i] = v.ctypes.data
+            tables.append((data, offs, val, width, keep))
+        return tables
+
+    def _open_range(self, schema_handle: int, r: int, lo: int, hi: int):
+        """Rows [lo, hi) of run r as a device run that starts at the 8-row boundary below lo (validity bitmaps
+        are byte-granular); var-len columns keep absolute offsets and the whole payload as `data`
+        (pg_run_open copies [offsets[0], offsets[n])).  Returns (run handle, start row)."""
+        data, offs, val, width, _ = self._tables[r]
         lo8 = lo & ~7
-        cols = []
-        for col in run.columns:
-            valid = None if col.valid is None else col.valid[lo8 // 8:(hi + 7) // 8]
-            if col.offsets is not None:
-                # offsets stay absolute, data is the whole payload: pg_run_open copies [offsets[0], offsets[n])
-                cols.append(Column(col.type, col.data, col.offsets[lo8:hi + 1], valid))
-            else:
-                cols.append(Column(col.type, col.data[lo8:hi], None, valid))
-        return KeyValueBatch(self.schema, cols), lo - lo8
+        arr = np.empty((len(data), 3), np.uint64)
+        arr[:, 0] = data + width * np.uint64(lo8)
+        arr[:, 1] = np.where(offs != 0, offs + np.uint64(4 * lo8), 0)
+        arr[:, 2] = np.where(val != 0, val + np.uint64(lo8 // 8), 0)
+        cols = (N.PgColumn * len(data)).from_buffer(arr)
+        desc = N.PgRunDesc(hi - lo8, cols)
+        h = C.c_uint64(0)
+        N.check(self.lib.pg_run_open(schema_handle, C.byref(desc), N.PG_MEM_HOST, C.byref(h)))
+        return h.value, lo - lo8
 
     def _worker(self, w: int):
         rd = None
+        k = len(self.runs)
         try:
             for j in range(w, len(self.ranges), self.depth):
                 with self._cv:                          # bounded look-ahead: at most `depth` batches not yet consumed
@@ -411,22 +441,22 @@ class RangeStreamingMergeReader(RecordReader):
                         self._cv.wait()
                     if self._closed:
                         return
-                subs, starts = [], []
-                for run, (lo, hi) in zip(self.runs, self.ranges[j]):
-                    b, s0 = self._sub_run(run, lo, hi)
-                    subs.append(b)
-                    starts.append(s0)
-                readers = [SortedRunReader(self.schema, b) for b in subs]
                 if rd is None:
-                    rd = SortMergeReader(readers, self.spec, None, self.device, start_rows=starts)
-                else:
-                    rd.rebind(readers, starts)
-                rd.execute()
-                alloc = self.allocator_factory() if self.allocator_factory else None
-                out = rd.fetch(allocator=alloc)
-                st = rd.stats()
-                for r in readers:
-                    r.close()
+                    rd = SortMergeReader([], self.spec, None, self.device, schema=self.schema)
+                handles = (C.c_uint64 * max(k, 1))()
+                starts = np.zeros(max(k, 1), np.int64)
+                try:
+                    for r, (lo, hi) in enumerate(self.ranges[j]):
+                        handles[r], starts[r] = self._open_range(rd._schema_h.handle, r, lo, hi)
+                    N.check(self.lib.pg_merge_rebind(rd._merge_h, handles, k, _np_ptr(starts)))
+                    rd.execute()
+                    alloc = self.allocator_factory() if self.allocator_factory else None
+                    out = rd.fetch(allocator=alloc)
+                    st = rd.stats()
+                finally:
+                    for r in range(k):
+                        if handles[r]:
+                            self.lib.pg_run_free(handles[r])
                 with self._cv:
                     self.bytes_h2d += st.bytes_h2d
                     self.bytes_d2h += st.bytes_d2h
@@ -438,7 +468,6 @@ class RangeStreamingMergeReader(RecordReader):
                 self._cv.notify_all()
         finally:
             if rd is not None:
-                rd.readers = []
                 rd.close()
 
     def read_batch(self) -> Optional[KeyValueBatch]:
