@@ -157,6 +157,36 @@ JNIEXPORT jlong JNICALL Java_org_apache_paimon_gpu_NativeMerge_mergeOpen(JNIEnv 
     return (jlong)h;
 }
 
+// Re-use the merge handle for other runs of the same schema (the key-range streaming reader)
+JNIEXPORT jint JNICALL Java_org_apache_paimon_gpu_NativeMerge_mergeRebind(JNIEnv *env, jclass, jlong merge,
+                                                                          jlongArray runs, jlongArray startRows) {
+    jsize k = env->GetArrayLength(runs);
+    std::vector<jlong> r(k), sr(k, 0);
+    env->GetLongArrayRegion(runs, 0, k, r.data());
+    if (startRows) env->GetLongArrayRegion(startRows, 0, k, sr.data());
+    std::vector<uint64_t> ru(r.begin(), r.end());
+    std::vector<int64_t> st(sr.begin(), sr.end());
+    PG_CHECK(pg_merge_rebind((uint64_t)merge, ru.data(), k, st.data()));
+    return 0;
+}
+
+// Format seam: one Parquet data file (bytes read by the Java FileIO into a direct buffer) -> device-resident run
+JNIEXPORT jlong JNICALL Java_org_apache_paimon_gpu_NativeMerge_parquetOpen(JNIEnv *env, jclass, jlong schema,
+                                                                           jobject fileBytes, jlong size) {
+    uint64_t h = 0;
+    PG_CHECK(pg_parquet_open((uint64_t)schema, env->GetDirectBufferAddress(fileBytes), (int64_t)size, &h));
+    return (jlong)h;
+}
+JNIEXPORT jlong JNICALL Java_org_apache_paimon_gpu_NativeMerge_parquetReadRun(JNIEnv *env, jclass, jlong file) {
+    uint64_t run = 0;
+    PG_CHECK(pg_parquet_read_run((uint64_t)file, &run));
+    return (jlong)run;
+}
+JNIEXPORT jint JNICALL Java_org_apache_paimon_gpu_NativeMerge_parquetFree(JNIEnv *env, jclass, jlong file) {
+    PG_CHECK(pg_parquet_free((uint64_t)file));
+    return 0;
+}
+
 // readBatch(): runs the merge; returns the row count.  Column sizes follow via batchColumnBytes().
 JNIEXPORT jlong JNICALL Java_org_apache_paimon_gpu_NativeMerge_mergeExecute(JNIEnv *env, jclass, jlong merge) {
     PG_CHECK(pg_merge_execute((uint64_t)merge));
