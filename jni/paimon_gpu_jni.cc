@@ -174,7 +174,7 @@ JNIEXPORT jint JNICALL Java_org_apache_paimon_gpu_NativeMerge_mergeRebind(JNIEnv
 JNIEXPORT jlong JNICALL Java_org_apache_paimon_gpu_NativeMerge_parquetOpen(JNIEnv *env, jclass, jlong schema,
                                                                            jobject fileBytes, jlong size) {
     uint64_t h = 0;
-    PG_CHECK(pg_parquet_open((uint64_t)schema, env->GetDirectBufferAddress(fileBytes), (int64_t)size, &h));
+    PG_CHECK(pg_parquet_open((uint64_t)schema, (const uint8_t *)env->GetDirectBufferAddress(fileBytes), (int64_t)size, &h));
     return (jlong)h;
 }
 JNIEXPORT jlong JNICALL Java_org_apache_paimon_gpu_NativeMerge_parquetReadRun(JNIEnv *env, jclass, jlong file) {
