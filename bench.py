@@ -43,19 +43,35 @@ WORKLOADS = {
                desc="8-run deduplicate, int64 pk + 10 int64 cols, 100M rows"),
     "c1": dict(n_runs=2, rows=1_000_000, engine="deduplicate", null_prob=0.0,
                desc="2-run deduplicate, int64 pk + int64 val, 1M rows"),
+    # one bucket of the full-compaction config: string key, deletes, drop-delete, then the
+    # merged batch is re-encoded to Parquet on the device (reported under "rewrite")
+    "c4": dict(n_runs=32, rows=16_000_000, engine="deduplicate", null_prob=0.5, delete_prob=0.05, drop_delete=True,
+               desc="one bucket of a full compaction rewrite: 32 runs x 500K rows, varchar(16) pk + 4 i64 + 2 f64 + "
+                    "2 i32 + 3 varchar, 5% deletes, drop-delete, output re-encoded to Parquet"),
 }
+
+
+def schema_c4():
+    from paimon_b200.types import DataField, KeyValueSchema, RowType
+    fields = [DataField("pk", "VARCHAR(16)", False)]
+    fields += [DataField(f"i{i}", "BIGINT", True) for i in range(4)]
+    fields += [DataField(f"d{i}", "DOUBLE", True) for i in range(2)]
+    fields += [DataField(f"n{i}", "INT", True) for i in range(2)]
+    fields += [DataField(f"s{i}", "VARCHAR(64)", True) for i in range(3)]
+    return KeyValueSchema.of(RowType(tuple(fields)), ["pk"])
 
 
 def make_schema(workload):
     from paimon_b200 import datagen
-    return {"c1": datagen.schema_c1, "c2": datagen.schema_c2, "c3": datagen.schema_c3}[workload]()
+    return {"c1": datagen.schema_c1, "c2": datagen.schema_c2, "c3": datagen.schema_c3, "c4": schema_c4}[workload]()
 
 
 def make_spec(workload, schema):
     from paimon_b200.merge_function import DeduplicateMergeFunction, PartialUpdateMergeFunction
     if WORKLOADS[workload]["engine"] == "partial-update":
         return PartialUpdateMergeFunction.factory({}, schema.value_type, ["pk"]).create()
-    return DeduplicateMergeFunction.factory().create()
+    spec = DeduplicateMergeFunction.factory().create()
+    return spec.with_drop_delete() if WORKLOADS[workload].get("drop_delete") else spec
 
 
 # ------------------------------------------------------------------ device-side synthetic runs
@@ -68,7 +84,18 @@ def _splitmix64(x):
     return x ^ ((x >> 31) & ((1 << 33) - 1))
 
 
-def gen_device_run(schema, run_index, n, key_space, null_prob, seed, dev):
+def _hex_keys(keys, dev):
+    """int64 keys -> 16-character lower-case hex strings (big endian: string order == integer order)."""
+    import torch
+    sh = torch.arange(60, -4, -4, device=dev, dtype=torch.int64)
+    nib = ((keys[:, None] >> sh) & 15).to(torch.uint8)
+    data = torch.where(nib < 10, nib + 48, nib + 87).flatten()
+    data = torch.cat([data, torch.zeros(16, device=dev, dtype=torch.uint8)]).contiguous()
+    offs = (torch.arange(keys.numel() + 1, device=dev, dtype=torch.int64) * 16).to(torch.int32).contiguous()
+    return data, offs
+
+
+def gen_device_run(schema, run_index, n, key_space, null_prob, seed, dev, delete_prob=0.0):
     """One sorted run generated directly in HBM.  Returns (columns, keepalive tensors, key tensor)."""
     import torch
     from paimon_b200.sort_merge_reader import DeviceColumn
@@ -78,19 +105,30 @@ def gen_device_run(schema, run_index, n, key_space, null_prob, seed, dev):
     keys = torch.randperm(key_space, device=dev, generator=g)[:n].sort().values.contiguous()
     keep = [keys]
     cols = []
+    string_key = schema.key_type.fields[0].physical == PhysicalType.STRING
+    if string_key:
+        kdata, koffs = _hex_keys(keys, dev)
+        keep += [kdata, koffs]
+        key_col = DeviceColumn(kdata.data_ptr(), koffs.data_ptr())
+        key_bytes = n * 16 + 4 * (n + 1)
+    else:
+        key_col = DeviceColumn(keys.data_ptr())
+        key_bytes = n * 8
     for _ in schema.key_type.fields:
-        cols.append(DeviceColumn(keys.data_ptr()))
+        cols.append(key_col)
     seq = (torch.arange(n, device=dev, dtype=torch.int64) + (run_index << 32)).contiguous()
     kind = torch.zeros(n, device=dev, dtype=torch.int8)
+    if delete_prob > 0:
+        kind[torch.rand(n, device=dev, generator=g) < delete_prob] = 3
     keep += [seq, kind]
     cols += [DeviceColumn(seq.data_ptr()), DeviceColumn(kind.data_ptr())]
-    nbytes = keys.numel() * 8 + seq.numel() * 8 + kind.numel()
+    nbytes = key_bytes + seq.numel() * 8 + kind.numel()
     pk_names = {f.name[len("_KEY_"):] for f in schema.key_type.fields}
     for ci, f in enumerate(schema.value_type.fields):
         t = f.physical
         if f.name in pk_names:
-            cols.append(DeviceColumn(keys.data_ptr()))
-            nbytes += keys.numel() * 8
+            cols.append(key_col)
+            nbytes += key_bytes
             continue
         h = _splitmix64(keys ^ ((run_index + 1) * 0x100 + ci << 40))
         valid_ptr = 0
@@ -108,6 +146,11 @@ def gen_device_run(schema, run_index, n, key_space, null_prob, seed, dev):
             keep.append(h)
             cols.append(DeviceColumn(h.data_ptr(), 0, valid_ptr))
             nbytes += n * 8
+        elif t == PhysicalType.INT32:
+            v = (h & 0x7fffffff).to(torch.int32).contiguous()
+            keep.append(v)
+            cols.append(DeviceColumn(v.data_ptr(), 0, valid_ptr))
+            nbytes += n * 4
         elif t == PhysicalType.DOUBLE:
             d = ((h >> 11) & ((1 << 53) - 1)).to(torch.float64) * (2000.0 / (1 << 53)) - 1000.0
             keep.append(d)
@@ -128,7 +171,7 @@ def gen_device_run(schema, run_index, n, key_space, null_prob, seed, dev):
             del lens, offs, bits
         else:
             raise ValueError(f"bench generator: unsupported type {t}")
-    return cols, keep, keys, nbytes
+    return cols, keep, keys, nbytes, kind
 
 
 def device_runs(workload, schema, rows, dev, seed):
@@ -138,14 +181,16 @@ def device_runs(workload, schema, rows, dev, seed):
     n_runs = w["n_runs"]
     per_run = rows // n_runs
     key_space = max(rows // 2, per_run)
-    readers, all_keys, in_bytes = [], [], 0
+    readers, all_keys, all_kinds, in_bytes = [], [], [], 0
     for r in range(n_runs):
-        cols, keep, keys, nb = gen_device_run(schema, r, per_run, key_space, w["null_prob"], seed, dev)
+        cols, keep, keys, nb, kind = gen_device_run(schema, r, per_run, key_space, w["null_prob"], seed, dev,
+                                                    w.get("delete_prob", 0.0))
         readers.append(SortedRunReader.from_device(schema, per_run, cols, keepalive=keep))
         all_keys.append(keys)
+        all_kinds.append(kind)
         in_bytes += nb
     torch.cuda.synchronize()
-    return readers, all_keys, in_bytes
+    return readers, all_keys, in_bytes, all_kinds
 
 
 # ------------------------------------------------------------------ clocks sampling
@@ -298,7 +343,7 @@ def main():
     schema = make_schema(args.workload)
     spec = make_spec(args.workload, schema)
     N.init(local_rank)
-    readers, all_keys, in_bytes = device_runs(args.workload, schema, rows, dev, seed=100 + rank)
+    readers, all_keys, in_bytes, all_kinds = device_runs(args.workload, schema, rows, dev, seed=100 + rank)
     n_in = sum(r.n_rows for r in readers)
     rd = SortMergeReader.create_sort_merge_reader(readers, None, None, spec, device=local_rank)
 
@@ -313,8 +358,20 @@ def main():
     st = rd.stats()
     n_out = st.rows_out
     # sanity at full size (size-independent properties): row conservation + strictly increasing keys
-    uniq = torch.unique(torch.cat(all_keys)).numel()
-    assert n_out == uniq, f"merged rows {n_out} != distinct keys {uniq}"
+    if w.get("drop_delete"):
+        # the newest record of a key wins (sequence = run << 32 | row); keys whose winner is a DELETE drop out
+        cat_k = torch.cat(all_keys)
+        cat_r = torch.cat([torch.full_like(k, r) for r, k in enumerate(all_keys)])
+        cat_d = torch.cat(all_kinds).to(torch.int64)
+        order = torch.argsort(cat_k * 64 + cat_r)
+        sk, sd = cat_k[order], cat_d[order]
+        last = torch.ones_like(sk, dtype=torch.bool)
+        last[:-1] = sk[1:] != sk[:-1]
+        uniq = int((last & (sd == 0)).sum().item())
+        del cat_k, cat_r, cat_d, order, sk, sd, last
+    else:
+        uniq = torch.unique(torch.cat(all_keys)).numel()
+    assert n_out == uniq, f"merged rows {n_out} != expected rows {uniq}"
     out_bytes = st.bytes_out
 
     ext = torch.cuda.ExternalStream(rd.cuda_stream(), device=dev)
@@ -369,6 +426,26 @@ def main():
                 "phase_ms": {"partition": ms_part / args.steps, "plan+scan": ms_plan / args.steps,
                              "size_readback+alloc": ms_alloc / args.steps, "emit": emit_ms,
                              "device_total": ms_tot / args.steps}}
+
+    # ---------------- compaction rewrite: encode the merged batch to Parquet on the device (C4)
+    rewrite = None
+    if w.get("drop_delete"):
+        import ctypes as C
+        from paimon_b200.compact_rewriter import file_column_names
+        names = file_column_names(schema)
+        arr = (C.c_char_p * len(names))(*[nm.encode() for nm in names])
+        lib = N.load()
+        enc_ms, fbytes, pages = [], 0, 0
+        for _ in range(3):
+            fh = C.c_uint64(0)
+            N.check(lib.pg_parquet_encode(rd._merge_h, arr, 0, -1, None, C.byref(fh)))
+            fm = N.PgFileMeta()
+            N.check(lib.pg_parquet_file_meta(fh.value, C.byref(fm)))
+            enc_ms.append(float(fm.ms_encode)); fbytes = int(fm.file_bytes); pages = int(fm.n_pages)
+            lib.pg_parquet_file_free(fh.value)
+        em = min(enc_ms)
+        rewrite = {"encode_ms": em, "file_bytes": fbytes, "pages": pages, "encode_GBps": fbytes / (em * 1e-3) / 1e9,
+                   "merge_plus_encode_rows_per_s": n_in / ((step_ms + em) * 1e-3)}
 
     # ---------------- e2e: host buffers in, host batch out, through the public reader API
     e2e = None
@@ -474,6 +551,8 @@ def main():
                 "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config,
                 "rows_in_per_gpu": int(n_in), "rows_out_per_gpu": int(n_out), "wall_ms_per_step": 1e3 * wall / args.steps,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+        if rewrite is not None:
+            line["rewrite"] = rewrite
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -226,6 +226,42 @@ pg_status pg_parquet_describe(uint64_t reader, pg_parquet_info *out);
 pg_status pg_parquet_read_run(uint64_t reader, uint64_t *out_run);
 pg_status pg_parquet_free(uint64_t reader);
 
+/* ---- compaction output encode: device batch -> Parquet data file ------------------------------------------
+ * Replaces KeyValueDataFileWriter.write()/result() (paimon-core/.../io/KeyValueDataFileWriter.java:108-184: row
+ * count, min/max key, min/max sequence number, delete row count, per-column stats -> DataFileMeta) and the
+ * Parquet writer behind it (paimon-format/.../parquet/writer/ParquetRowDataWriter.java,
+ * RowDataParquetBuilder.java:58-119; type mapping ParquetSchemaConverter.java:76-160) on the rewrite side of
+ * MergeTreeCompactRewriter.rewriteCompaction (:78-116).  `source` is a merge handle holding a batch or a run
+ * handle; rows [row0, row0 + n_rows) are encoded (row0 a multiple of 8, n_rows < 0 = to the end), so a rolling
+ * writer (RollingFileWriterImpl.java:64-105) cuts one batch into several files.  Written: data pages V1, PLAIN,
+ * uncompressed, definition levels for nullable columns, per-chunk statistics. */
+typedef struct {
+    int64_t row_group_rows;        /* 0 = 1 Mi rows */
+    int64_t page_rows;             /* 0 = 32 Ki rows; rounded up to a multiple of 8 */
+} pg_parquet_write_options;
+
+typedef struct {
+    int64_t n_rows;
+    int64_t file_bytes;
+    int64_t min_sequence_number;
+    int64_t max_sequence_number;
+    int64_t delete_row_count;      /* rows whose _VALUE_KIND is a retract (UPDATE_BEFORE / DELETE) */
+    int32_t n_row_groups;
+    int32_t n_pages;
+    float ms_encode;               /* CUDA-event time of the encode */
+    int32_t launches;
+} pg_file_meta;
+
+pg_status pg_parquet_encode(uint64_t source, const char *const *column_names, int64_t row0, int64_t n_rows,
+                            const pg_parquet_write_options *options, uint64_t *out_file);
+pg_status pg_parquet_file_meta(uint64_t file, pg_file_meta *out);
+/* whole-file statistics of one column: null count; min / max for fixed-width columns (integers and BOOLEAN as
+ * int64, FLOAT / DOUBLE as double; absent when every value is NULL or a NaN was seen) */
+pg_status pg_parquet_file_column_stats(uint64_t file, int32_t column, int64_t *null_count, int32_t *has_min_max,
+                                       void *min8, void *max8);
+pg_status pg_parquet_file_fetch(uint64_t file, void *host_buffer, int64_t capacity);
+pg_status pg_parquet_file_free(uint64_t file);
+
 /* IntervalPartition over int64 (min,max) key bounds of data files: section and run id per file */
 pg_status pg_interval_partition(int32_t n_files, const int64_t *min_key, const int64_t *max_key,
                                 int32_t *section_of, int32_t *run_of, int32_t *n_sections);

@@ -12,6 +12,7 @@
 #if __has_include(<jni.h>)
 #include <jni.h>
 
+#include <string>
 #include <vector>
 
 #include "paimon_gpu.h"
@@ -184,6 +185,45 @@ JNIEXPORT jlong JNICALL Java_org_apache_paimon_gpu_NativeMerge_parquetReadRun(JN
 }
 JNIEXPORT jint JNICALL Java_org_apache_paimon_gpu_NativeMerge_parquetFree(JNIEnv *env, jclass, jlong file) {
     PG_CHECK(pg_parquet_free((uint64_t)file));
+    return 0;
+}
+
+// Compaction output encode: rows [row0, row0 + nRows) of a merge batch / run -> one Parquet file on the device
+JNIEXPORT jlong JNICALL Java_org_apache_paimon_gpu_NativeMerge_parquetEncode(JNIEnv *env, jclass, jlong source,
+                                                                             jobjectArray names, jlong row0,
+                                                                             jlong nRows, jlong rowGroupRows,
+                                                                             jlong pageRows) {
+    jsize nc = env->GetArrayLength(names);
+    std::vector<std::string> keep(nc);
+    std::vector<const char *> ptrs(nc);
+    for (jsize c = 0; c < nc; c++) {
+        jstring js = (jstring)env->GetObjectArrayElement(names, c);
+        const char *u = env->GetStringUTFChars(js, nullptr);
+        keep[c] = u;
+        env->ReleaseStringUTFChars(js, u);
+        ptrs[c] = keep[c].c_str();
+    }
+    pg_parquet_write_options opt{rowGroupRows, pageRows};
+    uint64_t h = 0;
+    PG_CHECK(pg_parquet_encode((uint64_t)source, ptrs.data(), row0, nRows, &opt, &h));
+    return (jlong)h;
+}
+JNIEXPORT jlongArray JNICALL Java_org_apache_paimon_gpu_NativeMerge_fileMeta(JNIEnv *env, jclass, jlong file) {
+    pg_file_meta m{};
+    pg_status fst = pg_parquet_file_meta((uint64_t)file, &m);
+    if (fst != PG_OK) { throw_for(env, fst); return nullptr; }
+    jlong v[7] = {m.n_rows, m.file_bytes, m.min_sequence_number, m.max_sequence_number, m.delete_row_count,
+                  m.n_row_groups, m.n_pages};
+    jlongArray out = env->NewLongArray(7);
+    env->SetLongArrayRegion(out, 0, 7, v);
+    return out;
+}
+JNIEXPORT jint JNICALL Java_org_apache_paimon_gpu_NativeMerge_fileFetch(JNIEnv *env, jclass, jlong file, jobject dst) {
+    PG_CHECK(pg_parquet_file_fetch((uint64_t)file, env->GetDirectBufferAddress(dst), env->GetDirectBufferCapacity(dst)));
+    return 0;
+}
+JNIEXPORT jint JNICALL Java_org_apache_paimon_gpu_NativeMerge_fileFree(JNIEnv *env, jclass, jlong file) {
+    PG_CHECK(pg_parquet_file_free((uint64_t)file));
     return 0;
 }
 

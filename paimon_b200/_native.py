@@ -65,6 +65,16 @@ class PgParquetInfo(C.Structure):
                 ("launches", C.c_int32)]
 
 
+class PgParquetWriteOptions(C.Structure):
+    _fields_ = [("row_group_rows", C.c_int64), ("page_rows", C.c_int64)]
+
+
+class PgFileMeta(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("file_bytes", C.c_int64), ("min_sequence_number", C.c_int64),
+                ("max_sequence_number", C.c_int64), ("delete_row_count", C.c_int64), ("n_row_groups", C.c_int32),
+                ("n_pages", C.c_int32), ("ms_encode", C.c_float), ("launches", C.c_int32)]
+
+
 class PaimonGpuError(RuntimeError):
     """A non-zero pg_status.  `.status` holds the code (PG_ERR_*)."""
 
@@ -111,6 +121,13 @@ _SIGNATURES = {
     "pg_parquet_describe": (C.c_int32, [C.c_uint64, C.POINTER(PgParquetInfo)]),
     "pg_parquet_read_run": (C.c_int32, [C.c_uint64, C.POINTER(C.c_uint64)]),
     "pg_parquet_free": (C.c_int32, [C.c_uint64]),
+    "pg_parquet_encode": (C.c_int32, [C.c_uint64, C.POINTER(C.c_char_p), C.c_int64, C.c_int64,
+                                      C.POINTER(PgParquetWriteOptions), C.POINTER(C.c_uint64)]),
+    "pg_parquet_file_meta": (C.c_int32, [C.c_uint64, C.POINTER(PgFileMeta)]),
+    "pg_parquet_file_column_stats": (C.c_int32, [C.c_uint64, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
+                                                 C.c_void_p, C.c_void_p]),
+    "pg_parquet_file_fetch": (C.c_int32, [C.c_uint64, C.c_void_p, C.c_int64]),
+    "pg_parquet_file_free": (C.c_int32, [C.c_uint64]),
 }
 
 _lib: Optional[C.CDLL] = None

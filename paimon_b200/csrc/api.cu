@@ -237,6 +237,27 @@ Schema *schema_from_handle(uint64_t h) { return g_schemas.get(h); }
 uint64_t register_run(std::unique_ptr<Run> run) { return g_runs.put(std::move(run)); }
 pg_status require_device() { return ensure_device(); }
 
+// parquet_encode.cu: the columns of a merge handle's current batch, or of a run
+pg_status batch_columns(uint64_t handle, const Schema **schema, std::vector<DevColumn> *cols, int64_t *n_rows) {
+    if ((handle >> 56) == 4) {
+        Merge *m = g_merges.get(handle);
+        if (!m) return fail(PG_ERR_INVALID, "unknown merge handle");
+        if (!m->has_batch) return fail(PG_ERR_INVALID, "no batch: call pg_merge_execute first");
+        if (m->stream) PG_CUDA(cudaStreamSynchronize(m->stream));
+        *schema = m->schema;
+        *n_rows = m->n_out;
+        cols->clear();
+        for (const pg_out_column &oc : m->out_cols) cols->push_back(DevColumn{oc.data, oc.offsets, oc.validity});
+        return PG_OK;
+    }
+    Run *r = g_runs.get(handle);
+    if (!r) return fail(PG_ERR_INVALID, "unknown run / merge handle");
+    *schema = r->schema;
+    *n_rows = r->n_rows;
+    *cols = r->cols;
+    return PG_OK;
+}
+
 // drop the current batch; the arena itself is kept for the next execute unless `release_memory`
 static void free_outputs(Merge *m, bool release_memory = false) {
     m->out_cols.clear();
@@ -494,7 +515,7 @@ static pg_status execute(Merge *m) {
 
     // ---- level sizes
     const int S = kSampleStride;
-    const int q = kTileMax / S - 2 * k;
+    const int q = kPlanTile / S - 2 * k;
     if (q < 1) return fail(PG_ERR_UNSUPPORTED, "too many runs for one merge call");
     std::vector<LevelView> views;
     std::vector<int64_t> level_total;
@@ -511,7 +532,7 @@ static pg_status execute(Merge *m) {
             }
             views.push_back(lv);
             level_total.push_back(tot);
-            if (tot <= kTileMax) break;
+            if (tot <= kPlanTile) break;
             stride *= S;
         }
     }
@@ -679,7 +700,9 @@ static pg_status execute(Merge *m) {
     // ---- emit
     EmitArgs ea{};
     ea.bounds = bounds0;
-    ea.n_tiles = T;
+    ea.n_tiles = (T + 1) / 2;
+    ea.n_plan_tiles = T;
+    ea.tile_rows = tile_rows;
     ea.k = k;
     ea.plan = plan;
     ea.row_base = row_base;

@@ -36,7 +36,7 @@ __host__ __device__ inline EmitLayout emit_layout(int k) {
     EmitLayout L;
     L.rt = kTileMax + 64 * k;
     L.stage_bytes = (((size_t)L.rt * 8 + (size_t)L.rt / 32 * 4) + 127) & ~(size_t)127;
-    L.total = kStages * L.stage_bytes + (size_t)kTileMax * (2 + 2 + 1) + (PG_MAX_RUNS + 1) * 4 * 2 +
+    L.total = kStages * L.stage_bytes + (size_t)kTileMax * (2 + 2 + 1) + (PG_MAX_RUNS + 1) * 4 * 3 +
               PG_MAX_RUNS * 8 + kStages * PG_MAX_RUNS * 8 + kStages * 8 + 34 * 4 + 64;
     return L;
 }
@@ -214,7 +214,13 @@ struct TileView {
     int o_shift;
     int64_t out_base;
     int64_t in_base;
+    int n_out_a;                 // output rows of the first plan tile of the pair
+    int seq_shift;               // tmp_seq / tmp_kind are laid out per plan tile: rows of the second one sit
+                                 // (n_a - n_out_a) entries further
 };
+__device__ __forceinline__ int64_t result_index(const TileView &tv, int ob) {
+    return tv.in_base + ob + (ob >= tv.n_out_a ? tv.seq_shift : 0);
+}
 
 // one output validity word per warp iteration: interior words are plain stores, tile-boundary words OR
 __device__ __forceinline__ void put_validity_word(uint8_t *validity, int64_t out_base, int wb, int n_out,
@@ -253,9 +259,9 @@ __device__ __forceinline__ void emit_fixed_column(const EmitArgs &ea, const ColD
             } else if (cd.mode == CM_KEY) {
                 val = lds_fixed<W>(vals, tv.pm[last] & kPmPosMask); is_valid = true;
             } else if (cd.mode == CM_SEQ) {
-                val = (uint64_t)ea.tmp_seq[tv.in_base + ob]; is_valid = true;
+                val = (uint64_t)ea.tmp_seq[result_index(tv, ob)]; is_valid = true;
             } else if (cd.mode == CM_KIND) {
-                val = (uint8_t)ea.tmp_kind[tv.in_base + ob]; is_valid = true;
+                val = (uint8_t)ea.tmp_kind[result_index(tv, ob)]; is_valid = true;
             } else {
                 fold_fixed(cd, tv.pm, vw, vals, last, &val, &is_valid, ea.err);
                 if (!is_valid) val = 0;
@@ -286,6 +292,7 @@ k_emit(EmitArgs ea) {
     uint64_t *mbar = (uint64_t *)p;            p += kStages * 8;
     int64_t *s_i64 = (int64_t *)p;             p += 16;
     int *seg = (int *)p;                       p += (PG_MAX_RUNS + 1) * 4;
+    int *seg_a = (int *)p;                     p += (PG_MAX_RUNS + 1) * 4;        // first plan tile: slot base per run
     int *rr = (int *)p;                        p += (PG_MAX_RUNS + 1) * 4;         // staged row base per run
     int *ws = (int *)p;                        p += 34 * 4;
     int *s_i32 = (int *)p;                     p += 16;
@@ -298,18 +305,24 @@ k_emit(EmitArgs ea) {
     }
     __syncthreads();
     const int tile = s_i32[0];
+    // an emit tile is two consecutive plan tiles (the last one may be single)
+    const int plan_a = 2 * tile, plan_end = min(plan_a + 2, ea.n_plan_tiles);
     if (tid == 0) {
-        int acc = 0, racc = 0;
+        int acc = 0, racc = 0, acc_a = 0;
         for (int r = 0; r < k; r++) {
-            int64_t b0 = ea.bounds[(int64_t)tile * k + r], b1 = ea.bounds[(int64_t)(tile + 1) * k + r];
+            int64_t b0 = ea.bounds[(int64_t)plan_a * k + r], bm = ea.bounds[(int64_t)(plan_a + 1) * k + r],
+                    b1 = ea.bounds[(int64_t)plan_end * k + r];
             rstart[r] = b0;
             seg[r] = acc;
+            seg_a[r] = acc_a;
             rr[r] = racc;
             int len = (int)(b1 - b0);
             acc += len;
+            acc_a += (int)(bm - b0);
             racc += (((int)(b0 & 31) + len + 1) + 31) & ~31;
         }
         seg[k] = acc;
+        seg_a[k] = acc_a;
         rr[k] = racc;
     }
     __syncthreads();
@@ -327,18 +340,22 @@ k_emit(EmitArgs ea) {
     // is not in use yet (glast, stage 1)
     uint16_t *spos = glast;
     uint8_t *srun = stage_vals[1];
+    // plan slots are run-major inside their plan tile: table index = slot (first tile) or n_a + slot (second)
+    const int n_a = seg_a[k];
     for (int r = 0; r < k; r++) {
-        const int s0 = seg[r], s1 = seg[r + 1];
-        const int delta = rr[r] + (int)(rstart[r] & 31) - s0;
-        for (int sl = s0 + tid; sl < s1; sl += kEmitThreads) {
-            spos[sl] = (uint16_t)(sl + delta);
-            srun[sl] = (uint8_t)r;
+        const int len_a = seg_a[r + 1] - seg_a[r], len = seg[r + 1] - seg[r];
+        const int p0r = rr[r] + (int)(rstart[r] & 31);                  // staged position of the run's first row
+        const int sb0 = n_a + (seg[r] - seg_a[r]);                      // second tile: slot base of run r
+        for (int j = tid; j < len; j += kEmitThreads) {
+            const int idx = j < len_a ? seg_a[r] + j : sb0 + (j - len_a);
+            spos[idx] = (uint16_t)(p0r + j);
+            srun[idx] = (uint8_t)r;
         }
     }
     __syncthreads();
     for (int i = p0; i < p1; i++) {
         uint16_t e = ea.plan[in_base + i];
-        int slot = e & kPlanSlotMask;
+        int slot = (e & kPlanSlotMask) + (i < n_a ? 0 : n_a);
         mrun[i] = srun[slot];
         uint32_t pos = spos[slot];
         uint32_t op = (e >> kPlanOpShift) & 3;
@@ -370,9 +387,11 @@ k_emit(EmitArgs ea) {
     tv.pm = pm;
     tv.glast = glast;
     tv.n_out = n_out;
-    tv.out_base = ea.row_base[tile];
+    tv.out_base = ea.row_base[plan_a];
     tv.o_shift = (int)(tv.out_base & 31);
     tv.in_base = in_base;
+    tv.n_out_a = ea.tile_rows[plan_a];
+    tv.seq_shift = n_a - tv.n_out_a;
     const int ncols = ea.n_cols;
     uint32_t phase = 0;                                // bit s = parity to wait for on stage s
 

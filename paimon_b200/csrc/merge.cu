@@ -5,7 +5,7 @@
 // LoserTree.java:95-170) with a data-parallel pipeline over columnar runs resident in HBM:
 //
 //   1. sampled partition   every S-th key of each run forms the next level; levels are merged
-//                          top-down so that level 0 is cut into key-range tiles of <= kTileMax rows
+//                          top-down so that level 0 is cut into key-range tiles of <= kPlanTile rows
 //                          (all rows of one key fall into one tile => the reduce is tile-local)
 //   2. plan kernel         one CTA per tile: k sorted segments -> shared memory -> log2(k) rounds of
 //                          merge-path pair merges -> key groups -> members ordered by sequence number
@@ -115,7 +115,7 @@ __global__ void k_partition(int k, KeyDesc kd, KeySrc ks, LevelView lv, const ui
 // shared-memory index padding: one extra slot per 16 elements, so that the merge-path threads (which start
 // 16 elements apart) fall into different banks instead of all hitting the same one
 #define PADI(i) ((i) + ((i) >> 4))
-constexpr int kTilePad = kTileMax + kTileMax / 16;
+constexpr int kTilePad = kPlanTile + kPlanTile / 16;
 
 struct TileCtx {
     uint64_t *key[2];
@@ -140,7 +140,7 @@ __device__ bool merge_tile(TileCtx &tc, int k, const KeyDesc &kd, const KeySrc &
             tc.seg[r] = acc;
             tc.lb[0][r] = acc;
             int64_t len = b1 - b0;
-            if (len < 0 || acc + len > kTileMax) { len = 0; acc = kTileMax + 1; }
+            if (len < 0 || acc + len > kPlanTile) { len = 0; acc = kPlanTile + 1; }
             else acc += (int)len;
         }
         tc.seg[k] = acc;
@@ -148,7 +148,7 @@ __device__ bool merge_tile(TileCtx &tc, int k, const KeyDesc &kd, const KeySrc &
     }
     __syncthreads();
     tc.n = tc.seg[k];
-    if (tc.n > kTileMax) {
+    if (tc.n > kPlanTile) {
         if (tid == 0) atomicCAS(err, KERR_NONE, KERR_TILE_OVERFLOW);
         return false;
     }
@@ -175,7 +175,7 @@ __device__ bool merge_tile(TileCtx &tc, int k, const KeyDesc &kd, const KeySrc &
     };
 
     int L = k, cur = 0;
-    constexpr int VT = kTileMax / kThreads;
+    constexpr int VT = kPlanTile / kThreads;
     while (L > 1) {
         const uint64_t *sk = tc.key[cur];
         const uint16_t *si = tc.idx[cur];
@@ -376,18 +376,18 @@ struct PlanSmemExtra {
     uint8_t *res_kind;    // per head position: result RowKind
     int *ws;              // 33 ints scan scratch
 };
-constexpr size_t kPlanSmem = kTileSmem + (size_t)kTileMax * 3 + 34 * 4 + 16;
+constexpr size_t kPlanSmem = kTileSmem + (size_t)kPlanTile * 3 + 34 * 4 + 16;
 
 template <bool EXACT>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 4)
 k_plan(int k, KeyDesc kd, KeySrc ks, PlanArgs pa, int32_t *err) {
     extern __shared__ __align__(16) unsigned char smem[];
     TileCtx tc;
     carve_tile(tc, smem, k);
     PlanSmemExtra px;
     px.res_slot = (uint16_t *)(smem + ((kTileSmem + 15) & ~(size_t)15));
-    px.res_kind = (uint8_t *)(px.res_slot + kTileMax);
-    px.ws = (int *)(px.res_kind + kTileMax);
+    px.res_kind = (uint8_t *)(px.res_slot + kPlanTile);
+    px.ws = (int *)(px.res_kind + kPlanTile);
 
     const int tile = blockIdx.x, tid = threadIdx.x;
     if (!merge_tile<EXACT>(tc, k, kd, ks, pa.bounds, tile, 1, nullptr, err)) {
@@ -399,7 +399,7 @@ k_plan(int k, KeyDesc kd, KeySrc ks, PlanArgs pa, int32_t *err) {
     uint16_t *fi = tc.idx[tc.fin];
     int64_t *seq_s = (int64_t *)tc.key[tc.fin ^ 1];          // staged by slot
     uint8_t *kind_s = (uint8_t *)tc.idx[tc.fin ^ 1];          // first 4 KiB: kinds by slot
-    uint8_t *ops = kind_s + kTileMax;                         // second 4 KiB: op per merged position
+    uint8_t *ops = kind_s + kPlanTile;                         // second 4 KiB: op per merged position
 
     int64_t in_base = 0;
     for (int r = 0; r < k; r++) in_base += tc.rstart[r];
@@ -425,7 +425,7 @@ k_plan(int k, KeyDesc kd, KeySrc ks, PlanArgs pa, int32_t *err) {
     }
     __syncthreads();
 
-    constexpr int VT = kTileMax / kThreads;
+    constexpr int VT = kPlanTile / kThreads;
     const int p0 = tid * VT, p1 = min(p0 + VT, n);
     const MergeFlags fl = pa.flags;
     int my_emit = 0;

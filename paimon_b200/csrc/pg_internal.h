@@ -11,9 +11,11 @@
 
 namespace pg {
 
-constexpr int kTileMax = 4096;       // rows merged by one CTA (shared-memory tile)
-constexpr int kSampleStride = 32;    // S: every S-th key of a level is a sample of the next level
-constexpr int kThreads = 512;         // plan / merge-keys CTAs (2 per SM: shared memory bound)
+constexpr int kPlanTile = 2048;      // rows merged by one plan / merge-keys CTA (shared-memory tile)
+constexpr int kTileMax = 2 * kPlanTile;   // rows of one emit CTA: two consecutive plan tiles (fewer, fatter
+                                     // column passes in the emit kernel; more CTAs per SM in the plan kernel)
+constexpr int kSampleStride = 16;    // S: every S-th key of a level is a sample of the next level
+constexpr int kThreads = 256;        // plan / merge-keys CTAs (4 per SM)
 constexpr int kMaxCols = 256;
 
 // ---- plan entry (one uint16 per merged input position) ----
@@ -197,11 +199,13 @@ void launch_plan(const MergeLaunch &ml, const PlanArgs &pa);
 void launch_scan(cudaStream_t stream, const int32_t *tile_rows, int n_tiles, int64_t *row_base, int64_t *totals);
 
 struct EmitArgs {
-    const int64_t *bounds;
-    int n_tiles;
+    const int64_t *bounds;             // plan-tile bounds [(n_plan_tiles + 1) * k]
+    int n_tiles;                       // emit tiles = ceil(n_plan_tiles / 2)
+    int n_plan_tiles;
+    const int32_t *tile_rows;          // output rows per plan tile
     int k;
     const uint16_t *plan;
-    const int64_t *row_base;           // [n_tiles]
+    const int64_t *row_base;           // [n_plan_tiles]
     const int64_t *tmp_seq;
     const int8_t *tmp_kind;
     const uint32_t *gplan;             // sequence-group marks (see PlanArgs), NULL without groups

@@ -9,7 +9,7 @@ from paimon_b200.types import PhysicalType, is_varlen
 
 _PA = {PhysicalType.INT8: pa.int8(), PhysicalType.INT16: pa.int16(), PhysicalType.INT32: pa.int32(),
        PhysicalType.INT64: pa.int64(), PhysicalType.FLOAT: pa.float32(), PhysicalType.DOUBLE: pa.float64(),
-       PhysicalType.STRING: pa.string(), PhysicalType.BINARY: pa.binary()}
+       PhysicalType.STRING: pa.string(), PhysicalType.BINARY: pa.binary(), PhysicalType.BOOL: pa.bool_()}
 
 
 def to_arrow(batch: KeyValueBatch) -> pa.Table:
@@ -22,7 +22,10 @@ def to_arrow(batch: KeyValueBatch) -> pa.Table:
             vals = col.to_pylist()
             arr = pa.array(vals, type=_PA[t])
         else:
-            arr = pa.array(np.asarray(col.data[:n]), type=_PA[t], mask=mask)
+            data = np.asarray(col.data[:n])
+            if t == PhysicalType.BOOL:
+                data = data.astype(bool)
+            arr = pa.array(data, type=_PA[t], mask=mask)
         fields.append(pa.field(f.name, _PA[t], nullable=f.nullable))
         arrays.append(arr)
     return pa.Table.from_arrays(arrays, schema=pa.schema(fields))
