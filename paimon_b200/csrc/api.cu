@@ -546,7 +546,7 @@ static pg_status execute(Merge *m) {
     PG_CUDA(cudaMemsetAsync(m->d_err, 0, sizeof(int32_t), sm));
     PG_CUDA(cudaEventRecord(m->ev[0], sm));
 
-    MergeLaunch ml{k, m->key, KeySrc{m->d_key_ptrs, m->d_key_offs}, sm, m->d_err};
+    MergeLaunch ml{k, m->key, KeySrc{m->d_key_ptrs, m->d_key_offs}, sm, m->d_err, nullptr};
     // Workspace: one grow-only device allocation per merge handle, carved with a bump pointer.  Its size
     // depends only on the input shapes, so a reader that is executed repeatedly (or a pool of readers of
     // one bucket layout) never goes back to the driver allocator.
@@ -569,6 +569,14 @@ static pg_status execute(Merge *m) {
     };
     auto free_temps = [&]() {};
 
+    if (!m->key.exact) {
+        // window keys start behind the prefix all keys share (strings like "user_0000123", wide composites)
+        int *d_skip = nullptr;
+        PG_CUDA(talloc(sizeof(int), (void **)&d_skip));
+        launch_key_lcp(ml, views[0], d_skip);
+        ml.skip = d_skip;
+        launches++;
+    }
     int64_t *bounds0 = nullptr;
     uint64_t *sk_above = nullptr;         // sorted sample keys of the level above the current one
     uint64_t *sref_above = nullptr;       // ... and the rows they came from (non-exact keys)

@@ -32,32 +32,74 @@ __device__ __forceinline__ uint64_t norm_field(const void *base, int type, int64
     }
 }
 
-// Order-preserving 64-bit prefix of a row's primary key: the key fields laid out big-endian, most
-// significant first, cut after 8 bytes.  prefix(a) < prefix(b) implies a < b; equal prefixes decide nothing
-// unless kd.exact (all fields fixed-width and together <= 8 bytes).  A var-len field contributes its first
-// bytes (zero padded) and ends the prefix.
-__device__ __forceinline__ uint64_t load_key(const KeySrc &ks, const KeyDesc &kd, int run, int64_t row) {
-    if (kd.n_fields == 1 && kd.width[0] == 8) return norm_field(ks.data[run], kd.type[0], row);
+// Order-preserving 64-bit window of a row's primary key.  The key is read as a byte stream: the key fields
+// big-endian, most significant first; a var-len field contributes its bytes and ends the stream.  The window
+// holds stream bytes [skip, skip + 8), zero padded.  With `skip` = a common prefix length of all keys that are
+// compared with each other, window(a) < window(b) implies a < b; equal windows decide nothing unless the keys
+// are known to end inside the window (kd.exact, or a tile whose keys all have the same covered length).
+__device__ __forceinline__ uint64_t load_key(const KeySrc &ks, const KeyDesc &kd, int run, int64_t row, int skip = 0) {
+    if (kd.n_fields == 1 && kd.width[0] == 8 && skip == 0) return norm_field(ks.data[run], kd.type[0], row);
     uint64_t k = 0;
-    int pos = 0;                                         // bytes of the prefix already filled
-    for (int f = 0; f < kd.n_fields && pos < 8; f++) {
+    int pos = 0;                                         // stream offset of the current field
+    const int end = skip + 8;
+    for (int f = 0; f < kd.n_fields && pos < end; f++) {
         const void *base = ks.data[run * kd.n_fields + f];
         const int w = kd.width[f];
         if (w > 0) {
-            uint64_t v = norm_field(base, kd.type[f], row);
-            int room = 8 - pos;
-            if (w <= room) k |= v << ((room - w) * 8);
-            else k |= v >> ((w - room) * 8);
+            if (pos + w > skip) {
+                const uint64_t v = norm_field(base, kd.type[f], row);
+                for (int j = max(0, skip - pos); j < w && pos + j < end; j++)
+                    k |= ((v >> (8 * (w - 1 - j))) & 0xFF) << (8 * (7 - (pos + j - skip)));
+            }
             pos += w;
         } else {
             const int32_t *offs = ks.offsets[run * kd.n_fields + f];
             const uint8_t *bytes = (const uint8_t *)base + offs[row];
-            int len = offs[row + 1] - offs[row];
-            for (int b = 0; b < len && pos < 8; b++, pos++) k |= (uint64_t)bytes[b] << ((7 - pos) * 8);
-            pos = 8;
+            const int len = offs[row + 1] - offs[row];
+            for (int j = max(0, skip - pos); j < len && pos + j < end; j++)
+                k |= (uint64_t)bytes[j] << (8 * (7 - (pos + j - skip)));
+            pos = end;
         }
     }
     return k;
+}
+
+// Length of the key's byte stream (see load_key); -1 when the stream does not cover the whole key (a var-len
+// field that is not the last one)
+__device__ __forceinline__ int key_stream_len(const KeySrc &ks, const KeyDesc &kd, int run, int64_t row) {
+    int pos = 0;
+    for (int f = 0; f < kd.n_fields; f++) {
+        const int w = kd.width[f];
+        if (w > 0) pos += w;
+        else {
+            if (f != kd.n_fields - 1) return -1;
+            const int32_t *offs = ks.offsets[run * kd.n_fields + f];
+            pos += offs[row + 1] - offs[row];
+        }
+    }
+    return pos;
+}
+
+// Number of leading stream bytes two rows' keys have in common
+__device__ int key_stream_lcp(const KeySrc &ks, const KeyDesc &kd, int ra, int64_t row_a, int rb, int64_t row_b) {
+    int pos = 0;
+    for (int f = 0; f < kd.n_fields; f++) {
+        const void *da = ks.data[ra * kd.n_fields + f], *db = ks.data[rb * kd.n_fields + f];
+        const int w = kd.width[f];
+        if (w > 0) {
+            const uint64_t x = norm_field(da, kd.type[f], row_a), y = norm_field(db, kd.type[f], row_b);
+            if (x != y) return pos + (__clzll((long long)(x ^ y)) >> 3) - (8 - w);
+            pos += w;
+        } else {
+            const int32_t *oa = ks.offsets[ra * kd.n_fields + f], *ob = ks.offsets[rb * kd.n_fields + f];
+            const uint8_t *pa = (const uint8_t *)da + oa[row_a], *pb = (const uint8_t *)db + ob[row_b];
+            const int la = oa[row_a + 1] - oa[row_a], lb = ob[row_b + 1] - ob[row_b];
+            int j = 0;
+            while (j < la && j < lb && pa[j] == pb[j]) j++;
+            return pos + j;                              // a var-len field ends the stream
+        }
+    }
+    return pos;
 }
 
 // Full comparison of two rows' keys, field by field, with the generated comparator's rules
@@ -83,7 +125,9 @@ __device__ int full_key_compare(const KeySrc &ks, const KeyDesc &kd, int ra, int
 // ------------------------------------------------------------------ partition
 
 __global__ void k_partition(int k, KeyDesc kd, KeySrc ks, LevelView lv, const uint64_t *__restrict__ sk,
-                            const uint64_t *__restrict__ sref, int q, int n_tiles, int64_t *bounds) {
+                            const uint64_t *__restrict__ sref, int q, int n_tiles, int64_t *bounds,
+                            const int *__restrict__ skip_p) {
+    const int skip = skip_p ? *skip_p : 0;
     int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (idx >= (int64_t)(n_tiles + 1) * k) return;
     int t = (int)(idx / k), r = (int)(idx % k);
@@ -99,7 +143,7 @@ __global__ void k_partition(int k, KeyDesc kd, KeySrc ks, LevelView lv, const ui
         while (lo < hi) {                      // lower_bound: first j with key(j) >= splitter key
             int64_t mid = (lo + hi) >> 1;
             const int64_t row = lv.row0[r] + (mid + 1) * lv.stride - 1;
-            uint64_t km = load_key(ks, kd, r, row);
+            uint64_t km = load_key(ks, kd, r, row, skip);
             bool less = km < x;
             if (!less && km == x && !kd.exact) less = full_key_compare(ks, kd, r, row, s_run, s_row) < 0;
             if (less) lo = mid + 1; else hi = mid;
@@ -125,13 +169,16 @@ struct TileCtx {
     int64_t *rstart;     // first row (at this level) of every run's segment
     int n;               // rows in the tile
     int fin;             // which buffer holds the merged result
+    bool exact;          // equal windows mean equal keys in this tile
 };
 
 // Loads the tile's k segments and merges them.  Returns false when the tile overflows.
 template <bool EXACT>
 __device__ bool merge_tile(TileCtx &tc, int k, const KeyDesc &kd, const KeySrc &ks,
-                           const int64_t *bounds, int tile, int64_t stride, const int64_t *row0, int32_t *err) {
+                           const int64_t *bounds, int tile, int64_t stride, const int64_t *row0, int32_t *err,
+                           int skip, bool refine) {
     const int tid = threadIdx.x;
+    __shared__ int s_skip, s_len0;
     if (tid == 0) {
         int acc = 0;
         for (int r = 0; r < k; r++) {
@@ -153,21 +200,51 @@ __device__ bool merge_tile(TileCtx &tc, int k, const KeyDesc &kd, const KeySrc &
         return false;
     }
     const int n = tc.n;
+    tc.exact = EXACT;
+    if (!EXACT && refine) {
+        // the tile's keys share at least the prefix its 2k segment end points share with one of them: start the
+        // 8-byte window behind it, so that keys with a long common prefix ("user_0000123") still sort by window
+        if (tid == 0) { s_skip = 0x7fffffff; s_len0 = -2; }
+        __syncthreads();
+        int ref_r = 0;
+        while (ref_r < k && tc.seg[ref_r + 1] == tc.seg[ref_r]) ref_r++;
+        if (tid < 2 * k && ref_r < k) {
+            const int r = tid >> 1;
+            const int len = tc.seg[r + 1] - tc.seg[r];
+            if (len > 0) {
+                const int64_t row = ((tid & 1) ? tc.rstart[r] + len - 1 : tc.rstart[r]);
+                atomicMin(&s_skip, key_stream_lcp(ks, kd, ref_r, tc.rstart[ref_r], r, row));
+            }
+        }
+        __syncthreads();
+        skip = s_skip == 0x7fffffff ? 0 : s_skip;
+    }
+    bool odd_len = false;                            // a key that does not end inside the window, or whose length
+    int len0 = -2;                                   // differs from the tile's first key
+    if (!EXACT && refine && n > 0) {
+        int ref_r = 0;
+        while (tc.seg[ref_r + 1] == tc.seg[ref_r]) ref_r++;
+        len0 = key_stream_len(ks, kd, ref_r, tc.rstart[ref_r]);
+        if (len0 < 0 || len0 > skip + 8) odd_len = true;
+    }
     for (int r = 0; r < k; r++) {                    // coalesced per run segment
         const int s0 = tc.seg[r], s1 = tc.seg[r + 1];
         const int64_t j0 = tc.rstart[r] - s0;
         const int64_t rb = row0 ? row0[r] : 0;           // (level 0 bounds are absolute rows already)
         for (int i = s0 + tid; i < s1; i += blockDim.x) {
-            tc.key[0][PADI(i)] = load_key(ks, kd, r, rb + (j0 + i + 1) * stride - 1);
+            const int64_t row = rb + (j0 + i + 1) * stride - 1;
+            tc.key[0][PADI(i)] = load_key(ks, kd, r, row, skip);
             tc.idx[0][PADI(i)] = (uint16_t)i;
+            if (!EXACT && refine && !odd_len && key_stream_len(ks, kd, r, row) != len0) odd_len = true;
         }
     }
-    __syncthreads();
+    if (!EXACT && refine) tc.exact = !__syncthreads_or(odd_len);
+    else __syncthreads();
 
     // a <= b on (prefix, slot) pairs; equal prefixes of a non-exact key fall back to the full comparison
     auto le = [&](uint64_t ka, int sa, uint64_t kb, int sb) -> bool {
         if (ka != kb) return ka < kb;
-        if (EXACT) return true;
+        if (EXACT || tc.exact) return true;
         const int ra = run_of_slot(tc.seg, k, sa), rb = run_of_slot(tc.seg, k, sb);
         const int64_t row_a = (row0 ? row0[ra] : 0) + (tc.rstart[ra] + (sa - tc.seg[ra]) + 1) * stride - 1;
         const int64_t row_b = (row0 ? row0[rb] : 0) + (tc.rstart[rb] + (sb - tc.seg[rb]) + 1) * stride - 1;
@@ -241,12 +318,12 @@ constexpr size_t kTileSmem = (size_t)kTilePad * (8 + 8 + 2 + 2) + PG_MAX_RUNS * 
 template <bool EXACT>
 __global__ void __launch_bounds__(kThreads)
 k_merge_keys(int k, KeyDesc kd, KeySrc ks, LevelView lv, const int64_t *bounds, uint64_t *sorted_keys,
-             uint64_t *sorted_refs, int32_t *err) {
+             uint64_t *sorted_refs, int32_t *err, const int *__restrict__ skip_p) {
     extern __shared__ __align__(16) unsigned char smem[];
     TileCtx tc;
     carve_tile(tc, smem, k);
     int tile = blockIdx.x;
-    if (!merge_tile<EXACT>(tc, k, kd, ks, bounds, tile, lv.stride, lv.row0, err)) return;
+    if (!merge_tile<EXACT>(tc, k, kd, ks, bounds, tile, lv.stride, lv.row0, err, skip_p ? *skip_p : 0, false)) return;
     int64_t base = 0;
     for (int r = 0; r < k; r++) base += tc.rstart[r];
     const uint64_t *fk = tc.key[tc.fin];
@@ -390,7 +467,7 @@ k_plan(int k, KeyDesc kd, KeySrc ks, PlanArgs pa, int32_t *err) {
     px.ws = (int *)(px.res_kind + kPlanTile);
 
     const int tile = blockIdx.x, tid = threadIdx.x;
-    if (!merge_tile<EXACT>(tc, k, kd, ks, pa.bounds, tile, 1, nullptr, err)) {
+    if (!merge_tile<EXACT>(tc, k, kd, ks, pa.bounds, tile, 1, nullptr, err, 0, true)) {
         if (tid == 0) pa.tile_rows[tile] = 0;
         return;
     }
@@ -407,7 +484,7 @@ k_plan(int k, KeyDesc kd, KeySrc ks, PlanArgs pa, int32_t *err) {
     // do the merged positions a and b hold the same key?  (equal prefixes decide only for exact keys)
     auto same_key = [&](int a, int b) -> bool {
         if (fk[PADI(a)] != fk[PADI(b)]) return false;
-        if (EXACT) return true;
+        if (EXACT || tc.exact) return true;
         const int sa = fi[PADI(a)], sb = fi[PADI(b)];
         const int ra = run_of_slot(tc.seg, k, sa), rb = run_of_slot(tc.seg, k, sb);
         return full_key_compare(ks, kd, ra, tc.rstart[ra] + (sa - tc.seg[ra]), rb, tc.rstart[rb] + (sb - tc.seg[rb])) == 0;
@@ -609,6 +686,26 @@ k_plan(int k, KeyDesc kd, KeySrc ks, PlanArgs pa, int32_t *err) {
     if (tid == 0) pa.tile_rows[tile] = total;
 }
 
+// ------------------------------------------------------------------ common key prefix of a whole merge
+
+// *skip = number of leading key-stream bytes all rows of all runs share (from the runs' first and last rows)
+__global__ void k_key_lcp(int k, KeyDesc kd, KeySrc ks, LevelView lv, int *skip) {
+    __shared__ int s;
+    if (threadIdx.x == 0) s = 0x7fffffff;
+    __syncthreads();
+    int ref = 0;
+    while (ref < k && lv.count[ref] == 0) ref++;
+    if ((int)threadIdx.x < 2 * k && ref < k) {
+        const int r = threadIdx.x >> 1;
+        if (lv.count[r] > 0) {
+            const int64_t row = (threadIdx.x & 1) ? lv.row0[r] + lv.count[r] - 1 : lv.row0[r];
+            atomicMin(&s, key_stream_lcp(ks, kd, ref, lv.row0[ref], r, row));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *skip = s == 0x7fffffff ? 0 : s;
+}
+
 // ------------------------------------------------------------------ scan of tile row counts
 
 __global__ void k_scan(const int32_t *tile_rows, int n_tiles, int64_t *row_base, int64_t *totals) {
@@ -646,7 +743,7 @@ void launch_partition(const MergeLaunch &ml, const LevelView &lv, const uint64_t
     int64_t total = (int64_t)(n_tiles + 1) * ml.k;
     int blocks = (int)((total + 127) / 128);
     k_partition<<<blocks, 128, 0, ml.stream>>>(ml.k, ml.key, ml.ks, lv, splitter_keys, splitter_refs, q, n_tiles,
-                                                 bounds);
+                                                 bounds, ml.skip);
 }
 
 void launch_merge_keys(const MergeLaunch &ml, const LevelView &lv, const int64_t *bounds, int n_tiles,
@@ -654,10 +751,14 @@ void launch_merge_keys(const MergeLaunch &ml, const LevelView &lv, const int64_t
     set_attrs();
     if (ml.key.exact)
         k_merge_keys<true><<<n_tiles, kThreads, kTileSmem, ml.stream>>>(ml.k, ml.key, ml.ks, lv, bounds, sorted_keys,
-                                                                          sorted_refs, ml.err);
+                                                                          sorted_refs, ml.err, nullptr);
     else
         k_merge_keys<false><<<n_tiles, kThreads, kTileSmem, ml.stream>>>(ml.k, ml.key, ml.ks, lv, bounds,
-                                                                           sorted_keys, sorted_refs, ml.err);
+                                                                           sorted_keys, sorted_refs, ml.err, ml.skip);
+}
+
+void launch_key_lcp(const MergeLaunch &ml, const LevelView &lv0, int *skip) {
+    k_key_lcp<<<1, 64, 0, ml.stream>>>(ml.k, ml.key, ml.ks, lv0, skip);
 }
 
 void launch_plan(const MergeLaunch &ml, const PlanArgs &pa) {

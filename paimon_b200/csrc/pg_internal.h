@@ -142,11 +142,13 @@ struct MergeLaunch {
     KeySrc ks;                         // device: [k][n_key] key column data / offsets pointers
     cudaStream_t stream;
     int32_t *err;                      // device error word
+    const int *skip;                   // device: key-stream bytes all rows share (NULL for exact keys = 0)
 };
 
 // B[(t) * k + r] for t in [0, n_tiles]: tile boundaries per run at this level.
 void launch_partition(const MergeLaunch &ml, const LevelView &lv, const uint64_t *splitter_keys,
                       const uint64_t *splitter_refs, int q, int n_tiles, int64_t *bounds);
+void launch_key_lcp(const MergeLaunch &ml, const LevelView &lv0, int *skip);
 void launch_merge_keys(const MergeLaunch &ml, const LevelView &lv, const int64_t *bounds, int n_tiles,
                        uint64_t *sorted_keys, uint64_t *sorted_refs);
 
