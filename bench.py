@@ -289,6 +289,8 @@ def main():
     ap.add_argument("--e2e-range-rows", type=int, default=8 << 20,
                     help="e2e: input rows per key range of the streaming reader (0 = one batch, no overlap)")
     ap.add_argument("--e2e-depth", type=int, default=3, help="e2e: key ranges in flight")
+    ap.add_argument("--e2e-frac", type=float, default=0.0,
+                    help="e2e: fraction of the key space to stream (0 = all of it if page-locked memory allows)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-rows", type=int, default=None)
     ap.add_argument("--cpu-threads", type=int, default=None)
@@ -452,33 +454,61 @@ def main():
     if not args.no_e2e:
         ftypes = schema.physical_types()
         # device -> pinned host copies of every input buffer (the step's inputs live in page-locked memory)
+        # Page-locked host memory is finite and every rank of the box needs its own copy of the inputs and room for
+        # the outputs: when that does not fit comfortably, the end-to-end leg streams a key-range PREFIX of the
+        # bucket (the first e2e_frac of the key space; same runs, same shape) and reports rows/s on it.
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        e2e_frac = args.e2e_frac
+        if e2e_frac <= 0:
+            try:
+                avail = next(int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable"))
+            except Exception:
+                avail = 256 << 30
+            need = (in_bytes + out_bytes * 1.05) * local_world
+            e2e_frac = 1.0 if need <= 0.5 * avail else max(0.05, 0.5 * avail / need)
+        hi_rows = [r.n_rows for r in readers]
+        e2e_rows_in, e2e_rows_out = n_in, n_out
+        if e2e_frac < 1.0 and schema.n_key == 1 and not w.get("drop_delete"):
+            cut = all_keys[0][min(int(e2e_frac * all_keys[0].numel()), all_keys[0].numel() - 1)]
+            hi_rows = [int(torch.searchsorted(k_, cut).item()) for k_ in all_keys]
+            hi_rows = [max(h, 1) for h in hi_rows]
+            e2e_rows_in = sum(hi_rows)
+            e2e_rows_out = torch.unique(torch.cat([k_[:h] for k_, h in zip(all_keys, hi_rows)])).numel()
+        else:
+            e2e_frac = 1.0
         host_runs = []
-        for r in readers:
+        e2e_out_bytes = int(out_bytes * (e2e_rows_in / max(n_in, 1)) * 1.1) if e2e_frac < 1.0 else int(out_bytes)
+        for r, hi in zip(readers, hi_rows):
             cols = []
             byptr = {tt.data_ptr(): tt for tt in r.keepalive}
             cache = {}
 
-            def to_host(ptr, byptr=byptr, cache=cache):
+            def to_host(ptr, count=None, byptr=byptr, cache=cache):
                 if not ptr:
                     return None
                 if ptr not in cache:
                     tt = byptr[ptr]
+                    if count is not None:
+                        tt = tt[:count]
                     hb = torch.empty(tt.shape, dtype=tt.dtype, pin_memory=True)
                     hb.copy_(tt)
                     cache[ptr] = hb.numpy()
                 return cache[ptr]
             for ci, dc in enumerate(r.device_columns):
                 t_ = ftypes[ci]
-                data, offs, val = to_host(dc.data), to_host(dc.offsets), to_host(dc.validity)
+                offs = to_host(dc.offsets, hi + 1)
                 if offs is not None:
-                    data = data.view(np.uint8)
-                cols.append(Column(t_, data, offs, val))
+                    data = to_host(dc.data, int(offs[hi]) + 16).view(np.uint8)
+                else:
+                    data = to_host(dc.data, hi)
+                val = to_host(dc.validity, (hi + 7) // 8 + 8)
+                cols.append(Column(t_, data[:hi] if offs is None else data, offs, val))
             host_runs.append(KeyValueBatch(schema, cols))
         torch.cuda.synchronize()
         rd.close()
         del readers, all_keys
         torch.cuda.empty_cache()
-        arena = torch.empty(int(out_bytes * 1.02) + (64 << 20), dtype=torch.uint8, pin_memory=True)
+        arena = torch.empty(int(e2e_out_bytes * 1.02) + (64 << 20), dtype=torch.uint8, pin_memory=True)
         arena_np = arena.numpy()
         e2e_times, h2d_b, d2h_b = [], 0, 0
         import threading
@@ -520,14 +550,18 @@ def main():
                 h2d_b, d2h_b = s.bytes_h2d, s.bytes_d2h
                 rows_out = out.n_rows
                 mr.close()
-            assert rows_out == n_out, (rows_out, n_out)
+            assert rows_out == e2e_rows_out, (rows_out, e2e_rows_out)
             if it_ > 0:
                 e2e_times.append(dt)
         tt = torch.tensor([sum(e2e_times) / len(e2e_times)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * n_in / float(tt.item()), "unit": "rows/s", "h2d_bytes_per_step": int(h2d_b),
+        e2e = {"value": world * e2e_rows_in / float(tt.item()), "unit": "rows/s", "h2d_bytes_per_step": int(h2d_b),
                "d2h_bytes_per_step": int(d2h_b), "ms_per_step": 1e3 * float(tt.item()), "steps": len(e2e_times),
+               "rows_in_per_step": int(e2e_rows_in), "rows_out_per_step": int(e2e_rows_out),
+               "sample": ("the whole bucket" if e2e_frac >= 1.0 else
+                          f"key-range prefix of the bucket ({e2e_frac:.2f} of the key space): page-locked host memory "
+                          f"for {local_world} ranks' full inputs + outputs was not available"),
                "api": ("RangeStreamingMergeReader(host runs).read_batch() loop over the C ABI: key ranges of "
                        f"~{args.e2e_range_rows} rows, {args.e2e_depth} in flight (H2D | merge | D2H overlap)")
                if single_key and args.e2e_range_rows > 0 else

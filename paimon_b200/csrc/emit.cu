@@ -472,6 +472,7 @@ k_emit(EmitArgs ea) {
             uint16_t *vsrc = (uint16_t *)(vals + (size_t)L.rt * 4);
             int *wpre = (int *)(vsrc + kTileMax);                                   // per warp: 33 ints
             const uint8_t **wsrc = (const uint8_t **)(wpre + ((kEmitWarps * 33 + 1) & ~1));   // 8-byte aligned
+            int *wend = (int *)(wsrc + kEmitWarps * 32);                             // per warp: 32 ints
             const uint8_t *const *cd_data = cdata + s * PG_MAX_RUNS;
             // Rows are dealt to warps in contiguous chunks of RW rows (RW a multiple of 32, aligned to the
             // output's 32-row validity words), so that offsets come from warp-level scans and the only
@@ -548,6 +549,7 @@ k_emit(EmitArgs ea) {
             // pass 2: offsets, validity, payload copy — warp-local
             int carry = ws[warp];
             int *my_pre = wpre + warp * 33;
+            int *my_end = wend + warp * 32;
             const uint8_t **my_src = wsrc + warp * 32;
             for (int ob0 = wbeg; ob0 < wbeg + RW && ob0 < n_out; ob0 += 32) {
                 const int ob = ob0 + lane;
@@ -571,17 +573,24 @@ k_emit(EmitArgs ea) {
                 if (active) oc.offsets[tv.out_base + ob] = (int32_t)(byte_base + off);
                 if (oc.validity != nullptr) put_validity_word(oc.validity, tv.out_base, ob0, n_out, has);
                 // warp-cooperative payload copy: the warp's 32 rows form one contiguous destination range;
-                // 8 lanes serve one row (so stores coalesce and short strings do not idle a whole warp), two
-                // row groups are in flight at a time and all loads are issued before the stores
-                my_pre[lane] = off;
-                my_src[lane] = sp;
-                if (lane == 31) my_pre[32] = off + len;
+                // rows without payload (NULL / empty) are squeezed out first, then 8 lanes serve one row (so
+                // stores coalesce and short strings do not idle a whole warp), two row groups are in flight at
+                // a time and all loads are issued before the stores
+                const unsigned pay = __ballot_sync(0xffffffffu, len > 0);
+                const int n_pay = __popc(pay);
+                if (len > 0) {
+                    const int ci = __popc(pay & ((1u << lane) - 1));
+                    my_pre[ci] = off;
+                    my_end[ci] = off + len;
+                    my_src[ci] = sp;
+                }
                 __syncwarp();
-#pragma unroll
-                for (int rg = 0; rg < 32; rg += 8) {
+                for (int rg = 0; rg < n_pay; rg += 8) {
                     const int ra = rg + (lane >> 3), rb = ra + 4;
-                    const int a0 = my_pre[ra], a1 = my_pre[ra + 1], b0 = my_pre[rb], b1 = my_pre[rb + 1];
-                    const uint8_t *pa = my_src[ra] - a0, *pb = my_src[rb] - b0;
+                    int a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+                    const uint8_t *pa = nullptr, *pb = nullptr;
+                    if (ra < n_pay) { a0 = my_pre[ra]; a1 = my_end[ra]; pa = my_src[ra] - a0; }
+                    if (rb < n_pay) { b0 = my_pre[rb]; b1 = my_end[rb]; pb = my_src[rb] - b0; }
                     const int ia = a0 + (lane & 7), ib = b0 + (lane & 7);
                     uint8_t xa0 = 0, xa1 = 0, xa2 = 0, xb0 = 0, xb1 = 0, xb2 = 0;
                     if (ia < a1) xa0 = pa[ia];

@@ -334,6 +334,23 @@ class SortMergeReader(RecordReader):
             self._schema_h = None
 
 
+def cut_key_ranges(keys: Sequence[np.ndarray], target_rows: int):
+    """Cut k sorted key arrays into key ranges of about `target_rows` rows in total: a list of ranges, each a
+    list of (lo, hi) row bounds per run.  Splitter keys are quantiles of a sample of all runs; a range holds
+    every row whose key lies in [splitter[j-1], splitter[j])."""
+    total = sum(len(k) for k in keys)
+    n_ranges = max(1, -(-total // max(1, int(target_rows))))
+    if n_ranges == 1 or total == 0:
+        return [[(0, len(k)) for k in keys]]
+    stride = max(1, total // (n_ranges * 64 * max(len(keys), 1)))
+    sample = np.sort(np.concatenate([k[stride - 1::stride] for k in keys if len(k)]))
+    if len(sample) == 0:
+        return [[(0, len(k)) for k in keys]]
+    cut_keys = np.unique(sample[(np.arange(1, n_ranges) * len(sample)) // n_ranges])
+    cuts = [np.concatenate([[0], np.searchsorted(k, cut_keys, side="left"), [len(k)]]) for k in keys]
+    return [[(int(c[j]), int(c[j + 1])) for c in cuts] for j in range(len(cut_keys) + 1)]
+
+
 class RangeStreamingMergeReader(RecordReader):
     """Merge of HOST-resident sorted runs that flows through the device in key ranges.
 
@@ -374,20 +391,8 @@ class RangeStreamingMergeReader(RecordReader):
         for t in self._threads:
             t.start()
 
-    # -- range cuts: per run the row where each splitter key starts
     def _cut_ranges(self, target_rows: int):
-        keys = [np.asarray(r.columns[0].data) for r in self.runs]
-        total = sum(len(k) for k in keys)
-        n_ranges = max(1, -(-total // target_rows))
-        if n_ranges == 1 or total == 0:
-            return [[(0, len(k)) for k in keys]]
-        stride = max(1, total // (n_ranges * 64 * max(len(keys), 1)))
-        sample = np.sort(np.concatenate([k[stride - 1::stride] for k in keys if len(k)]))
-        if len(sample) == 0:
-            return [[(0, len(k)) for k in keys]]
-        cut_keys = np.unique(sample[(np.arange(1, n_ranges) * len(sample)) // n_ranges])
-        cuts = [np.concatenate([[0], np.searchsorted(k, cut_keys, side="left"), [len(k)]]) for k in keys]
-        return [[(int(c[j]), int(c[j + 1])) for c in cuts] for j in range(len(cut_keys) + 1)]
+        return cut_key_ranges([np.asarray(r.columns[0].data) for r in self.runs], target_rows)
 
     def _pointer_tables(self):
         """Per run: base address / element width of every column buffer, so that a range's pg_run_desc is a few

@@ -62,3 +62,27 @@ def test_two_ranks_gloo():
         assert stats["rows_in"] == sum(1000 * (b + 1) for b in range(11))   # whole-job rows
         assert stats["buckets"] == 11
         assert stats["step_ms"] == 11.0                                      # max over ranks
+
+
+def test_cut_key_ranges_are_key_disjoint_and_cover_every_row():
+    """Host logic of the key-range streaming reader (no GPU): the ranges partition every run, and no key appears in
+    two ranges."""
+    import numpy as np
+    from paimon_b200.sort_merge_reader import cut_key_ranges
+    rng = np.random.default_rng(5)
+    keys = [np.sort(rng.choice(100000, size=n, replace=False)).astype(np.int64) for n in (5000, 1, 0, 20000, 37)]
+    for target in (100, 3000, 10 ** 9):
+        ranges = cut_key_ranges(keys, target)
+        assert all(len(r) == len(keys) for r in ranges)
+        for i, k in enumerate(keys):
+            assert ranges[0][i][0] == 0 and ranges[-1][i][1] == len(k)
+            for a, b in zip(ranges, ranges[1:]):
+                assert a[i][1] == b[i][0]
+        for a, b in zip(ranges, ranges[1:]):            # every key of range j is below every key of range j+1
+            hi = max((k[r[1] - 1] for k, r in zip(keys, a) if r[1] > r[0]), default=None)
+            lo = min((k[r[0]] for k, r in zip(keys, b) if r[1] > r[0]), default=None)
+            assert hi is None or lo is None or hi < lo
+        if target == 100:
+            assert len(ranges) > 50
+        if target == 10 ** 9:
+            assert len(ranges) == 1
