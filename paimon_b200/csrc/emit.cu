@@ -11,6 +11,8 @@
 // resolved from the other stage; validity words of column c+1 are prefetched into registers.
 // Var-len columns get their output byte offsets from a decoupled look-back over tiles (tiles are taken
 // in ticket order), so no second pass over the data is needed to size them.
+#include <stdio.h>
+
 #include "device_utils.cuh"
 
 namespace pg {
@@ -272,6 +274,13 @@ __device__ __forceinline__ void emit_fixed_column(const EmitArgs &ea, const ColD
     }
 }
 
+#ifdef PG_EMIT_TIMING
+__device__ long long g_emit_ts[64 * 256];
+#define TS(slot) do { if (tid == 0 && ts_on) g_emit_ts[(ts_tile) * 256 + (slot)] = clock64(); } while (0)
+#else
+#define TS(slot) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(kEmitThreads, 2)
 k_emit(EmitArgs ea) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -305,6 +314,11 @@ k_emit(EmitArgs ea) {
     }
     __syncthreads();
     const int tile = s_i32[0];
+#ifdef PG_EMIT_TIMING
+    const bool ts_on = tile >= 2000 && tile < 2064;
+    const int ts_tile = tile - 2000;
+#endif
+    TS(0);
     // an emit tile is two consecutive plan tiles (the last one may be single)
     const int plan_a = 2 * tile, plan_end = min(plan_a + 2, ea.n_plan_tiles);
     if (tid == 0) {
@@ -446,6 +460,7 @@ k_emit(EmitArgs ea) {
     if (tid < n_vw && ncols > 0) stage_vw[0][tid] = load_vw(ea.col_order[0]);
     __syncthreads();
 
+    TS(1);
     for (int ci = 0; ci < ncols; ci++) {
         const int s = ci & 1;
         const int c = ea.col_order[ci];
@@ -502,6 +517,7 @@ k_emit(EmitArgs ea) {
             for (int d = 16; d > 0; d >>= 1) my_bytes += __shfl_xor_sync(0xffffffffu, my_bytes, d);
             if (lane == 0) ws[warp] = my_bytes;
             __syncthreads();
+            if (ci < 60) TS(8 + 4 * ci + 0);
             // warp 0: exclusive scan of the 16 warp totals + decoupled look-back over earlier tiles
             uint64_t *state = ea.vl_state + (int64_t)cd.varlen_index * ea.n_tiles;
             if (warp == 0) {
@@ -544,6 +560,7 @@ k_emit(EmitArgs ea) {
                 }
             }
             __syncthreads();
+            if (ci < 60) TS(8 + 4 * ci + 1);
             const int64_t byte_base = s_i64[0];
             uint8_t *dbase = (uint8_t *)oc.data + byte_base;
             // pass 2: offsets, validity, payload copy — warp-local
@@ -613,8 +630,33 @@ k_emit(EmitArgs ea) {
         }
         if (cn >= 0 && tid < n_vw) stage_vw[s ^ 1][tid] = next_vw;
         __syncthreads();
+        if (ci < 60) TS(8 + 4 * ci + 3);
     }
 }
+
+#ifdef PG_EMIT_TIMING
+void emit_timing_dump() {
+    static long long h[64 * 256];
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(h, g_emit_ts, sizeof(h));
+    double acc[256] = {0};
+    int cntv[256] = {0};
+    for (int t = 0; t < 64; t++)
+        for (int sl = 1; sl < 256; sl++) {
+            if (h[t * 256 + sl] == 0) continue;
+            int pv = sl - 1;
+            while (pv > 0 && h[t * 256 + pv] == 0) pv--;
+            if (h[t * 256 + pv] == 0) continue;
+            acc[sl] += (double)(h[t * 256 + sl] - h[t * 256 + pv]);
+            cntv[sl]++;
+        }
+    fprintf(stderr, "[emit timing] cycles since previous slot (avg over tiles):");
+    for (int sl = 1; sl < 256; sl++) if (cntv[sl]) fprintf(stderr, " %d:%.0f", sl, acc[sl] / cntv[sl]);
+    fprintf(stderr, "\n");
+    static long long z[64 * 256];
+    cudaMemcpyToSymbol(g_emit_ts, z, sizeof(z));
+}
+#endif
 
 static bool g_emit_attr = false;
 void launch_emit(const EmitArgs &ea) {
@@ -624,6 +666,9 @@ void launch_emit(const EmitArgs &ea) {
         g_emit_attr = true;
     }
     k_emit<<<ea.n_tiles, kEmitThreads, L.total, ea.stream>>>(ea);
+#ifdef PG_EMIT_TIMING
+    emit_timing_dump();
+#endif
 }
 
 }  // namespace pg
