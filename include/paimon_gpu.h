@@ -226,6 +226,12 @@ pg_status pg_parquet_describe(uint64_t reader, pg_parquet_info *out);
 pg_status pg_parquet_read_run(uint64_t reader, uint64_t *out_run);
 pg_status pg_parquet_free(uint64_t reader);
 
+/* ApplyDeletionVectorReader (paimon-core/.../deletionvectors/ApplyDeletionVectorReader.java:31-54): a new run holding
+ * the rows of `run` whose file position is NOT set in the deletion vector.  `deleted_bitmap` is host memory, LSB
+ * first, bit i = row i of the file is deleted (the Java side expands its RoaringBitmap32; DeletionVector.java);
+ * positions >= n_bits are kept.  The input run stays valid. */
+pg_status pg_run_apply_deletion_vector(uint64_t run, const uint8_t *deleted_bitmap, int64_t n_bits, uint64_t *out_run);
+
 /* ---- compaction output encode: device batch -> Parquet data file ------------------------------------------
  * Replaces KeyValueDataFileWriter.write()/result() (paimon-core/.../io/KeyValueDataFileWriter.java:108-184: row
  * count, min/max key, min/max sequence number, delete row count, per-column stats -> DataFileMeta) and the

@@ -23,17 +23,7 @@ pg_status fail(pg_status code, const std::string &msg) {
     return code;
 }
 
-static int type_width(int t) {
-    switch (t) {
-        case PG_INT8: case PG_BOOL: return 1;
-        case PG_INT16: return 2;
-        case PG_INT32: case PG_FLOAT: return 4;
-        case PG_INT64: case PG_DOUBLE: return 8;
-        default: return 0;
-    }
-}
-static bool type_ok(int t) { return t >= PG_INT8 && t <= PG_BINARY; }
-static bool is_varlen(int t) { return t == PG_STRING || t == PG_BINARY; }
+
 
 // grow-only device arena with a bump pointer
 struct Arena {
@@ -234,6 +224,7 @@ static cudaStream_t copy_stream() {                   // one non-blocking copy s
 
 // hooks for the other translation units (parquet_decode.cu)
 Schema *schema_from_handle(uint64_t h) { return g_schemas.get(h); }
+Run *run_from_handle(uint64_t h) { return g_runs.get(h); }
 uint64_t register_run(std::unique_ptr<Run> run) { return g_runs.put(std::move(run)); }
 pg_status require_device() { return ensure_device(); }
 

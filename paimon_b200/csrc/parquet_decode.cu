@@ -632,6 +632,176 @@ static pg_status pq_read_run(PqReader *rd, uint64_t *out_run) {
     return PG_OK;
 }
 
+// ------------------------------------------------------------------ deletion vectors
+//
+// ApplyDeletionVectorReader (paimon-core/.../deletionvectors/ApplyDeletionVectorReader.java:31-54) skips the rows of
+// a data file whose position is marked in the file's deletion vector.  Here: a device run minus the marked rows.
+
+__global__ void k_dv_keep(const uint8_t *deleted, int64_t n_bits, int64_t n, int32_t *keep) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool del = i < n_bits && ((deleted[i >> 3] >> (i & 7)) & 1);
+    keep[i] = del ? 0 : 1;
+}
+// src[j] = input row of output row j (incl = inclusive scan of keep)
+__global__ void k_dv_sources(const int32_t *incl, int64_t n, int32_t *src) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t cur = incl[i], prev = i ? incl[i - 1] : 0;
+    if (cur != prev) src[cur - 1] = (int32_t)i;
+}
+__global__ void k_dv_gather_fixed(const void *in, int width, const int32_t *src, int64_t m, void *out) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    store_fixed(out, width, j, load_fixed(in, width, src[j]));
+}
+__global__ void k_dv_gather_bits(const uint8_t *in, const int32_t *src, int64_t m, uint32_t *out) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool v = j < m && valid_bit(in, src[j]);
+    const unsigned w = __ballot_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && j < m) out[j >> 5] = w;
+}
+__global__ void k_dv_lengths(const int32_t *offs, const int32_t *src, int64_t m, int32_t *out_offsets) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j == 0) out_offsets[0] = 0;
+    if (j >= m) return;
+    out_offsets[1 + j] = offs[src[j] + 1] - offs[src[j]];
+}
+__global__ void k_dv_copy_bytes(const uint8_t *data, const int32_t *offs, const int32_t *src, const int32_t *out_offsets,
+                                uint8_t *out, int64_t m) {
+    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    if (row >= m) return;
+    const uint8_t *s = data + offs[src[row]];
+    const int o0 = out_offsets[row], o1 = out_offsets[row + 1];
+    for (int b = o0 + (threadIdx.x & 7); b < o1; b += 8) out[b] = s[b - o0];
+}
+
+Run *run_from_handle(uint64_t h);                          // api.cu
+
+static pg_status apply_deletion_vector(uint64_t run_h, const uint8_t *deleted, int64_t n_bits, uint64_t *out_run) {
+    Run *in = run_from_handle(run_h);
+    if (!in || !out_run || (n_bits > 0 && !deleted)) return fail(PG_ERR_INVALID, "unknown run handle or null argument");
+    pg_status st = require_device();
+    if (st) return st;
+    const Schema *s = in->schema;
+    const int nc = s->n_cols();
+    const int64_t n = in->n_rows;
+    if (n_bits < 0) return fail(PG_ERR_INVALID, "negative deletion vector size");
+    auto run = std::make_unique<Run>();
+    run->own_schema = *s;
+    run->schema = &run->own_schema;
+    run->cols.resize(nc);
+    run->varlen_bytes.assign(nc, 0);
+    run->varlen_base.assign(nc, 0);
+    auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    cudaStream_t sm = 0;
+    // ---- kept rows
+    uint8_t *d_del = nullptr;
+    int32_t *d_incl = nullptr, *d_src = nullptr, *d_err = nullptr;
+    int64_t *d_sums = nullptr;
+    const int64_t nb = std::max<int64_t>((n + 4095) / 4096, 1);
+    std::vector<void *> temps;
+    auto tmp = [&](size_t bytes, void **p) -> cudaError_t {
+        cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+        if (e == cudaSuccess) temps.push_back(*p);
+        return e;
+    };
+    auto free_temps = [&]() { for (void *p : temps) cudaFree(p); };
+#define DV_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { free_temps(); for (void *q : run->owned) cudaFree(q); \
+        return fail(PG_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(_e)); } } while (0)
+    DV_CUDA(tmp((size_t)(n_bits + 7) / 8 + 16, (void **)&d_del));
+    DV_CUDA(tmp(sizeof(int32_t) * (size_t)(n + 1), (void **)&d_incl));
+    DV_CUDA(tmp(sizeof(int64_t) * (size_t)nb, (void **)&d_sums));
+    DV_CUDA(tmp(16, (void **)&d_err));
+    DV_CUDA(cudaMemsetAsync(d_err, 0, 4, sm));
+    if (n_bits > 0) DV_CUDA(cudaMemcpyAsync(d_del, deleted, (size_t)(n_bits + 7) / 8, cudaMemcpyHostToDevice, sm));
+    int64_t m = 0;
+    if (n > 0) {
+        k_dv_keep<<<(int)((n + 255) / 256), 256, 0, sm>>>(d_del, n_bits, n, d_incl);
+        k_scan_block_sums<<<(int)nb, 256, 0, sm>>>(d_incl, n, d_sums);
+        k_scan_block_prefix<<<1, 32, 0, sm>>>(d_sums, nb, d_err);
+        k_scan_apply<<<(int)nb, 256, 0, sm>>>(d_incl, n, d_sums);
+        int32_t last = 0;
+        DV_CUDA(cudaMemcpyAsync(&last, d_incl + n - 1, 4, cudaMemcpyDeviceToHost, sm));
+        DV_CUDA(cudaStreamSynchronize(sm));
+        m = last;
+    }
+    run->n_rows = m;
+    DV_CUDA(tmp(sizeof(int32_t) * (size_t)std::max<int64_t>(m, 1), (void **)&d_src));
+    if (n > 0) k_dv_sources<<<(int)((n + 255) / 256), 256, 0, sm>>>(d_incl, n, d_src);
+    // ---- one allocation for fixed-width data, offsets and validity; payloads follow once their sizes are known
+    std::vector<size_t> o_data(nc), o_off(nc), o_val(nc);
+    size_t total = 0;
+    for (int c = 0; c < nc; c++) {
+        pg_field f = s->field(c);
+        o_data[c] = total; total += is_varlen(f.type) ? 0 : pad((size_t)m * type_width(f.type) + 16);
+        o_off[c] = total; total += is_varlen(f.type) ? pad(sizeof(int32_t) * (size_t)(m + 1) + 16) : 0;
+        o_val[c] = total; total += in->cols[c].validity ? pad((size_t)((m + 31) / 32) * 4 + 16) : 0;
+    }
+    unsigned char *base = nullptr;
+    DV_CUDA(cudaMalloc(&base, total + 256));
+    run->owned.push_back(base);
+    const int gm = (int)((std::max<int64_t>(m, 1) + 255) / 256);
+    std::vector<int64_t *> sums(nc, nullptr);
+    for (int c = 0; c < nc; c++) {
+        pg_field f = s->field(c);
+        const DevColumn &ic = in->cols[c];
+        DevColumn oc;
+        if (ic.validity) {
+            oc.validity = base + o_val[c];
+            if (m > 0) k_dv_gather_bits<<<gm, 256, 0, sm>>>(ic.validity, d_src, m, (uint32_t *)(base + o_val[c]));
+        }
+        if (!is_varlen(f.type)) {
+            oc.data = base + o_data[c];
+            if (m > 0) k_dv_gather_fixed<<<gm, 256, 0, sm>>>(ic.data, type_width(f.type), d_src, m, base + o_data[c]);
+        } else {
+            int32_t *oo = (int32_t *)(base + o_off[c]);
+            oc.offsets = oo;
+            k_dv_lengths<<<gm, 256, 0, sm>>>(ic.offsets, d_src, m, oo);
+            if (m > 0) {
+                const int64_t mb = (m + 4095) / 4096;
+                DV_CUDA(tmp(sizeof(int64_t) * (size_t)mb, (void **)&sums[c]));
+                k_scan_block_sums<<<(int)mb, 256, 0, sm>>>(oo + 1, m, sums[c]);
+                k_scan_block_prefix<<<1, 32, 0, sm>>>(sums[c], mb, d_err);
+                k_scan_apply<<<(int)mb, 256, 0, sm>>>(oo + 1, m, sums[c]);
+            }
+        }
+        run->cols[c] = oc;
+    }
+    // payload sizes: one read-back for all var-len columns
+    std::vector<int32_t> totals(nc, 0);
+    for (int c = 0; c < nc; c++)
+        if (is_varlen(s->field(c).type) && m > 0)
+            DV_CUDA(cudaMemcpyAsync(&totals[c], run->cols[c].offsets + m, 4, cudaMemcpyDeviceToHost, sm));
+    int32_t herr = 0;
+    DV_CUDA(cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, sm));
+    DV_CUDA(cudaStreamSynchronize(sm));
+    size_t ptotal = 0;
+    for (int c = 0; c < nc; c++) if (is_varlen(s->field(c).type)) ptotal += pad((size_t)totals[c] + 64);
+    unsigned char *pl = nullptr;
+    if (ptotal) { DV_CUDA(cudaMalloc(&pl, ptotal)); run->owned.push_back(pl); }
+    size_t pt = 0;
+    for (int c = 0; c < nc; c++) {
+        if (!is_varlen(s->field(c).type)) continue;
+        run->cols[c].data = pl ? pl + pt : base;
+        run->varlen_bytes[c] = totals[c];
+        if (m > 0)
+            k_dv_copy_bytes<<<(int)((m * 8 + 255) / 256), 256, 0, sm>>>((const uint8_t *)in->cols[c].data, in->cols[c].offsets,
+                                                                        d_src, run->cols[c].offsets, pl + pt, m);
+        pt += pad((size_t)totals[c] + 64);
+    }
+    DV_CUDA(cudaStreamSynchronize(sm));
+    DV_CUDA(cudaGetLastError());
+    free_temps();
+#undef DV_CUDA
+    if (herr != KERR_NONE) {
+        for (void *q : run->owned) cudaFree(q);
+        return fail(PG_ERR_INTERNAL, "deletion vector: a var-len column exceeds 2 GiB of payload");
+    }
+    *out_run = register_run(std::move(run));
+    return PG_OK;
+}
+
 }  // namespace pg
 
 using namespace pg;
@@ -668,6 +838,10 @@ pg_status pg_parquet_read_run(uint64_t reader, uint64_t *out_run) {
     pg_status st = require_device();          // fails loudly without pg_init / a CUDA device: no CPU fallback
     if (st) return st;
     return pq_read_run(rd, out_run);
+}
+
+pg_status pg_run_apply_deletion_vector(uint64_t run, const uint8_t *deleted_bitmap, int64_t n_bits, uint64_t *out_run) {
+    return apply_deletion_vector(run, deleted_bitmap, n_bits, out_run);
 }
 
 pg_status pg_parquet_free(uint64_t reader) {

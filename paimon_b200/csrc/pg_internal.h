@@ -118,6 +118,18 @@ struct KeySrc {
     const int32_t *const *offsets;      // var-len fields, else NULL entries
 };
 
+inline int type_width(int t) {
+    switch (t) {
+        case PG_INT8: case PG_BOOL: return 1;
+        case PG_INT16: return 2;
+        case PG_INT32: case PG_FLOAT: return 4;
+        case PG_INT64: case PG_DOUBLE: return 8;
+        default: return 0;
+    }
+}
+static bool type_ok(int t) { return t >= PG_INT8 && t <= PG_BINARY; }
+inline bool is_varlen(int t) { return t == PG_STRING || t == PG_BINARY; }
+
 void set_error(const std::string &msg);
 pg_status fail(pg_status code, const std::string &msg);
 

@@ -146,10 +146,14 @@ class KeyValueFileReaderFactory:
     """createRecordReader(file) — KeyValueFileReaderFactory.java:119-172: format by file suffix, decode on the
     device.  (Schema evolution mappings and deletion vectors are applied on the Java side today.)"""
 
-    def __init__(self, schema: KeyValueSchema, file_io: Optional[LocalFileIO] = None, device: int = 0):
+    def __init__(self, schema: KeyValueSchema, file_io: Optional[LocalFileIO] = None, device: int = 0,
+                 dv_factory: Optional[Callable[[str], Optional[Sequence[int]]]] = None):
         self.schema = schema
         self.file_io = file_io or LocalFileIO()
         self.device = device
+        # DeletionVector.Factory (KeyValueFileReaderFactory.java:119-172 wraps the reader in
+        # ApplyDeletionVectorReader when the file has a deletion vector): file name -> deleted row positions
+        self.dv_factory = dv_factory
 
     def create_record_reader(self, meta: DataFileMeta):
         suffix = meta.file_name.rsplit(".", 1)[-1]
@@ -167,7 +171,14 @@ class MergeTreeReaders:
         out = []
         for meta in run.files:
             fr = reader_factory.create_record_reader(meta)
-            out.append((fr, fr.as_sorted_run_reader()))
+            rr = fr.as_sorted_run_reader()
+            deleted = reader_factory.dv_factory(meta.file_name) if reader_factory.dv_factory else None
+            if deleted is not None and len(deleted):
+                from .sort_merge_reader import apply_deletion_vector
+                filtered = apply_deletion_vector(reader_factory.schema, rr, deleted, device=reader_factory.device)
+                rr.close()
+                rr = filtered
+            out.append((fr, rr))
         return out
 
     @staticmethod

@@ -139,6 +139,36 @@ class SortedRunReader(RecordReader):
             self._handle = 0
 
 
+def apply_deletion_vector(schema: KeyValueSchema, reader: "SortedRunReader", deleted_positions, schema_handle: int = 0,
+                          device: int = 0) -> "SortedRunReader":
+    """ApplyDeletionVectorReader (paimon-core/.../deletionvectors/ApplyDeletionVectorReader.java:31-54): the run
+    without the rows whose file position is in `deleted_positions` (an iterable of row ordinals — what
+    DeletionVector.isDeleted answers — or a ready LSB-first bitmap as np.uint8).  Runs on the device."""
+    lib = N.init(device)
+    own = None
+    if not reader._handle:
+        own = _SchemaHandle(schema, device)
+        reader._open(own.handle)
+    try:
+        if isinstance(deleted_positions, np.ndarray) and deleted_positions.dtype == np.uint8:
+            bitmap = np.ascontiguousarray(deleted_positions)
+            n_bits = len(bitmap) * 8
+        else:
+            pos = np.asarray(sorted(set(int(p) for p in deleted_positions)), np.int64)
+            n_bits = int(pos[-1]) + 1 if len(pos) else 0
+            flags = np.zeros(n_bits, bool)
+            flags[pos] = True
+            bitmap = np.packbits(flags, bitorder="little") if n_bits else np.zeros(1, np.uint8)
+        h = C.c_uint64(0)
+        N.check(lib.pg_run_apply_deletion_vector(reader._handle, bitmap.ctypes.data, n_bits, C.byref(h)))
+        n_rows = C.c_int64(0)
+        N.check(lib.pg_run_layout(h.value, C.byref(n_rows), None, None, schema.n_cols))
+        return SortedRunReader.from_native_run(schema, int(n_rows.value), h.value, keepalive=None)
+    finally:
+        if own is not None:
+            own.close()
+
+
 def fetch_run(schema: KeyValueSchema, run_handle: int) -> KeyValueBatch:
     """Device-resident run -> host columns (pg_run_layout + pg_run_fetch)."""
     lib = N.load()

@@ -173,3 +173,65 @@ def test_merge_file_split_read_end_to_end(tmp_path):
         got = concat_batches(schema, batches)
         want = pyoracle.merge(schema, spec.create().with_drop_delete(not keep_delete), file_runs)
         assert got.equals(want), got.first_difference(want)
+
+
+def _filter_batch(schema, batch, deleted):
+    keep = np.ones(batch.n_rows, bool)
+    keep[[d for d in deleted if d < batch.n_rows]] = False
+    rows = [r for r, k in zip(batch.to_rows(), keep) if k]
+    return KeyValueBatch.from_rows(schema, rows)
+
+
+@pytest.mark.parametrize("n,frac", [(0, 0.0), (1, 1.0), (37, 0.3), (5000, 0.0), (5000, 0.5), (5000, 1.0), (70000, 0.1)])
+def test_apply_deletion_vector(n, frac):
+    """ApplyDeletionVectorReader: rows whose file position is in the deletion vector disappear
+    (paimon-core/.../deletionvectors/ApplyDeletionVectorReader.java:31-54), every column type, nulls kept."""
+    from paimon_b200.sort_merge_reader import SortedRunReader, apply_deletion_vector
+    schema = datagen.schema_c3(n_i64=2, n_f64=1, n_str=2)
+    run = datagen.make_runs(schema, 1, 2 * n, seed=13, null_prob=0.3, delete_prob=0.1)[0] if n else \
+        KeyValueBatch.from_rows(schema, [])
+    rng = np.random.default_rng(n)
+    deleted = sorted(rng.choice(run.n_rows, size=int(run.n_rows * frac), replace=False).tolist()) if run.n_rows else []
+    rd = SortedRunReader(schema, run)
+    out = apply_deletion_vector(schema, rd, deleted + [10 ** 6] if frac not in (0.0, 1.0) else deleted)
+    try:
+        got = out.read_batch()
+    finally:
+        out.close()
+        rd.close()
+    want = _filter_batch(schema, run, deleted)
+    if want.n_rows == 0:
+        assert got is None or got.n_rows == 0
+    else:
+        assert got.equals(want), got.first_difference(want)
+
+
+def test_merge_with_deletion_vectors(tmp_path):
+    """KeyValueFileReaderFactory with a DeletionVector.Factory: the merge sees the files minus their deleted rows."""
+    from paimon_b200.merge_tree_readers import (DataFileMeta, IntervalPartition, KeyValueFileReaderFactory,
+                                                MergeTreeReaders, concat_batches)
+    schema = datagen.schema_c3(n_i64=2, n_f64=1, n_str=1)
+    runs = datagen.make_runs(schema, 4, 8000, seed=6, null_prob=0.3)
+    rng = np.random.default_rng(3)
+    metas, dvs, filtered = [], {}, []
+    for i, run in enumerate(runs):
+        path = str(tmp_path / f"f{i}.parquet")
+        write_kv_parquet(run, path)
+        k = run.columns[0].data
+        metas.append(DataFileMeta(path, 0, run.n_rows, int(k[0]), int(k[-1])))
+        dvs[path] = sorted(rng.choice(run.n_rows, size=run.n_rows // (i + 2), replace=False).tolist()) if i != 2 else None
+        filtered.append(_filter_batch(schema, run, dvs[path] or []))
+    factory = KeyValueFileReaderFactory(schema, dv_factory=lambda name: dvs[name])
+    spec = DeduplicateMergeFunction.factory().create()
+    sections = IntervalPartition(metas).partition()
+    rd = MergeTreeReaders.reader_for_merge_tree(sections, factory, None, spec)
+    batches = []
+    while True:
+        b = rd.read_batch()
+        if b is None:
+            break
+        batches.append(b)
+    rd.close()
+    got = concat_batches(schema, batches)
+    want = pyoracle.merge(schema, spec, filtered)
+    assert got.equals(want), got.first_difference(want)
