@@ -536,3 +536,17 @@ def test_range_streaming_equals_single_batch(engine, target_rows, depth):
     assert got.equals(want), got.first_difference(want)
     for a, b in zip(batches, batches[1:]):          # key-disjoint and ascending
         assert a.columns[0].data[a.n_rows - 1] < b.columns[0].data[0]
+
+
+def test_device_matches_golden_file():
+    """The committed golden vectors (reference test inputs + the reference calculators' results), through the C ABI."""
+    from golden_util import load_cases, records, spec_for
+    from reusing_test_data import from_batch
+    n = 0
+    for case in load_cases():
+        runs = [to_batch(records(r)) for r in case["readers"]]
+        for name, want in case["expected"].items():
+            got = merge_runs(SCHEMA, spec_for(name), runs)
+            assert from_batch(got) == records(want), (case["name"], name)
+            n += 1
+    assert n >= 100

@@ -521,3 +521,31 @@ def test_interval_partition_random_properties():      # IntervalPartitionTest.te
             for r in s:                               # files inside a run do not overlap
                 for a, b in zip(r, r[1:]):
                     assert a[1] < b[0]
+
+
+# ---------------------------------------------------------------- committed golden file
+
+def test_golden_file_is_current():
+    """tests/golden/sort_merge_reader_vectors.json is what tests/golden/make_golden.py writes."""
+    import json
+    import subprocess
+    import sys
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    before = open(os.path.join(here, "golden", "sort_merge_reader_vectors.json")).read()
+    subprocess.check_call([sys.executable, os.path.join(here, "golden", "make_golden.py")], stdout=subprocess.DEVNULL)
+    assert open(os.path.join(here, "golden", "sort_merge_reader_vectors.json")).read() == before
+    assert len(json.loads(before)["cases"]) == 25
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_oracle_matches_golden_file(engine):
+    from golden_util import load_cases, records, spec_for
+    n = 0
+    for case in load_cases():
+        readers = [records(r) for r in case["readers"]]
+        for name, want in case["expected"].items():
+            got = run_merge(readers, spec_for(name), engine)
+            assert got == records(want), (case["name"], name)
+            n += 1
+    assert n >= 100
