@@ -183,6 +183,13 @@ JNIEXPORT jlong JNICALL Java_org_apache_paimon_gpu_NativeMerge_parquetReadRun(JN
     PG_CHECK(pg_parquet_read_run((uint64_t)file, &run));
     return (jlong)run;
 }
+// ApplyDeletionVectorReader: the run minus the rows whose file position is set in the (expanded) deletion vector
+JNIEXPORT jlong JNICALL Java_org_apache_paimon_gpu_NativeMerge_applyDeletionVector(JNIEnv *env, jclass, jlong run,
+                                                                                   jobject bitmap, jlong nBits) {
+    uint64_t out = 0;
+    PG_CHECK(pg_run_apply_deletion_vector((uint64_t)run, (const uint8_t *)env->GetDirectBufferAddress(bitmap), nBits, &out));
+    return (jlong)out;
+}
 JNIEXPORT jint JNICALL Java_org_apache_paimon_gpu_NativeMerge_parquetFree(JNIEnv *env, jclass, jlong file) {
     PG_CHECK(pg_parquet_free((uint64_t)file));
     return 0;

@@ -453,7 +453,7 @@ struct PlanSmemExtra {
     uint8_t *res_kind;    // per head position: result RowKind
     int *ws;              // 33 ints scan scratch
 };
-constexpr size_t kPlanSmem = kTileSmem + (size_t)kPlanTile * 3 + 34 * 4 + 16;
+constexpr size_t kPlanSmem = kTileSmem + (size_t)kPlanTile * 3 + 34 * 4 + kPlanTile / 8 + 16;
 
 template <bool EXACT>
 __global__ void __launch_bounds__(kThreads, 4)
@@ -465,6 +465,7 @@ k_plan(int k, KeyDesc kd, KeySrc ks, PlanArgs pa, int32_t *err) {
     px.res_slot = (uint16_t *)(smem + ((kTileSmem + 15) & ~(size_t)15));
     px.res_kind = (uint8_t *)(px.res_slot + kPlanTile);
     px.ws = (int *)(px.res_kind + kPlanTile);
+    uint8_t *head_bits = (uint8_t *)(px.ws + 34);            // bit i: merged position i starts a key group
 
     const int tile = blockIdx.x, tid = threadIdx.x;
     if (!merge_tile<EXACT>(tc, k, kd, ks, pa.bounds, tile, 1, nullptr, err, 0, true)) {
@@ -507,11 +508,22 @@ k_plan(int k, KeyDesc kd, KeySrc ks, PlanArgs pa, int32_t *err) {
     const MergeFlags fl = pa.flags;
     int my_emit = 0;
 
+    // group heads first, for every position, BEFORE any group is re-ordered: same_key() of a non-exact key reads
+    // the slots of both positions, and the position in front of a head belongs to another thread's group
+    static_assert(kPlanTile / kThreads == 8, "one byte of head bits per thread");
+    {
+        uint32_t hb = 0;
+        for (int i = p0; i < p1; i++)
+            if (i == 0 || !same_key(i - 1, i)) hb |= 1u << (i - p0);
+        head_bits[tid] = (uint8_t)hb;
+    }
+    __syncthreads();
+    auto is_head = [&](int i) -> bool { return (head_bits[i >> 3] >> (i & 7)) & 1; };
+
     for (int i = p0; i < p1; i++) {
-        bool head = (i == 0) || !same_key(i - 1, i);
-        if (!head) continue;
+        if (!is_head(i)) continue;
         int e = i + 1;
-        while (e < n && same_key(i, e)) e++;
+        while (e < n && !is_head(e)) e++;
         const int g = e - i;
         // members in ascending sequence order (SortMergeReaderWithLoserTree.java:52-65); ties (which the
         // reference leaves unspecified) resolve by run order = slot order
@@ -669,7 +681,7 @@ k_plan(int k, KeyDesc kd, KeySrc ks, PlanArgs pa, int32_t *err) {
     int total = 0;
     int o = block_scan_excl(my_emit, px.ws, &total);
     for (int i = p0; i < p1; i++) {
-        bool head = (i == 0) || !same_key(i - 1, i);
+        const bool head = is_head(i);
         uint16_t entry = (uint16_t)(fi[PADI(i)] | (ops[i] << kPlanOpShift));
         if (head) {
             entry |= kPlanHead;

@@ -285,6 +285,77 @@ k_pq_assemble(const PqPageJob *jobs, const PqDictJob *dicts, const PqCol *cols, 
     }
 }
 
+// ---- Snappy page decompression (parquet-mr hands compressed pages to snappy-java 1.1.10.8; the format restated
+// here is the public Snappy format description: a varint uncompressed length, then literal and copy elements).
+// One warp per page: the element stream is parsed by all lanes in lock step, the bytes of a literal / copy are
+// moved lane-parallel.  A copy may overlap its own output (offset < length): byte i comes from
+// out - offset + (i mod offset), which always lies in front of the copy.
+struct SnappyJob {
+    const uint8_t *src;       // device: [prefix bytes copied verbatim (data page V2 levels)][snappy stream]
+    uint8_t *dst;
+    int32_t src_len, dst_len, prefix, pad;
+};
+__global__ void k_pq_snappy(const SnappyJob *jobs, int n_jobs, int32_t *err) {
+    const int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (w >= n_jobs) return;
+    const SnappyJob j = jobs[w];
+    for (int i = lane; i < j.prefix; i += 32) j.dst[i] = j.src[i];
+    const uint8_t *src = j.src + j.prefix;
+    uint8_t *dst = j.dst + j.prefix;
+    const int n_src = j.src_len - j.prefix, n_dst = j.dst_len - j.prefix;
+    int pos = 0, out = 0;
+    // preamble: uncompressed length
+    uint32_t ulen = 0;
+    for (int sh = 0; pos < n_src && sh < 35; sh += 7) {
+        const uint8_t b = src[pos++];
+        ulen |= (uint32_t)(b & 0x7f) << sh;
+        if (!(b & 0x80)) break;
+    }
+    bool bad = (int)ulen != n_dst;
+    while (!bad && pos < n_src) {
+        const uint32_t tag = src[pos];
+        int len, offset = 0;
+        if ((tag & 3) == 0) {
+            len = (int)(tag >> 2) + 1;
+            pos += 1;
+            if (len > 60) {
+                const int extra = len - 60;
+                if (pos + extra > n_src) { bad = true; break; }
+                len = 0;
+                for (int b = 0; b < extra; b++) len |= (int)src[pos + b] << (8 * b);
+                len += 1;
+                pos += extra;
+            }
+            if (len < 0 || pos + len > n_src || out + len > n_dst) { bad = true; break; }
+            for (int i = lane; i < len; i += 32) dst[out + i] = src[pos + i];
+            pos += len;
+        } else {
+            if ((tag & 3) == 1) {
+                if (pos + 2 > n_src) { bad = true; break; }
+                len = 4 + (int)((tag >> 2) & 7);
+                offset = (int)((tag >> 5) << 8) | src[pos + 1];
+                pos += 2;
+            } else if ((tag & 3) == 2) {
+                if (pos + 3 > n_src) { bad = true; break; }
+                len = 1 + (int)(tag >> 2);
+                offset = src[pos + 1] | (src[pos + 2] << 8);
+                pos += 3;
+            } else {
+                if (pos + 5 > n_src) { bad = true; break; }
+                len = 1 + (int)(tag >> 2);
+                offset = (int)(src[pos + 1] | (src[pos + 2] << 8) | (src[pos + 3] << 16) | ((uint32_t)src[pos + 4] << 24));
+                pos += 5;
+            }
+            if (offset <= 0 || offset > out || out + len > n_dst) { bad = true; break; }
+            const uint8_t *from = dst + out - offset;
+            for (int i = lane; i < len; i += 32) dst[out + i] = from[i % offset];
+        }
+        out += len;
+        __syncwarp();                                    // later copies may read what other lanes just wrote
+    }
+    if ((bad || out != n_dst) && lane == 0) atomicCAS(err, KERR_NONE, KERR_BAD_PAGE);
+}
+
 // ---- device-wide inclusive scan of int32 (three small kernels; offsets of one var-len column)
 __global__ void k_scan_block_sums(const int32_t *data, int64_t n, int64_t *block_sums) {
     __shared__ int64_t sh[256];
@@ -338,6 +409,11 @@ struct PqReader {
     std::vector<int64_t> dict_entries_per_col;
     int64_t n_rows = 0;
     int64_t dict_entries = 0;
+    // compressed page bodies (Snappy), decompressed on the device before the decode kernels run
+    struct Unc { int64_t src_off; int32_t src_len, dst_len, prefix; int64_t dst_off; };
+    std::vector<Unc> unc;
+    std::vector<int32_t> job_unc, dict_unc;    // per page / dictionary job: index into unc, -1 = stored uncompressed
+    int64_t unc_bytes = 0;
     float ms_decode = 0;
     int launches = 0;
 };
@@ -404,9 +480,19 @@ static pg_status pq_open(uint64_t schema_h, const uint8_t *bytes, int64_t size, 
         if ((int)g.columns.size() != nc) return fail(PG_ERR_FORMAT, "parquet: row group with a different column count");
         for (int c = 0; c < nc; c++) {
             const pq::ColumnChunk &cc = g.columns[c];
-            if (cc.codec != pq::C_UNCOMPRESSED)
-                return fail(PG_ERR_UNSUPPORTED, "parquet: compressed pages (codec " + std::to_string(cc.codec) +
-                                                ") are not decoded on device yet; write with 'file.compression'='none'");
+            if (cc.codec != pq::C_UNCOMPRESSED && cc.codec != pq::C_SNAPPY)
+                return fail(PG_ERR_UNSUPPORTED, "parquet: compression codec " + std::to_string(cc.codec) +
+                                                " is not decoded on device (UNCOMPRESSED and SNAPPY are); write with "
+                                                "'file.compression'='none' / 'snappy' or let the Java side decompress");
+            const bool snappy = cc.codec == pq::C_SNAPPY;
+            // returns the index of the decompression item of a page body, or -1 when it is stored as is
+            auto add_unc = [&](int64_t body, const pq::PageHeader &h, int32_t prefix, bool compressed) -> int32_t {
+                if (!snappy || !compressed) return -1;
+                PqReader::Unc u{body, h.compressed_size, h.uncompressed_size, prefix, rd->unc_bytes};
+                rd->unc_bytes += ((int64_t)h.uncompressed_size + 63) & ~(int64_t)63;
+                rd->unc.push_back(u);
+                return (int32_t)rd->unc.size() - 1;
+            };
             const int max_def = m.schema[c + 1].repetition == pq::R_OPTIONAL ? 1 : 0;
             int64_t pos = cc.start(), vals = 0, page_row = row0;
             int dict_index = -1;
@@ -431,6 +517,8 @@ static pg_status pq_open(uint64_t schema_h, const uint8_t *bytes, int64_t size, 
                     dj.entry_base = rd->dict_entries;
                     if (cc.type == pq::T_BYTE_ARRAY) rd->dict_entries += h.num_values;
                     dict_index = (int)rd->dicts.size();
+                    rd->dict_unc.push_back(add_unc(body, h, 0, true));
+                    if (rd->dict_unc.back() >= 0) dj.body_len = h.uncompressed_size;
                     rd->dicts.push_back(dj);
                 } else if (h.type == pq::P_DATA || h.type == pq::P_DATA_V2) {
                     bool is_dict = h.encoding == pq::E_PLAIN_DICTIONARY || h.encoding == pq::E_RLE_DICTIONARY;
@@ -451,6 +539,11 @@ static pg_status pq_open(uint64_t schema_h, const uint8_t *bytes, int64_t size, 
                     pj.v2_def_len = h.def_levels_byte_length;
                     pj.dict = is_dict ? dict_index : -1;
                     pj.row0 = page_row;
+                    // V1: the whole body (levels + values) is one compressed block; V2: the levels stay as they
+                    // are in front of the (optionally) compressed values
+                    const int32_t prefix = h.type == pq::P_DATA_V2 ? h.def_levels_byte_length + h.rep_levels_byte_length : 0;
+                    rd->job_unc.push_back(add_unc(body, h, prefix, h.type == pq::P_DATA_V2 ? h.is_compressed : true));
+                    if (rd->job_unc.back() >= 0) pj.body_len = h.uncompressed_size;
                     rd->jobs.push_back(pj);
                     page_row += h.num_values;
                     vals += h.num_values;
@@ -486,7 +579,8 @@ static pg_status pq_read_run(PqReader *rd, uint64_t *out_run) {
     size_t scratch = pad(rd->file.size() + 64) + pad(sizeof(PqPageJob) * rd->jobs.size() + 64) +
                      pad(sizeof(PqDictJob) * rd->dicts.size() + 64) + pad(sizeof(PqCol) * nc) +
                      pad(sizeof(PqPageState) * rd->jobs.size() + 64) + pad(sizeof(void *) * (rd->dict_entries + 1)) +
-                     pad(4 * (rd->dict_entries + 1)) + 4096;
+                     pad(4 * (rd->dict_entries + 1)) + 4096 + pad((size_t)rd->unc_bytes + 64) +
+                     pad(sizeof(SnappyJob) * rd->unc.size() + 64) + 256;
     size_t outb = 4096;
     std::vector<PqCol> cols(nc);
     for (int c = 0; c < nc; c++) {
@@ -524,6 +618,27 @@ static pg_status pq_read_run(PqReader *rd, uint64_t *out_run) {
     std::vector<PqDictJob> dicts = rd->dicts;
     for (auto &j : jobs) j.body = d_file + (uintptr_t)j.body;
     for (auto &d : dicts) d.body = d_file + (uintptr_t)d.body;
+    int32_t *d_err_early = nullptr;
+    if (!rd->unc.empty()) {
+        // Snappy pages: one warp per page decompresses into a scratch image the decode kernels then read
+        uint8_t *d_unc = stake((size_t)rd->unc_bytes + 64);
+        SnappyJob *d_sj = (SnappyJob *)stake(sizeof(SnappyJob) * rd->unc.size());
+        d_err_early = (int32_t *)stake(16);
+        std::vector<SnappyJob> sj(rd->unc.size());
+        for (size_t i = 0; i < sj.size(); i++) {
+            const PqReader::Unc &u = rd->unc[i];
+            sj[i] = SnappyJob{d_file + u.src_off, d_unc + u.dst_off, u.src_len, u.dst_len, u.prefix, 0};
+        }
+        PG_CUDA(cudaMemsetAsync(d_err_early, 0, 4, sm));
+        PG_CUDA(cudaMemcpyAsync(d_sj, sj.data(), sizeof(SnappyJob) * sj.size(), cudaMemcpyHostToDevice, sm));
+        PG_CUDA(cudaStreamSynchronize(sm));           // sj is a local vector
+        const int64_t threads = (int64_t)sj.size() * 32;
+        k_pq_snappy<<<(int)((threads + 127) / 128), 128, 0, sm>>>(d_sj, (int)sj.size(), d_err_early);
+        for (size_t i = 0; i < jobs.size(); i++)
+            if (rd->job_unc[i] >= 0) jobs[i].body = d_unc + rd->unc[rd->job_unc[i]].dst_off;
+        for (size_t i = 0; i < dicts.size(); i++)
+            if (rd->dict_unc[i] >= 0) dicts[i].body = d_unc + rd->unc[rd->dict_unc[i]].dst_off;
+    }
     PqPageJob *d_jobs = (PqPageJob *)stake(sizeof(PqPageJob) * jobs.size() + 64);
     PqDictJob *d_dicts = (PqDictJob *)stake(sizeof(PqDictJob) * dicts.size() + 64);
     PqCol *d_cols = (PqCol *)stake(sizeof(PqCol) * nc);
@@ -610,12 +725,18 @@ static pg_status pq_read_run(PqReader *rd, uint64_t *out_run) {
     PG_CUDA(cudaEventRecord(e1, sm));
     int32_t herr = 0;
     PG_CUDA(cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, sm));
+    int32_t herr_pages = 0;
+    if (d_err_early) PG_CUDA(cudaMemcpyAsync(&herr_pages, d_err_early, 4, cudaMemcpyDeviceToHost, sm));
     PG_CUDA(cudaStreamSynchronize(sm));
     PG_CUDA(cudaGetLastError());
     cudaEventElapsedTime(&rd->ms_decode, e0, e1);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     rd->launches = launches;
+    if (herr_pages != KERR_NONE) {
+        for (void *p : run->owned) cudaFree(p);
+        return fail(PG_ERR_FORMAT, "parquet: a Snappy page does not decompress to its declared size");
+    }
     if (herr != KERR_NONE) {
         for (void *p : run->owned) cudaFree(p);
         return fail(PG_ERR_INTERNAL, "parquet: a var-len column exceeds 2 GiB of payload");

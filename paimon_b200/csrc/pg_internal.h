@@ -35,7 +35,8 @@ enum : int {
     KERR_FIRST_ROW_RETRACT = 3,      // FirstRowMergeFunction.java:56-60
     KERR_AGG_RETRACT = 4,            // FieldAggregator.java:47-54
     KERR_OFFSET_OVERFLOW = 5,        // a var-len output column exceeds int32 offsets
-    KERR_DIV_ZERO = 6                // FieldProductAgg retract: integer division by zero
+    KERR_DIV_ZERO = 6,               // FieldProductAgg retract: integer division by zero
+    KERR_BAD_PAGE = 7                // a compressed Parquet page does not decompress to its declared size
 };
 
 struct Schema {

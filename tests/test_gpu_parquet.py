@@ -53,6 +53,9 @@ WRITER_OPTS = [
     dict(row_group_size=10),
     dict(row_group_size=1000, data_page_size=512),
     dict(data_page_size=256, dictionary_pagesize_limit=512),       # dictionary overflow -> PLAIN fallback pages
+    dict(compression="snappy"),                                    # Snappy pages are decompressed on the device
+    dict(compression="snappy", use_dictionary=False, data_page_version="2.0"),
+    dict(compression="snappy", row_group_size=1000, data_page_size=512),
 ]
 
 
@@ -132,6 +135,31 @@ def test_fused_decode_then_merge_matches_oracle(tmp_path, engine):
 def test_unsupported_format_is_refused():
     with pytest.raises(N.UnsupportedOnDevice):
         FileFormat.from_identifier("orc")
+
+
+def test_unsupported_codec_is_refused(tmp_path):
+    """zstd / gzip pages are not decoded on the device: refused when the file is opened, no CPU fallback."""
+    schema = datagen.schema_c2()
+    run = datagen.make_runs(schema, 1, 200, seed=2)[0]
+    path = str(tmp_path / "z.parquet")
+    write_kv_parquet(run, path, compression="zstd")
+    with pytest.raises(N.UnsupportedOnDevice):
+        decode(schema, path)
+
+
+def test_snappy_large_pages_and_long_matches(tmp_path):
+    """Snappy streams with long literals, long and overlapping copies (runs of equal bytes), several pages."""
+    vt = RowType((DataField("pk", "BIGINT", False), DataField("s", "STRING", True), DataField("z", "BIGINT", True)))
+    schema = KeyValueSchema.of(vt, ["pk"])
+    rows = []
+    for k in range(30000):
+        text = ("a" * (k % 300)) + ("xyz" * (k % 17)) + str(k * 7919 % 1000003)
+        rows.append((k, k, 0, k, None if k % 11 == 0 else text, 0 if k % 3 else k))
+    batch = KeyValueBatch.from_rows(schema, rows)
+    for opts in (dict(compression="snappy", use_dictionary=False),
+                 dict(compression="snappy", use_dictionary=False, data_page_version="2.0", data_page_size=1 << 16),
+                 dict(compression="snappy")):
+        check_file(schema, batch, str(tmp_path / "snappy.parquet"), **opts)
 
 
 def test_merge_file_split_read_end_to_end(tmp_path):
