@@ -530,22 +530,40 @@ k_emit(EmitArgs ea) {
                     __threadfence();
                     atomicExch((unsigned long long *)&state[tile], kFlagAgg | (uint64_t)tile_bytes);
                 }
+                // The CTAs of a wave reach a column at about the same time, so the nearest tile that already knows
+                // its prefix is usually a whole wave (~300 tiles) back: every lane looks at kLook consecutive
+                // predecessors per step (all loads of a step are independent).
+                constexpr int kLook = 8;
                 int t = tile - 1;
                 while (t >= 0) {
-                    int idx = t - lane;
-                    uint64_t sv = idx >= 0 ? *((volatile uint64_t *)&state[idx]) : kFlagPrefix;
-                    unsigned flag = (unsigned)(sv >> 62);
-                    unsigned inval = __ballot_sync(0xffffffffu, flag == 0);
-                    unsigned pref = __ballot_sync(0xffffffffu, flag == 2);
-                    int first = pref ? __ffs(pref) - 1 : 32;
-                    unsigned need = first >= 31 ? 0xffffffffu : ((1u << (first + 1)) - 1);
-                    if (inval & need) continue;                      // a needed predecessor has not published yet
-                    uint64_t contrib = lane <= first ? (sv & kValMask) : 0;
+                    uint64_t sv[kLook];
+#pragma unroll
+                    for (int q = 0; q < kLook; q++) {
+                        const int idx = t - (lane * kLook + q);
+                        sv[q] = idx >= 0 ? *((volatile uint64_t *)&state[idx]) : kFlagPrefix;
+                    }
+                    // position p = lane * kLook + q (0 = nearest predecessor): first prefix, nothing unpublished in front
+                    int lp = 32 * kLook;
+#pragma unroll
+                    for (int q = kLook - 1; q >= 0; q--) if ((unsigned)(sv[q] >> 62) == 2) lp = lane * kLook + q;
+                    int first = lp;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, d));
+                    bool inval = false;
+                    uint64_t contrib = 0;
+#pragma unroll
+                    for (int q = 0; q < kLook; q++) {
+                        if (lane * kLook + q <= first) {
+                            if ((unsigned)(sv[q] >> 62) == 0) inval = true;
+                            contrib += sv[q] & kValMask;
+                        }
+                    }
+                    if (__any_sync(0xffffffffu, inval)) continue;      // a needed predecessor has not published yet
 #pragma unroll
                     for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
                     excl += contrib;
-                    if (first < 32) break;
-                    t -= 32;
+                    if (first < 32 * kLook) break;
+                    t -= 32 * kLook;
                 }
                 if (lane == 0) {
                     __threadfence();
