@@ -80,6 +80,7 @@ struct Merge {
     int32_t *d_tile_counter = nullptr;
     int32_t *d_col_order = nullptr;
     const SeqGroups *d_groups = nullptr;
+    bool has_group_aggs = false;
     pg_out_column *d_out_cols = nullptr;
     int64_t *d_totals = nullptr;       // [1 + n_varlen]
     int32_t *d_err = nullptr;
@@ -360,7 +361,8 @@ static pg_status build_descriptors(Merge *m) {
                 cd.nullable = 1;
                 cd.retract = ign ? RT_IGNORE : (agg_supports_retract(agg) ? RT_OK : RT_ERROR);
             } else {
-                if (sp->engine == PG_ENGINE_PARTIAL_UPDATE && agg != PG_AGG_NONE &&
+                const bool in_group = sp->n_groups() > 0 && sp->field_group[vi] >= 0;
+                if (sp->engine == PG_ENGINE_PARTIAL_UPDATE && !in_group && agg != PG_AGG_NONE &&
                     agg != PG_AGG_LAST_NON_NULL_VALUE && agg != PG_AGG_PRIMARY_KEY)
                     return fail(PG_ERR_INVALID, "Must use sequence group for aggregation functions");
                 cd.mode = CM_SELECT;
@@ -372,6 +374,14 @@ static pg_status build_descriptors(Merge *m) {
                     cd.mode = is_seq ? CM_GSEQ : CM_GVAL;
                     cd.agg = g;
                     cd.nullable = 1;                // a retract NULLs the group's fields whatever the schema says
+                    if (!is_seq && agg != PG_AGG_NONE) {
+                        // a group field with an aggregate function (PartialUpdateMergeFunction.java:228-244)
+                        cd.mode = CM_GAGG;
+                        cd.agg = agg;
+                        cd.group = g;
+                        cd.retract = ign ? RT_IGNORE : (agg_supports_retract(agg) ? RT_OK : RT_ERROR);
+                        m->has_group_aggs = true;
+                    }
                 }
             }
         }
@@ -551,7 +561,7 @@ static pg_status execute(Merge *m) {
         int64_t skipped = 0;                      // plan-sized arrays are indexed by sums of absolute rows
         for (int r = 0; r < k; r++) skipped += m->row0[r];
         const size_t N_ = (size_t)(m->n_in + skipped), T_ = (size_t)n_tiles[0];
-        add(2 * N_ + 16); add(m->d_groups ? 4 * N_ + 16 : 16); add(4 * T_); add(8 * N_ + 16); add(N_ + 16); add(8 * T_); add(8 * T_ * std::max(nv, 1));
+        add(2 * N_ + 16); add(m->d_groups ? 4 * N_ + 16 : 16); add(m->has_group_aggs ? 4 * N_ + 16 : 16); add(4 * T_); add(8 * N_ + 16); add(N_ + 16); add(8 * T_); add(8 * T_ * std::max(nv, 1));
         PG_CUDA(m->work.reserve(need));
     }
     auto talloc = [&](size_t bytes, void **out) -> cudaError_t {
@@ -603,6 +613,8 @@ static pg_status execute(Merge *m) {
     PG_CUDA(talloc(sizeof(uint16_t) * (size_t)N + 16, (void **)&plan));
     uint32_t *gplan = nullptr;
     if (m->d_groups) PG_CUDA(talloc(sizeof(uint32_t) * (size_t)N + 16, (void **)&gplan));
+    uint32_t *gagg = nullptr;
+    if (m->has_group_aggs) PG_CUDA(talloc(sizeof(uint32_t) * (size_t)N + 16, (void **)&gagg));
     PG_CUDA(talloc(sizeof(int32_t) * (size_t)T, (void **)&tile_rows));
     PG_CUDA(talloc(sizeof(int64_t) * (size_t)N + 16, (void **)&tmp_seq));
     PG_CUDA(talloc((size_t)N + 16, (void **)&tmp_kind));
@@ -625,6 +637,7 @@ static pg_status execute(Merge *m) {
     pa.tmp_kind = tmp_kind;
     pa.groups = m->d_groups;
     pa.gplan = gplan;
+    pa.gagg = gagg;
     launch_plan(ml, pa);
     launch_scan(sm, tile_rows, T, row_base, m->d_totals);
     launches += 2;
@@ -708,6 +721,7 @@ static pg_status execute(Merge *m) {
     ea.tmp_seq = tmp_seq;
     ea.tmp_kind = tmp_kind;
     ea.gplan = gplan;
+    ea.gagg = gagg;
     ea.cols = m->d_cols;
     ea.col_order = m->d_col_order;
     ea.ptrs = m->d_ptrs;
@@ -856,9 +870,20 @@ pg_status pg_merge_spec_create(uint64_t schema, const pg_merge_spec *spec, uint6
         for (int f = 0; f < s->n_val; f++) {
             if (sp->field_group[f] < -1 || sp->field_group[f] >= ng)
                 return fail(PG_ERR_INVALID, "field_group out of range");
-            if (sp->field_group[f] >= 0 && !sp->agg.empty() && sp->agg[f] != PG_AGG_NONE)
-                return fail(PG_ERR_UNSUPPORTED, "aggregate functions inside a sequence group are not implemented "
-                                                "on the device");
+            if (sp->field_group[f] >= 0 && !sp->agg.empty() && sp->agg[f] != PG_AGG_NONE) {
+                const int agg = sp->agg[f], t = s->val_fields[f].type;
+                if (is_varlen(t))
+                    return fail(PG_ERR_UNSUPPORTED, "aggregate functions on var-len fields inside a sequence group "
+                                                    "are not implemented on the device");
+                if (agg < PG_AGG_SUM || agg > PG_AGG_PRIMARY_KEY)
+                    return fail(PG_ERR_UNSUPPORTED, "aggregate function not implemented on the device");
+                const bool numeric = t == PG_INT8 || t == PG_INT16 || t == PG_INT32 || t == PG_INT64 ||
+                                     t == PG_FLOAT || t == PG_DOUBLE;
+                if ((agg == PG_AGG_SUM || agg == PG_AGG_PRODUCT) && !numeric)
+                    return fail(PG_ERR_INVALID, "sum/product need a numeric column");
+                if ((agg == PG_AGG_BOOL_AND || agg == PG_AGG_BOOL_OR) && t != PG_BOOL)
+                    return fail(PG_ERR_INVALID, "bool_and/bool_or need a BOOLEAN column");
+            }
         }
     }
     if (sp->engine == PG_ENGINE_PARTIAL_UPDATE && sp->ignore_delete && sp->remove_record_on_delete)

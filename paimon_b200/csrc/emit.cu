@@ -63,6 +63,8 @@ __device__ __forceinline__ int select_pos(const uint16_t *pm, const uint32_t *vw
     while (true) {
         uint32_t e = pm[j];
         uint32_t op = (e >> kPmOpShift) & 3;
+        // a RETRACT member leaves select columns alone, unless it is the group's first record (initRow: verbatim)
+        if (op == OP_RETRACT) op = (e & kPmHead) ? OP_SET : OP_NOOP;
         if (op != OP_NOOP) {
             int pj = e & kPmPosMask;
             if (staged_valid(vw, pj)) return pj;
@@ -78,6 +80,7 @@ __device__ __forceinline__ int select_member_idx(const uint16_t *pm, const uint3
     while (true) {
         uint32_t e = pm[j];
         uint32_t op = (e >> kPmOpShift) & 3;
+        if (op == OP_RETRACT) op = (e & kPmHead) ? OP_SET : OP_NOOP;
         if (op != OP_NOOP) {
             if (staged_valid(vw, e & kPmPosMask)) return j;
             if (op == OP_SET) return -1;
@@ -209,6 +212,91 @@ __device__ void fold_fixed(const ColDesc &cd, const uint16_t *pm, const uint32_t
     *out_valid = is_valid;
 }
 
+// agg(accumulator = a, input = b) of a fixed-width aggregator as a function of both operands, so that
+// aggReversed(acc, in) = agg(in, acc) (FieldAggregator.java:40-42) can be evaluated too
+__device__ void agg_pair(const ColDesc &cd, uint64_t a, bool av, uint64_t b, bool bv, bool *initialized,
+                         uint64_t *out, bool *out_valid, int32_t *err) {
+    const int w = cd.width;
+    switch (cd.agg) {
+        case PG_AGG_SUM: case PG_AGG_PRODUCT:
+            if (!av || !bv) { *out = av ? a : b; *out_valid = av || bv; }
+            else { *out = arith(cd.type, w, cd.agg == PG_AGG_SUM ? 0 : 2, a, b, err); *out_valid = true; }
+            return;
+        case PG_AGG_MAX: case PG_AGG_MIN:
+            if (!av || !bv) { *out = av ? a : b; *out_valid = av || bv; return; }
+            {
+                const int d = compare_fixed(cd.type, w, a, b);
+                const bool take_b = cd.agg == PG_AGG_MAX ? d < 0 : !(d < 0);
+                *out = take_b ? b : a; *out_valid = true;
+            }
+            return;
+        case PG_AGG_BOOL_AND: case PG_AGG_BOOL_OR:
+            if (!av || !bv) { *out = av ? a : b; *out_valid = av || bv; return; }
+            *out = cd.agg == PG_AGG_BOOL_AND ? ((a != 0) && (b != 0)) : ((a != 0) || (b != 0));
+            *out_valid = true;
+            return;
+        case PG_AGG_LAST_VALUE: case PG_AGG_PRIMARY_KEY: *out = b; *out_valid = bv; return;
+        case PG_AGG_LAST_NON_NULL_VALUE: *out = bv ? b : a; *out_valid = bv ? true : av; return;
+        case PG_AGG_FIRST_VALUE:
+            if (!*initialized) { *initialized = true; *out = b; *out_valid = bv; }
+            else { *out = a; *out_valid = av; }
+            return;
+        case PG_AGG_FIRST_NON_NULL_VALUE:
+            if (!*initialized && bv) { *initialized = true; *out = b; *out_valid = true; }
+            else { *out = a; *out_valid = av; }
+            return;
+        default: *out = a; *out_valid = av; return;
+    }
+}
+
+// Field of a partial-update sequence group that has an aggregate function
+// (PartialUpdateMergeFunction.updateWithSequenceGroup :228-244, retractWithSequenceGroup :323-339): every member
+// whose group is not empty takes part — in order (agg) when its group sequence is >= the accumulated one, else
+// reversed (aggReversed); retract members call retract(); the first record of a key initialises the row.
+__device__ void fold_group_agg(const ColDesc &cd, const uint16_t *pm, const uint32_t *gagg, const uint32_t *vw,
+                               const unsigned char *vals, int last, uint64_t *out_val, bool *out_valid, int32_t *err) {
+    const int w = cd.width, g = cd.group;
+    uint64_t val = 0;
+    bool is_valid = false, initialized = false;
+    for (int j = group_first(pm, last); j <= last; j++) {
+        const uint32_t e = pm[j];
+        const int op = (e >> kPmOpShift) & 3;
+        if (op == OP_NOOP) continue;
+        const int pj = e & kPmPosMask;
+        const bool v = staged_valid(vw, pj);
+        const uint64_t in = v ? load_fixed(vals, w, pj) : 0;
+        if (op == OP_SET) { val = in; is_valid = v; continue; }            // initRow / row restart: verbatim
+        const uint32_t marks = gagg[j];
+        if (op == OP_RETRACT) {
+            if (e & kPmHead) { val = in; is_valid = v; }                    // initRow, then the retract itself
+            if (!((marks >> g) & 1) || cd.retract == RT_IGNORE) continue;
+            switch (cd.agg) {
+                case PG_AGG_SUM:
+                    if (!is_valid) { if (v) { val = negate_fixed(cd.type, w, in); is_valid = true; } }
+                    else if (v) val = arith(cd.type, w, 1, val, in, err);
+                    break;
+                case PG_AGG_PRODUCT:
+                    if (is_valid && v) val = arith(cd.type, w, 3, val, in, err);
+                    break;
+                case PG_AGG_LAST_VALUE: is_valid = false; val = 0; break;
+                case PG_AGG_LAST_NON_NULL_VALUE: if (v) { is_valid = false; val = 0; } break;
+                case PG_AGG_PRIMARY_KEY: val = in; is_valid = v; break;
+                default: atomicCAS(err, KERR_NONE, KERR_AGG_RETRACT); break;
+            }
+            continue;
+        }
+        uint64_t r;
+        bool rv;
+        if ((marks >> g) & 1) agg_pair(cd, val, is_valid, in, v, &initialized, &r, &rv, err);
+        else if ((marks >> (16 + g)) & 1) agg_pair(cd, in, v, val, is_valid, &initialized, &r, &rv, err);
+        else continue;                                                       // empty group in this record
+        val = rv ? r : 0;
+        is_valid = rv;
+    }
+    *out_val = val;
+    *out_valid = is_valid;
+}
+
 struct TileView {
     const uint16_t *pm;
     const uint16_t *glast;
@@ -258,6 +346,9 @@ __device__ __forceinline__ void emit_fixed_column(const EmitArgs &ea, const ColD
                     const int pj = tv.pm[j] & kPmPosMask;
                     if (staged_valid(vw, pj)) { val = lds_fixed<W>(vals, pj); is_valid = true; }
                 }
+            } else if (cd.mode == CM_GAGG) {
+                fold_group_agg(cd, tv.pm, ea.gagg + tv.in_base, vw, vals, last, &val, &is_valid, ea.err);
+                if (!is_valid) val = 0;
             } else if (cd.mode == CM_KEY) {
                 val = lds_fixed<W>(vals, tv.pm[last] & kPmPosMask); is_valid = true;
             } else if (cd.mode == CM_SEQ) {

@@ -553,6 +553,7 @@ k_plan(int k, KeyDesc kd, KeySrc ks, PlanArgs pa, int32_t *err) {
             res_slot = fi[PADI(i)];
             res_kind = kind_s[fi[PADI(i)]];
             if (pa.groups) pa.gplan[in_base + i] = 0xFFFFFFFFu;      // every group field from this record
+            if (pa.gagg) pa.gagg[in_base + i] = 0;
         } else if (fl.engine == PG_ENGINE_DEDUPLICATE) {
             // DeduplicateMergeFunction.java:47-60
             int win = -1;
@@ -594,20 +595,25 @@ k_plan(int k, KeyDesc kd, KeySrc ks, PlanArgs pa, int32_t *err) {
                 if (ng > 0) {
                     const int slot = fi[PADI(j)];
                     const int mj = j - i;
+                    uint32_t am = 0;                                             // aggregation marks of this member
                     if (kind_is_retract(kind)) {
                         if (!filled) {                                           // initRow: every field verbatim
                             op = OP_SET; filled = true;
                             for (int g = 0; g < ng; g++) { seq_src[g] = (int8_t)mj; val_src[g] = (int8_t)mj; }
                         }
                         if (!fl.ignore_delete) {
+                            // (a retract that is also the first record: op RETRACT on the head = initRow, then
+                            // the retract; the select / fold code treats a RETRACT head like SET first)
+                            op = OP_RETRACT;
                             res_slot = (uint16_t)slot;
                             for (int g = 0; g < ng; g++) {
                                 if (group_is_empty(*sg, g, pa.ptrs, k, tc.seg, tc.rstart, slot)) continue;
+                                am |= 1u << g;                                   // aggregated fields retract either way
                                 const int sb = seq_src[g] < 0 ? -1 : fi[PADI(i + seq_src[g])];
                                 if (compare_group_seq(*sg, g, pa.ptrs, k, tc.seg, tc.rstart, slot, sb) < 0) continue;
                                 if (kind == PG_DELETE && sg->partial_delete[g]) {
                                     // remove-record-on-sequence-group: the row restarts from this record
-                                    cur_del = true; op = OP_SET;
+                                    cur_del = true; op = OP_SET; am = 0;
                                     for (int h = 0; h < ng; h++) { seq_src[h] = (int8_t)mj; val_src[h] = (int8_t)mj; }
                                     break;
                                 }
@@ -623,9 +629,13 @@ k_plan(int k, KeyDesc kd, KeySrc ks, PlanArgs pa, int32_t *err) {
                             const int sb = seq_src[g] < 0 ? -1 : fi[PADI(i + seq_src[g])];
                             if (compare_group_seq(*sg, g, pa.ptrs, k, tc.seg, tc.rstart, slot, sb) >= 0) {
                                 seq_src[g] = (int8_t)mj; val_src[g] = (int8_t)mj;
+                                am |= 1u << g;
+                            } else {
+                                am |= 1u << (16 + g);                            // aggReversed
                             }
                         }
                     }
+                    if (pa.gagg) pa.gagg[in_base + j] = am;
                     ops[j] = (uint8_t)op;
                     continue;
                 }

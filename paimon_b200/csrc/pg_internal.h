@@ -94,11 +94,13 @@ struct ColDesc {
     int32_t agg;         // PG_AGG_* for CM_FOLD
     int32_t retract;     // RT_*
     int32_t varlen_index;// index among var-len columns, -1 otherwise
-    int32_t pad;
+    int32_t group;       // CM_GAGG: the sequence group of the field
 };
 // CM_GVAL / CM_GSEQ: field / sequence field of partial-update sequence group `agg`: the cell of the member the
 // plan kernel marked for the group (verbatim, NULL included), NULL when no member is marked
-enum : int { CM_SELECT = 0, CM_FOLD = 1, CM_KEY = 2, CM_SEQ = 3, CM_KIND = 4, CM_GVAL = 5, CM_GSEQ = 6 };
+// CM_GAGG: field of a sequence group with an aggregate function (`agg`): folded over the members the plan kernel
+// marked as taking part, in order or reversed (PartialUpdateMergeFunction.java:228-244), retracts included
+enum : int { CM_SELECT = 0, CM_FOLD = 1, CM_KEY = 2, CM_SEQ = 3, CM_KIND = 4, CM_GVAL = 5, CM_GSEQ = 6, CM_GAGG = 7 };
 enum : int { RT_OK = 0, RT_IGNORE = 1, RT_ERROR = 2 };
 
 struct MergeFlags {
@@ -207,6 +209,8 @@ struct PlanArgs {
     const SeqGroups *groups;           // device; NULL without sequence groups
     uint32_t *gplan;                   // [N] per merged position: bit g = value source of group g, bit 16+g = its
                                        // sequence-field source
+    uint32_t *gagg;                    // [N] (only with aggregates inside groups) bit g = the member's group-g
+                                       // fields are aggregated in order, bit 16+g = reversed (older group sequence)
 };
 void launch_plan(const MergeLaunch &ml, const PlanArgs &pa);
 
@@ -224,6 +228,7 @@ struct EmitArgs {
     const int64_t *tmp_seq;
     const int8_t *tmp_kind;
     const uint32_t *gplan;             // sequence-group marks (see PlanArgs), NULL without groups
+    const uint32_t *gagg;
     const ColDesc *cols;
     const int32_t *col_order;          // device [n_cols]: order in which the emit kernel walks the columns
     ColPtrs ptrs;

@@ -490,14 +490,100 @@ def test_sequence_groups_match_oracle(mode, n_runs, total):
 
 
 def test_sequence_group_specs_the_device_refuses():
-    rt = _int_row_type(5)
-    schema = KeyValueSchema(RowType((DataField("_KEY_k", "INT", False),)), rt)
-    run = KeyValueBatch.from_rows(schema, [(1, 0, 0, 1, 1, 1, 1, 1)])
-    # an aggregate function inside a sequence group
-    spec = PartialUpdateMergeFunction.factory({"fields.f1.sequence-group": "f2,f3",
-                                               "fields.f2.aggregate-function": "sum"}, rt, ["f0"]).create()
+    vt = RowType((DataField("f0", "INT", True), DataField("f1", "INT", True), DataField("f2", "STRING", True)))
+    schema = KeyValueSchema(RowType((DataField("_KEY_k", "INT", False),)), vt)
+    run = KeyValueBatch.from_rows(schema, [(1, 0, 0, 1, 1, "a")])
+    # an aggregate function on a var-len field inside a sequence group
+    spec = PartialUpdateMergeFunction.factory({"fields.f1.sequence-group": "f2",
+                                               "fields.f2.aggregate-function": "last_value"}, vt, ["f0"]).create()
     with pytest.raises(N.UnsupportedOnDevice):
         merge_runs(schema, spec, [run])
+
+
+def test_sequence_group_aggregates_known_answers():
+    """Aggregate functions inside sequence groups (PartialUpdateMergeFunction.java:228-244, 323-339):
+    PartialUpdateMergeFunctionTest.java:219-275 (default agg), :569-616 (first_value / last_value, in order and
+    reversed), :618-742 (sum / last_value / last_non_null_value with retracts and ignore-retract)."""
+    rt = _int_row_type(7)
+    opts = dict(SEQ_GROUP_OPTS, **{"fields.default-aggregate-function": "last_non_null_value"})
+    d = GpuFuncDriver(PartialUpdateMergeFunction.factory(opts, rt, ["f0"]), rt)
+    d.add(1, 1, 1, 1, 1, 1, 1)
+    d.add(1, 2, 2, 2, 2, 2, None)
+    d.validate(1, 2, 2, 2, 1, 1, 1)
+    d.add(1, 3, 3, 1, 3, 3, 3)
+    d.validate(1, 2, 2, 2, 3, 3, 3)
+    d.add(1, 4, None, 4, 5, None, 5)
+    d.validate(1, 4, 2, 4, 5, 3, 5)
+
+    rt = _int_row_type(9)
+    opts = dict(MULTI_SEQ_OPTS, **{"fields.default-aggregate-function": "last_non_null_value"})
+    d = GpuFuncDriver(PartialUpdateMergeFunction.factory(opts, rt, ["f0"]), rt)
+    d.add(1, 1, 1, 1, 1, 1, 1, 1, 1)
+    d.add(1, 2, 2, 2, 2, 2, 2, None, None)
+    d.validate(1, 2, 2, 2, 2, 1, 1, 1, 1)
+    d.add(1, 3, 3, 1, 1, 3, 3, 3, 3)
+    d.validate(1, 2, 2, 2, 2, 3, 3, 3, 3)
+    d.add(1, 4, None, 4, 4, 5, None, 5, 5)
+    d.validate(1, 4, 2, 4, 4, 5, 3, 5, 5)
+
+    rt = _int_row_type(4)
+    opts = {"fields.f1.sequence-group": "f2,f3", "fields.f2.aggregate-function": "first_value",
+            "fields.f3.aggregate-function": "last_value"}
+    d = GpuFuncDriver(PartialUpdateMergeFunction.factory(opts, rt, ["f0"]), rt)
+    d.add(1, 1, 1, 1)
+    d.add(1, 2, 2, 2)
+    d.validate(1, 2, 1, 2)
+    d.add(1, 0, 3, 3)
+    d.validate(1, 2, 3, 2)
+
+    rt = _int_row_type(5)
+    opts = {"fields.f1,f2.sequence-group": "f3,f4", "fields.f3.aggregate-function": "first_value",
+            "fields.f4.aggregate-function": "last_value"}
+    d = GpuFuncDriver(PartialUpdateMergeFunction.factory(opts, rt, ["f0"]), rt)
+    d.add(1, 1, 1, 1, 1)
+    d.add(1, 2, 2, 2, 2)
+    d.validate(1, 2, 2, 1, 2)
+    d.add(1, 0, 1, 3, 3)
+    d.validate(1, 2, 2, 3, 2)
+
+    rt = _int_row_type(8)
+    opts = {"fields.f1.sequence-group": "f2,f3,f4", "fields.f7.sequence-group": "f6",
+            "fields.f0.aggregate-function": "listagg", "fields.f2.aggregate-function": "sum",
+            "fields.f4.aggregate-function": "last_value", "fields.f6.aggregate-function": "last_non_null_value",
+            "fields.f4.ignore-retract": "true", "fields.f6.ignore-retract": "true"}
+    d = GpuFuncDriver(PartialUpdateMergeFunction.factory(opts, rt, ["f0"]), rt)
+    d.add(1, 1, 1, 1, 1, 1, 1, 1)
+    d.add(1, 2, 1, 2, 2, 2, 2, 0)
+    d.validate(1, 2, 2, 2, 2, 2, 1, 1)
+    d.add(1, 1, 1, 1, 1, 1, 2, 0)
+    d.validate(1, 2, 3, 2, 2, 1, 1, 1)
+    d.add(1, 1, -1, 1, 1, 2, 2, 0)
+    d.add(1, 3, None, None, None, None, None, 2)
+    d.validate(1, 3, 2, None, None, 2, 1, 2)
+    d.add(1, 3, 1, 1, 1, 1, 1, 3)
+    d.validate(1, 3, 3, 1, 1, 1, 1, 3)
+    d.add(1, 3, 2, 1, 1, 1, 1, 3, kind=RowKind.UPDATE_BEFORE)
+    d.validate(1, 3, 1, None, 1, 1, 1, 3)
+    d.add(1, 3, 2, 1, 1, 1, 1, 3, kind=_D)
+    d.validate(1, 3, -1, None, 1, 1, 1, 3)
+    d.add(1, 2, 2, 1, 1, 1, 1, 3, kind=_D)
+    d.validate(1, 3, -3, None, 1, 1, 1, 3)
+
+
+@pytest.mark.parametrize("mode", ["inserts_only", "retract"])
+def test_sequence_group_aggregates_match_oracle(mode):
+    schema = _seq_group_schema()
+    opts = {"fields.g1.sequence-group": "a,b", "fields.g2a,g2b.sequence-group": "c,d",
+            "fields.a.aggregate-function": "sum", "fields.c.aggregate-function": "max",
+            "fields.d.aggregate-function": "first_value"}
+    if mode == "retract":
+        opts.update({"fields.c.ignore-retract": "true", "fields.d.ignore-retract": "true"})
+    for n_runs, total in ((3, 4000), (16, 60000)):
+        runs = datagen.make_runs(schema, n_runs, total, seed=23, null_prob=0.3,
+                                 delete_prob=0.15 if mode == "retract" else 0.0)
+        runs = _coarsen_sequence_fields(schema, runs, ["g1", "g2a", "g2b"], 3)
+        spec = PartialUpdateMergeFunction.factory(opts, schema.value_type, ["pk"]).create()
+        assert_same(schema, spec, runs)
 
 
 # ---------------------------------------------------------------- streaming in key ranges

@@ -65,7 +65,7 @@ def test_unsupported_files_are_refused(tmp_path):
     p = str(tmp_path / "z.parquet")
     write_kv_parquet(run, p, compression="zstd")
     st, _, _ = _open(sh, p)
-    assert st == 2 and b"compressed pages" in lib.pg_last_error()          # PG_ERR_UNSUPPORTED
+    assert st == 2 and b"compression codec" in lib.pg_last_error()         # PG_ERR_UNSUPPORTED
     p = str(tmp_path / "delta.parquet")
     write_kv_parquet(run, p, use_dictionary=False, column_encoding="DELTA_BINARY_PACKED")
     st, _, _ = _open(sh, p)
