@@ -618,6 +618,10 @@ static pg_status pq_read_run(PqReader *rd, uint64_t *out_run) {
     std::vector<PqDictJob> dicts = rd->dicts;
     for (auto &j : jobs) j.body = d_file + (uintptr_t)j.body;
     for (auto &d : dicts) d.body = d_file + (uintptr_t)d.body;
+    cudaEvent_t e0, e1;
+    PG_CUDA(cudaEventCreate(&e0));
+    PG_CUDA(cudaEventCreate(&e1));
+    PG_CUDA(cudaEventRecord(e0, sm));
     int32_t *d_err_early = nullptr;
     if (!rd->unc.empty()) {
         // Snappy pages: one warp per page decompresses into a scratch image the decode kernels then read
@@ -673,10 +677,6 @@ static pg_status pq_read_run(PqReader *rd, uint64_t *out_run) {
         PG_CUDA(cudaMemcpyAsync(d_dicts, dicts.data(), sizeof(PqDictJob) * dicts.size(), cudaMemcpyHostToDevice, sm));
     PG_CUDA(cudaMemcpyAsync(d_cols, cols.data(), sizeof(PqCol) * nc, cudaMemcpyHostToDevice, sm));
 
-    cudaEvent_t e0, e1;
-    PG_CUDA(cudaEventCreate(&e0));
-    PG_CUDA(cudaEventCreate(&e1));
-    PG_CUDA(cudaEventRecord(e0, sm));
     const int nj = (int)jobs.size(), nd = (int)dicts.size();
     int launches = 0;
     if (nj > 0) {

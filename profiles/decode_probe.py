@@ -9,7 +9,8 @@ schema = datagen.schema_c3(n_i64=6, n_f64=4, n_str=4)
 run = datagen.make_runs(schema, 1, 4_000_000, seed=3, null_prob=0.5)[0]
 mode = sys.argv[1] if len(sys.argv) > 1 else "dict"
 path = "/tmp/probe_%s.parquet" % mode
-write_kv_parquet(run, path, row_group_size=1_000_000, use_dictionary=(mode == "dict"))
+write_kv_parquet(run, path, row_group_size=1_000_000, use_dictionary=(mode in ("dict", "snappy")),
+                 compression="snappy" if mode.startswith("snappy") else "none")
 rd = FileFormat.from_identifier("parquet").create_reader_factory(schema).create_reader(FormatReaderContext(LocalFileIO(), path))
 for _ in range(3):
     t0 = time.perf_counter(); r = rd.as_sorted_run_reader(); dt = time.perf_counter() - t0
