@@ -15,7 +15,7 @@ rows = int(sys.argv[1]) if len(sys.argv) > 1 else 500_000
 mode = sys.argv[2] if len(sys.argv) > 2 else "plain"
 schema = datagen.schema_c3()
 n_runs = 16
-runs = datagen.make_runs(schema, n_runs, rows * n_runs * 2, seed=5, null_prob=0.5)
+runs = datagen.make_runs(schema, n_runs, rows * n_runs, seed=5, null_prob=0.5)
 paths, file_bytes = [], 0
 for i, run in enumerate(runs):
     p = f"/tmp/dm_{mode}_{i}.parquet"
