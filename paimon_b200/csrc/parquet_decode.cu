@@ -356,6 +356,92 @@ __global__ void k_pq_snappy(const SnappyJob *jobs, int n_jobs, int32_t *err) {
     if ((bad || out != n_dst) && lane == 0) atomicCAS(err, KERR_NONE, KERR_BAD_PAGE);
 }
 
+// ---- DELTA_BINARY_PACKED (VectorizedDeltaBinaryPackedReader.java; the layout restated here is the public Parquet
+// encoding specification): <block size> <miniblocks per block> <total count> <first value> then per block
+// <min delta> <bit width per miniblock> <bit-packed miniblocks>.  One warp per page expands the values into a
+// PLAIN image (the level bytes in front are copied), so the PLAIN assemble path reads the page afterwards.
+struct DeltaJob {
+    const uint8_t *src;       // device: page body
+    uint8_t *dst;
+    int32_t src_len, prefix;  // prefix = level bytes in front of the values
+    int32_t width, max_values;
+};
+__device__ __forceinline__ uint64_t dl_varint(const uint8_t *p, int n, int &pos) {
+    uint64_t v = 0;
+    for (int sh = 0; pos < n && sh < 70; sh += 7) {
+        const uint8_t b = p[pos++];
+        v |= (uint64_t)(b & 0x7f) << sh;
+        if (!(b & 0x80)) break;
+    }
+    return v;
+}
+__global__ void k_pq_delta(const DeltaJob *jobs, int n_jobs, int32_t *err) {
+    const int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (w >= n_jobs) return;
+    const DeltaJob j = jobs[w];
+    for (int i = lane; i < j.prefix; i += 32) j.dst[i] = j.src[i];
+    const uint8_t *p = j.src + j.prefix;
+    const int n = j.src_len - j.prefix;
+    uint8_t *out = j.dst + j.prefix;
+    int pos = 0;
+    const int block_size = (int)dl_varint(p, n, pos);
+    const int n_mini = (int)dl_varint(p, n, pos);
+    const int64_t total = (int64_t)dl_varint(p, n, pos);
+    const uint64_t zz = dl_varint(p, n, pos);
+    uint64_t last = (zz >> 1) ^ (0 - (zz & 1));               // first value
+    bool bad = n_mini <= 0 || block_size <= 0 || block_size % n_mini != 0 || total > j.max_values || total < 0;
+    const int mini = bad ? 1 : block_size / n_mini;
+    if (!bad && total > 0 && lane == 0) {
+        if (j.width == 8) memcpy(out, &last, 8); else { uint32_t x = (uint32_t)last; memcpy(out, &x, 4); }
+    }
+    int64_t done = 1;
+    while (!bad && done < total) {
+        const uint64_t mz = dl_varint(p, n, pos);
+        const uint64_t min_delta = (mz >> 1) ^ (0 - (mz & 1));
+        const int bw_pos = pos;
+        pos += n_mini;
+        if (pos > n) { bad = true; break; }
+        for (int m = 0; m < n_mini && done < total; m++) {
+            const int bw = p[bw_pos + m];
+            if (bw > 64 || pos + (int64_t)mini * bw / 8 > n) { bad = true; break; }
+            for (int v0 = 0; v0 < mini && done < total; v0 += 32) {
+                const int v = v0 + lane;
+                uint64_t d = 0;
+                if (v < mini && bw > 0) {
+                    const int64_t bit = (int64_t)v * bw;
+                    const uint8_t *q = p + pos + (bit >> 3);
+                    const int sh = (int)(bit & 7);
+                    // up to 9 bytes hold the value
+                    uint64_t lo = 0;
+                    const int nb = (sh + bw + 7) >> 3;
+                    for (int b = 0; b < nb && b < 8; b++) lo |= (uint64_t)q[b] << (8 * b);
+                    d = lo >> sh;
+                    if (nb > 8) d |= (uint64_t)q[8] << (64 - sh);
+                    if (bw < 64) d &= ((uint64_t)1 << bw) - 1;
+                }
+                uint64_t x = v < mini ? d + min_delta : 0;
+                // inclusive scan of the deltas over the warp, then the running value
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+                    if (lane >= o) x += y;
+                }
+                const uint64_t val = last + x;
+                const int64_t idx = done + lane;
+                if (v < mini && idx < total) {
+                    if (j.width == 8) memcpy(out + idx * 8, &val, 8);
+                    else { uint32_t t = (uint32_t)val; memcpy(out + idx * 4, &t, 4); }
+                }
+                const int cnt = min(32, mini - v0);
+                last = __shfl_sync(0xffffffffu, val, cnt - 1);
+                done += cnt;
+            }
+            pos += mini * bw / 8;
+        }
+    }
+    if (bad && lane == 0) atomicCAS(err, KERR_NONE, KERR_BAD_PAGE);
+}
+
 // ---- device-wide inclusive scan of int32 (three small kernels; offsets of one var-len column)
 __global__ void k_scan_block_sums(const int32_t *data, int64_t n, int64_t *block_sums) {
     __shared__ int64_t sh[256];
@@ -414,6 +500,11 @@ struct PqReader {
     std::vector<Unc> unc;
     std::vector<int32_t> job_unc, dict_unc;    // per page / dictionary job: index into unc, -1 = stored uncompressed
     int64_t unc_bytes = 0;
+    // DELTA_BINARY_PACKED pages, expanded to PLAIN images on the device
+    struct Delta { int64_t src_off; int32_t src_len, prefix, width, max_values; int64_t dst_off; };
+    std::vector<Delta> delta;
+    std::vector<int32_t> job_delta;            // per page job: index into delta, -1 = none
+    int64_t delta_bytes = 0;
     float ms_decode = 0;
     int launches = 0;
 };
@@ -522,9 +613,12 @@ static pg_status pq_open(uint64_t schema_h, const uint8_t *bytes, int64_t size, 
                     rd->dicts.push_back(dj);
                 } else if (h.type == pq::P_DATA || h.type == pq::P_DATA_V2) {
                     bool is_dict = h.encoding == pq::E_PLAIN_DICTIONARY || h.encoding == pq::E_RLE_DICTIONARY;
-                    if (!is_dict && h.encoding != pq::E_PLAIN)
+                    const bool is_delta = h.encoding == pq::E_DELTA_BINARY_PACKED &&
+                                          (cc.type == pq::T_INT32 || cc.type == pq::T_INT64) && !snappy;
+                    if (!is_dict && !is_delta && h.encoding != pq::E_PLAIN)
                         return fail(PG_ERR_UNSUPPORTED, "parquet: value encoding " + std::to_string(h.encoding) +
-                                                        " (only PLAIN and dictionary encodings are decoded on device)");
+                                                        " (PLAIN, dictionary and DELTA_BINARY_PACKED on uncompressed "
+                                                        "integer pages are decoded on device)");
                     if (is_dict && dict_index < 0) return fail(PG_ERR_FORMAT, "parquet: dictionary-encoded page without dictionary");
                     if (h.type == pq::P_DATA_V2 && h.rep_levels_byte_length != 0)
                         return fail(PG_ERR_UNSUPPORTED, "parquet: repetition levels");
@@ -544,6 +638,25 @@ static pg_status pq_open(uint64_t schema_h, const uint8_t *bytes, int64_t size, 
                     const int32_t prefix = h.type == pq::P_DATA_V2 ? h.def_levels_byte_length + h.rep_levels_byte_length : 0;
                     rd->job_unc.push_back(add_unc(body, h, prefix, h.type == pq::P_DATA_V2 ? h.is_compressed : true));
                     if (rd->job_unc.back() >= 0) pj.body_len = h.uncompressed_size;
+                    int32_t di = -1;
+                    if (is_delta) {
+                        // level bytes in front of the values: V1 = 4-byte length + RLE levels (OPTIONAL only)
+                        int32_t lv = prefix;
+                        if (h.type == pq::P_DATA && max_def > 0) {
+                            if (h.compressed_size < 4) return fail(PG_ERR_FORMAT, "parquet: truncated page");
+                            uint32_t l4;
+                            memcpy(&l4, bytes + body, 4);
+                            lv = 4 + (int32_t)l4;
+                        }
+                        if (lv < 0 || lv > h.compressed_size) return fail(PG_ERR_FORMAT, "parquet: bad level length");
+                        const int32_t width = cc.type == pq::T_INT32 ? 4 : 8;
+                        PqReader::Delta d{body, h.compressed_size, lv, width, h.num_values, rd->delta_bytes};
+                        rd->delta_bytes += ((int64_t)lv + (int64_t)h.num_values * width + 63) & ~(int64_t)63;
+                        rd->delta.push_back(d);
+                        di = (int32_t)rd->delta.size() - 1;
+                        pj.body_len = lv + h.num_values * width;
+                    }
+                    rd->job_delta.push_back(di);
                     rd->jobs.push_back(pj);
                     page_row += h.num_values;
                     vals += h.num_values;
@@ -580,7 +693,8 @@ static pg_status pq_read_run(PqReader *rd, uint64_t *out_run) {
                      pad(sizeof(PqDictJob) * rd->dicts.size() + 64) + pad(sizeof(PqCol) * nc) +
                      pad(sizeof(PqPageState) * rd->jobs.size() + 64) + pad(sizeof(void *) * (rd->dict_entries + 1)) +
                      pad(4 * (rd->dict_entries + 1)) + 4096 + pad((size_t)rd->unc_bytes + 64) +
-                     pad(sizeof(SnappyJob) * rd->unc.size() + 64) + 256;
+                     pad(sizeof(SnappyJob) * rd->unc.size() + 64) + 256 + pad((size_t)rd->delta_bytes + 64) +
+                     pad(sizeof(DeltaJob) * rd->delta.size() + 64) + 256;
     size_t outb = 4096;
     std::vector<PqCol> cols(nc);
     for (int c = 0; c < nc; c++) {
@@ -642,6 +756,25 @@ static pg_status pq_read_run(PqReader *rd, uint64_t *out_run) {
             if (rd->job_unc[i] >= 0) jobs[i].body = d_unc + rd->unc[rd->job_unc[i]].dst_off;
         for (size_t i = 0; i < dicts.size(); i++)
             if (rd->dict_unc[i] >= 0) dicts[i].body = d_unc + rd->unc[rd->dict_unc[i]].dst_off;
+    }
+    if (!rd->delta.empty()) {
+        uint8_t *d_delta = stake((size_t)rd->delta_bytes + 64);
+        DeltaJob *d_dj = (DeltaJob *)stake(sizeof(DeltaJob) * rd->delta.size());
+        if (!d_err_early) {
+            d_err_early = (int32_t *)stake(16);
+            PG_CUDA(cudaMemsetAsync(d_err_early, 0, 4, sm));
+        }
+        std::vector<DeltaJob> dj(rd->delta.size());
+        for (size_t i = 0; i < dj.size(); i++) {
+            const PqReader::Delta &d = rd->delta[i];
+            dj[i] = DeltaJob{d_file + d.src_off, d_delta + d.dst_off, d.src_len, d.prefix, d.width, d.max_values};
+        }
+        PG_CUDA(cudaMemcpyAsync(d_dj, dj.data(), sizeof(DeltaJob) * dj.size(), cudaMemcpyHostToDevice, sm));
+        PG_CUDA(cudaStreamSynchronize(sm));           // dj is a local vector
+        const int64_t threads = (int64_t)dj.size() * 32;
+        k_pq_delta<<<(int)((threads + 127) / 128), 128, 0, sm>>>(d_dj, (int)dj.size(), d_err_early);
+        for (size_t i = 0; i < jobs.size(); i++)
+            if (rd->job_delta[i] >= 0) jobs[i].body = d_delta + rd->delta[rd->job_delta[i]].dst_off;
     }
     PqPageJob *d_jobs = (PqPageJob *)stake(sizeof(PqPageJob) * jobs.size() + 64);
     PqDictJob *d_dicts = (PqDictJob *)stake(sizeof(PqDictJob) * dicts.size() + 64);
@@ -735,7 +868,7 @@ static pg_status pq_read_run(PqReader *rd, uint64_t *out_run) {
     rd->launches = launches;
     if (herr_pages != KERR_NONE) {
         for (void *p : run->owned) cudaFree(p);
-        return fail(PG_ERR_FORMAT, "parquet: a Snappy page does not decompress to its declared size");
+        return fail(PG_ERR_FORMAT, "parquet: a Snappy / DELTA_BINARY_PACKED page does not expand to its declared size");
     }
     if (herr != KERR_NONE) {
         for (void *p : run->owned) cudaFree(p);

@@ -66,8 +66,13 @@ def test_unsupported_files_are_refused(tmp_path):
     write_kv_parquet(run, p, compression="zstd")
     st, _, _ = _open(sh, p)
     assert st == 2 and b"compression codec" in lib.pg_last_error()         # PG_ERR_UNSUPPORTED
-    p = str(tmp_path / "delta.parquet")
+    p = str(tmp_path / "delta.parquet")                 # DELTA_BINARY_PACKED integers are accepted ...
     write_kv_parquet(run, p, use_dictionary=False, column_encoding="DELTA_BINARY_PACKED")
+    st, h_ok, _ = _open(sh, p)
+    assert st == 0
+    lib.pg_parquet_free(h_ok)
+    p = str(tmp_path / "bss.parquet")                   # ... BYTE_STREAM_SPLIT is not
+    write_kv_parquet(run, p, use_dictionary=False, column_encoding="BYTE_STREAM_SPLIT")
     st, _, _ = _open(sh, p)
     assert st == 2 and b"encoding" in lib.pg_last_error()
     junk = np.frombuffer(b"not a parquet file at all.....", dtype=np.uint8)
