@@ -210,7 +210,8 @@ pg_status pg_run_fetch(uint64_t run, const pg_out_column *host_cols, int32_t n_c
  * Java FileIO) are parsed on the host for footer + page headers and decoded on the device straight into the
  * columnar run the merge consumes.  ABI v1 decodes flat schemas, INT32/INT64/FLOAT/DOUBLE/BYTE_ARRAY, PLAIN and
  * dictionary encodings, data pages V1/V2, uncompressed and Snappy-compressed pages (decompressed on the device);
- * anything else (zstd, gzip, DELTA_* encodings, nested columns) returns PG_ERR_UNSUPPORTED. */
+ * DELTA_BINARY_PACKED integers on uncompressed pages; anything else (zstd, gzip, byte-array DELTA encodings,
+ * nested columns) returns PG_ERR_UNSUPPORTED. */
 typedef struct {
     int64_t n_rows;
     int32_t n_row_groups;
