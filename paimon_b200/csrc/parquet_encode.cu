@@ -336,10 +336,12 @@ static pg_status encode(uint64_t source, const char *const *names, int64_t row0,
     StatJob *d_sjobs = nullptr;
     int64_t *d_counts = nullptr, *d_stats = nullptr;
     std::vector<int64_t> counts(2 * nj + 2), stats(4 * nsj + 4);
-    auto cleanup = [&]() {
-        cudaFree(d_cols); cudaFree(d_jobs); cudaFree(d_sjobs); cudaFree(d_counts); cudaFree(d_stats);
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
-    };
+    // temporaries are released on every path out of this function (PG_CUDA returns early)
+    struct Guard {
+        EncColumn *&a; EncJob *&b; StatJob *&c; int64_t *&d; int64_t *&e; cudaEvent_t &e0; cudaEvent_t &e1;
+        ~Guard() { cudaFree(a); cudaFree(b); cudaFree(c); cudaFree(d); cudaFree(e); cudaEventDestroy(e0); cudaEventDestroy(e1); }
+    } guard{d_cols, d_jobs, d_sjobs, d_counts, d_stats, e0, e1};
+    auto cleanup = []() {};
     PG_CUDA(cudaMalloc(&d_cols, sizeof(EncColumn) * nc));
     PG_CUDA(cudaMalloc(&d_jobs, sizeof(EncJob) * std::max<size_t>(nj, 1)));
     PG_CUDA(cudaMalloc(&d_sjobs, sizeof(StatJob) * std::max<size_t>(nsj, 1)));
