@@ -226,6 +226,10 @@ static cudaStream_t copy_stream() {                   // one non-blocking copy s
 // hooks for the other translation units (parquet_decode.cu)
 Schema *schema_from_handle(uint64_t h) { return g_schemas.get(h); }
 Run *run_from_handle(uint64_t h) { return g_runs.get(h); }
+// recycled device buffers and the calling thread's copy stream, for the format readers
+void *device_buffer_take(size_t bytes, size_t *got) { return buf_take(bytes, got); }
+void device_buffer_give(void *p, size_t bytes) { buf_give(p, bytes); }
+cudaStream_t thread_stream() { return copy_stream(); }
 uint64_t register_run(std::unique_ptr<Run> run) { return g_runs.put(std::move(run)); }
 pg_status require_device() { return ensure_device(); }
 

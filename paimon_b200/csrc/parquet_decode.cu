@@ -536,6 +536,9 @@ static bool phys_compatible(int pg_t, int phys) {
 }
 
 Schema *schema_from_handle(uint64_t h);                 // api.cu
+void *device_buffer_take(size_t bytes, size_t *got);    // api.cu: recycled device buffers
+void device_buffer_give(void *p, size_t bytes);
+cudaStream_t thread_stream();                           // api.cu: the calling thread's non-blocking stream
 uint64_t register_run(std::unique_ptr<Run> run);        // api.cu
 pg_status require_device();                             // api.cu
 
@@ -685,7 +688,8 @@ static pg_status pq_read_run(PqReader *rd, uint64_t *out_run) {
     run->n_rows = n;
     run->cols.resize(nc);
     run->varlen_bytes.assign(nc, 0);
-    cudaStream_t sm = 0;
+    // every reader thread decodes on its own stream: the files of a section decode concurrently
+    cudaStream_t sm = thread_stream();
     auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
 
     // ---- device memory: file bytes + scratch (freed at the end) and the output columns (owned by the run)
@@ -717,10 +721,15 @@ static pg_status pq_read_run(PqReader *rd, uint64_t *out_run) {
         }
     }
     unsigned char *d_scratch = nullptr, *d_out = nullptr;
-    PG_CUDA(cudaMalloc((void **)&d_scratch, scratch));
-    auto guard = std::unique_ptr<unsigned char, void (*)(unsigned char *)>(d_scratch, [](unsigned char *p) { cudaFree(p); });
-    PG_CUDA(cudaMalloc((void **)&d_out, outb));
+    // recycled buffers (no cudaMalloc / cudaFree, which would serialise concurrent decodes)
+    size_t scratch_got = 0, out_got = 0;
+    d_scratch = (unsigned char *)device_buffer_take(scratch, &scratch_got);
+    if (!d_scratch) return fail(PG_ERR_CUDA, "parquet: out of device memory");
+    struct ScratchGuard { unsigned char *p; size_t n; ~ScratchGuard() { device_buffer_give(p, n); } } guard{d_scratch, scratch_got};
+    d_out = (unsigned char *)device_buffer_take(outb, &out_got);
+    if (!d_out) return fail(PG_ERR_CUDA, "parquet: out of device memory");
     run->owned.push_back(d_out);
+    run->owned_bytes.push_back(out_got);
     size_t st = 0, ot = 0;
     auto stake = [&](size_t b) { unsigned char *p = d_scratch + st; st += pad(b); return p; };
     auto otake = [&](size_t b) { unsigned char *p = d_out + ot; ot += pad(b); return p; };
@@ -840,7 +849,10 @@ static pg_status pq_read_run(PqReader *rd, uint64_t *out_run) {
         for (int c = 0; c < nc; c++) if (cols[c].phys == pq::T_BYTE_ARRAY) sum += pad((size_t)totals[c] + 64);
         unsigned char *pl = nullptr;
         if (n > 0 && sum > 256) {
-            PG_CUDA(cudaMalloc((void **)&pl, sum));
+            size_t pl_got = 0;
+            pl = (unsigned char *)device_buffer_take(sum, &pl_got);
+            if (!pl) return fail(PG_ERR_CUDA, "parquet: out of device memory");
+            run->owned_bytes.push_back(pl_got);
             run->owned.push_back(pl);
         }
         size_t pt = 0;
@@ -867,11 +879,11 @@ static pg_status pq_read_run(PqReader *rd, uint64_t *out_run) {
     cudaEventDestroy(e1);
     rd->launches = launches;
     if (herr_pages != KERR_NONE) {
-        for (void *p : run->owned) cudaFree(p);
+        for (size_t q = 0; q < run->owned.size(); q++) device_buffer_give(run->owned[q], run->owned_bytes[q]);
         return fail(PG_ERR_FORMAT, "parquet: a Snappy / DELTA_BINARY_PACKED page does not expand to its declared size");
     }
     if (herr != KERR_NONE) {
-        for (void *p : run->owned) cudaFree(p);
+        for (size_t q = 0; q < run->owned.size(); q++) device_buffer_give(run->owned[q], run->owned_bytes[q]);
         return fail(PG_ERR_INTERNAL, "parquet: a var-len column exceeds 2 GiB of payload");
     }
     for (int c = 0; c < nc; c++) {

@@ -164,29 +164,43 @@ class KeyValueFileReaderFactory:
 
 class MergeTreeReaders:
     @staticmethod
+    def _open_file(meta: DataFileMeta, reader_factory: KeyValueFileReaderFactory):
+        """One data file -> (format reader, device-resident sorted run), deletion vector applied."""
+        fr = reader_factory.create_record_reader(meta)
+        rr = fr.as_sorted_run_reader()
+        deleted = reader_factory.dv_factory(meta.file_name) if reader_factory.dv_factory else None
+        if deleted is not None and len(deleted):
+            from .sort_merge_reader import apply_deletion_vector
+            filtered = apply_deletion_vector(reader_factory.schema, rr, deleted, device=reader_factory.device)
+            rr.close()
+            rr = filtered
+        return fr, rr
+
+    @staticmethod
     def reader_for_run(run: SortedRun, reader_factory: KeyValueFileReaderFactory) -> List[SortedRunReader]:
         """A run = its files in key order.  Each decoded file is handed to the merge as its own sorted input:
         files of one run never share keys, so giving them to the k-way merge separately yields the same rows as
-        concatenating them first (MergeTreeReaders.java:94-101)."""
-        out = []
-        for meta in run.files:
-            fr = reader_factory.create_record_reader(meta)
-            rr = fr.as_sorted_run_reader()
-            deleted = reader_factory.dv_factory(meta.file_name) if reader_factory.dv_factory else None
-            if deleted is not None and len(deleted):
-                from .sort_merge_reader import apply_deletion_vector
-                filtered = apply_deletion_vector(reader_factory.schema, rr, deleted, device=reader_factory.device)
-                rr.close()
-                rr = filtered
-            out.append((fr, rr))
-        return out
+        concatenating them first (MergeTreeReaders.java:94-101).  The files are read and decoded concurrently
+        (every worker thread has its own CUDA stream in the library): small files are latency-bound."""
+        if len(run.files) <= 1:
+            return [MergeTreeReaders._open_file(m, reader_factory) for m in run.files]
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(8, len(run.files))) as ex:
+            return list(ex.map(lambda m: MergeTreeReaders._open_file(m, reader_factory), run.files))
 
     @staticmethod
     def reader_for_section(section: Sequence[SortedRun], reader_factory: KeyValueFileReaderFactory,
                            user_defined_seq_comparator, merge_function_wrapper: MergeSpec) -> RecordReader:
-        opened = []
-        for run in section:
-            opened += MergeTreeReaders.reader_for_run(run, reader_factory)
+        metas = [m for run in section for m in run.files]
+        if len(metas) > 32:
+            raise N.UnsupportedOnDevice(2, "more than 32 files in one section: merge in rounds is not implemented yet")
+        # all files of the section decode concurrently (order preserved: run by run, file by file)
+        from concurrent.futures import ThreadPoolExecutor
+        if len(metas) > 1:
+            with ThreadPoolExecutor(max_workers=min(8, len(metas))) as ex:
+                opened = list(ex.map(lambda m: MergeTreeReaders._open_file(m, reader_factory), metas))
+        else:
+            opened = [MergeTreeReaders._open_file(m, reader_factory) for m in metas]
         if len(opened) > 32:
             raise N.UnsupportedOnDevice(2, "more than 32 files in one section: merge in rounds is not implemented yet")
         merge = SortMergeReader.create_sort_merge_reader([r for _, r in opened], None, user_defined_seq_comparator,
