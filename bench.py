@@ -39,6 +39,11 @@ import numpy as np  # noqa: E402
 WORKLOADS = {
     "c3": dict(n_runs=16, rows=100_000_000, engine="partial-update", null_prob=0.5,
                desc="16-run partial-update, 50-col wide row (pk+20 i64+15 f64+14 varchar), 100M rows"),
+    # SURVEY §8d "C3-agg": same rows as C3, merge-engine aggregation: the 15 doubles and 20 bigints use `sum`
+    # (ordered left fold, bit-exact), the strings last_non_null_value
+    "c3agg": dict(n_runs=16, rows=100_000_000, engine="aggregate", null_prob=0.5,
+                  desc="16-run aggregation (sum over 20 i64 + 15 f64, last_non_null_value over 14 varchar), 50-col wide "
+                       "row, 100M rows"),
     "c2": dict(n_runs=8, rows=100_000_000, engine="deduplicate", null_prob=0.0,
                desc="8-run deduplicate, int64 pk + 10 int64 cols, 100M rows"),
     "c1": dict(n_runs=2, rows=1_000_000, engine="deduplicate", null_prob=0.0,
@@ -63,11 +68,17 @@ def schema_c4():
 
 def make_schema(workload):
     from paimon_b200 import datagen
-    return {"c1": datagen.schema_c1, "c2": datagen.schema_c2, "c3": datagen.schema_c3, "c4": schema_c4}[workload]()
+    return {"c1": datagen.schema_c1, "c2": datagen.schema_c2, "c3": datagen.schema_c3, "c3agg": datagen.schema_c3,
+            "c4": schema_c4}[workload]()
 
 
 def make_spec(workload, schema):
-    from paimon_b200.merge_function import DeduplicateMergeFunction, PartialUpdateMergeFunction
+    from paimon_b200.merge_function import (AggregateMergeFunction, DeduplicateMergeFunction,
+                                            PartialUpdateMergeFunction)
+    if WORKLOADS[workload]["engine"] == "aggregate":
+        opts = {f"fields.{f.name}.aggregate-function": "sum" for f in schema.value_type.fields
+                if f.name != "pk" and f.physical.name in ("INT64", "DOUBLE")}
+        return AggregateMergeFunction.factory(opts, schema.value_type, ["pk"]).create()
     if WORKLOADS[workload]["engine"] == "partial-update":
         return PartialUpdateMergeFunction.factory({}, schema.value_type, ["pk"]).create()
     spec = DeduplicateMergeFunction.factory().create()
