@@ -325,7 +325,7 @@ __device__ __forceinline__ void put_validity_word(uint8_t *validity, int64_t out
     }
 }
 
-template <int W>
+template <int W, bool GAGG>
 __device__ __forceinline__ void emit_fixed_column(const EmitArgs &ea, const ColDesc &cd, const pg_out_column &oc,
                                                   const TileView &tv, const unsigned char *vals, const uint32_t *vw) {
     const int tid = threadIdx.x, lane = tid & 31;
@@ -346,7 +346,7 @@ __device__ __forceinline__ void emit_fixed_column(const EmitArgs &ea, const ColD
                     const int pj = tv.pm[j] & kPmPosMask;
                     if (staged_valid(vw, pj)) { val = lds_fixed<W>(vals, pj); is_valid = true; }
                 }
-            } else if (cd.mode == CM_GAGG) {
+            } else if (GAGG && cd.mode == CM_GAGG) {
                 fold_group_agg(cd, tv.pm, ea.gagg + tv.in_base, vw, vals, last, &val, &is_valid, ea.err);
                 if (!is_valid) val = 0;
             } else if (cd.mode == CM_KEY) {
@@ -372,6 +372,9 @@ __device__ long long g_emit_ts[64 * 256];
 #define TS(slot) do { } while (0)
 #endif
 
+// GAGG: the merge has aggregate functions inside sequence groups (the fold for them is compiled into its own
+// kernel variant: inlined into the common one it costs every workload registers and spills)
+template <bool GAGG>
 __global__ void __launch_bounds__(kEmitThreads, 2)
 k_emit(EmitArgs ea) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -567,10 +570,10 @@ k_emit(EmitArgs ea) {
         const unsigned char *vals = stage_vals[s];
         const uint32_t *vw = stage_vw[s];
 
-        if (cd.width == 8) emit_fixed_column<8>(ea, cd, oc, tv, vals, vw);
-        else if (cd.width == 4) emit_fixed_column<4>(ea, cd, oc, tv, vals, vw);
-        else if (cd.width == 1) emit_fixed_column<1>(ea, cd, oc, tv, vals, vw);
-        else if (cd.width == 2) emit_fixed_column<2>(ea, cd, oc, tv, vals, vw);
+        if (cd.width == 8) emit_fixed_column<8, GAGG>(ea, cd, oc, tv, vals, vw);
+        else if (cd.width == 4) emit_fixed_column<4, GAGG>(ea, cd, oc, tv, vals, vw);
+        else if (cd.width == 1) emit_fixed_column<1, GAGG>(ea, cd, oc, tv, vals, vw);
+        else if (cd.width == 2) emit_fixed_column<2, GAGG>(ea, cd, oc, tv, vals, vw);
         else {
             // ---- var-len column: offsets staged as int32 at the staged row positions; the upper half of the
             // stage is free (offsets are 4 bytes per row) and holds the per-row source + per-warp scratch
@@ -771,10 +774,12 @@ static bool g_emit_attr = false;
 void launch_emit(const EmitArgs &ea) {
     EmitLayout L = emit_layout(ea.k);
     if (!g_emit_attr) {
-        cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_emit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_emit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         g_emit_attr = true;
     }
-    k_emit<<<ea.n_tiles, kEmitThreads, L.total, ea.stream>>>(ea);
+    if (ea.gagg) k_emit<true><<<ea.n_tiles, kEmitThreads, L.total, ea.stream>>>(ea);
+    else k_emit<false><<<ea.n_tiles, kEmitThreads, L.total, ea.stream>>>(ea);
 #ifdef PG_EMIT_TIMING
     emit_timing_dump();
 #endif
