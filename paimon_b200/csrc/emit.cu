@@ -58,13 +58,15 @@ template <> __device__ __forceinline__ void stg_fixed<8>(void *d, int64_t r, uin
 
 // ops-based select, newest member first: the newest UPD member with a non-null cell wins; a SET member
 // ends the scan (its cell, null or not, is the result).  Returns the staged position or -1 (NULL).
+template <bool GAGG>
 __device__ __forceinline__ int select_pos(const uint16_t *pm, const uint32_t *vw, int last) {
     int j = last;
     while (true) {
         uint32_t e = pm[j];
         uint32_t op = (e >> kPmOpShift) & 3;
-        // a RETRACT member leaves select columns alone, unless it is the group's first record (initRow: verbatim)
-        if (op == OP_RETRACT) op = (e & kPmHead) ? OP_SET : OP_NOOP;
+        // (only with aggregates inside sequence groups does the plan mark retracts on a partial-update merge) a
+        // RETRACT member leaves select columns alone, unless it is the group's first record (initRow: verbatim)
+        if (GAGG && op == OP_RETRACT) op = (e & kPmHead) ? OP_SET : OP_NOOP;
         if (op != OP_NOOP) {
             int pj = e & kPmPosMask;
             if (staged_valid(vw, pj)) return pj;
@@ -75,12 +77,13 @@ __device__ __forceinline__ int select_pos(const uint16_t *pm, const uint32_t *vw
     }
 }
 // same, but returns the member's merged position (needed for its run id)
+template <bool GAGG>
 __device__ __forceinline__ int select_member_idx(const uint16_t *pm, const uint32_t *vw, int last) {
     int j = last;
     while (true) {
         uint32_t e = pm[j];
         uint32_t op = (e >> kPmOpShift) & 3;
-        if (op == OP_RETRACT) op = (e & kPmHead) ? OP_SET : OP_NOOP;
+        if (GAGG && op == OP_RETRACT) op = (e & kPmHead) ? OP_SET : OP_NOOP;
         if (op != OP_NOOP) {
             if (staged_valid(vw, e & kPmPosMask)) return j;
             if (op == OP_SET) return -1;
@@ -337,7 +340,7 @@ __device__ __forceinline__ void emit_fixed_column(const EmitArgs &ea, const ColD
             uint64_t val = 0;
             const int last = tv.glast[ob];
             if (cd.mode == CM_SELECT) {
-                int pj = select_pos(tv.pm, vw, last);
+                int pj = select_pos<GAGG>(tv.pm, vw, last);
                 if (pj >= 0) { val = lds_fixed<W>(vals, pj); is_valid = true; }
             } else if (cd.mode == CM_GVAL || cd.mode == CM_GSEQ) {
                 const uint32_t gbit = 1u << (cd.agg + (cd.mode == CM_GSEQ ? 16 : 0));
@@ -602,7 +605,7 @@ k_emit(EmitArgs ea) {
                         src = select_marked_idx(pm, ea.gplan + in_base,
                                                 1u << (cd.agg + (cd.mode == CM_GSEQ ? 16 : 0)), last);
                         if (src >= 0 && !staged_valid(vw, pm[src] & kPmPosMask)) src = -1;
-                    } else src = select_member_idx(pm, vw, last);
+                    } else src = select_member_idx<GAGG>(pm, vw, last);
                     vsrc[ob] = src < 0 ? (uint16_t)0xFFFF : (uint16_t)src;
                     if (src >= 0) { int ps = pm[src] & kPmPosMask; my_bytes += offs[ps + 1] - offs[ps]; }
                 }

@@ -604,7 +604,7 @@ k_plan(int k, KeyDesc kd, KeySrc ks, PlanArgs pa, int32_t *err) {
                         if (!fl.ignore_delete) {
                             // (a retract that is also the first record: op RETRACT on the head = initRow, then
                             // the retract; the select / fold code treats a RETRACT head like SET first)
-                            op = OP_RETRACT;
+                            if (pa.gagg) op = OP_RETRACT;           // only the aggregate-in-group fold needs to see it
                             res_slot = (uint16_t)slot;
                             for (int g = 0; g < ng; g++) {
                                 if (group_is_empty(*sg, g, pa.ptrs, k, tc.seg, tc.rstart, slot)) continue;
