@@ -268,14 +268,15 @@ def cpu_baseline(workload, total_sample_rows, threads, steps=1, seed=7):
     w = WORKLOADS[workload]
     per_bucket = max(total_sample_rows // threads, w["n_runs"] * 64)
     n_distinct = min(threads, 8)        # distinct synthetic buckets; threads beyond that re-merge a copy's inputs
-    buckets = [datagen.make_runs(schema, w["n_runs"], per_bucket, seed=seed + b, null_prob=w["null_prob"])
+    buckets = [datagen.make_runs(schema, w["n_runs"], per_bucket, seed=seed + b, null_prob=w["null_prob"],
+                                 delete_prob=w.get("delete_prob", 0.0))
                for b in range(n_distinct)]
     prepared = [pyoracle.prepare(schema, spec, buckets[b % n_distinct]) for b in range(threads)]
 
     def work(b):
         return pyoracle.run_prepared(prepared[b])          # C call only; the GIL is released
 
-    times = []
+    times, outs = [], []
     with ThreadPoolExecutor(max_workers=threads) as ex:
         for _ in range(steps):
             t0 = time.perf_counter()

@@ -61,8 +61,15 @@ def make_run(schema: KeyValueSchema, run_index: int, keys: np.ndarray, seed: int
     rng = np.random.default_rng(seed * 1000003 + run_index)
     n = len(keys)
     cols: List[Column] = []
+    def key_column(t):
+        if t in (PhysicalType.STRING, PhysicalType.BINARY):
+            # 16-character lower-case hex of the key (big endian: string order == integer order)
+            hexes = np.array([b"%016x" % int(k) for k in keys], dtype="S16") if n else np.zeros(0, "S16")
+            data = np.frombuffer(hexes.tobytes(), np.uint8).copy()
+            return Column(t, data, (np.arange(n + 1, dtype=np.int64) * 16).astype(np.int32))
+        return Column(t, keys.astype(np.int64))
     for f in schema.key_type.fields:
-        cols.append(Column(f.physical, keys.astype(np.int64)))
+        cols.append(key_column(f.physical))
     cols.append(Column(PhysicalType.INT64, (np.int64(run_index) << np.int64(32)) + np.arange(n, dtype=np.int64)))
     kinds = np.zeros(n, np.int8)
     if delete_prob > 0:
@@ -77,7 +84,7 @@ def make_run(schema: KeyValueSchema, run_index: int, keys: np.ndarray, seed: int
         if f.name not in pk_names and f.nullable and null_prob > 0:
             valid = pack_validity(rng.random(n) >= null_prob)
         if f.name in pk_names:
-            cols.append(Column(t, keys.astype(np.int64)))
+            cols.append(key_column(t))
         elif t == PhysicalType.INT64:
             cols.append(Column(t, h.view(np.int64), None, valid))
         elif t == PhysicalType.DOUBLE:

@@ -549,3 +549,18 @@ def test_oracle_matches_golden_file(engine):
             assert got == records(want), (case["name"], name)
             n += 1
     assert n >= 100
+
+
+def test_string_key_compaction_shape_engines_agree():
+    """The C4 shape of bench.py (hex string key, deletes, drop-delete): loser tree, min-heap and brute force agree."""
+    import bench
+    from paimon_b200 import datagen
+    schema = bench.make_schema("c4")
+    spec = bench.make_spec("c4", schema)
+    runs = datagen.make_runs(schema, 7, 7000, seed=5, null_prob=0.5, delete_prob=0.05)
+    outs = [pyoracle.merge(schema, spec, runs, e) for e in ENGINES]
+    assert outs[0].equals(outs[1]) and outs[0].equals(outs[2])
+    kinds = np.asarray(outs[0].columns[schema.n_key + 1].data[: outs[0].n_rows])
+    assert not np.isin(kinds, [1, 3]).any()             # drop-delete
+    keys = outs[0].columns[0].to_pylist()
+    assert keys == sorted(keys) and len(set(keys)) == len(keys)
