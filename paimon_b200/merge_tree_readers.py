@@ -242,8 +242,22 @@ class MergeFileSplitRead:
         self.force_keep_delete = True
         return self
 
+    def with_key_filter(self, lower=None, upper=None) -> "MergeFileSplitRead":
+        """withFilter (MergeFileSplitRead.java:181-217): only KEY predicates may be pushed below the merge — a value
+        predicate would drop the newer version of a row and resurrect an older one (comment :204-213).  Here the
+        key predicate is a closed range on the primary key; it prunes data files by their key bounds before
+        IntervalPartition (a file without keys in range cannot contribute to any key in range).  Rows outside
+        the range that live in surviving files are still returned: the engine filters above the reader, as in
+        the reference."""
+        self.key_lower, self.key_upper = lower, upper
+        return self
+
+    def _prune(self, files: Sequence[DataFileMeta]) -> List[DataFileMeta]:
+        lo, hi = getattr(self, "key_lower", None), getattr(self, "key_upper", None)
+        return [f for f in files if not ((lo is not None and f.max_key < lo) or (hi is not None and f.min_key > hi))]
+
     def create_merge_reader(self, files: Sequence[DataFileMeta], keep_delete: Optional[bool] = None) -> RecordReader:
         keep = self.force_keep_delete if keep_delete is None else keep_delete
         spec = self.mf_factory.create().with_drop_delete(not keep)      # DropDeleteReader fused into the merge
-        sections = IntervalPartition(files).partition()
+        sections = IntervalPartition(self._prune(files)).partition()
         return MergeTreeReaders.reader_for_merge_tree(sections, self.reader_factory, self.udsc, spec)

@@ -86,3 +86,15 @@ def test_cut_key_ranges_are_key_disjoint_and_cover_every_row():
             assert len(ranges) > 50
         if target == 10 ** 9:
             assert len(ranges) == 1
+
+
+def test_key_filter_prunes_files_by_key_bounds():
+    """MergeFileSplitRead.with_key_filter: host logic only (file metadata), no GPU."""
+    from paimon_b200.merge_tree_readers import DataFileMeta, MergeFileSplitRead
+    files = [DataFileMeta(f"f{i}", 0, 10, lo, hi) for i, (lo, hi) in enumerate([(0, 9), (5, 20), (21, 30), (100, 200)])]
+    read = MergeFileSplitRead.__new__(MergeFileSplitRead)          # no device needed for the pruning logic
+    assert [f.file_name for f in read.with_key_filter(10, 25)._prune(files)] == ["f1", "f2"]
+    assert [f.file_name for f in read.with_key_filter(None, 4)._prune(files)] == ["f0"]
+    assert [f.file_name for f in read.with_key_filter(31, None)._prune(files)] == ["f3"]
+    assert len(read.with_key_filter(None, None)._prune(files)) == 4
+    assert read.with_key_filter(201, 300)._prune(files) == []
