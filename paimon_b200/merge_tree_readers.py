@@ -36,12 +36,22 @@ class DataFileMeta:
     file_name: str
     file_size: int
     row_count: int
-    min_key: int                 # single integer key column: the key bounds as integers
-    max_key: int
+    min_key: object              # key bounds: an integer, a string / bytes, or a tuple of those (composite keys)
+    max_key: object
     min_sequence_number: int = 0
     max_sequence_number: int = 0
     level: int = 0
     delete_row_count: int = 0
+
+
+def comparable_key(k):
+    """Key bound in the reference's comparison order: strings compare as their UTF-8 bytes
+    (BinaryString.java:109-126), tuples field by field."""
+    if isinstance(k, str):
+        return k.encode("utf-8")
+    if isinstance(k, tuple):
+        return tuple(comparable_key(x) for x in k)
+    return k
 
 
 @dataclass
@@ -56,7 +66,7 @@ class SortedRun:
 
     def validate(self) -> None:                       # SortedRun.java:85-95
         for a, b in zip(self.files, self.files[1:]):
-            if not a.max_key < b.min_key:
+            if not comparable_key(a.max_key) < comparable_key(b.min_key):
                 raise ValueError("SortedRun is not sorted and may contain overlapping key intervals")
 
     def total_size(self) -> int:
@@ -75,8 +85,15 @@ class IntervalPartition:
         if n == 0:
             return []
         lib = N.load()
-        mn = np.array([f.min_key for f in self.files], np.int64)
-        mx = np.array([f.max_key for f in self.files], np.int64)
+        lo = [comparable_key(f.min_key) for f in self.files]
+        hi = [comparable_key(f.max_key) for f in self.files]
+        if all(isinstance(k, (int, np.integer)) for k in lo + hi):
+            mn, mx = np.array(lo, np.int64), np.array(hi, np.int64)
+        else:
+            # the algorithm only compares key bounds: dense ranks of the bounds give the same sections and runs
+            rank = {k: i for i, k in enumerate(sorted(set(lo + hi)))}
+            mn = np.array([rank[k] for k in lo], np.int64)
+            mx = np.array([rank[k] for k in hi], np.int64)
         sec = np.zeros(n, np.int32)
         run = np.zeros(n, np.int32)
         ns = C.c_int32(0)
@@ -89,7 +106,7 @@ class IntervalPartition:
         for s in sections:
             runs = []
             for rid in sorted(s):
-                files = sorted(s[rid], key=lambda f: (f.min_key, f.max_key))
+                files = sorted(s[rid], key=lambda f: (comparable_key(f.min_key), comparable_key(f.max_key)))
                 runs.append(SortedRun.from_sorted(files))
             out.append(runs)
         return out
@@ -254,7 +271,10 @@ class MergeFileSplitRead:
 
     def _prune(self, files: Sequence[DataFileMeta]) -> List[DataFileMeta]:
         lo, hi = getattr(self, "key_lower", None), getattr(self, "key_upper", None)
-        return [f for f in files if not ((lo is not None and f.max_key < lo) or (hi is not None and f.min_key > hi))]
+        lo = None if lo is None else comparable_key(lo)
+        hi = None if hi is None else comparable_key(hi)
+        return [f for f in files if not ((lo is not None and comparable_key(f.max_key) < lo) or
+                                         (hi is not None and comparable_key(f.min_key) > hi))]
 
     def create_merge_reader(self, files: Sequence[DataFileMeta], keep_delete: Optional[bool] = None) -> RecordReader:
         keep = self.force_keep_delete if keep_delete is None else keep_delete

@@ -74,3 +74,24 @@ def test_interval_partition_host_logic_matches_oracle():
                 g.setdefault((a, b), []).append(i)
             return sorted(g.values())
         assert groups(sec, run) == groups(osec, orun)
+
+
+def test_interval_partition_with_string_and_composite_key_bounds():
+    """IntervalPartition over non-integer key bounds (strings compare as UTF-8 bytes, tuples field by field): the same
+    sections / runs as over integer bounds with the same order."""
+    import random
+    from paimon_b200.merge_tree_readers import DataFileMeta, IntervalPartition
+    rng = random.Random(9)
+    for trial in range(20):
+        n = rng.randrange(1, 30)
+        bounds = []
+        for _ in range(n):
+            a, b = sorted((rng.randrange(100), rng.randrange(100)))
+            bounds.append((a, b))
+        def shape(files):
+            return [[[f.file_name for f in run.files] for run in sec] for sec in IntervalPartition(files).partition()]
+        ints = [DataFileMeta(f"f{i}", 0, 1, a, b) for i, (a, b) in enumerate(bounds)]
+        strs = [DataFileMeta(f"f{i}", 0, 1, "k%03dé" % a, "k%03dé" % b) for i, (a, b) in enumerate(bounds)]
+        tups = [DataFileMeta(f"f{i}", 0, 1, (a // 10, "x%d" % (a % 10)), (b // 10, "x%d" % (b % 10)))
+                for i, (a, b) in enumerate(bounds)]
+        assert shape(ints) == shape(strs) == shape(tups)
