@@ -45,7 +45,7 @@ class FormatReaderContext:
     file_io: LocalFileIO
     file_path: str
     file_size: Optional[int] = None
-    selection: Optional[object] = None      # RoaringBitmap32 row selection: not supported on device yet
+    selection: Optional[object] = None      # RoaringBitmap32 row selection: refused (deletion vectors: dv_factory)
 
 
 class FileRecordReader(RecordReader):
@@ -122,7 +122,8 @@ class ParquetReaderFactory(FormatReaderFactory):
 
     def create_reader(self, context: FormatReaderContext) -> ParquetFileRecordReader:
         if context.selection is not None:
-            raise N.UnsupportedOnDevice(2, "row selections (deletion-vector pushdown) are not decoded on device yet")
+            raise N.UnsupportedOnDevice(2, "RoaringBitmap32 row selections are not pushed into the device decoder; deletion "
+                                          "vectors are applied after the decode (KeyValueFileReaderFactory(dv_factory=...))")
         return ParquetFileRecordReader(self.data_schema, context.file_io.read_bytes(context.file_path), self.device)
 
 
