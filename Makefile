@@ -3,7 +3,8 @@ NVCC ?= /usr/local/cuda/bin/nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Iinclude -Ipaimon_b200/csrc
 SRCS := paimon_b200/csrc/merge.cu paimon_b200/csrc/emit.cu paimon_b200/csrc/api.cu \
-	paimon_b200/csrc/parquet_decode.cu paimon_b200/csrc/parquet_encode.cu paimon_b200/csrc/parquet_meta.cc
+	paimon_b200/csrc/parquet_decode.cu paimon_b200/csrc/parquet_encode.cu paimon_b200/csrc/parquet_meta.cc \
+	paimon_b200/csrc/arrow_export.cu
 HDRS := include/paimon_gpu.h paimon_b200/csrc/pg_internal.h paimon_b200/csrc/device_utils.cuh paimon_b200/csrc/parquet_meta.h
 LIB := paimon_b200/libpaimon_gpu.so
 
@@ -15,6 +16,10 @@ $(LIB): $(SRCS) $(HDRS)
 ptxas-info: $(SRCS) $(HDRS)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c -o /dev/null paimon_b200/csrc/merge.cu
 
+# the JNI shim against the JNI specification's signatures (no JDK in the image: jni/stub/jni.h)
+jni-check:
+	g++ -std=c++17 -fsyntax-only -Wall -Ijni/stub -Iinclude jni/paimon_gpu_jni.cc
+
 oracle:
 	$(MAKE) -C oracle -s
 
@@ -22,4 +27,4 @@ clean:
 	rm -f $(LIB)
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle clean ptxas-info
+.PHONY: all oracle clean ptxas-info jni-check

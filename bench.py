@@ -1,31 +1,43 @@
 #!/usr/bin/env python
 """bench.py — merged rows/s of the LSM merge hot path on B200 (BASELINE.json metric).
 
-One "step" = one pass of the hot path (sampled partition -> plan -> scan -> emit) over one bucket of
-synthetic sorted runs.  Workloads (BASELINE.json configs):
-  c3 (default, the configuration the metric is quoted on): 16 runs x 6.25 M rows = 100 M rows,
-      partial-update merge engine, 50-column wide row (pk + 20 BIGINT + 15 DOUBLE + 14 VARCHAR(8..24)),
-      every non-pk cell NULL with p = 0.5
+One "step" = one pass of the hot path over one bucket of synthetic sorted runs:
+  --source parquet (default for c3):  Parquet file bytes in HBM -> column-chunk decode (one launch set for the
+      section) -> sampled partition -> plan -> scan -> emit.  The 16 run files are written once, outside the timed
+      region, by the device encoder (PLAIN data pages V1, 20 000-row pages, 400 000-row row groups, uncompressed).
+  --source columns: the merge alone over pre-decoded columns resident in HBM (round 1's measurement; reported for
+      c3 under "extra" as well).
+
+Workloads (BASELINE.json configs):
+  c3 (default, the configuration the metric is quoted on): 16 runs x 6.25 M rows = 100 M rows, partial-update merge
+      engine, 50-column wide row (pk + 20 BIGINT + 15 DOUBLE + 14 VARCHAR(8..24)), every non-pk cell NULL with p = 0.5
+  c3agg: same rows, merge-engine aggregation (sum over the numeric columns: ordered left fold, bit-exact)
   c2: 8 runs x 12.5 M rows = 100 M rows, deduplicate, BIGINT pk + 10 BIGINT columns
   c1: 2 runs x 500 K rows, deduplicate, BIGINT pk + BIGINT value
+  c4: one bucket of a full compaction rewrite (32 runs, VARCHAR(16) key, deletes, drop-delete, re-encode)
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c1] [--rows R]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c3agg|c2|c1|c4] [--rows R] [--source ...]
     python bench.py --impl reference ...     # the reference algorithm on the host cores (CPU)
 
-`value`     whole-job merged (= input) rows/s with the runs already resident in HBM.
-`e2e`       same metric through the public reader API with HOST buffers: every step copies the runs
-            host->device (pinned memory) and the merged batch device->host.
-`roofline`  achieved HBM GB/s of the dominant kernel (emit) on the algorithmic bytes
-            N_in*B + N_out*B, against MEASURED_PEAKS.json.
+`value`     whole-job merged (= input) rows/s with the inputs (file bytes / columns) already resident in HBM.
+`e2e`       same metric through the public reader API with HOST buffers: every step copies the Parquet files
+            host->device (pinned memory), decodes, merges, and copies the merged batch device->host; consecutive
+            steps are pipelined (the D2H of bucket i overlaps the H2D of bucket i+1, like consecutive splits of a scan).
+`roofline`  achieved HBM GB/s of the dominant kernel (emit) on the algorithmic bytes N_in*B + N_out*B,
+            `roofline_decode` the same for the decode stage on encoded page bytes + decoded bytes, both against
+            MEASURED_PEAKS.json.
+`parity_sample`  a key range of the full-size result compared bit-for-bit with the CPU oracle.
 `cpu_baseline`  the oracle (C restatement of LoserTree + MergeFunction) timed on this box's host cores.
-Multi-GPU: one process per GPU (torchrun); buckets are independent, so every rank merges its own
-bucket and there is no data-path collective ("weak" scaling).
+Multi-GPU: one process per GPU (torchrun); buckets are independent, so every rank merges its own bucket and there
+is no data-path collective ("weak" scaling).
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
+import queue
 import subprocess
 import sys
 import threading
@@ -33,6 +45,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# decoded runs (48 GB per step on c3) are recycled through the library's buffer cache instead of the driver allocator
+os.environ.setdefault("PG_RUN_CACHE_BYTES", str(150 << 30))
 
 import numpy as np  # noqa: E402
 
@@ -54,6 +68,8 @@ WORKLOADS = {
                desc="one bucket of a full compaction rewrite: 32 runs x 500K rows, varchar(16) pk + 4 i64 + 2 f64 + "
                     "2 i32 + 3 varchar, 5% deletes, drop-delete, output re-encoded to Parquet"),
 }
+PARQUET_PAGE_ROWS = 20_000          # parquet-mr's page row limit (RowDataParquetBuilder.java:63-99 pulls the defaults)
+PARQUET_GROUP_ROWS = 400_000        # ~128 MiB row groups at c3's ~310 encoded bytes per row
 
 
 def schema_c4():
@@ -85,10 +101,34 @@ def make_spec(workload, schema):
     return spec.with_drop_delete() if WORKLOADS[workload].get("drop_delete") else spec
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank's threads (and, by first touch, its page-locked buffers) to the CPUs of the NUMA node its GPU
+    hangs off: the end-to-end leg moves tens of GB per step between host DRAM and the device."""
+    try:
+        out = subprocess.run(["nvidia-smi", f"--id={local_rank}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not out:
+            return None
+        dom, rest = out.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:]}:{rest}/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------ device-side synthetic runs
 
 def _splitmix64(x):
-    import torch
     x = x + (-7046029254386353131)                       # 0x9E3779B97F4A7C15 as int64
     x = (x ^ ((x >> 30) & ((1 << 34) - 1))) * (-4658895280553007687)   # 0xBF58476D1CE4E5B9
     x = (x ^ ((x >> 27) & ((1 << 37) - 1))) * (-7723592293110705685)   # 0x94D049BB133111EB
@@ -107,7 +147,7 @@ def _hex_keys(keys, dev):
 
 
 def gen_device_run(schema, run_index, n, key_space, null_prob, seed, dev, delete_prob=0.0):
-    """One sorted run generated directly in HBM.  Returns (columns, keepalive tensors, key tensor)."""
+    """One sorted run generated directly in HBM.  Returns (columns, keepalive tensors, key tensor, bytes, kinds)."""
     import torch
     from paimon_b200.sort_merge_reader import DeviceColumn
     from paimon_b200.types import PhysicalType
@@ -204,6 +244,47 @@ def device_runs(workload, schema, rows, dev, seed):
     return readers, all_keys, in_bytes, all_kinds
 
 
+def device_parquet_files(workload, schema, rows, dev, seed, lib):
+    """The bucket's runs as Parquet files whose bytes sit in HBM: every run is generated on the device, encoded by
+    pg_parquet_encode (PLAIN, data page V1) and dropped; the file images stay.  Returns (encoded-file handles,
+    [(device pointer, size)], key tensors, kind tensors)."""
+    import torch
+    from paimon_b200 import _native as N
+    from paimon_b200.compact_rewriter import file_column_names
+    from paimon_b200.sort_merge_reader import SortedRunReader, _SchemaHandle
+    w = WORKLOADS[workload]
+    n_runs = w["n_runs"]
+    per_run = rows // n_runs
+    key_space = max(rows // 2, per_run)
+    names = file_column_names(schema)
+    arr = (C.c_char_p * len(names))(*[nm.encode() for nm in names])
+    sh = _SchemaHandle(schema, dev.index or 0)
+    handles, images, all_keys, all_kinds = [], [], [], []
+    try:
+        for r in range(n_runs):
+            cols, keep, keys, _, kind = gen_device_run(schema, r, per_run, key_space, w["null_prob"], seed, dev,
+                                                       w.get("delete_prob", 0.0))
+            rd = SortedRunReader.from_device(schema, per_run, cols, keepalive=keep)
+            try:
+                fh = C.c_uint64(0)
+                opts = N.PgParquetWriteOptions(PARQUET_GROUP_ROWS, PARQUET_PAGE_ROWS)
+                N.check(lib.pg_parquet_encode(rd._open(sh.handle), arr, 0, -1, C.byref(opts), C.byref(fh)))
+                ptr, size = C.c_void_p(0), C.c_int64(0)
+                N.check(lib.pg_parquet_file_device_image(fh.value, C.byref(ptr), C.byref(size)))
+                handles.append(fh.value)
+                images.append((ptr.value, size.value))
+            finally:
+                rd.close()
+            all_keys.append(keys)
+            all_kinds.append(kind)
+            del cols, keep, rd
+            torch.cuda.empty_cache()
+    finally:
+        sh.close()
+    torch.cuda.synchronize()
+    return handles, images, all_keys, all_kinds
+
+
 # ------------------------------------------------------------------ clocks sampling
 
 class ClockSampler:
@@ -286,6 +367,70 @@ def cpu_baseline(workload, total_sample_rows, threads, steps=1, seed=7):
     return rows, times, sum(outs)
 
 
+def load_peak():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    return peak, ("measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s")
+
+
+def expected_rows(w, all_keys, all_kinds):
+    """Size-independent sanity at full size: the number of rows the merge must produce."""
+    import torch
+    if w.get("drop_delete"):
+        # the newest record of a key wins (sequence = run << 32 | row); keys whose winner is a DELETE drop out
+        cat_k = torch.cat(all_keys)
+        cat_r = torch.cat([torch.full_like(k, r) for r, k in enumerate(all_keys)])
+        cat_d = torch.cat(all_kinds).to(torch.int64)
+        order = torch.argsort(cat_k * 64 + cat_r)
+        sk, sd = cat_k[order], cat_d[order]
+        last = torch.ones_like(sk, dtype=torch.bool)
+        last[:-1] = sk[1:] != sk[:-1]
+        return int((last & (sd == 0)).sum().item())
+    return torch.unique(torch.cat(all_keys)).numel()
+
+
+def parity_sample(schema, spec, rd, run_handles, all_keys, n_out, target_rows=300_000):
+    """Compare a key range from the middle of the FULL-size merged batch with the CPU oracle, bit for bit: the input
+    rows of the range are read back from the device-resident runs, the oracle merges them, and the result must equal
+    the rows of the big batch that carry those keys."""
+    import torch
+    from oracle import pyoracle
+    from paimon_b200.sort_merge_reader import fetch_slice
+    n_in = sum(k.numel() for k in all_keys)
+    k0 = all_keys[0]
+    i0 = int(k0.numel() * 0.37)
+    c0 = int(k0[i0].item())
+    span = max(1, int(target_rows / max(n_in, 1) * k0.numel()))
+    c1 = int(k0[min(i0 + span, k0.numel() - 1)].item())
+    bounds = [(int(torch.searchsorted(k, c0).item()), int(torch.searchsorted(k, c1).item())) for k in all_keys]
+    slices = [fetch_slice(schema, h, lo, hi) for h, (lo, hi) in zip(run_handles, bounds)]
+    want = pyoracle.merge(schema, spec, slices)
+
+    def key_at(i):
+        return int(fetch_slice(schema, rd._merge_h, i, i + 1).columns[0].data[0])
+
+    def lower_bound(c):
+        lo, hi = 0, n_out
+        while lo < hi:
+            mid = (lo + hi) // 2
+            if key_at(mid) < c:
+                lo = mid + 1
+            else:
+                hi = mid
+        return lo
+    o0, o1 = lower_bound(c0), lower_bound(c1)
+    got = fetch_slice(schema, rd._merge_h, o0, o1)
+    ok = got.equals(want)
+    return {"result": "ok" if ok else "MISMATCH: " + got.first_difference(want), "rows_in": sum(hi - lo for lo, hi in bounds),
+            "rows_out": int(o1 - o0), "key_range": [c0, c1],
+            "checked": "every column of the merged rows with keys in the range, taken from the full-size batch, "
+                       "bit-exact against the oracle's merge of the same input rows"}
+
+
 # ------------------------------------------------------------------ main
 
 def main():
@@ -294,16 +439,20 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--source", default=None, choices=["parquet", "columns"],
+                    help="timed region starts from Parquet file bytes in HBM (default for c3) or from decoded columns")
     ap.add_argument("--rows", type=int, default=None, help="override total input rows per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-range-rows", type=int, default=8 << 20,
-                    help="e2e: input rows per key range of the streaming reader (0 = one batch, no overlap)")
-    ap.add_argument("--e2e-depth", type=int, default=3, help="e2e: key ranges in flight")
+                    help="e2e (--source columns): input rows per key range of the streaming reader (0 = one batch)")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="e2e (--source columns): key ranges in flight")
     ap.add_argument("--e2e-frac", type=float, default=0.0,
-                    help="e2e: fraction of the key space to stream (0 = all of it if page-locked memory allows)")
+                    help="e2e (--source columns): fraction of the key space to stream (0 = all if page-locked memory allows)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra sub-lines (merge-only c3, c3agg, c2, c4)")
+    ap.add_argument("--no-parity-sample", action="store_true")
     ap.add_argument("--cpu-sample-rows", type=int, default=None)
     ap.add_argument("--cpu-threads", type=int, default=None)
     args = ap.parse_args()
@@ -313,21 +462,27 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     w = WORKLOADS[args.workload]
     rows = args.rows or w["rows"]
+    source = args.source or ("parquet" if args.workload == "c3" else "columns")
     metric = "merged rows/sec at 16 runs x 100M rows" if args.workload == "c3" else f"merged rows/sec ({args.workload})"
+    threads = args.cpu_threads or min(os.cpu_count() or 1, 64)
+    cpu_sample = min(args.cpu_sample_rows or threads * (250_000 if args.workload in ("c3", "c3agg") else 1_000_000), rows)
     config = {"workload": f"{args.workload}: {w['desc']}", "rows_per_gpu": rows, "n_runs": w["n_runs"],
               "merge_engine": w["engine"], "buckets_per_gpu": 1, "parallelism": f"bucket-per-gpu x{world}",
-              "l2": "inputs (>50 GB) far exceed the 126 MB L2; no explicit flush" if rows >= 10_000_000
+              "source": ("parquet: the timed step starts from the bucket's 16 Parquet files resident in HBM (PLAIN data pages "
+                         f"V1, {PARQUET_PAGE_ROWS}-row pages, {PARQUET_GROUP_ROWS}-row row groups, uncompressed: the "
+                         "synthetic values are random bits), decodes them on the device and merges")
+              if source == "parquet" else "columns: decoded columns resident in HBM, merge only",
+              "reference_arm_sample": f"the CPU arm merges a {cpu_sample}-row sample of this shape ({threads} buckets, one "
+                                      "thread each) from decoded columns, no Parquet decode",
+              "l2": "inputs (>30 GB) far exceed the 126 MB L2; no explicit flush" if rows >= 10_000_000
                     else "small input: L2-resident (not a headline configuration)"}
 
     # ---------------- reference arm: the reference's CPU algorithm on the host cores
     if args.impl == "reference":
         if rank != 0:
             return
-        threads = args.cpu_threads or min(os.cpu_count() or 1, 64)
-        sample = args.cpu_sample_rows or threads * (250_000 if args.workload == "c3" else 1_000_000)
-        sample = min(sample, rows)
-        cpu_baseline(args.workload, min(sample, 200_000), threads, steps=max(args.warmup, 1) if args.warmup else 0)
-        nrows, times, _ = cpu_baseline(args.workload, sample, threads, steps=args.steps)
+        cpu_baseline(args.workload, min(cpu_sample, 200_000), threads, steps=max(args.warmup, 1) if args.warmup else 0)
+        nrows, times, _ = cpu_baseline(args.workload, cpu_sample, threads, steps=args.steps)
         total = sum(times)
         val = nrows * len(times) / total
         line = {"impl": "reference", "metric": metric, "value": val, "unit": "rows/s", "n_gpus": args.gpus,
@@ -336,12 +491,14 @@ def main():
                 "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": val, "unit": "rows/s", "cores": threads, "kind": "port",
                                  "sample": f"{threads} buckets x {nrows // threads} rows of the same shape, one "
-                                           f"thread per bucket (C restatement of LoserTree+MergeFunction; no JVM in the image)"},
+                                           f"thread per bucket (C restatement of LoserTree+MergeFunction over decoded "
+                                           f"columns; no JVM in the image)"},
                 "e2e": {"value": val, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
 
     # ---------------- B200 arm
+    numa = bind_to_gpu_numa_node(local_rank)
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -352,14 +509,14 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     from paimon_b200 import _native as N
     from paimon_b200.columnar import Column, KeyValueBatch
+    from paimon_b200.format import read_section
     from paimon_b200.sort_merge_reader import RangeStreamingMergeReader, SortedRunReader, SortMergeReader
 
     schema = make_schema(args.workload)
     spec = make_spec(args.workload, schema)
-    N.init(local_rank)
-    readers, all_keys, in_bytes, all_kinds = device_runs(args.workload, schema, rows, dev, seed=100 + rank)
-    n_in = sum(r.n_rows for r in readers)
-    rd = SortMergeReader.create_sort_merge_reader(readers, None, None, spec, device=local_rank)
+    lib = N.init(local_rank)
+    peak, peak_kind = load_peak()
+    n_runs = w["n_runs"]
 
     def barrier():
         torch.cuda.synchronize()
@@ -367,60 +524,105 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        rd.execute()
-    st = rd.stats()
-    n_out = st.rows_out
-    # sanity at full size (size-independent properties): row conservation + strictly increasing keys
-    if w.get("drop_delete"):
-        # the newest record of a key wins (sequence = run << 32 | row); keys whose winner is a DELETE drop out
-        cat_k = torch.cat(all_keys)
-        cat_r = torch.cat([torch.full_like(k, r) for r, k in enumerate(all_keys)])
-        cat_d = torch.cat(all_kinds).to(torch.int64)
-        order = torch.argsort(cat_k * 64 + cat_r)
-        sk, sd = cat_k[order], cat_d[order]
-        last = torch.ones_like(sk, dtype=torch.bool)
-        last[:-1] = sk[1:] != sk[:-1]
-        uniq = int((last & (sd == 0)).sum().item())
-        del cat_k, cat_r, cat_d, order, sk, sd, last
-    else:
-        uniq = torch.unique(torch.cat(all_keys)).numel()
-    assert n_out == uniq, f"merged rows {n_out} != expected rows {uniq}"
-    out_bytes = st.bytes_out
+    warm = max(args.warmup, 3)
+    extra = {}
+    parity = None
+    roofline_decode = None
 
-    ext = torch.cuda.ExternalStream(rd.cuda_stream(), device=dev)
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ms_emit = ms_plan = ms_part = ms_tot = ms_alloc = 0.0
-    launches = 0
-    t0 = time.perf_counter()
-    e0.record(ext)
-    for _ in range(args.steps):
-        rd.execute()
-        s = rd.stats()
-        ms_emit += s.ms_emit; ms_plan += s.ms_plan; ms_part += s.ms_partition; ms_tot += s.ms_total
-        ms_alloc += s.ms_alloc
-        launches += s.launches
-    e1.record(ext)
-    barrier()
-    wall = time.perf_counter() - t0
-    clocks = sampler.stop()
-    dev_ms = e0.elapsed_time(e1)
+    if source == "parquet":
+        enc_handles, images, all_keys, all_kinds = device_parquet_files(args.workload, schema, rows, dev, 100 + rank, lib)
+        n_in = sum(k.numel() for k in all_keys)
+        files = [(img, r) for r, img in enumerate(images)]
+        rd = SortMergeReader([], spec, None, local_rank, schema=schema)
+        dstream = C.c_void_p(0)
+        N.check(lib.pg_thread_stream(C.byref(dstream)))
+
+        def one_step(keep_runs=False):
+            readers, info = read_section(schema, files, n_runs, local_rank)
+            rd.rebind(readers)
+            rd.execute()
+            st_ = rd.stats()
+            if not keep_runs:
+                for r_ in readers:
+                    r_.close()
+                rd.readers = []
+            return info, st_, readers
+
+        for _ in range(warm):
+            info, st, _ = one_step()
+        n_out = st.rows_out
+        assert info.n_rows == n_in
+        uniq = expected_rows(w, all_keys, all_kinds)
+        assert n_out == uniq, f"merged rows {n_out} != expected rows {uniq}"
+        in_bytes, out_bytes, page_bytes, file_bytes = info.decoded_bytes, st.bytes_out, info.page_bytes, info.file_bytes
+
+        ext_dec = torch.cuda.ExternalStream(dstream.value or 0, device=dev)
+        ext_mrg = torch.cuda.ExternalStream(rd.cuda_stream(), device=dev)
+        sampler = ClockSampler(local_rank)
+        barrier()
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ms_emit = ms_plan = ms_part = ms_tot = ms_alloc = ms_dec = 0.0
+        launches = 0
+        t0 = time.perf_counter()
+        e0.record(ext_dec)
+        for _ in range(args.steps):
+            info, s, _ = one_step()
+            ms_dec += info.ms_decode
+            ms_emit += s.ms_emit; ms_plan += s.ms_plan; ms_part += s.ms_partition; ms_tot += s.ms_total
+            ms_alloc += s.ms_alloc
+            launches += s.launches + info.launches
+        e1.record(ext_mrg)
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop()
+        dev_ms = e0.elapsed_time(e1)
+        dec_ms = ms_dec / args.steps
+        dec_alg = page_bytes + in_bytes
+        roofline_decode = {"bound": "hbm", "stage": "parquet decode (page walk + levels + value walk + expand)",
+                           "achieved": dec_alg / (dec_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                           "frac": dec_alg / (dec_ms * 1e-3) / 1e9 / peak, "stage_ms": dec_ms,
+                           "algorithmic_bytes": int(dec_alg), "encoded_page_bytes": int(page_bytes),
+                           "decoded_bytes": int(in_bytes), "file_bytes": int(file_bytes),
+                           "pages": int(info.n_data_pages), "chunks": int(info.n_chunks), "launches": int(info.launches)}
+    else:
+        readers, all_keys, in_bytes, all_kinds = device_runs(args.workload, schema, rows, dev, seed=100 + rank)
+        n_in = sum(r.n_rows for r in readers)
+        rd = SortMergeReader.create_sort_merge_reader(readers, None, None, spec, device=local_rank)
+        for _ in range(warm):
+            rd.execute()
+        st = rd.stats()
+        n_out = st.rows_out
+        uniq = expected_rows(w, all_keys, all_kinds)
+        assert n_out == uniq, f"merged rows {n_out} != expected rows {uniq}"
+        out_bytes = st.bytes_out
+        ext = torch.cuda.ExternalStream(rd.cuda_stream(), device=dev)
+        sampler = ClockSampler(local_rank)
+        barrier()
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ms_emit = ms_plan = ms_part = ms_tot = ms_alloc = 0.0
+        launches = 0
+        t0 = time.perf_counter()
+        e0.record(ext)
+        for _ in range(args.steps):
+            rd.execute()
+            s = rd.stats()
+            ms_emit += s.ms_emit; ms_plan += s.ms_plan; ms_part += s.ms_partition; ms_tot += s.ms_total
+            ms_alloc += s.ms_alloc
+            launches += s.launches
+        e1.record(ext)
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop()
+        dev_ms = e0.elapsed_time(e1)
+
     t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     step_ms = float(t.item()) / args.steps
     value = world * n_in / (step_ms * 1e-3)
 
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_kind = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     alg_bytes = in_bytes + out_bytes
     emit_ms = ms_emit / args.steps
     # DRAM traffic of the dominant kernel from the committed ncu capture of this workload at its full size
@@ -435,20 +637,65 @@ def main():
     achieved = alg_bytes / (emit_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_emit", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_kind, "traffic": traffic,
-                "algorithmic_bytes": alg_bytes, "kernel_ms": emit_ms,
+                "algorithmic_bytes": int(alg_bytes), "kernel_ms": emit_ms,
                 "step_frac": alg_bytes / (step_ms * 1e-3) / 1e9 / peak,
-                "phase_ms": {"partition": ms_part / args.steps, "plan+scan": ms_plan / args.steps,
+                "phase_ms": {"decode": (ms_dec / args.steps) if source == "parquet" else None,
+                             "partition": ms_part / args.steps, "plan+scan": ms_plan / args.steps,
                              "size_readback+alloc": ms_alloc / args.steps, "emit": emit_ms,
-                             "device_total": ms_tot / args.steps}}
+                             "merge_total": ms_tot / args.steps, "step": step_ms}}
+    if source == "parquet":
+        # the whole decode+merge step on its minimal traffic: encoded pages in, merged batch out
+        fused_alg = page_bytes + out_bytes
+        roofline["step_frac_fused_definition"] = fused_alg / (step_ms * 1e-3) / 1e9 / peak
+        roofline["fused_algorithmic_bytes"] = int(fused_alg)
+
+    # ---------------- parity sample at full size + extras that reuse the decoded runs
+    if source == "parquet":
+        info, st, run_readers = one_step(keep_runs=True)       # decoded runs + the full-size batch stay on the device
+        if not args.no_parity_sample and schema.n_key == 1 and not w.get("drop_delete"):
+            t0p = time.perf_counter()
+            parity = parity_sample(schema, spec, rd, [r_._handle for r_ in run_readers], all_keys, n_out)
+            parity["seconds"] = round(time.perf_counter() - t0p, 2)
+        if world == 1 and not args.no_extra:
+            # round 1's measurement: the merge alone over the decoded runs
+            tms = {"emit": 0.0, "total": 0.0, "plan": 0.0}
+            for _ in range(5):
+                rd.execute()
+                s = rd.stats()
+                tms["emit"] += s.ms_emit / 5; tms["total"] += s.ms_total / 5; tms["plan"] += s.ms_plan / 5
+            extra[f"{args.workload}_merge_only"] = {
+                "what": "merge of the decoded runs (columns resident in HBM), device-timed", "rows_per_s": n_in / (tms["total"] * 1e-3),
+                "ms_per_step": tms["total"], "emit_ms": tms["emit"], "plan_scan_ms": tms["plan"],
+                "emit_frac_of_hbm_peak": alg_bytes / (tms["emit"] * 1e-3) / 1e9 / peak}
+            if args.workload == "c3":
+                spec_agg = make_spec("c3agg", schema)
+                ra = SortMergeReader([], spec_agg, None, local_rank, schema=schema)
+                try:
+                    ra.rebind(run_readers)
+                    for _ in range(2):
+                        ra.execute()
+                    tm = {"emit": 0.0, "total": 0.0}
+                    for _ in range(3):
+                        ra.execute()
+                        s = ra.stats()
+                        tm["emit"] += s.ms_emit / 3; tm["total"] += s.ms_total / 3
+                    extra["c3agg_merge_only"] = {
+                        "what": WORKLOADS["c3agg"]["desc"], "rows_per_s": n_in / (tm["total"] * 1e-3), "ms_per_step": tm["total"],
+                        "emit_ms": tm["emit"], "rows_out": int(s.rows_out),
+                        "emit_frac_of_hbm_peak": (in_bytes + s.bytes_out) / (tm["emit"] * 1e-3) / 1e9 / peak}
+                finally:
+                    ra.readers = []
+                    ra.close()
+        for r_ in run_readers:
+            r_.close()
+        rd.readers = []
 
     # ---------------- compaction rewrite: encode the merged batch to Parquet on the device (C4)
     rewrite = None
     if w.get("drop_delete"):
-        import ctypes as C
         from paimon_b200.compact_rewriter import file_column_names
         names = file_column_names(schema)
         arr = (C.c_char_p * len(names))(*[nm.encode() for nm in names])
-        lib = N.load()
         enc_ms, fbytes, pages = [], 0, 0
         for _ in range(3):
             fh = C.c_uint64(0)
@@ -463,7 +710,90 @@ def main():
 
     # ---------------- e2e: host buffers in, host batch out, through the public reader API
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and source == "parquet":
+        # the files move to page-locked host memory; the device copies are dropped
+        host_files = []
+        for fh, (ptr, size) in zip(enc_handles, images):
+            hb = torch.empty(size, dtype=torch.uint8, pin_memory=True)
+            N.check(lib.pg_parquet_file_fetch(fh, hb.data_ptr(), size))
+            host_files.append(hb.numpy())
+            lib.pg_parquet_file_free(fh)
+        enc_handles = []
+        rd.close()
+        torch.cuda.empty_cache()
+        lib.pg_trim()
+        arena = torch.empty(int(out_bytes * 1.02) + (64 << 20), dtype=torch.uint8, pin_memory=True)
+        arena_np = arena.numpy()
+        hfiles = [(hf, r) for r, hf in enumerate(host_files)]
+        mrs = [SortMergeReader([], spec, None, local_rank, schema=schema) for _ in range(2)]
+        free_q, full_q = queue.Queue(), queue.Queue()
+        for m_ in mrs:
+            free_q.put(m_)
+        d2h_bytes = [0]
+        rows_seen = []
+        errors = []
+
+        def consumer():
+            try:
+                while True:
+                    m_ = full_q.get()
+                    if m_ is None:
+                        return
+                    top = [0]
+
+                    def alloc(nbytes):
+                        a = (top[0] + 63) & ~63
+                        top[0] = a + nbytes
+                        return arena_np[a:a + nbytes]
+                    out = m_.fetch(allocator=alloc)                   # D2H of the merged batch
+                    d2h_bytes[0] = m_.stats().bytes_d2h
+                    rows_seen.append(out.n_rows)
+                    m_.release_batch()
+                    free_q.put(m_)
+            except BaseException as e:                                # surfaced below
+                errors.append(e)
+                free_q.put(None)
+
+        n_e2e = max(1, args.e2e_steps)
+        for phase in ("warm", "timed"):
+            th = threading.Thread(target=consumer, daemon=True)
+            th.start()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(1 if phase == "warm" else n_e2e):
+                m_ = free_q.get()
+                if m_ is None:
+                    raise errors[0]
+                rdrs, sec = read_section(schema, hfiles, n_runs, local_rank)   # H2D of the file bytes + decode
+                m_.rebind(rdrs)
+                m_.execute()
+                for r_ in rdrs:
+                    r_.close()
+                m_.readers = []
+                full_q.put(m_)
+            full_q.put(None)
+            th.join()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if errors:
+                raise errors[0]
+        assert all(x == n_out for x in rows_seen), (rows_seen, n_out)
+        tt = torch.tensor([dt / n_e2e], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        h2d = int(sum(len(hf) for hf in host_files))
+        e2e = {"value": world * n_in / float(tt.item()), "unit": "rows/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": int(d2h_bytes[0]), "ms_per_step": 1e3 * float(tt.item()), "steps": n_e2e,
+               "rows_in_per_step": int(n_in), "rows_out_per_step": int(n_out), "sample": "the whole bucket",
+               "numa": numa,
+               "api": "format.read_section(host Parquet file bytes) -> SortMergeReader.rebind/execute -> fetch() over the C "
+                      "ABI; wall clock of K consecutive buckets / K, the D2H of bucket i overlapping the H2D + decode + merge "
+                      "of bucket i+1 (two merge handles), pinned buffers bound to the GPU's NUMA node",
+               "pcie_floor_ms": 1e3 * max(h2d, int(d2h_bytes[0])) / 55e9}
+        for m_ in mrs:
+            m_.close()
+        del arena, arena_np, host_files
+    elif not args.no_e2e:
         ftypes = schema.physical_types()
         # device -> pinned host copies of every input buffer (the step's inputs live in page-locked memory)
         # Page-locked host memory is finite and every rank of the box needs its own copy of the inputs and room for
@@ -523,9 +853,8 @@ def main():
         arena = torch.empty(int(e2e_out_bytes * 1.02) + (64 << 20), dtype=torch.uint8, pin_memory=True)
         arena_np = arena.numpy()
         e2e_times, h2d_b, d2h_b = [], 0, 0
-        import threading
         single_key = schema.n_key == 1
-        for it_ in range(args.e2e_steps + 1):
+        for it_ in range(max(args.e2e_steps, 2)):
             top = [0]
             lock = threading.Lock()
 
@@ -570,7 +899,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * e2e_rows_in / float(tt.item()), "unit": "rows/s", "h2d_bytes_per_step": int(h2d_b),
                "d2h_bytes_per_step": int(d2h_b), "ms_per_step": 1e3 * float(tt.item()), "steps": len(e2e_times),
-               "rows_in_per_step": int(e2e_rows_in), "rows_out_per_step": int(e2e_rows_out),
+               "rows_in_per_step": int(e2e_rows_in), "rows_out_per_step": int(e2e_rows_out), "numa": numa,
                "sample": ("the whole bucket" if e2e_frac >= 1.0 else
                           f"key-range prefix of the bucket ({e2e_frac:.2f} of the key space): page-locked host memory "
                           f"for {local_world} ranks' full inputs + outputs was not available"),
@@ -580,25 +909,68 @@ def main():
                "SortMergeReader.create_sort_merge_reader(host runs).execute()+fetch() over the C ABI"}
     else:
         rd.close()
+        if source == "parquet":
+            for fh in enc_handles:
+                lib.pg_parquet_file_free(fh)
+
+    # ---------------- extra sub-lines: other BASELINE configs in the same invocation (merge of decoded columns)
+    if world == 1 and not args.no_extra and args.workload == "c3" and rows == w["rows"]:
+        torch.cuda.empty_cache()
+        lib.pg_trim()
+        for wl in ("c2", "c4"):
+            try:
+                sc2 = make_schema(wl)
+                sp2 = make_spec(wl, sc2)
+                rds2, keys2, inb2, kinds2 = device_runs(wl, sc2, WORKLOADS[wl]["rows"], dev, seed=100)
+                r2 = SortMergeReader.create_sort_merge_reader(rds2, None, None, sp2, device=local_rank)
+                try:
+                    for _ in range(3):
+                        r2.execute()
+                    assert r2.stats().rows_out == expected_rows(WORKLOADS[wl], keys2, kinds2)
+                    tm = {"emit": 0.0, "total": 0.0, "plan": 0.0, "part": 0.0}
+                    for _ in range(5):
+                        r2.execute()
+                        s = r2.stats()
+                        tm["emit"] += s.ms_emit / 5; tm["total"] += s.ms_total / 5; tm["plan"] += s.ms_plan / 5
+                        tm["part"] += s.ms_partition / 5
+                    n2 = sum(x.n_rows for x in rds2)
+                    alg2 = inb2 + s.bytes_out
+                    extra[f"{wl}_merge_only"] = {
+                        "what": WORKLOADS[wl]["desc"], "rows_per_s": n2 / (tm["total"] * 1e-3), "ms_per_step": tm["total"],
+                        "emit_ms": tm["emit"], "plan_scan_ms": tm["plan"], "partition_ms": tm["part"],
+                        "rows_in": int(n2), "rows_out": int(s.rows_out),
+                        "emit_frac_of_hbm_peak": alg2 / (tm["emit"] * 1e-3) / 1e9 / peak,
+                        "step_frac_of_hbm_peak": alg2 / (tm["total"] * 1e-3) / 1e9 / peak}
+                finally:
+                    r2.close()
+                    del rds2, keys2, kinds2
+                    torch.cuda.empty_cache()
+                    lib.pg_trim()
+            except Exception as e:                                   # an extra must not take the headline line down
+                extra[f"{wl}_merge_only"] = {"error": repr(e)[:300]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = args.cpu_threads or min(os.cpu_count() or 1, 64)
-        sample = args.cpu_sample_rows or threads * (250_000 if args.workload == "c3" else 1_000_000)
-        sample = min(sample, rows)
-        nrows, times, _ = cpu_baseline(args.workload, sample, threads, steps=2)
+        nrows, times, _ = cpu_baseline(args.workload, cpu_sample, threads, steps=2)
         cpu = {"value": nrows / min(times), "unit": "rows/s", "cores": threads, "kind": "port",
                "sample": f"{threads} buckets x {nrows // threads} rows of the same shape, one thread per bucket; "
-                         f"oracle = C restatement of LoserTree+MergeFunction (no JVM in the image)"}
+                         f"oracle = C restatement of LoserTree+MergeFunction over decoded columns (no JVM in the image)"}
 
     if rank == 0:
         line = {"metric": metric, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+                "warmup": warm, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config,
                 "rows_in_per_gpu": int(n_in), "rows_out_per_gpu": int(n_out), "wall_ms_per_step": 1e3 * wall / args.steps,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+        if roofline_decode is not None:
+            line["roofline_decode"] = roofline_decode
+        if parity is not None:
+            line["parity_sample"] = parity["result"]
+            line["parity_sample_detail"] = parity
         if rewrite is not None:
             line["rewrite"] = rewrite
+        if extra:
+            line["extra"] = extra
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

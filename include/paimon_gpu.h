@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define PG_ABI_VERSION 1
+#define PG_ABI_VERSION 2
 #define PG_MAX_RUNS 32          /* runs merged by one call; more => merge in rounds on the host */
 #define PG_MAX_SEQ_GROUPS 16
 #define PG_MAX_KEY_FIELDS 4
@@ -161,7 +161,9 @@ typedef struct {
 const char *pg_last_error(void);
 int32_t pg_abi_version(void);
 
-/* bind the calling thread's library state to a device; idempotent */
+/* bind the library to a device; idempotent for the same ordinal.  One process drives ONE GPU (one process per GPU,
+ * like bucket_scheduler / torchrun): a second ordinal is refused — handles, streams and the recycled device buffers
+ * all belong to the first one. */
 pg_status pg_init(int32_t device_ordinal);
 pg_status pg_shutdown(void);
 /* give the cached device buffers of freed host-opened runs back to the driver */
@@ -169,6 +171,7 @@ pg_status pg_trim(void);
 
 pg_status pg_schema_create(const pg_schema_desc *desc, uint64_t *out_schema);
 pg_status pg_schema_free(uint64_t schema);
+pg_status pg_schema_info(uint64_t schema, int32_t *n_key, int32_t *n_val);
 
 pg_status pg_merge_spec_create(uint64_t schema, const pg_merge_spec *spec, uint64_t *out_spec);
 pg_status pg_merge_spec_free(uint64_t spec);
@@ -192,7 +195,8 @@ pg_status pg_merge_rebind(uint64_t merge, const uint64_t *runs, int32_t k, const
 pg_status pg_merge_execute(uint64_t merge);
 /* the single output batch, device-resident (pointers are device pointers) */
 pg_status pg_merge_device_batch(uint64_t merge, pg_batch *out);
-/* copy the output batch into caller-allocated host buffers (sizes from pg_merge_device_batch) */
+/* copy the output batch into caller-allocated host buffers (sizes from pg_merge_device_batch); host_cols[c].data_bytes
+ * is the CAPACITY of host_cols[c].data and is checked (offsets need 4 * (n_rows + 1) bytes, validity (n_rows + 7) / 8) */
 pg_status pg_merge_fetch(uint64_t merge, const pg_out_column *host_cols, int32_t n_cols);
 pg_status pg_merge_release(uint64_t merge);      /* releaseBatch(): drop the output buffers */
 pg_status pg_merge_stats(uint64_t merge, pg_stats *out);
@@ -203,15 +207,67 @@ pg_status pg_merge_free(uint64_t merge);
 pg_status pg_run_layout(uint64_t run, int64_t *n_rows, int64_t *data_bytes, int32_t *has_validity, int32_t n_cols);
 pg_status pg_run_fetch(uint64_t run, const pg_out_column *host_cols, int32_t n_cols);
 
+/* ---- Arrow C Data Interface export: the batch the JVM imports ------------------------------------
+ * The struct definitions restate the public Arrow C Data Interface (https://arrow.apache.org/docs/format/
+ * CDataInterface.html); they are guarded with the specification's own macro so that including Arrow's abi.h first
+ * is fine. */
+#ifndef ARROW_C_DATA_INTERFACE
+#define ARROW_C_DATA_INTERFACE
+struct ArrowSchema {
+    const char *format;
+    const char *name;
+    const char *metadata;
+    int64_t flags;
+    int64_t n_children;
+    struct ArrowSchema **children;
+    struct ArrowSchema *dictionary;
+    void (*release)(struct ArrowSchema *);
+    void *private_data;
+};
+struct ArrowArray {
+    int64_t length;
+    int64_t null_count;
+    int64_t offset;
+    int64_t n_buffers;
+    int64_t n_children;
+    const void **buffers;
+    struct ArrowArray **children;
+    struct ArrowArray *dictionary;
+    void (*release)(struct ArrowArray *);
+    void *private_data;
+};
+#endif
+/* Rows [row0, row0 + n_rows) (n_rows < 0 = to the end) of a merge handle's current batch, or of a run handle, as
+ * one Arrow struct array whose children are the file columns, named `column_names[i]` (the Paimon field names
+ * _KEY_*, _SEQUENCE_NUMBER, _VALUE_KIND, value fields: paimon-arrow's ArrowBatchReader.java:74-115 maps columns by
+ * name).  The buffers are page-locked host memory owned by `out` and freed by out->release (what the Java reader's
+ * releaseBatch() / close() call after Data.importVectorSchemaRoot); BOOLEAN columns are bit-packed as Arrow wants
+ * them.  A reader hands a large batch out piece by piece by calling this with consecutive row ranges
+ * (RecordReader.readBatch(), paimon-common/.../reader/RecordReader.java:42-72). */
+pg_status pg_export_arrow(uint64_t source, const char *const *column_names, int64_t row0, int64_t n_rows,
+                          struct ArrowArray *out, struct ArrowSchema *out_schema);
+
+/* A VIEW (no copy) of rows [row_lo, row_hi) of a run handle, or of the current batch of a merge handle: a new run
+ * handle whose columns point into the source's device buffers (the source must outlive it; pg_run_free drops the
+ * view only).  The view starts at the 128-row boundary at or below row_lo (every buffer stays 16-byte aligned);
+ * *start_row receives row_lo's position inside the view — pass it as start_rows[i] to pg_merge_rebind, or skip that
+ * many rows after pg_run_fetch.  Used to re-merge / read back a key range of a bucket (parity samples at full size,
+ * readers that hand out a large batch piece by piece). */
+pg_status pg_run_slice(uint64_t source, int64_t row_lo, int64_t row_hi, uint64_t *out_run, int64_t *start_row);
+
+/* the CUDA stream the calling thread's format readers (pg_parquet_*) launch on, for event timing */
+pg_status pg_thread_stream(void **out_cuda_stream);
+
 /* ---- format seam: Parquet data file -> device-resident sorted run -------------------------------------
  * Replaces FormatReaderFactory.createReader(context) + FileRecordReader.readBatch()
  * (paimon-common/.../format/FormatReaderFactory.java:33-57, paimon-format/.../parquet/ParquetReaderFactory.java:
  * 113-148, reader/VectorizedParquetRecordReader.java:178-241) for KeyValue data files: the file bytes (read by the
  * Java FileIO) are parsed on the host for footer + page headers and decoded on the device straight into the
- * columnar run the merge consumes.  ABI v1 decodes flat schemas, INT32/INT64/FLOAT/DOUBLE/BYTE_ARRAY, PLAIN and
- * dictionary encodings, data pages V1/V2, uncompressed and Snappy-compressed pages (decompressed on the device);
- * DELTA_BINARY_PACKED integers on uncompressed pages; anything else (zstd, gzip, byte-array DELTA encodings,
- * nested columns) returns PG_ERR_UNSUPPORTED. */
+ * columnar run the merge consumes.  Decoded: flat schemas, BOOLEAN/INT32/INT64/FLOAT/DOUBLE/BYTE_ARRAY, PLAIN and
+ * dictionary encodings, RLE booleans, DELTA_BINARY_PACKED integers, data pages V1/V2, uncompressed and
+ * Snappy-compressed pages (decompressed on the device); anything else (gzip, lz4, byte-array DELTA encodings,
+ * INT96 / FIXED_LEN_BYTE_ARRAY, nested columns) returns PG_ERR_UNSUPPORTED.  pg_parquet_open walks the page headers
+ * on the host once so that such files are refused before any device work. */
 typedef struct {
     int64_t n_rows;
     int32_t n_row_groups;
@@ -227,6 +283,38 @@ pg_status pg_parquet_describe(uint64_t reader, pg_parquet_info *out);
 /* decode the whole file into a run handle (free it with pg_run_free); usable directly in pg_merge_open */
 pg_status pg_parquet_read_run(uint64_t reader, uint64_t *out_run);
 pg_status pg_parquet_free(uint64_t reader);
+
+/* ---- a whole SECTION in one batch of launches ------------------------------------------------------------
+ * Replaces MergeTreeReaders.readerForSection's reader construction (paimon-core/.../mergetree/MergeTreeReaders.java:
+ * 67-101): every data file of every sorted run of a section is decoded by one set of kernel launches, and the files
+ * of one run (key-disjoint, ascending: SortedRun.java:59-61) are CONCATENATED into one device run, exactly as
+ * readerForRun's ConcatRecordReader does — the k-way merge then sees k = number of runs inputs, not number of files.
+ * `files[i].run` names the output run of file i; files of a run must be listed in key order.  `bytes` is host memory
+ * (copied to the device by the call) or device memory (PG_MEM_DEVICE: the bytes already sit in HBM, e.g. read by
+ * GPUDirect storage or produced by pg_parquet_encode; must stay valid during the call only).  Only the footers are
+ * parsed on the host; page headers are parsed on the device.  `column_names` (n_key + 2 + n_val entries, or NULL)
+ * are the field names the read schema expects: a file whose column names differ is refused (the reference maps
+ * columns by name, ParquetReaderFactory.java:113-148, and files of older schemas need the Java-side evolution
+ * mapping).  out_runs[n_runs] receives run handles (pg_run_free each). */
+typedef struct {
+    const uint8_t *bytes;
+    int64_t size;
+    int32_t mem;                   /* PG_MEM_HOST / PG_MEM_DEVICE */
+    int32_t run;                   /* output run of this file, 0 <= run < n_runs */
+} pg_file_desc;
+
+typedef struct {
+    int64_t n_rows;
+    int64_t file_bytes;            /* sum of the file sizes */
+    int64_t page_bytes;            /* uncompressed page bodies: the encoded bytes the decode kernels read */
+    int64_t decoded_bytes;         /* bytes of the decoded columns (values, offsets, payload, validity) */
+    int32_t n_files, n_runs, n_chunks, n_data_pages, n_dictionary_pages;
+    int32_t launches;
+    float ms_decode;               /* CUDA-event time from the first copy / kernel to the last kernel */
+} pg_section_info;
+
+pg_status pg_parquet_read_section(uint64_t schema, const pg_file_desc *files, int32_t n_files, int32_t n_runs,
+                                  const char *const *column_names, uint64_t *out_runs, pg_section_info *info);
 
 /* ApplyDeletionVectorReader (paimon-core/.../deletionvectors/ApplyDeletionVectorReader.java:31-54): a new run holding
  * the rows of `run` whose file position is NOT set in the deletion vector.  `deleted_bitmap` is host memory, LSB
@@ -268,6 +356,10 @@ pg_status pg_parquet_file_meta(uint64_t file, pg_file_meta *out);
 pg_status pg_parquet_file_column_stats(uint64_t file, int32_t column, int64_t *null_count, int32_t *has_min_max,
                                        void *min8, void *max8);
 pg_status pg_parquet_file_fetch(uint64_t file, void *host_buffer, int64_t capacity);
+/* the complete file image in device memory (page headers and footer patched in on first use); valid until
+ * pg_parquet_file_free.  Lets a compaction hand its output to the next read without leaving HBM, and is how the
+ * benchmark builds 100 M-row Parquet inputs. */
+pg_status pg_parquet_file_device_image(uint64_t file, const uint8_t **device_bytes, int64_t *size);
 pg_status pg_parquet_file_free(uint64_t file);
 
 /* IntervalPartition over int64 (min,max) key bounds of data files: section and run id per file */

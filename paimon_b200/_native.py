@@ -65,6 +65,17 @@ class PgParquetInfo(C.Structure):
                 ("launches", C.c_int32)]
 
 
+class PgFileDesc(C.Structure):
+    _fields_ = [("bytes", C.c_void_p), ("size", C.c_int64), ("mem", C.c_int32), ("run", C.c_int32)]
+
+
+class PgSectionInfo(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("file_bytes", C.c_int64), ("page_bytes", C.c_int64),
+                ("decoded_bytes", C.c_int64), ("n_files", C.c_int32), ("n_runs", C.c_int32), ("n_chunks", C.c_int32),
+                ("n_data_pages", C.c_int32), ("n_dictionary_pages", C.c_int32), ("launches", C.c_int32),
+                ("ms_decode", C.c_float)]
+
+
 class PgParquetWriteOptions(C.Structure):
     _fields_ = [("row_group_rows", C.c_int64), ("page_rows", C.c_int64)]
 
@@ -99,6 +110,7 @@ _SIGNATURES = {
     "pg_shutdown": (C.c_int32, []),
     "pg_schema_create": (C.c_int32, [C.POINTER(PgSchemaDesc), C.POINTER(C.c_uint64)]),
     "pg_schema_free": (C.c_int32, [C.c_uint64]),
+    "pg_schema_info": (C.c_int32, [C.c_uint64, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "pg_merge_spec_create": (C.c_int32, [C.c_uint64, C.POINTER(PgMergeSpec), C.POINTER(C.c_uint64)]),
     "pg_merge_spec_free": (C.c_int32, [C.c_uint64]),
     "pg_run_open": (C.c_int32, [C.c_uint64, C.POINTER(PgRunDesc), C.c_int32, C.POINTER(C.c_uint64)]),
@@ -117,10 +129,16 @@ _SIGNATURES = {
                                           C.POINTER(C.c_int32)]),
     "pg_run_layout": (C.c_int32, [C.c_uint64, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p, C.c_int32]),
     "pg_run_fetch": (C.c_int32, [C.c_uint64, C.POINTER(PgOutColumn), C.c_int32]),
+    "pg_run_slice": (C.c_int32, [C.c_uint64, C.c_int64, C.c_int64, C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]),
+    "pg_thread_stream": (C.c_int32, [C.POINTER(C.c_void_p)]),
+    "pg_export_arrow": (C.c_int32, [C.c_uint64, C.POINTER(C.c_char_p), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "pg_parquet_open": (C.c_int32, [C.c_uint64, C.c_void_p, C.c_int64, C.POINTER(C.c_uint64)]),
     "pg_parquet_describe": (C.c_int32, [C.c_uint64, C.POINTER(PgParquetInfo)]),
     "pg_parquet_read_run": (C.c_int32, [C.c_uint64, C.POINTER(C.c_uint64)]),
     "pg_parquet_free": (C.c_int32, [C.c_uint64]),
+    "pg_parquet_read_section": (C.c_int32, [C.c_uint64, C.POINTER(PgFileDesc), C.c_int32, C.c_int32,
+                                            C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.POINTER(PgSectionInfo)]),
+    "pg_parquet_file_device_image": (C.c_int32, [C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "pg_run_apply_deletion_vector": (C.c_int32, [C.c_uint64, C.c_void_p, C.c_int64, C.POINTER(C.c_uint64)]),
     "pg_parquet_encode": (C.c_int32, [C.c_uint64, C.POINTER(C.c_char_p), C.c_int64, C.c_int64,
                                       C.POINTER(PgParquetWriteOptions), C.POINTER(C.c_uint64)]),

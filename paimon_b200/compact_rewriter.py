@@ -45,8 +45,7 @@ class WrittenFile:
 
 def file_column_names(schema: KeyValueSchema) -> List[str]:
     """[_KEY_*, _SEQUENCE_NUMBER, _VALUE_KIND, value...] (KeyValue.schema, KeyValue.java:130-138)."""
-    return ([f.name for f in schema.key_type.fields] + ["_SEQUENCE_NUMBER", "_VALUE_KIND"] +
-            [f.name for f in schema.value_type.fields])
+    return [f.name for f in schema.file_fields()]
 
 
 class KeyValueDataFileWriter:
@@ -77,13 +76,27 @@ class KeyValueDataFileWriter:
             stats = [self._column_stats(fh.value, c) for c in range(self.schema.n_cols)]
         finally:
             self.lib.pg_parquet_file_free(fh.value)
-        key = stats[0]
-        dfm = DataFileMeta(file_name=self.path, file_size=int(meta.file_bytes), row_count=int(meta.n_rows),
-                           min_key=key.min, max_key=key.max,
+        # min / max key = the key ROW of the first / last record of the file (the batch is sorted by key):
+        # KeyValueDataFileWriter.java:116-118,166-167 keeps the first and the last key it saw.  Every key field,
+        # var-len ones included — column statistics would truncate composite keys and have nothing for strings.
+        n_file = int(meta.n_rows)
+        min_key = max_key = None
+        if n_file > 0:
+            min_key = self._key_row(source_handle, row0)
+            max_key = self._key_row(source_handle, row0 + n_file - 1)
+        dfm = DataFileMeta(file_name=self.path, file_size=int(meta.file_bytes), row_count=n_file,
+                           min_key=min_key, max_key=max_key,
                            min_sequence_number=int(meta.min_sequence_number),
                            max_sequence_number=int(meta.max_sequence_number), level=self.level,
                            delete_row_count=int(meta.delete_row_count))
         return WrittenFile(dfm, stats[self.schema.n_key + 2:], float(meta.ms_encode), int(meta.n_pages))
+
+    def _key_row(self, source_handle: int, row: int):
+        """The primary key of one row of the device batch: a scalar for single-field keys, else a tuple."""
+        from .sort_merge_reader import fetch_slice
+        one = fetch_slice(self.schema, source_handle, row, row + 1)
+        vals = [one.columns[i].to_pylist()[0] for i in range(self.schema.n_key)]
+        return vals[0] if len(vals) == 1 else tuple(vals)
 
     def _column_stats(self, fh: int, c: int) -> SimpleColStats:
         nulls, has = C.c_int64(0), C.c_int32(0)
@@ -155,12 +168,15 @@ class MergeTreeCompactRewriter:
         rolling = RollingFileWriter(self.schema, self.directory, output_level, self.target_file_rows, self.file_io,
                                     prefix=f"compact-l{output_level}", **self.writer_args)
         for section in sections:
-            opened = []
             for run in section:
                 result.before += run.files
-                opened += MergeTreeReaders.reader_for_run(run, self.reader_factory)
-            merge = SortMergeReader.create_sort_merge_reader([r for _, r in opened], None, self.udsc, spec,
-                                                             device=self.device)
+            runs = MergeTreeReaders.open_runs(section, self.reader_factory)
+            try:
+                merge = SortMergeReader.create_sort_merge_reader(runs, None, self.udsc, spec, device=self.device)
+            except Exception:
+                for r in runs:
+                    r.close()
+                raise
             try:
                 merge.execute()
                 n_out = merge.device_batch().n_rows
@@ -168,8 +184,6 @@ class MergeTreeCompactRewriter:
                     rolling.write(merge._merge_h, n_out)
             finally:
                 merge.close()
-                for fr, _ in opened:
-                    fr.close()
         result.written = rolling.results
         result.after = [w.meta for w in rolling.results]
         return result

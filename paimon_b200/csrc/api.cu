@@ -79,6 +79,8 @@ struct Merge {
     ColDesc *d_cols = nullptr;
     int32_t *d_tile_counter = nullptr;
     int32_t *d_col_order = nullptr;
+    int32_t *d_varlen_cols = nullptr;
+    int n_passes = 0;
     const SeqGroups *d_groups = nullptr;
     bool has_group_aggs = false;
     pg_out_column *d_out_cols = nullptr;
@@ -408,7 +410,8 @@ static pg_status build_descriptors(Merge *m) {
     size_t o_err = o_tot + align(sizeof(int64_t) * (nv + 1));
     size_t o_cnt = o_err + 256;
     size_t o_ord = o_cnt + 256;
-    size_t o_sg = o_ord + align(sizeof(int32_t) * nc);
+    size_t o_vlc = o_ord + align(sizeof(int32_t) * (2 * (size_t)nc + 2));
+    size_t o_sg = o_vlc + align(sizeof(int32_t) * (size_t)(nv + 1));
     size_t total = o_sg + align(sizeof(SeqGroups));
     std::vector<unsigned char> host(total, 0);
     m->varlen_bound.assign(nv, 0);
@@ -430,11 +433,18 @@ static pg_status build_descriptors(Merge *m) {
     }
     memcpy(host.data() + o_cols, m->cols.data(), sizeof(ColDesc) * nc);
     {
-        // var-len columns first (see k_emit), then the fixed-width ones in schema order
+        // the emit kernel's pass list (see k_emit): columns without staged data, the size pass of every var-len
+        // column, the fixed-width columns, the copy pass of every var-len column.  phase ids = emit.cu PH_*
         int32_t *ord = (int32_t *)(host.data() + o_ord);
+        int32_t *vlc = (int32_t *)(host.data() + o_vlc);
         int n = 0;
-        for (int c = 0; c < nc; c++) if (m->cols[c].width == 0) ord[n++] = c;
-        for (int c = 0; c < nc; c++) if (m->cols[c].width != 0) ord[n++] = c;
+        auto plain = [&](int c) { return m->cols[c].mode == CM_SEQ || m->cols[c].mode == CM_KIND; };
+        for (int c = 0; c < nc; c++) if (plain(c)) ord[n++] = c | (0 << 16);
+        for (int c = 0; c < nc; c++) if (m->cols[c].width == 0) ord[n++] = c | (1 << 16);
+        for (int c = 0; c < nc; c++) if (m->cols[c].width != 0 && !plain(c)) ord[n++] = c | (2 << 16);
+        for (int c = 0; c < nc; c++) if (m->cols[c].width == 0) ord[n++] = c | (3 << 16);
+        m->n_passes = n;
+        for (int v = 0; v < nv; v++) vlc[v] = m->varlen_cols[v];
     }
     m->d_groups = nullptr;
     if (sp->n_groups() > 0) {
@@ -472,6 +482,7 @@ static pg_status build_descriptors(Merge *m) {
     m->d_err = (int32_t *)(d + o_err);
     m->d_tile_counter = (int32_t *)(d + o_cnt);
     m->d_col_order = (int32_t *)(d + o_ord);
+    m->d_varlen_cols = (int32_t *)(d + o_vlc);
     if (sp->n_groups() > 0) m->d_groups = (const SeqGroups *)(d + o_sg);
     if (!m->h_totals) PG_CUDA(cudaMallocHost((void **)&m->h_totals, sizeof(int64_t) * (nv + 1) + 16));
     m->h_err = (int32_t *)(m->h_totals + nv + 1);
@@ -672,6 +683,7 @@ static pg_status execute(Merge *m) {
             if (cd.width > 0) need += pad((size_t)n_out * cd.width + 64);
             else need += pad((size_t)m->varlen_bound[cd.varlen_index] + 64) + pad(4 * (size_t)(n_out + 1) + 64);
         }
+        if (nv > 0) need += pad(sizeof(uint16_t) * (size_t)nv * (size_t)(n_out + 64) + 64);   // k_emit's source scratch
         PG_CUDA(m->outbuf.reserve(need + vbytes));
         if (vbytes) {
             void *v0 = m->outbuf.take(vbytes);
@@ -710,6 +722,8 @@ static pg_status execute(Merge *m) {
         if (cd.width > 0) bytes_out += oc.data_bytes;
     }
     m->stats.bytes_out = bytes_out;
+    uint16_t *vsrc = nullptr;
+    if (nv > 0) PG_CUDA(oalloc(sizeof(uint16_t) * (size_t)nv * (size_t)(n_out + 64) + 64, (void **)&vsrc));
     PG_CUDA(cudaMemcpyAsync(m->d_out_cols, m->out_cols.data(), sizeof(pg_out_column) * nc,
                             cudaMemcpyHostToDevice, sm));
 
@@ -728,6 +742,10 @@ static pg_status execute(Merge *m) {
     ea.gagg = gagg;
     ea.cols = m->d_cols;
     ea.col_order = m->d_col_order;
+    ea.n_passes = m->n_passes;
+    ea.varlen_cols = m->d_varlen_cols;
+    ea.vsrc = vsrc;
+    ea.vsrc_stride = n_out + 64;
     ea.ptrs = m->d_ptrs;
     ea.run_rows = m->d_run_rows;
     ea.n_cols = nc;
@@ -785,6 +803,9 @@ pg_status pg_init(int32_t device_ordinal) {
         return fail(PG_ERR_CUDA, std::string("no CUDA device: libpaimon_gpu has no CPU fallback (") +
                                      cudaGetErrorString(e) + ")");
     if (device_ordinal < 0 || device_ordinal >= n) return fail(PG_ERR_INVALID, "bad device ordinal");
+    if (g_device >= 0 && g_device != device_ordinal)
+        return fail(PG_ERR_INVALID, "pg_init: this process is already bound to device " + std::to_string(g_device) +
+                                    " (one process per GPU: handles, streams and cached buffers belong to it)");
     PG_CUDA(cudaSetDevice(device_ordinal));
     g_device = device_ordinal;
     cudaMemPool_t pool;
@@ -824,6 +845,14 @@ pg_status pg_schema_create(const pg_schema_desc *desc, uint64_t *out_schema) {
     return PG_OK;
 }
 
+pg_status pg_schema_info(uint64_t schema, int32_t *n_key, int32_t *n_val) {
+    Schema *s = g_schemas.get(schema);
+    if (!s) return fail(PG_ERR_INVALID, "unknown schema handle");
+    if (n_key) *n_key = s->n_key;
+    if (n_val) *n_val = s->n_val;
+    return PG_OK;
+}
+
 pg_status pg_schema_free(uint64_t schema) {
     return g_schemas.take(schema) ? PG_OK : fail(PG_ERR_INVALID, "unknown schema handle");
 }
@@ -848,7 +877,12 @@ pg_status pg_merge_spec_create(uint64_t schema, const pg_merge_spec *spec, uint6
     sp->remove_record_on_delete = spec->remove_record_on_delete != 0;
     sp->drop_delete = spec->drop_delete != 0;
     sp->seq_ascending = spec->seq_ascending;
-    for (int i = 0; i < spec->n_seq_fields; i++) sp->seq_fields.push_back(spec->seq_fields[i]);
+    if (spec->n_seq_fields < 0 || (spec->n_seq_fields > 0 && !spec->seq_fields))
+        return fail(PG_ERR_INVALID, "bad sequence.field description");
+    for (int i = 0; i < spec->n_seq_fields; i++) {
+        if (spec->seq_fields[i] < 0 || spec->seq_fields[i] >= s->n_val) return fail(PG_ERR_INVALID, "sequence.field index out of range");
+        sp->seq_fields.push_back(spec->seq_fields[i]);
+    }
     if (spec->agg) sp->agg.assign(spec->agg, spec->agg + s->n_val);
     if (spec->ignore_retract) sp->ignore_retract.assign(spec->ignore_retract, spec->ignore_retract + s->n_val);
     if (spec->n_sequence_groups > 0) {
@@ -1035,6 +1069,8 @@ pg_status pg_run_fetch(uint64_t run, const pg_out_column *host_cols, int32_t n_c
         const DevColumn &dc = r->cols[c];
         const pg_out_column &hc = host_cols[c];
         size_t db = is_varlen(f.type) ? (size_t)r->varlen_bytes[c] : (size_t)n * type_width(f.type);
+        if (db && hc.data && (size_t)hc.data_bytes < db)
+            return fail(PG_ERR_INVALID, "pg_run_fetch: data buffer of column " + std::to_string(c) + " is too small");
         if (db && hc.data)
             PG_CUDA(cudaMemcpy(hc.data, (const unsigned char *)dc.data + (c < (int)r->varlen_base.size() ? r->varlen_base[c] : 0),
                                db, cudaMemcpyDeviceToHost));
@@ -1043,6 +1079,66 @@ pg_status pg_run_fetch(uint64_t run, const pg_out_column *host_cols, int32_t n_c
         if (dc.validity && hc.validity)
             PG_CUDA(cudaMemcpy(hc.validity, dc.validity, (size_t)((n + 7) / 8), cudaMemcpyDeviceToHost));
     }
+    return PG_OK;
+}
+
+}  // extern "C"
+
+// a view of rows [row_lo & ~127, row_hi) of a run or of a merge handle's batch: no copy, the columns point into the
+// source's buffers (128 rows keep every buffer 16-byte aligned: 1-byte values, 4-byte offsets, 1-bit validity)
+static pg_status make_slice(uint64_t source, int64_t row_lo, int64_t row_hi, uint64_t *out_run, int64_t *start_row) {
+    const Schema *s = nullptr;
+    std::vector<DevColumn> cols;
+    int64_t n = 0;
+    pg_status st = batch_columns(source, &s, &cols, &n);
+    if (st) return st;
+    if (row_lo < 0 || row_hi < row_lo || row_hi > n) return fail(PG_ERR_INVALID, "slice outside the source");
+    const int64_t lo = row_lo & ~(int64_t)127;
+    auto run = std::make_unique<Run>();
+    run->own_schema = *s;
+    run->schema = &run->own_schema;
+    run->n_rows = row_hi - lo;
+    const int nc = s->n_cols();
+    run->cols.resize(nc);
+    run->varlen_bytes.assign(nc, 0);
+    run->varlen_base.assign(nc, 0);
+    for (int c = 0; c < nc; c++) {
+        const pg_field f = s->field(c);
+        DevColumn dc = cols[c];
+        if (is_varlen(f.type)) {
+            if (dc.offsets && run->n_rows > 0) {
+                int32_t b[2] = {0, 0};
+                PG_CUDA(cudaMemcpy(&b[0], dc.offsets + lo, 4, cudaMemcpyDeviceToHost));
+                PG_CUDA(cudaMemcpy(&b[1], dc.offsets + row_hi, 4, cudaMemcpyDeviceToHost));
+                run->varlen_base[c] = b[0];
+                run->varlen_bytes[c] = b[1] - b[0];
+            }
+            if (dc.offsets) dc.offsets += lo;             // `data` stays the address of byte 0 of the offsets' space
+        } else if (dc.data) {
+            dc.data = (const unsigned char *)dc.data + lo * type_width(f.type);
+        }
+        if (dc.validity) dc.validity += lo / 8;
+        run->cols[c] = dc;
+    }
+    if (start_row) *start_row = row_lo - lo;
+    *out_run = g_runs.put(std::move(run));
+    return PG_OK;
+}
+
+extern "C" {
+
+pg_status pg_run_slice(uint64_t source, int64_t row_lo, int64_t row_hi, uint64_t *out_run, int64_t *start_row) {
+    if (!out_run) return fail(PG_ERR_INVALID, "null argument");
+    pg_status st = ensure_device();
+    if (st) return st;
+    return make_slice(source, row_lo, row_hi, out_run, start_row);
+}
+
+pg_status pg_thread_stream(void **out_cuda_stream) {
+    if (!out_cuda_stream) return fail(PG_ERR_INVALID, "null argument");
+    pg_status st = ensure_device();
+    if (st) return st;
+    *out_cuda_stream = (void *)copy_stream();
     return PG_OK;
 }
 
@@ -1150,6 +1246,9 @@ pg_status pg_merge_fetch(uint64_t merge, const pg_out_column *host_cols, int32_t
         const pg_out_column &oc = m->out_cols[c];
         const pg_out_column &hc = host_cols[c];
         if (oc.data_bytes && hc.data) {
+            if (hc.data_bytes < oc.data_bytes)
+                return fail(PG_ERR_INVALID, "pg_merge_fetch: data buffer of column " + std::to_string(c) + " holds " +
+                                            std::to_string(hc.data_bytes) + " bytes, the batch needs " + std::to_string(oc.data_bytes));
             cp_dst.push_back(hc.data); cp_src.push_back(oc.data); cp_size.push_back((size_t)oc.data_bytes);
             bytes += oc.data_bytes;
         }

@@ -1,17 +1,32 @@
-// parquet_decode.cu — Parquet column-chunk decode on the device, feeding the merge without leaving HBM.
+// parquet_decode.cu — Parquet column-chunk decode on the device, one batch of launches per SECTION, feeding the
+// merge without leaving HBM.
 //
 // Reference being replaced (paths under /root/reference/paimon-format/src/main/java/org/apache/paimon/format/):
-//   parquet/ParquetReaderFactory.java:113-148          createReader (footer, schema clip, vectors)
+//   parquet/ParquetReaderFactory.java:113-148          createReader (footer, schema clip by field NAME, vectors)
 //   parquet/reader/VectorizedParquetRecordReader.java:178-241   nextBatch / row-group loop
 //   parquet/reader/VectorizedColumnReader.java:143-383 page loop: V1 = [def RLE][values], V2 = separate levels
 //   parquet/reader/VectorizedRleValuesReader.java:928-1019     RLE / bit-packed hybrid
-//   parquet/reader/VectorizedPlainValuesReader.java:117-189    PLAIN fixed width and BYTE_ARRAY
+//   parquet/reader/VectorizedPlainValuesReader.java:68-84,117-189,275-288   PLAIN booleans, fixed width, BYTE_ARRAY
+//   parquet/reader/VectorizedDeltaBinaryPackedReader.java      DELTA_BINARY_PACKED
 //   parquet/ParquetSchemaConverter.java:76-160         TINYINT/SMALLINT/INT/DATE -> INT32, BIGINT -> INT64, ...
-// The reference fills 1024-row ColumnVectors on one CPU thread; here the whole file is staged to HBM once,
-// the host walks the (tiny) Thrift page headers, and every page is decoded by its own warp / CTA into the
-// Arrow-layout columns the merge kernels consume.  ABI v1 scope: flat schema, INT32 / INT64 / FLOAT / DOUBLE /
-// BYTE_ARRAY, PLAIN and RLE/PLAIN_DICTIONARY encodings, data pages V1 and V2, max definition level 1,
-// UNCOMPRESSED pages.  Anything else is refused with PG_ERR_UNSUPPORTED (no CPU fallback).
+// and, one level up, the way the files of a sorted run are concatenated into ONE merge input
+//   paimon-core/.../mergetree/MergeTreeReaders.java:94-101 (readerForRun -> ConcatRecordReader of the run's files).
+//
+// The reference fills 1024-row ColumnVectors on one CPU thread per file.  Here a whole section (every file of every
+// sorted run that overlaps one key interval) is decoded by ONE set of launches:
+//   host    footers only (Thrift FileMetaData) -> a table of column chunks, ordered (run, column, file, row group)
+//   walk    one thread per column chunk parses the Thrift page headers ON THE DEVICE (count pass, scan, fill pass)
+//           -> one page table for the section
+//   inflate Snappy pages -> scratch images; DELTA_BINARY_PACKED pages -> PLAIN images
+//   levels  one warp per page: definition levels -> the output validity bitmap (bit-packed runs are copied 32 bits
+//           at a time), dictionary ids -> scratch, per-page non-null counts and var-len payload sizes
+//   scan    per (run, var-len column): payload base of every page (files of a run continue each other's offsets)
+//   walkba  one warp per PLAIN BYTE_ARRAY page: the serial [len][bytes] walk -> value start offsets
+//   expand  one CTA per page: rank of every row under the validity bits -> values / dictionary lookups / offsets and
+//           payload bytes at their final positions in the run's columns
+// A file's rows land at its row offset inside its RUN: the k-way merge sees runs, not files.
+// Anything the kernels do not implement is refused with PG_ERR_UNSUPPORTED (no CPU fallback).
+#include <algorithm>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -20,50 +35,65 @@
 
 #include "device_utils.cuh"
 #include "parquet_meta.h"
+#include "zstd_device.cuh"
 
 namespace pg {
 
-struct PqPageJob {
-    const uint8_t *body;      // device: page body (after the Thrift header)
-    int32_t body_len;
-    int32_t num_values;       // rows in the page (flat schema: values incl. nulls)
-    int32_t col;
-    int32_t page_type;        // pq::P_DATA / pq::P_DATA_V2
-    int32_t is_dict;          // values are dictionary ids
-    int32_t max_def;          // 0 = REQUIRED, 1 = OPTIONAL
-    int32_t v2_def_len;
-    int32_t dict;             // index into PqDictJob, -1 = none
-    int64_t row0;             // absolute row of the page's first value
+enum : int { ENC_PLAIN = 0, ENC_DICT = 1, ENC_DELTA_BP = 2, ENC_RLE_BOOL = 3 };
+
+// one column chunk of one file; host-built from the footer, counts and bases filled on the device
+struct PqChunk {
+    const uint8_t *base;      // device: first page header of the chunk
+    int64_t avail;            // bytes from `base` to the end of the chunk (clipped to the file)
+    int64_t num_values;
+    int64_t row0;             // first row of the chunk inside its output run
+    int32_t col, run, file, codec;
+    int32_t max_def, phys, phys_width, pad;
+    // count pass
+    int32_t n_pages, n_dicts;
+    int64_t scratch_bytes;    // inflate / delta images this chunk needs
+    int64_t dict_entries;     // BYTE_ARRAY dictionary entries
+    int64_t ids_entries;      // dictionary ids / RLE booleans to materialise
+    int64_t page_bytes;       // uncompressed page body bytes (the encoded bytes the decode stage reads)
+    // chunk scan
+    int32_t page_base, dict_base;
+    int64_t scratch_base, dict_entry_base, ids_base;
 };
 
-struct PqDictJob {
-    const uint8_t *body;
-    int32_t body_len;
-    int32_t num_values;
-    int32_t col;
-    int32_t pad;
-    int64_t entry_base;       // first entry in the dict_ptr / dict_len tables (BYTE_ARRAY only)
+struct PqPage {
+    const uint8_t *src;       // page body as stored in the file
+    const uint8_t *body;      // page body as the decode kernels read it (inflated / delta-expanded image)
+    uint8_t *aux;             // DELTA_BINARY_PACKED: where the PLAIN image goes
+    int32_t src_len, body_len;
+    int32_t num_values, chunk;
+    int8_t type, enc, compressed, bad;
+    int32_t def_len;          // data page V2: bytes of definition levels in front of the values
+    int64_t row0;             // first row inside the run
+    // levels pass
+    int32_t values_off, nnz;
+    int64_t ids_base;         // first id of the page in the ids scratch
+    int64_t payload_bytes;    // var-len: payload bytes of the page's values
+    // page scan (var-len columns)
+    int64_t payload_base;     // output byte offset of the page's first value
+    int64_t vs_base;          // PLAIN BYTE_ARRAY: first entry of the page in the value-start scratch
+    int32_t is_last, pad;
+    int64_t entry_base;       // dictionary page of a BYTE_ARRAY column: first entry in dict_off / dict_len
 };
 
-struct PqCol {
-    int32_t phys;             // pq::PhysType
-    int32_t phys_width;       // 4 / 8, 0 for BYTE_ARRAY
+// output column of one run: [run * n_cols + col]
+struct PqOut {
+    void *data;               // fixed width values, or the var-len payload (set after the size read-back)
+    int32_t *offsets;
+    uint32_t *validity;       // zeroed; bits are OR-ed in
     int32_t out_width;        // bytes of the output type, 0 for var-len
-    int32_t nullable;
-    void *out_data;
-    int32_t *out_offsets;
-    uint32_t *out_validity;   // zeroed; bits are OR-ed in
-    uint8_t *defs;            // scratch [n_rows], optional columns
-    int32_t *ids;             // scratch [n_rows], dictionary ids by (page row0 + value ordinal)
-    const uint8_t **vptr;     // scratch [n_rows], BYTE_ARRAY PLAIN: value payload pointer by (row0 + ordinal)
-    int32_t *vlen;            // scratch [n_rows]
-    const uint8_t **rowsrc;   // scratch [n_rows], var-len: payload pointer per row
+    int32_t is_bool;
 };
 
-// page-derived values written by k_pq_hybrid
-struct PqPageState {
-    int32_t values_off;       // offset of the values section inside the body
-    int32_t n_nonnull;
+// a (run, var-len column) pair: its chunks are contiguous in the chunk table, its pages in the page table
+struct PqPair {
+    int32_t run, col, chunk0, chunk1;
+    int64_t vs_rows_base;     // rows of the pairs in front of this one (value-start scratch indexing)
+    int32_t idx, pad;
 };
 
 __device__ __forceinline__ uint32_t pq_varint(const uint8_t *&p, const uint8_t *end) {
@@ -78,234 +108,259 @@ __device__ __forceinline__ uint32_t pq_varint(const uint8_t *&p, const uint8_t *
     return v;
 }
 
-// Warp-cooperative RLE / bit-packed hybrid decode (VectorizedRleValuesReader.java:928-1019).
-// Calls out(i, value) for i in [0, count).  Returns the number of values equal to `count_eq` (for def levels).
-template <typename Out>
-__device__ int pq_hybrid_decode(const uint8_t *p, const uint8_t *end, int bw, int count, uint32_t count_eq, Out out) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t mask = bw >= 32 ? 0xffffffffu : ((1u << bw) - 1);
-    int pos = 0, matches = 0;
-    while (pos < count) {
-        if (bw == 0) {                        // a zero-width stream encodes only zeros
-            for (int i = pos + lane; i < count; i += 32) { out(i, 0u); matches += (count_eq == 0); }
-            break;
+// ------------------------------------------------------------------ Thrift compact protocol, device side
+//
+// parquet-mr reads page headers with org.apache.parquet.format.Util.readPageHeader (Thrift compact protocol; the
+// dependency is not under /root/reference, call site PQ3P/hadoop/ParquetFileReader.java:1345 Chunk.readAllPages).
+// The encoding restated here is the public Thrift compact protocol + parquet.thrift field ids.
+
+struct TRd {
+    const uint8_t *p, *end;
+    int bad;
+    __host__ __device__ uint32_t byte() {
+        if (p >= end) { bad = 1; return 0; }
+        return *p++;
+    }
+    __host__ __device__ uint64_t varint() {
+        uint64_t v = 0;
+        for (int sh = 0; sh < 70; sh += 7) {
+            const uint32_t b = byte();
+            v |= (uint64_t)(b & 0x7f) << sh;
+            if (!(b & 0x80)) return v;
         }
-        if (p >= end) break;
-        uint32_t h = pq_varint(p, end);
-        if (h & 1) {
-            int groups = (int)(h >> 1);
-            int nvals = groups * 8;
-            for (int i = lane; i < nvals && pos + i < count; i += 32) {
-                int64_t bit = (int64_t)i * bw;
-                const uint8_t *q = p + (bit >> 3);
-                uint64_t w = 0;
-#pragma unroll
-                for (int b = 0; b < 5; b++)
-                    if (q + b < end) w |= (uint64_t)q[b] << (8 * b);
-                uint32_t v = (uint32_t)(w >> (bit & 7)) & mask;
-                out(pos + i, v);
-                matches += (v == count_eq);
+        bad = 1;
+        return v;
+    }
+    __host__ __device__ int64_t zz() {
+        const uint64_t v = varint();
+        return (int64_t)(v >> 1) ^ -(int64_t)(v & 1);
+    }
+    // field header: returns the type (0 = STOP), updates the running field id
+    __host__ __device__ int field(int &id) {
+        const uint32_t h = byte();
+        if (h == 0 || bad) return 0;
+        const int d = (int)(h >> 4);
+        if (d == 0) id = (int)zz(); else id += d;
+        return (int)(h & 15);
+    }
+    __host__ __device__ void advance(uint64_t n) {
+        if ((uint64_t)(end - p) < n) { bad = 1; p = end; } else p += n;
+    }
+    // anything but a struct
+    __host__ __device__ void skip_flat(int t, bool in_container) {
+        switch (t) {
+            case 1: case 2: if (in_container) byte(); return;      // booleans live in the field header
+            case 3: byte(); return;
+            case 4: case 5: case 6: varint(); return;
+            case 7: advance(8); return;
+            case 8: advance(varint()); return;
+            case 9: case 10: {
+                const uint32_t h = byte();
+                const int et = (int)(h & 15);
+                uint64_t n = h >> 4;
+                if (n == 15) n = varint();
+                if (et == 9 || et == 10 || et == 11 || et == 12) { if (n) bad = 1; return; }   // nested containers: not in page headers
+                for (uint64_t i = 0; i < n && !bad; i++) skip_flat(et, true);
+                return;
             }
-            p += (int64_t)groups * bw;
-            pos += nvals;
-        } else {
-            int run = (int)(h >> 1);
-            uint32_t v = 0;
-            int nb = (bw + 7) / 8;
-            for (int b = 0; b < nb; b++)
-                if (p + b < end) v |= (uint32_t)p[b] << (8 * b);
-            p += nb;
-            for (int i = lane; i < run && pos + i < count; i += 32) { out(pos + i, v); matches += (v == count_eq); }
-            pos += run;
+            case 11: { if (varint() != 0) bad = 1; return; }     // maps: not in page headers
+            default: bad = 1; return;
         }
     }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) matches += __shfl_xor_sync(0xffffffffu, matches, d);
-    return matches;
-}
-
-// one warp per data page: definition levels and dictionary ids -> scratch
-__global__ void k_pq_hybrid(const PqPageJob *jobs, int n_jobs, const PqCol *cols, PqPageState *state) {
-    int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (j >= n_jobs) return;
-    const PqPageJob job = jobs[j];
-    const PqCol col = cols[job.col];
-    const uint8_t *body = job.body, *end = job.body + job.body_len;
-    int values_off = 0, n_nonnull = job.num_values;
-    if (job.max_def > 0) {
-        const uint8_t *dp;
-        int dlen;
-        if (job.page_type == pq::P_DATA_V2) { dp = body; dlen = job.v2_def_len; values_off = dlen; }
-        else {
-            dlen = (int)((uint32_t)body[0] | ((uint32_t)body[1] << 8) | ((uint32_t)body[2] << 16) | ((uint32_t)body[3] << 24));
-            dp = body + 4;
-            values_off = 4 + dlen;
-        }
-        uint8_t *defs = col.defs + job.row0;
-        const uint8_t *dend = dp + dlen < end ? dp + dlen : end;
-        n_nonnull = pq_hybrid_decode(dp, dend, 1, job.num_values, 1u,
-                                     [&](int i, uint32_t v) { defs[i] = (uint8_t)v; });
-    }
-    if (job.is_dict) {
-        const uint8_t *vp = body + values_off;
-        int bw = vp < end ? vp[0] : 0;
-        int32_t *ids = col.ids + job.row0;
-        pq_hybrid_decode(vp + 1, end, bw, n_nonnull, 0xffffffffu, [&](int i, uint32_t v) { ids[i] = (int32_t)v; });
-    }
-    if ((threadIdx.x & 31) == 0) state[j] = PqPageState{values_off, n_nonnull};
-}
-
-// One warp per PLAIN BYTE_ARRAY page (data or dictionary): walk the [len:4][bytes] stream
-// (VectorizedPlainValuesReader.java:275-288).  The lengths are embedded in the stream, so the walk itself is
-// sequential; the warp stages the page through shared memory in 2 KiB windows (coalesced 16-byte loads), lane 0
-// walks the window at shared-memory latency, and the (pointer, length) pairs go out coalesced.
-constexpr int kWalkWindow = 2048;
-constexpr int kWalkWarps = 8;
-
-__device__ void pq_walk_stream(const uint8_t *p, const uint8_t *end, int count, const uint8_t **out_ptr,
-                               int32_t *out_len, uint8_t *win, uint32_t *w_off, int32_t *w_len) {
-    const int lane = threadIdx.x & 31;
-    int done = 0;
-    while (done < count && p + 4 <= end) {
-        // window = [base, base + kWalkWindow + 16) clipped to the page, base 16-byte aligned
-        const uint8_t *base = (const uint8_t *)((uintptr_t)p & ~(uintptr_t)15);
-        const int skip = (int)(p - base);
-        const int avail = (int)min((int64_t)(end - base), (int64_t)(kWalkWindow + 16));
-        for (int o = lane * 16; o < avail; o += 32 * 16) *(uint4 *)(win + o) = *(const uint4 *)(base + o);
-        __syncwarp();
-        int nfound = 0, q = skip;
-        if (lane == 0) {
-            while (done + nfound < count && q + 4 <= avail && nfound < 256) {
-                int32_t len = (int32_t)((uint32_t)win[q] | ((uint32_t)win[q + 1] << 8) | ((uint32_t)win[q + 2] << 16) |
-                                        ((uint32_t)win[q + 3] << 24));
-                w_off[nfound] = (uint32_t)(q + 4);
-                w_len[nfound] = len;
-                nfound++;
-                q += 4 + len;
-                if (len < 0) { q = avail; break; }            // corrupt length: stop
-            }
-        }
-        nfound = __shfl_sync(0xffffffffu, nfound, 0);
-        q = __shfl_sync(0xffffffffu, q, 0);
-        __syncwarp();
-        for (int i = lane; i < nfound; i += 32) {
-            out_ptr[done + i] = base + w_off[i];
-            out_len[done + i] = w_len[i];
-        }
-        __syncwarp();
-        if (nfound == 0) break;                               // a length word straddles the page end: malformed
-        done += nfound;
-        p = base + q;
-    }
-}
-
-__global__ void __launch_bounds__(kWalkWarps * 32)
-k_pq_walk_bytes(const PqPageJob *jobs, int n_jobs, const PqDictJob *dicts, int n_dicts, const PqCol *cols,
-                const PqPageState *state, const uint8_t **dict_ptr, int32_t *dict_len) {
-    __shared__ __align__(16) uint8_t s_win[kWalkWarps][kWalkWindow + 32];
-    __shared__ uint32_t s_off[kWalkWarps][256];
-    __shared__ int32_t s_len[kWalkWarps][256];
-    const int w = threadIdx.x >> 5;
-    const int t = blockIdx.x * kWalkWarps + w;
-    if (t < n_jobs) {
-        const PqPageJob job = jobs[t];
-        const PqCol col = cols[job.col];
-        if (col.phys != pq::T_BYTE_ARRAY || job.is_dict) return;
-        pq_walk_stream(job.body + state[t].values_off, job.body + job.body_len, state[t].n_nonnull,
-                       col.vptr + job.row0, col.vlen + job.row0, s_win[w], s_off[w], s_len[w]);
-    } else if (t < n_jobs + n_dicts) {
-        const PqDictJob dj = dicts[t - n_jobs];
-        if (cols[dj.col].phys != pq::T_BYTE_ARRAY) return;
-        pq_walk_stream(dj.body, dj.body + dj.body_len, dj.num_values, dict_ptr + dj.entry_base,
-                       dict_len + dj.entry_base, s_win[w], s_off[w], s_len[w]);
-    }
-}
-
-__device__ __forceinline__ uint64_t pq_load_unaligned(const uint8_t *p, int w) {
-    uint64_t v = 0;
-    for (int b = 0; b < w; b++) v |= (uint64_t)p[b] << (8 * b);
-    return v;
-}
-
-// one CTA per data page: rows -> output values / lengths + validity
-__global__ void __launch_bounds__(256)
-k_pq_assemble(const PqPageJob *jobs, const PqDictJob *dicts, const PqCol *cols, const PqPageState *state,
-              const uint8_t *const *dict_ptr, const int32_t *dict_len) {
-    __shared__ int ws[34];
-    const PqPageJob job = jobs[blockIdx.x];
-    const PqCol col = cols[job.col];
-    const PqPageState st = state[blockIdx.x];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const uint8_t *values = job.body + st.values_off;
-    const PqDictJob *dj = job.dict >= 0 ? &dicts[job.dict] : nullptr;
-    int carry = 0;
-    for (int base = 0; base < job.num_values; base += blockDim.x) {
-        const int i = base + tid;
-        const bool in = i < job.num_values;
-        const int64_t row = job.row0 + i;
-        int valid = in ? (job.max_def ? col.defs[row] : 1) : 0;
-        int tot = 0;
-        int ord = carry + block_scan_excl(valid, ws, &tot);
-        carry += tot;
-        if (in) {
-            if (col.phys != pq::T_BYTE_ARRAY) {
-                uint64_t v = 0;
-                if (valid) {
-                    const uint8_t *src = job.is_dict ? dj->body + (int64_t)col.ids[job.row0 + ord] * col.phys_width
-                                                     : values + (int64_t)ord * col.phys_width;
-                    v = pq_load_unaligned(src, col.phys_width);
-                }
-                store_fixed(col.out_data, col.out_width, row, v);     // narrowing keeps the low bytes (INT32 -> TINYINT)
-            } else {
-                const uint8_t *src = nullptr;
-                int len = 0;
-                if (valid) {
-                    if (job.is_dict) {
-                        int64_t e = dj->entry_base + col.ids[job.row0 + ord];
-                        src = dict_ptr[e];
-                        len = dict_len[e];
-                    } else {
-                        src = col.vptr[job.row0 + ord];
-                        len = col.vlen[job.row0 + ord];
-                    }
-                }
-                col.rowsrc[row] = src;
-                col.out_offsets[row + 1] = len;                      // lengths now, prefix-summed afterwards
-            }
-        }
-        if (col.out_validity != nullptr) {
-            unsigned m = __ballot_sync(0xffffffffu, valid != 0);
-            if (lane == 0 && m) {
-                int64_t r0 = job.row0 + base + (tid & ~31);
-                int sh = (int)(r0 & 31);
-                atomicOr(&col.out_validity[r0 >> 5], m << sh);
-                if (sh) atomicOr(&col.out_validity[(r0 >> 5) + 1], m >> (32 - sh));
-            }
+    __host__ __device__ void skip(int t) {
+        if (t != 12) { skip_flat(t, false); return; }
+        int depth = 1;
+        while (depth > 0 && !bad) {
+            const uint32_t h = byte();
+            if (h == 0) { depth--; continue; }
+            if ((h >> 4) == 0) zz();
+            const int ft = (int)(h & 15);
+            if (ft == 12) depth++; else skip_flat(ft, false);
         }
     }
-}
-
-// ---- Snappy page decompression (parquet-mr hands compressed pages to snappy-java 1.1.10.8; the format restated
-// here is the public Snappy format description: a varint uncompressed length, then literal and copy elements).
-// One warp per page: the element stream is parsed by all lanes in lock step, the bytes of a literal / copy are
-// moved lane-parallel.  A copy may overlap its own output (offset < length): byte i comes from
-// out - offset + (i mod offset), which always lies in front of the copy.
-struct SnappyJob {
-    const uint8_t *src;       // device: [prefix bytes copied verbatim (data page V2 levels)][snappy stream]
-    uint8_t *dst;
-    int32_t src_len, dst_len, prefix, pad;
 };
-__global__ void k_pq_snappy(const SnappyJob *jobs, int n_jobs, int32_t *err) {
+
+struct PqHeader {
+    int type, unc, comp, nv, enc, def_enc, def_len, rep_len, is_compressed, hdr;
+};
+
+// parquet.thrift PageHeader {1 type, 2 uncompressed_page_size, 3 compressed_page_size, 5 DataPageHeader {1 num_values,
+// 2 encoding, 3 definition_level_encoding}, 7 DictionaryPageHeader {1 num_values, 2 encoding}, 8 DataPageHeaderV2
+// {1 num_values, 4 encoding, 5 definition_levels_byte_length, 6 repetition_levels_byte_length, 7 is_compressed}}
+__host__ __device__ inline bool pq_parse_header(const uint8_t *p, const uint8_t *end, PqHeader &h) {
+    TRd r{p, end, 0};
+    h.type = -1; h.unc = 0; h.comp = 0; h.nv = 0; h.enc = 0; h.def_enc = pq::E_RLE; h.def_len = 0; h.rep_len = 0;
+    h.is_compressed = 1;
+    int id = 0, t;
+    while ((t = r.field(id)) != 0 && !r.bad) {
+        if (id == 1 && t == 5) h.type = (int)r.zz();
+        else if (id == 2 && t == 5) h.unc = (int)r.zz();
+        else if (id == 3 && t == 5) h.comp = (int)r.zz();
+        else if ((id == 5 || id == 7 || id == 8) && t == 12) {
+            const int outer = id;
+            int i2 = 0, t2;
+            while ((t2 = r.field(i2)) != 0 && !r.bad) {
+                if (outer == 8) {
+                    if (i2 == 1 && t2 == 5) h.nv = (int)r.zz();
+                    else if (i2 == 4 && t2 == 5) h.enc = (int)r.zz();
+                    else if (i2 == 5 && t2 == 5) h.def_len = (int)r.zz();
+                    else if (i2 == 6 && t2 == 5) h.rep_len = (int)r.zz();
+                    else if (i2 == 7 && (t2 == 1 || t2 == 2)) h.is_compressed = t2 == 1;
+                    else r.skip(t2);
+                } else {
+                    if (i2 == 1 && t2 == 5) h.nv = (int)r.zz();
+                    else if (i2 == 2 && t2 == 5) h.enc = (int)r.zz();
+                    else if (i2 == 3 && t2 == 5 && outer == 5) h.def_enc = (int)r.zz();
+                    else r.skip(t2);
+                }
+            }
+        } else r.skip(t);
+    }
+    h.hdr = (int)(r.p - p);
+    return !r.bad && h.type >= 0;
+}
+
+__device__ __forceinline__ void pq_err(int32_t *err, int code) { atomicCAS(err, KERR_NONE, code); }
+__host__ __device__ __forceinline__ int64_t pq_al64(int64_t x) { return (x + 63) & ~(int64_t)63; }
+__host__ __device__ __forceinline__ int64_t pq_min64(int64_t a, int64_t b) { return a < b ? a : b; }
+
+// ------------------------------------------------------------------ page walk: one thread per column chunk
+//
+// VectorizedColumnReader's page loop (:143-383) / ParquetFileReader.Chunk.readAllPages: header, body, next header.
+// FILL = false counts (pages, dictionary entries, scratch bytes); FILL = true writes the page table.
+template <bool FILL>
+__global__ void k_pq_walk(PqChunk *chunks, int n_chunks, PqPage *pages, PqPage *dicts, uint8_t *scratch, int32_t *err) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    const PqChunk ch = chunks[c];
+    const uint8_t *p = ch.base, *end = ch.base + ch.avail;
+    int64_t vals = 0, sc = 0, dict_entries = 0, page_bytes = 0;
+    int n_pages = 0, n_dicts = 0;
+    bool needs_ids = false;
+    const bool codec_on = ch.codec != pq::C_UNCOMPRESSED;
+    while (vals < ch.num_values) {
+        PqHeader h;
+        if (p >= end || !pq_parse_header(p, end, h)) { pq_err(err, KERR_PQ_HEADER); break; }
+        const uint8_t *body = p + h.hdr;
+        if (h.comp < 0 || h.unc < 0 || h.nv < 0 || (int64_t)(end - body) < (int64_t)h.comp) { pq_err(err, KERR_PQ_HEADER); break; }
+        if (h.type == pq::P_DICTIONARY) {
+            if (n_dicts > 0 || n_pages > 0 || (h.enc != pq::E_PLAIN && h.enc != pq::E_PLAIN_DICTIONARY)) {
+                pq_err(err, KERR_PQ_ENCODING);
+                break;
+            }
+            const int body_len = codec_on ? h.unc : h.comp;
+            if (FILL) {
+                PqPage d;
+                memset(&d, 0, sizeof(d));
+                d.src = body; d.src_len = h.comp; d.body_len = body_len;
+                d.body = codec_on ? scratch + ch.scratch_base + sc : body;
+                d.num_values = h.nv; d.chunk = c; d.type = (int8_t)pq::P_DICTIONARY; d.compressed = codec_on;
+                d.entry_base = ch.dict_entry_base;
+                dicts[ch.dict_base] = d;
+            }
+            if (codec_on) sc += pq_al64((int64_t)h.unc + 16);
+            if (ch.phys == pq::T_BYTE_ARRAY) dict_entries += h.nv;
+            page_bytes += body_len;
+            n_dicts++;
+        } else if (h.type == pq::P_DATA || h.type == pq::P_DATA_V2) {
+            int enc = -1;
+            if (h.enc == pq::E_PLAIN) enc = ENC_PLAIN;
+            else if (h.enc == pq::E_PLAIN_DICTIONARY || h.enc == pq::E_RLE_DICTIONARY) enc = ENC_DICT;
+            else if (h.enc == pq::E_DELTA_BINARY_PACKED && (ch.phys == pq::T_INT32 || ch.phys == pq::T_INT64)) enc = ENC_DELTA_BP;
+            else if (h.enc == pq::E_RLE && ch.phys == pq::T_BOOLEAN) enc = ENC_RLE_BOOL;
+            if (enc < 0 || (enc == ENC_DICT && ch.phys == pq::T_BOOLEAN)) { pq_err(err, KERR_PQ_ENCODING); break; }
+            if (enc == ENC_DICT && n_dicts == 0) { pq_err(err, KERR_PQ_NO_DICT); break; }
+            const bool v2 = h.type == pq::P_DATA_V2;
+            if ((v2 && h.rep_len != 0) || (!v2 && ch.max_def > 0 && h.def_enc != pq::E_RLE) || (v2 && h.def_len < 0)) {
+                pq_err(err, KERR_PQ_LEVELS);
+                break;
+            }
+            const bool compressed = codec_on && (!v2 || h.is_compressed);
+            const int body_len = compressed ? h.unc : h.comp;
+            const int64_t unc_need = compressed ? pq_al64((int64_t)h.unc + 16) : 0;
+            const int64_t aux_need = enc == ENC_DELTA_BP ? pq_al64((int64_t)body_len + (int64_t)h.nv * ch.phys_width + 16) : 0;
+            if (FILL) {
+                PqPage g;
+                memset(&g, 0, sizeof(g));
+                g.src = body; g.src_len = h.comp; g.body_len = body_len;
+                g.body = compressed ? scratch + ch.scratch_base + sc : body;
+                g.aux = aux_need ? scratch + ch.scratch_base + sc + unc_need : nullptr;
+                g.num_values = h.nv; g.chunk = c; g.type = (int8_t)h.type; g.enc = (int8_t)enc; g.compressed = compressed;
+                g.def_len = v2 ? h.def_len : 0;
+                g.row0 = ch.row0 + vals;
+                g.ids_base = ch.ids_base + vals;
+                pages[ch.page_base + n_pages] = g;
+            }
+            sc += unc_need + aux_need;
+            if (enc == ENC_DICT || enc == ENC_RLE_BOOL) needs_ids = true;
+            page_bytes += body_len;
+            vals += h.nv;
+            n_pages++;
+        }                                                // index pages are skipped
+        p = body + h.comp;
+    }
+    if (vals != ch.num_values) pq_err(err, KERR_PQ_ROWS);
+    if (!FILL) {
+        PqChunk &o = chunks[c];
+        o.n_pages = n_pages; o.n_dicts = n_dicts; o.scratch_bytes = sc; o.dict_entries = dict_entries;
+        o.ids_entries = needs_ids ? ch.num_values : 0;
+        o.page_bytes = page_bytes;
+    }
+}
+
+// exclusive scans of the per-chunk counts -> bases; totals[0..5] = pages, dictionary pages, scratch bytes,
+// dictionary entries, ids, page bytes
+constexpr int kScanThreads = 512;
+__global__ void __launch_bounds__(kScanThreads) k_pq_chunk_scan(PqChunk *chunks, int n, int64_t *totals) {
+    __shared__ int64_t part[6][kScanThreads];
+    const int per = (n + kScanThreads - 1) / kScanThreads;
+    const int b = threadIdx.x * per, e = min(b + per, n);
+    int64_t s[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = b; i < e; i++) {
+        s[0] += chunks[i].n_pages; s[1] += chunks[i].n_dicts; s[2] += chunks[i].scratch_bytes;
+        s[3] += chunks[i].dict_entries; s[4] += chunks[i].ids_entries; s[5] += chunks[i].page_bytes;
+    }
+    for (int q = 0; q < 6; q++) part[q][threadIdx.x] = s[q];
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        int64_t acc = 0;
+        for (int i = 0; i < kScanThreads; i++) { const int64_t t = part[threadIdx.x][i]; part[threadIdx.x][i] = acc; acc += t; }
+        totals[threadIdx.x] = acc;
+    }
+    __syncthreads();
+    for (int q = 0; q < 6; q++) s[q] = part[q][threadIdx.x];
+    for (int i = b; i < e; i++) {
+        PqChunk &c = chunks[i];
+        c.page_base = (int32_t)s[0]; c.dict_base = (int32_t)s[1]; c.scratch_base = s[2]; c.dict_entry_base = s[3];
+        c.ids_base = s[4];
+        s[0] += c.n_pages; s[1] += c.n_dicts; s[2] += c.scratch_bytes; s[3] += c.dict_entries; s[4] += c.ids_entries;
+    }
+}
+
+// ------------------------------------------------------------------ Snappy page decompression
+//
+// parquet-mr hands compressed pages to snappy-java 1.1.10.8 (not under /root/reference); the format restated here is
+// the public Snappy format description: a varint uncompressed length, then literal and copy elements.  One warp per
+// page: the element stream is parsed by all lanes in lock step, the bytes of a literal / copy are moved
+// lane-parallel.  A copy may overlap its own output (offset < length): byte i comes from out - offset +
+// (i mod offset), which always lies in front of the copy.  Data page V2: the level bytes in front of the values are
+// stored uncompressed and copied verbatim.
+__global__ void k_pq_snappy(const PqPage *pages, int n_pages, const PqPage *dicts, int n_dicts, const PqChunk *chunks,
+                            int32_t *err) {
     const int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (w >= n_jobs) return;
-    const SnappyJob j = jobs[w];
-    for (int i = lane; i < j.prefix; i += 32) j.dst[i] = j.src[i];
-    const uint8_t *src = j.src + j.prefix;
-    uint8_t *dst = j.dst + j.prefix;
-    const int n_src = j.src_len - j.prefix, n_dst = j.dst_len - j.prefix;
+    if (w >= n_pages + n_dicts) return;
+    const PqPage &pg = w < n_pages ? pages[w] : dicts[w - n_pages];
+    if (!pg.compressed || chunks[pg.chunk].codec != pq::C_SNAPPY) return;
+    const int prefix = pg.type == pq::P_DATA_V2 ? pg.def_len : 0;
+    uint8_t *out0 = const_cast<uint8_t *>(pg.body);
+    const uint8_t *in0 = pg.src;
+    if (prefix > pg.src_len || prefix > pg.body_len) { if (lane == 0) pq_err(err, KERR_BAD_PAGE); return; }
+    for (int i = lane; i < prefix; i += 32) out0[i] = in0[i];
+    const uint8_t *src = in0 + prefix;
+    uint8_t *dst = out0 + prefix;
+    const int n_src = pg.src_len - prefix, n_dst = pg.body_len - prefix;
     int pos = 0, out = 0;
-    // preamble: uncompressed length
-    uint32_t ulen = 0;
+    uint32_t ulen = 0;                                    // preamble: uncompressed length
     for (int sh = 0; pos < n_src && sh < 35; sh += 7) {
         const uint8_t b = src[pos++];
         ulen |= (uint32_t)(b & 0x7f) << sh;
@@ -353,19 +408,47 @@ __global__ void k_pq_snappy(const SnappyJob *jobs, int n_jobs, int32_t *err) {
         out += len;
         __syncwarp();                                    // later copies may read what other lanes just wrote
     }
-    if ((bad || out != n_dst) && lane == 0) atomicCAS(err, KERR_NONE, KERR_BAD_PAGE);
+    if ((bad || out != n_dst) && lane == 0) pq_err(err, KERR_BAD_PAGE);
 }
 
-// ---- DELTA_BINARY_PACKED (VectorizedDeltaBinaryPackedReader.java; the layout restated here is the public Parquet
-// encoding specification): <block size> <miniblocks per block> <total count> <first value> then per block
-// <min delta> <bit width per miniblock> <bit-packed miniblocks>.  One warp per page expands the values into a
-// PLAIN image (the level bytes in front are copied), so the PLAIN assemble path reads the page afterwards.
-struct DeltaJob {
-    const uint8_t *src;       // device: page body
-    uint8_t *dst;
-    int32_t src_len, prefix;  // prefix = level bytes in front of the values
-    int32_t width, max_values;
-};
+// ------------------------------------------------------------------ Zstandard page decompression
+//
+// Paimon's default codec (CoreOptions.java:318-321).  The decoder is zstd_device.cuh (RFC 8878, written once for host
+// and device; the host build is pinned against libzstd-compressed buffers by tests/test_zstd_cpu.py).  A fixed grid of
+// warps pulls pages off a counter: every warp owns one set of FSE / Huffman tables in shared memory and one
+// 128 KiB literals buffer in global scratch; the lanes run the block decoder in lock step and move the bytes of
+// literal / match copies lane-parallel.
+constexpr int kZsWarps = 4;
+__global__ void __launch_bounds__(kZsWarps * 32)
+k_pq_zstd(const PqPage *pages, int n_pages, const PqPage *dicts, int n_dicts, const PqChunk *chunks, uint8_t *lit_scratch,
+          int32_t *counter, int32_t *err) {
+    __shared__ zs::Tables T[kZsWarps];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *lit = lit_scratch + ((size_t)blockIdx.x * kZsWarps + w) * (size_t)(zs::kMaxBlock + 64);
+    while (true) {
+        int j = 0;
+        if (lane == 0) j = atomicAdd(counter, 1);
+        j = __shfl_sync(0xffffffffu, j, 0);
+        if (j >= n_pages + n_dicts) return;
+        const PqPage &pg = j < n_pages ? pages[j] : dicts[j - n_pages];
+        if (!pg.compressed || chunks[pg.chunk].codec != pq::C_ZSTD) continue;
+        const int prefix = pg.type == pq::P_DATA_V2 ? pg.def_len : 0;
+        uint8_t *out0 = const_cast<uint8_t *>(pg.body);
+        if (prefix > pg.src_len || prefix > pg.body_len) { if (lane == 0) pq_err(err, KERR_BAD_PAGE); continue; }
+        for (int i = lane; i < prefix; i += 32) out0[i] = pg.src[i];
+        const int64_t want = pg.body_len - prefix;
+        const int64_t got = zs::decode(pg.src + prefix, pg.src_len - prefix, out0 + prefix, want, lit, T[w]);
+        if (got != want && lane == 0) pq_err(err, KERR_BAD_PAGE);
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ DELTA_BINARY_PACKED
+//
+// VectorizedDeltaBinaryPackedReader.java; the layout restated here is the public Parquet encoding specification:
+// <block size> <miniblocks per block> <total count> <first value> then per block <min delta> <bit width per
+// miniblock> <bit-packed miniblocks>.  One warp per page expands the values into a PLAIN image behind a copy of the
+// level bytes, and points the page at the image, so the PLAIN path reads the page afterwards.
 __device__ __forceinline__ uint64_t dl_varint(const uint8_t *p, int n, int &pos) {
     uint64_t v = 0;
     for (int sh = 0; pos < n && sh < 70; sh += 7) {
@@ -375,24 +458,36 @@ __device__ __forceinline__ uint64_t dl_varint(const uint8_t *p, int n, int &pos)
     }
     return v;
 }
-__global__ void k_pq_delta(const DeltaJob *jobs, int n_jobs, int32_t *err) {
+__global__ void k_pq_delta(PqPage *pages, int n_pages, const PqChunk *chunks, int32_t *err) {
     const int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (w >= n_jobs) return;
-    const DeltaJob j = jobs[w];
-    for (int i = lane; i < j.prefix; i += 32) j.dst[i] = j.src[i];
-    const uint8_t *p = j.src + j.prefix;
-    const int n = j.src_len - j.prefix;
-    uint8_t *out = j.dst + j.prefix;
+    if (w >= n_pages) return;
+    const PqPage pg = pages[w];
+    if (pg.enc != ENC_DELTA_BP) return;
+    const PqChunk &ch = chunks[pg.chunk];
+    const int width = ch.phys_width;
+    // level bytes in front of the values: V1 = 4-byte length + RLE levels (OPTIONAL only), V2 = def_len
+    int prefix = 0;
+    if (ch.max_def > 0) {
+        if (pg.type == pq::P_DATA_V2) prefix = pg.def_len;
+        else if (pg.body_len >= 4)
+            prefix = 4 + (int)((uint32_t)pg.body[0] | ((uint32_t)pg.body[1] << 8) | ((uint32_t)pg.body[2] << 16) | ((uint32_t)pg.body[3] << 24));
+        else prefix = -1;
+    }
+    if (prefix < 0 || prefix > pg.body_len) { if (lane == 0) { pq_err(err, KERR_BAD_PAGE); pages[w].bad = 1; } return; }
+    for (int i = lane; i < prefix; i += 32) pg.aux[i] = pg.body[i];
+    const uint8_t *p = pg.body + prefix;
+    const int n = pg.body_len - prefix;
+    uint8_t *out = pg.aux + prefix;
     int pos = 0;
     const int block_size = (int)dl_varint(p, n, pos);
     const int n_mini = (int)dl_varint(p, n, pos);
     const int64_t total = (int64_t)dl_varint(p, n, pos);
     const uint64_t zz = dl_varint(p, n, pos);
     uint64_t last = (zz >> 1) ^ (0 - (zz & 1));               // first value
-    bool bad = n_mini <= 0 || block_size <= 0 || block_size % n_mini != 0 || total > j.max_values || total < 0;
+    bool bad = n_mini <= 0 || block_size <= 0 || block_size % n_mini != 0 || total > pg.num_values || total < 0;
     const int mini = bad ? 1 : block_size / n_mini;
     if (!bad && total > 0 && lane == 0) {
-        if (j.width == 8) memcpy(out, &last, 8); else { uint32_t x = (uint32_t)last; memcpy(out, &x, 4); }
+        if (width == 8) memcpy(out, &last, 8); else { uint32_t x = (uint32_t)last; memcpy(out, &x, 4); }
     }
     int64_t done = 1;
     while (!bad && done < total) {
@@ -411,8 +506,7 @@ __global__ void k_pq_delta(const DeltaJob *jobs, int n_jobs, int32_t *err) {
                     const int64_t bit = (int64_t)v * bw;
                     const uint8_t *q = p + pos + (bit >> 3);
                     const int sh = (int)(bit & 7);
-                    // up to 9 bytes hold the value
-                    uint64_t lo = 0;
+                    uint64_t lo = 0;                             // up to 9 bytes hold the value
                     const int nb = (sh + bw + 7) >> 3;
                     for (int b = 0; b < nb && b < 8; b++) lo |= (uint64_t)q[b] << (8 * b);
                     d = lo >> sh;
@@ -420,16 +514,15 @@ __global__ void k_pq_delta(const DeltaJob *jobs, int n_jobs, int32_t *err) {
                     if (bw < 64) d &= ((uint64_t)1 << bw) - 1;
                 }
                 uint64_t x = v < mini ? d + min_delta : 0;
-                // inclusive scan of the deltas over the warp, then the running value
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
+                for (int o = 1; o < 32; o <<= 1) {                // inclusive scan of the deltas over the warp
                     const uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
                     if (lane >= o) x += y;
                 }
                 const uint64_t val = last + x;
                 const int64_t idx = done + lane;
                 if (v < mini && idx < total) {
-                    if (j.width == 8) memcpy(out + idx * 8, &val, 8);
+                    if (width == 8) memcpy(out + idx * 8, &val, 8);
                     else { uint32_t t = (uint32_t)val; memcpy(out + idx * 4, &t, 4); }
                 }
                 const int cnt = min(32, mini - v0);
@@ -439,10 +532,463 @@ __global__ void k_pq_delta(const DeltaJob *jobs, int n_jobs, int32_t *err) {
             pos += mini * bw / 8;
         }
     }
-    if (bad && lane == 0) atomicCAS(err, KERR_NONE, KERR_BAD_PAGE);
+    if (lane == 0) {
+        if (bad) { pq_err(err, KERR_BAD_PAGE); pages[w].bad = 1; }
+        pages[w].body = pg.aux;
+        pages[w].body_len = prefix + (int)(total > 0 && !bad ? total : 0) * width;
+    }
 }
 
-// ---- device-wide inclusive scan of int32 (three small kernels; offsets of one var-len column)
+// ------------------------------------------------------------------ levels, dictionary ids, page sizes
+//
+// Definition levels of a flat OPTIONAL column (bit width 1): the RLE / bit-packed hybrid stream
+// (VectorizedRleValuesReader.java:928-1019) is turned straight into the run's Arrow validity bitmap at bit
+// row0 + i.  A bit-packed run IS a bitmap: every lane moves 32 bits of it.  Returns the number of set bits.
+__device__ int pq_def_to_bits(const uint8_t *p, const uint8_t *end, int count, uint32_t *bm, int64_t row0) {
+    const int lane = threadIdx.x & 31;
+    int pos = 0, nnz = 0;
+    while (pos < count && p < end) {
+        const uint32_t h = pq_varint(p, end);
+        const bool packed = h & 1;
+        int64_t span = packed ? (int64_t)(h >> 1) * 8 : (int64_t)(h >> 1);       // values the run stands for
+        const uint8_t *src = p;
+        if (packed) {
+            int64_t groups = h >> 1;
+            if (groups > end - p) { groups = end - p; span = groups * 8; }
+            p += groups;
+        } else {
+            p += 1;
+        }
+        const int nv = (int)pq_min64(span, count - pos);
+        const bool ones = !packed && src < end && (src[0] & 1);
+        if (nv > 0 && (packed || ones)) {
+            const int64_t d0 = row0 + pos, d1 = d0 + nv;
+            for (int64_t w = (d0 >> 5) + lane; w <= ((d1 - 1) >> 5); w += 32) {
+                const int64_t lo = max(d0, w * 32), hi = min(d1, w * 32 + 32);
+                const int cnt = (int)(hi - lo);
+                uint32_t bits = 0xffffffffu;
+                if (packed) {
+                    const int sbit = (int)(lo - d0);
+                    const uint8_t *q = src + (sbit >> 3);
+                    uint64_t v = 0;
+#pragma unroll
+                    for (int b = 0; b < 5; b++)
+                        if (q + b < end) v |= (uint64_t)q[b] << (8 * b);
+                    bits = (uint32_t)(v >> (sbit & 7));
+                }
+                if (cnt < 32) bits &= (1u << cnt) - 1;
+                const uint32_t word = bits << (int)(lo - w * 32);
+                if (cnt == 32) bm[w] = word;
+                else if (word) atomicOr(&bm[w], word);
+                nnz += __popc(word);
+            }
+        }
+        pos += (int)pq_min64(span, (int64_t)count);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) nnz += __shfl_xor_sync(0xffffffffu, nnz, d);
+    return nnz;
+}
+
+// Warp-cooperative RLE / bit-packed hybrid decode of `count` values of bit width bw: out(i, value).
+template <typename Out>
+__device__ void pq_hybrid_decode(const uint8_t *p, const uint8_t *end, int bw, int count, Out out) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t mask = bw >= 32 ? 0xffffffffu : ((1u << bw) - 1);
+    int pos = 0;
+    while (pos < count) {
+        if (bw == 0) {                        // a zero-width stream encodes only zeros
+            for (int i = pos + lane; i < count; i += 32) out(i, 0u);
+            break;
+        }
+        if (p >= end) break;
+        const uint32_t h = pq_varint(p, end);
+        if (h & 1) {
+            const int64_t groups = (int64_t)(h >> 1);
+            const int64_t nvals = groups * 8;
+            for (int64_t i = lane; i < nvals && pos + i < count; i += 32) {
+                const int64_t bit = i * bw;
+                const uint8_t *q = p + (bit >> 3);
+                uint64_t w = 0;
+#pragma unroll
+                for (int b = 0; b < 5; b++)
+                    if (q + b < end) w |= (uint64_t)q[b] << (8 * b);
+                out(pos + (int)i, (uint32_t)(w >> (bit & 7)) & mask);
+            }
+            if (groups * bw > end - p) p = end; else p += groups * bw;
+            pos = (int)pq_min64((int64_t)pos + nvals, (int64_t)count);
+        } else {
+            const int run = (int)(h >> 1);
+            uint32_t v = 0;
+            const int nb = (bw + 7) / 8;
+            for (int b = 0; b < nb; b++)
+                if (p + b < end) v |= (uint32_t)p[b] << (8 * b);
+            p += nb;
+            for (int i = lane; i < run && pos + i < count; i += 32) out(pos + i, v & mask);
+            pos = (int)pq_min64((int64_t)pos + run, (int64_t)count);
+        }
+    }
+}
+
+// one warp per data page
+__global__ void k_pq_levels(PqPage *pages, int n_pages, const PqPage *dicts, const PqChunk *chunks, const PqOut *outs,
+                            int n_cols, int32_t *ids, const int32_t *dict_len, int32_t *err) {
+    const int j = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (j >= n_pages) return;
+    const PqPage pg = pages[j];
+    if (pg.bad) return;
+    const PqChunk &ch = chunks[pg.chunk];
+    const PqOut &out = outs[ch.run * n_cols + ch.col];
+    const uint8_t *body = pg.body;
+    const int nv = pg.num_values;
+    int values_off = 0, nnz = nv;
+    bool bad = false;
+    if (ch.max_def > 0) {
+        const uint8_t *dp = body;
+        int dlen = pg.def_len;
+        if (pg.type != pq::P_DATA_V2) {
+            if (pg.body_len < 4) bad = true;
+            else {
+                dlen = (int)((uint32_t)body[0] | ((uint32_t)body[1] << 8) | ((uint32_t)body[2] << 16) | ((uint32_t)body[3] << 24));
+                dp = body + 4;
+                values_off = 4;
+            }
+        }
+        if (!bad && (dlen < 0 || (int64_t)values_off + dlen > pg.body_len)) bad = true;
+        if (!bad) {
+            values_off += dlen;
+            nnz = pq_def_to_bits(dp, dp + dlen, nv, out.validity, pg.row0);
+        }
+    }
+    else if (out.validity != nullptr) {
+        // REQUIRED in this file, OPTIONAL in another file of the section: every row of the page is valid
+        const int64_t d0 = pg.row0, d1 = pg.row0 + nv;
+        for (int64_t w = (d0 >> 5) + lane; nv > 0 && w <= ((d1 - 1) >> 5); w += 32) {
+            const int64_t lo = max(d0, w * 32), hi = min(d1, w * 32 + 32);
+            const int cnt = (int)(hi - lo);
+            const uint32_t word = (cnt < 32 ? (1u << cnt) - 1 : 0xffffffffu) << (int)(lo - w * 32);
+            if (cnt == 32) out.validity[w] = word; else atomicOr(&out.validity[w], word);
+        }
+    }
+    int64_t payload = 0;
+    if (!bad) {
+        const uint8_t *vp = body + values_off, *end = body + pg.body_len;
+        const int64_t vbytes = pg.body_len - values_off;
+        if (pg.enc == ENC_DICT) {
+            const PqPage &dj = dicts[ch.dict_base];
+            const uint32_t n_entries = (uint32_t)dj.num_values;
+            const int bw = vp < end ? vp[0] : 0;
+            int32_t *dst = ids + pg.ids_base;
+            const bool ba = ch.phys == pq::T_BYTE_ARRAY;
+            const int32_t *dl = dict_len + dj.entry_base;
+            bool oob = false;
+            if (bw > 32) bad = true;
+            else pq_hybrid_decode(vp + 1, end, bw, nnz, [&](int i, uint32_t v) {
+                if (v >= n_entries) { oob = true; v = 0; }
+                dst[i] = (int32_t)v;
+                if (ba && n_entries) payload += dl[v];
+            });
+            if (__any_sync(0xffffffffu, oob)) { if (lane == 0) pq_err(err, KERR_PQ_DICT_ID); bad = true; }
+        } else if (pg.enc == ENC_RLE_BOOL) {
+            // RLE-encoded BOOLEAN values: <length:4> <hybrid stream of bit width 1>
+            int32_t *dst = ids + pg.ids_base;
+            if (vbytes < 4) bad = nnz > 0;
+            else pq_hybrid_decode(vp + 4, end, 1, nnz, [&](int i, uint32_t v) { dst[i] = (int32_t)v; });
+        } else if (ch.phys == pq::T_BYTE_ARRAY) {
+            payload = vbytes - 4 * (int64_t)nnz;
+            if (payload < 0) bad = true;
+        } else if (ch.phys == pq::T_BOOLEAN) {
+            if (vbytes < ((int64_t)nnz + 7) / 8) bad = true;
+        } else {
+            if (vbytes < (int64_t)nnz * ch.phys_width) bad = true;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) payload += __shfl_xor_sync(0xffffffffu, payload, d);
+    if (lane == 0) {
+        PqPage &o = pages[j];
+        o.values_off = values_off;
+        o.nnz = nnz;
+        o.payload_bytes = bad ? 0 : payload;
+        if (bad) { o.bad = 1; pq_err(err, KERR_BAD_PAGE); }
+    }
+}
+
+// one warp per (run, var-len column): payload base of every page; files of a run continue each other's offsets
+__global__ void k_pq_scan_pages(PqPage *pages, const PqChunk *chunks, const PqPair *pairs, int n_pairs, int64_t *totals,
+                                int32_t *err) {
+    const int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (w >= n_pairs) return;
+    const PqPair pr = pairs[w];
+    int64_t carry = 0;
+    if (pr.chunk1 > pr.chunk0) {
+        const int first = chunks[pr.chunk0].page_base;
+        const int last = chunks[pr.chunk1 - 1].page_base + chunks[pr.chunk1 - 1].n_pages;
+        for (int base = first; base < last; base += 32) {
+            const int i = base + lane;
+            const int64_t x = i < last ? pages[i].payload_bytes : 0;
+            int64_t incl = x;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int64_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += y;
+            }
+            if (i < last) {
+                pages[i].payload_base = carry + incl - x;
+                pages[i].vs_base = pr.vs_rows_base + pages[i].row0 + i + pr.idx;
+                pages[i].is_last = i == last - 1;
+            }
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    if (lane == 0) {
+        totals[w] = carry;
+        if (carry > 0x7fffffffLL) pq_err(err, KERR_OFFSET_OVERFLOW);
+    }
+}
+
+// ------------------------------------------------------------------ PLAIN BYTE_ARRAY walk
+//
+// [len:4][bytes][len:4][bytes]... (VectorizedPlainValuesReader.java:275-288).  The lengths are embedded in the
+// stream, so the walk itself is sequential; one warp per page stages the stream through shared memory in 2 KiB
+// windows (coalesced 16-byte loads), lane 0 walks the window at shared-memory latency, and the results go out
+// coalesced: emit(j, q, len) for value j whose length word sits at stream offset q.  Returns the stream offset
+// behind the last value walked (-1: malformed).
+constexpr int kWalkWindow = 2048;
+constexpr int kWalkWarps = 8;
+
+template <typename Emit>
+__device__ int64_t pq_walk_stream(const uint8_t *stream, int64_t stream_len, int count, uint8_t *win, uint32_t *w_off,
+                                  int32_t *w_len, Emit emit) {
+    const int lane = threadIdx.x & 31;
+    int done = 0;
+    int64_t pos = 0;                                   // stream offset of the next length word
+    while (done < count) {
+        if (pos + 4 > stream_len) return -1;
+        // window = [base, base + kWalkWindow + 16) clipped to the stream, base 16-byte aligned in memory
+        const uint8_t *p = stream + pos;
+        const uint8_t *base = (const uint8_t *)((uintptr_t)p & ~(uintptr_t)15);
+        const int skip = (int)(p - base);
+        const int avail = (int)min((int64_t)(stream + stream_len - base), (int64_t)(kWalkWindow + 16));
+        for (int o = lane * 16; o < avail; o += 32 * 16) *(uint4 *)(win + o) = *(const uint4 *)(base + o);
+        __syncwarp();
+        int nfound = 0, q = skip;
+        bool corrupt = false;
+        if (lane == 0) {
+            while (done + nfound < count && q + 4 <= avail && nfound < 256) {
+                const int32_t len = (int32_t)((uint32_t)win[q] | ((uint32_t)win[q + 1] << 8) | ((uint32_t)win[q + 2] << 16) |
+                                              ((uint32_t)win[q + 3] << 24));
+                if (len < 0) { corrupt = true; break; }
+                w_off[nfound] = (uint32_t)q;
+                w_len[nfound] = len;
+                nfound++;
+                if ((int64_t)q + 4 + len > 0x7fffffff) { corrupt = true; break; }
+                q += 4 + len;
+            }
+        }
+        nfound = __shfl_sync(0xffffffffu, nfound, 0);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        corrupt = __shfl_sync(0xffffffffu, (int)corrupt, 0);
+        __syncwarp();
+        const int64_t base_off = (int64_t)(base - stream);
+        for (int i = lane; i < nfound; i += 32) emit(done + i, base_off + w_off[i], w_len[i]);
+        __syncwarp();
+        if (corrupt || nfound == 0) return -1;            // a length word straddles the stream end: malformed
+        done += nfound;
+        pos = base_off + q;
+        if (pos > stream_len) return -1;
+    }
+    return pos;
+}
+
+// warps [0, n_pages): PLAIN BYTE_ARRAY data pages -> value start offsets in the OUTPUT payload;
+// warps [n_pages, n_pages + n_dicts): BYTE_ARRAY dictionary pages -> entry offsets / lengths.
+// `which`: 0 = dictionaries only (before the levels pass), 1 = data pages only (after the page scan)
+__global__ void __launch_bounds__(kWalkWarps * 32)
+k_pq_walk_bytes(PqPage *pages, int n_pages, const PqPage *dicts, int n_dicts, const PqChunk *chunks, int which,
+                int32_t *vstart, int32_t *dict_off, int32_t *dict_len, int32_t *err) {
+    __shared__ __align__(16) uint8_t s_win[kWalkWarps][kWalkWindow + 32];
+    __shared__ uint32_t s_off[kWalkWarps][256];
+    __shared__ int32_t s_len[kWalkWarps][256];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * kWalkWarps + w;
+    if (which == 1) {
+        if (t >= n_pages) return;
+        const PqPage pg = pages[t];
+        if (pg.bad || pg.enc != ENC_PLAIN || chunks[pg.chunk].phys != pq::T_BYTE_ARRAY) return;
+        int32_t *vs = vstart + pg.vs_base;
+        const int64_t pb = pg.payload_base;
+        const int64_t slen = pg.body_len - pg.values_off;
+        const int64_t endq = pq_walk_stream(pg.body + pg.values_off, slen, pg.nnz, s_win[w], s_off[w], s_len[w],
+                                            [&](int j, int64_t q, int32_t) { vs[j] = (int32_t)(pb + q - 4 * (int64_t)j); });
+        if (lane == 0) {
+            if (endq != slen) { pq_err(err, KERR_BAD_PAGE); pages[t].bad = 1; }
+            vs[pg.nnz] = (int32_t)(pb + slen - 4 * (int64_t)pg.nnz);
+        }
+    } else {
+        if (t >= n_dicts) return;
+        const PqPage dj = dicts[t];
+        if (chunks[dj.chunk].phys != pq::T_BYTE_ARRAY) return;
+        int32_t *doff = dict_off + dj.entry_base, *dlen = dict_len + dj.entry_base;
+        const int64_t endq = pq_walk_stream(dj.body, dj.body_len, dj.num_values, s_win[w], s_off[w], s_len[w],
+                                            [&](int j, int64_t q, int32_t len) { doff[j] = (int32_t)(q + 4); dlen[j] = len; });
+        if (lane == 0 && endq < 0) pq_err(err, KERR_BAD_PAGE);
+    }
+}
+
+// ------------------------------------------------------------------ expand: one CTA per data page
+//
+// Null cells occupy no space in the value stream (VectorizedRleValuesReader.java:260-289): the value of row r is the
+// rank(r)-th value of the page, rank = number of set validity bits in front of r inside the page.  The page's rows are
+// walked in windows of 256 validity words (aligned to the run's 32-row words, so pages that start in the middle of a
+// word mask their neighbours' bits out); a block scan of the word popcounts gives every word its rank base.
+constexpr int kExpThreads = 256;
+
+__device__ __forceinline__ uint64_t pq_load_unaligned(const uint8_t *p, int w) {
+    if (w == 8) {
+        const uintptr_t a = (uintptr_t)p;
+        const uint64_t *q = (const uint64_t *)(a & ~(uintptr_t)7);
+        const int sh = (int)(a & 7) * 8;
+        const uint64_t lo = q[0];
+        return sh ? (lo >> sh) | (q[1] << (64 - sh)) : lo;
+    }
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
+    const int sh = (int)(a & 3) * 8;
+    const uint32_t lo = q[0];
+    return sh ? (uint64_t)((lo >> sh) | (q[1] << (32 - sh))) : (uint64_t)lo;
+}
+
+__global__ void __launch_bounds__(kExpThreads)
+k_pq_expand(const PqPage *pages, const PqPage *dicts, const PqChunk *chunks, const PqOut *outs, int n_cols,
+            const int32_t *ids, const int32_t *vstart, const int32_t *dict_off, const int32_t *dict_len, int32_t *err) {
+    __shared__ uint32_t s_bits[kExpThreads];
+    __shared__ int s_rank[kExpThreads];
+    __shared__ int s_wlen[kExpThreads];
+    __shared__ int s_ws[34];
+    const PqPage pg = pages[blockIdx.x];
+    if (pg.bad || pg.num_values == 0) return;
+    const PqChunk ch = chunks[pg.chunk];
+    const PqOut out = outs[ch.run * n_cols + ch.col];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t row0 = pg.row0, row1 = pg.row0 + pg.num_values;
+    const int64_t g0 = row0 & ~(int64_t)31;
+    const int n_words = (int)((row1 - g0 + 31) >> 5);
+    const uint8_t *values = pg.body + pg.values_off;
+    const int pw = ch.phys_width;
+    const bool varlen = ch.phys == pq::T_BYTE_ARRAY;
+    const bool is_dict = pg.enc == ENC_DICT;
+    const PqPage *dj = is_dict ? &dicts[ch.dict_base] : nullptr;
+    const uint8_t *dbody = is_dict ? dj->body : nullptr;
+    const int64_t ebase = is_dict ? dj->entry_base : 0;
+    const int32_t *pids = ids + pg.ids_base;
+    const int32_t *vs = vstart + pg.vs_base;
+    uint8_t *payload = varlen ? (uint8_t *)out.data : nullptr;
+    int carry_rank = 0;
+    int64_t carry_bytes = pg.payload_base;
+    for (int w0 = 0; w0 < n_words; w0 += kExpThreads) {
+        // this thread's validity word, masked to the page's rows
+        const int jw = w0 + tid;
+        uint32_t bits = 0;
+        if (jw < n_words) {
+            const int64_t wrow = g0 + 32 * (int64_t)jw;
+            const int lo = wrow < row0 ? (int)(row0 - wrow) : 0;
+            const int64_t hi = pq_min64(32, row1 - wrow);
+            const uint32_t mask = (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1)) & ~((1u << lo) - 1);
+            bits = out.validity ? (out.validity[wrow >> 5] & mask) : mask;
+        }
+        int tot = 0;
+        const int excl = block_scan_excl(__popc(bits), s_ws, &tot);
+        s_bits[tid] = bits;
+        s_rank[tid] = carry_rank + excl;
+        __syncthreads();
+        const int nw = min(kExpThreads, n_words - w0);
+        if (varlen && is_dict) {
+            // dictionary strings: lengths per row -> offsets need a second scan level (bytes per word)
+            for (int jj = warp; jj < nw; jj += kExpThreads / 32) {
+                const uint32_t b = s_bits[jj];
+                int len = 0;
+                if ((b >> lane) & 1) len = dict_len[ebase + pids[s_rank[jj] + __popc(b & ((1u << lane) - 1))]];
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) len += __shfl_xor_sync(0xffffffffu, len, d);
+                if (lane == 0) s_wlen[jj] = len;
+            }
+            __syncthreads();
+            int wtot = 0;
+            const int wl = tid < nw ? s_wlen[tid] : 0;
+            const int wex = block_scan_excl(wl, s_ws, &wtot);
+            s_wlen[tid] = wex;
+            __syncthreads();
+            for (int jj = warp; jj < nw; jj += kExpThreads / 32) {
+                const uint32_t b = s_bits[jj];
+                const int64_t row = g0 + 32 * (int64_t)(w0 + jj) + lane;
+                const bool inpage = row >= row0 && row < row1;
+                int len = 0;
+                const uint8_t *src = nullptr;
+                if ((b >> lane) & 1) {
+                    const int id = pids[s_rank[jj] + __popc(b & ((1u << lane) - 1))];
+                    len = dict_len[ebase + id];
+                    src = dbody + dict_off[ebase + id];
+                }
+                const int incl = warp_scan_incl(len);
+                const int64_t off = carry_bytes + s_wlen[jj] + incl - len;
+                if (inpage) out.offsets[row] = (int32_t)off;
+                // payload: 8 lanes per row, 4 rows at a time
+                for (int r8 = 0; r8 < 32; r8 += 4) {
+                    const int sl = r8 + (lane >> 3);
+                    const int64_t o2 = __shfl_sync(0xffffffffu, off, sl);
+                    const int l2 = __shfl_sync(0xffffffffu, len, sl);
+                    const uint8_t *s2 = (const uint8_t *)__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)src, sl);
+                    for (int bb = lane & 7; bb < l2; bb += 8) payload[o2 + bb] = s2[bb];
+                }
+            }
+            carry_bytes += wtot;
+        } else {
+            for (int jj = warp; jj < nw; jj += kExpThreads / 32) {
+                const uint32_t b = s_bits[jj];
+                const int64_t row = g0 + 32 * (int64_t)(w0 + jj) + lane;
+                if (row < row0 || row >= row1) continue;
+                const bool valid = (b >> lane) & 1;
+                const int rank = s_rank[jj] + __popc(b & ((1u << lane) - 1));
+                if (varlen) {
+                    out.offsets[row] = vs[rank];                      // a NULL row starts where the next value starts
+                } else {
+                    uint64_t v = 0;
+                    if (valid) {
+                        if (pg.enc == ENC_RLE_BOOL) v = (uint64_t)(pids[rank] & 1);
+                        else if (ch.phys == pq::T_BOOLEAN) v = (values[rank >> 3] >> (rank & 7)) & 1;
+                        else if (is_dict) v = pq_load_unaligned(dbody + (int64_t)pids[rank] * pw, pw);
+                        else v = pq_load_unaligned(values + (int64_t)rank * pw, pw);
+                    }
+                    store_fixed(out.data, out.out_width, row, v);   // narrowing keeps the low bytes (INT32 -> TINYINT)
+                }
+            }
+        }
+        carry_rank += tot;
+        __syncthreads();
+    }
+    if (varlen) {
+        if (!is_dict) {
+            // PLAIN: the page's payload is its value stream without the 4-byte length words; 8 lanes per value
+            const int nnz = pg.nnz;
+            const int64_t pb = pg.payload_base;
+            for (int j = tid >> 3; j < nnz; j += kExpThreads / 8) {
+                const int s = vs[j], e = vs[j + 1];
+                const uint8_t *src = values + ((int64_t)s - pb) + 4 * (int64_t)(j + 1);
+                for (int bb = tid & 7; bb < e - s; bb += 8) payload[(int64_t)s + bb] = src[bb];
+            }
+        }
+        if (pg.is_last && tid == 0) out.offsets[row1] = (int32_t)(pg.payload_base + pg.payload_bytes);
+    }
+}
+
+// an empty run still needs offsets[0] = 0 for its var-len columns
+__global__ void k_pq_zero_first_offset(const PqOut *outs, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && outs[i].offsets) outs[i].offsets[0] = 0;
+}
+
+// ---- device-wide inclusive scan of int32 (three small kernels; used by the deletion-vector filter)
 __global__ void k_scan_block_sums(const int32_t *data, int64_t n, int64_t *block_sums) {
     __shared__ int64_t sh[256];
     int64_t b0 = (int64_t)blockIdx.x * 4096;
@@ -453,12 +999,23 @@ __global__ void k_scan_block_sums(const int32_t *data, int64_t n, int64_t *block
     for (int d = 128; d > 0; d >>= 1) { if (threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d]; __syncthreads(); }
     if (threadIdx.x == 0) block_sums[blockIdx.x] = sh[0];
 }
-__global__ void k_scan_block_prefix(int64_t *block_sums, int64_t n_blocks, int32_t *err) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
+__global__ void __launch_bounds__(1024) k_scan_block_prefix(int64_t *block_sums, int64_t n_blocks, int32_t *err) {
+    // exclusive scan of the block sums by one CTA: every thread owns a contiguous slice
+    __shared__ int64_t part[1024];
+    const int64_t per = (n_blocks + blockDim.x - 1) / blockDim.x;
+    const int64_t b = threadIdx.x * per, e = min(b + per, n_blocks);
+    int64_t s = 0;
+    for (int64_t i = b; i < e; i++) s += block_sums[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
         int64_t acc = 0;
-        for (int64_t i = 0; i < n_blocks; i++) { int64_t t = block_sums[i]; block_sums[i] = acc; acc += t; }
+        for (int i = 0; i < (int)blockDim.x; i++) { const int64_t t = part[i]; part[i] = acc; acc += t; }
         if (acc > 0x7fffffffLL) atomicCAS(err, KERR_NONE, KERR_OFFSET_OVERFLOW);
     }
+    __syncthreads();
+    int64_t acc = part[threadIdx.x];
+    for (int64_t i = b; i < e; i++) { const int64_t t = block_sums[i]; block_sums[i] = acc; acc += t; }
 }
 __global__ void __launch_bounds__(256) k_scan_apply(int32_t *data, int64_t n, const int64_t *block_sums) {
     __shared__ int ws[34];
@@ -474,44 +1031,14 @@ __global__ void __launch_bounds__(256) k_scan_apply(int32_t *data, int64_t n, co
     }
 }
 
-// payload copy: 8 lanes per row
-__global__ void k_pq_copy_bytes(const uint8_t *const *rowsrc, const int32_t *offsets, uint8_t *out, int64_t n_rows) {
-    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    if (row >= n_rows) return;
-    const uint8_t *src = rowsrc[row];
-    int o0 = offsets[row], o1 = offsets[row + 1];
-    for (int b = o0 + (threadIdx.x & 7); b < o1; b += 8) out[b] = src[b - o0];
-}
-
 // ------------------------------------------------------------------ host side
 
-struct PqReader {
-    const Schema *schema = nullptr;
-    uint64_t schema_h = 0;
-    pq::FileMetaData meta;
-    std::vector<uint8_t> file;             // host copy (page headers are parsed from it)
-    std::vector<PqPageJob> jobs;           // body pointers hold FILE OFFSETS until decode time
-    std::vector<PqDictJob> dicts;
-    std::vector<int64_t> dict_entries_per_col;
-    int64_t n_rows = 0;
-    int64_t dict_entries = 0;
-    // compressed page bodies (Snappy), decompressed on the device before the decode kernels run
-    struct Unc { int64_t src_off; int32_t src_len, dst_len, prefix; int64_t dst_off; };
-    std::vector<Unc> unc;
-    std::vector<int32_t> job_unc, dict_unc;    // per page / dictionary job: index into unc, -1 = stored uncompressed
-    int64_t unc_bytes = 0;
-    // DELTA_BINARY_PACKED pages, expanded to PLAIN images on the device
-    struct Delta { int64_t src_off; int32_t src_len, prefix, width, max_values; int64_t dst_off; };
-    std::vector<Delta> delta;
-    std::vector<int32_t> job_delta;            // per page job: index into delta, -1 = none
-    int64_t delta_bytes = 0;
-    float ms_decode = 0;
-    int launches = 0;
-};
-
-static std::mutex g_pq_mu;
-static std::unordered_map<uint64_t, std::unique_ptr<PqReader>> g_pq;
-static uint64_t g_pq_next = 1;
+Schema *schema_from_handle(uint64_t h);                 // api.cu
+void *device_buffer_take(size_t bytes, size_t *got);    // api.cu: recycled device buffers
+void device_buffer_give(void *p, size_t bytes);
+cudaStream_t thread_stream();                           // api.cu: the calling thread's non-blocking stream
+uint64_t register_run(std::unique_ptr<Run> run);        // api.cu
+pg_status require_device();                             // api.cu
 
 static int out_width_of(int t) {
     switch (t) {
@@ -530,30 +1057,20 @@ static bool phys_compatible(int pg_t, int phys) {
         case PG_INT64: return phys == pq::T_INT64;
         case PG_FLOAT: return phys == pq::T_FLOAT;
         case PG_DOUBLE: return phys == pq::T_DOUBLE;
+        case PG_BOOL: return phys == pq::T_BOOLEAN;
         case PG_STRING: case PG_BINARY: return phys == pq::T_BYTE_ARRAY;
         default: return false;
     }
 }
+static int phys_width_of(int phys) {
+    return phys == pq::T_INT32 || phys == pq::T_FLOAT ? 4 : (phys == pq::T_INT64 || phys == pq::T_DOUBLE ? 8 : 0);
+}
 
-Schema *schema_from_handle(uint64_t h);                 // api.cu
-void *device_buffer_take(size_t bytes, size_t *got);    // api.cu: recycled device buffers
-void device_buffer_give(void *p, size_t bytes);
-cudaStream_t thread_stream();                           // api.cu: the calling thread's non-blocking stream
-uint64_t register_run(std::unique_ptr<Run> run);        // api.cu
-pg_status require_device();                             // api.cu
-
-static pg_status pq_open(uint64_t schema_h, const uint8_t *bytes, int64_t size, uint64_t *out) {
-    Schema *s = schema_from_handle(schema_h);
-    if (!s || !bytes || !out) return fail(PG_ERR_INVALID, "bad schema handle or null argument");
-    auto rd = std::make_unique<PqReader>();
-    rd->schema = s;
-    rd->schema_h = schema_h;
-    try {
-        rd->meta = pq::parse_footer(bytes, size);
-    } catch (const std::exception &e) {
-        return fail(PG_ERR_FORMAT, e.what());
-    }
-    const pq::FileMetaData &m = rd->meta;
+// The file's columns against the KeyValue file schema [_KEY_*, _SEQUENCE_NUMBER, _VALUE_KIND, value...]: same
+// count, flat, compatible physical types and — when the caller passes the expected field names — the same names
+// in the same order (the reference resolves columns by name, ParquetReaderFactory.clipParquetSchema; a file written
+// under another table schema needs the schema-evolution mapping of the Java side and is refused here).
+static pg_status check_file_schema(const Schema *s, const pq::FileMetaData &m, const char *const *names) {
     const int nc = s->n_cols();
     if (m.schema.empty() || m.schema[0].num_children != nc || (int)m.schema.size() != nc + 1)
         return fail(PG_ERR_UNSUPPORTED, "parquet: only flat schemas whose columns match the KeyValue file schema "
@@ -565,112 +1082,494 @@ static pg_status pq_open(uint64_t schema_h, const uint8_t *bytes, int64_t size, 
         if (!phys_compatible(s->field(c).type, e.type))
             return fail(PG_ERR_UNSUPPORTED, "parquet: column " + e.name + " has a physical type the device decoder "
                                             "does not map to the table type");
+        if (names && names[c] && e.name != names[c])
+            return fail(PG_ERR_UNSUPPORTED, "parquet: file column " + std::to_string(c) + " is '" + e.name +
+                                            "' but the read schema expects '" + names[c] + "' (a file written under "
+                                            "another table schema needs the schema-evolution mapping; not on device)");
     }
-    rd->file.assign(bytes, bytes + size);
-    rd->n_rows = m.num_rows;
-    rd->dict_entries_per_col.assign(nc, 0);
-    int64_t row0 = 0;
     for (const pq::RowGroup &g : m.row_groups) {
         if ((int)g.columns.size() != nc) return fail(PG_ERR_FORMAT, "parquet: row group with a different column count");
+        for (const pq::ColumnChunk &cc : g.columns)
+            if (cc.codec != pq::C_UNCOMPRESSED && cc.codec != pq::C_SNAPPY && cc.codec != pq::C_ZSTD)
+                return fail(PG_ERR_UNSUPPORTED, "parquet: compression codec " + std::to_string(cc.codec) +
+                                                " is not decoded on device (UNCOMPRESSED, SNAPPY and ZSTD are); write with "
+                                                "'file.compression'='zstd' / 'snappy' / 'none' or let the Java side decompress");
+    }
+    return PG_OK;
+}
+
+static pg_status kernel_error_status(int code) {
+    switch (code) {
+        case KERR_NONE: return PG_OK;
+        case KERR_PQ_ENCODING:
+            return fail(PG_ERR_UNSUPPORTED, "parquet: a page uses a value encoding the device decoder does not implement "
+                                            "(PLAIN, dictionary, DELTA_BINARY_PACKED integers and RLE booleans are decoded)");
+        case KERR_PQ_LEVELS:
+            return fail(PG_ERR_UNSUPPORTED, "parquet: repetition levels / BIT_PACKED definition levels are not decoded on device");
+        case KERR_PQ_NO_DICT: return fail(PG_ERR_FORMAT, "parquet: dictionary-encoded page without dictionary");
+        case KERR_PQ_ROWS: return fail(PG_ERR_FORMAT, "parquet: page row counts do not add up");
+        case KERR_PQ_HEADER: return fail(PG_ERR_FORMAT, "parquet: malformed or truncated page header");
+        case KERR_PQ_DICT_ID: return fail(PG_ERR_FORMAT, "parquet: dictionary id outside the dictionary");
+        case KERR_OFFSET_OVERFLOW: return fail(PG_ERR_INTERNAL, "parquet: a var-len column exceeds 2 GiB of payload");
+        default: return fail(PG_ERR_FORMAT, "parquet: a page does not expand to its declared size");
+    }
+}
+
+struct SectionFile {
+    const uint8_t *bytes;
+    int64_t size;
+    int mem;                      // PG_MEM_HOST / PG_MEM_DEVICE
+    int run;
+    const pq::FileMetaData *meta; // already parsed (single-file reader), or NULL
+};
+
+// recycled device buffers taken during one decode; everything not moved into a Run goes back on scope exit
+struct BufList {
+    cudaStream_t stream = nullptr;                    // kernels still using the buffers run on this stream
+    std::vector<std::pair<void *, size_t>> bufs;
+    void *take(size_t bytes) {
+        size_t got = 0;
+        void *p = device_buffer_take(bytes ? bytes : 256, &got);
+        if (p) bufs.push_back({p, got});
+        return p;
+    }
+    ~BufList() {
+        if (stream && !bufs.empty()) cudaStreamSynchronize(stream);
+        for (auto &b : bufs) device_buffer_give(b.first, b.second);
+    }
+};
+
+static pg_status decode_section(const Schema *s, const std::vector<SectionFile> &files, int n_runs,
+                                const char *const *names, uint64_t *out_runs, pg_section_info *info) {
+    const int nc = s->n_cols();
+    const int nf = (int)files.size();
+    cudaStream_t sm = thread_stream();
+    auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    BufList scratch;                                   // file images, tables, scratch: released on return
+    scratch.stream = sm;
+    int launches = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    struct EvGuard { cudaEvent_t &a, &b; ~EvGuard() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } evg{e0, e1};
+    PG_CUDA(cudaEventCreate(&e0));
+    PG_CUDA(cudaEventCreate(&e1));
+
+    // ---- file bytes on the device, footers on the host
+    std::vector<const uint8_t *> d_file(nf, nullptr);
+    std::vector<pq::FileMetaData> own_meta(nf);
+    std::vector<const pq::FileMetaData *> meta(nf, nullptr);
+    int64_t file_bytes = 0, h2d = 0;
+    PG_CUDA(cudaEventRecord(e0, sm));
+    for (int f = 0; f < nf; f++) {
+        const SectionFile &sf = files[f];
+        if (!sf.bytes || sf.size < 12) return fail(PG_ERR_FORMAT, "parquet: missing PAR1 magic (encrypted or not a Parquet file)");
+        if (sf.run < 0 || sf.run >= n_runs) return fail(PG_ERR_INVALID, "parquet section: run index out of range");
+        file_bytes += sf.size;
+        if (sf.mem == PG_MEM_DEVICE) d_file[f] = sf.bytes;
+        else {
+            uint8_t *d = (uint8_t *)scratch.take((size_t)sf.size + 64);
+            if (!d) return fail(PG_ERR_CUDA, "parquet: out of device memory");
+            PG_CUDA(cudaMemcpyAsync(d, sf.bytes, (size_t)sf.size, cudaMemcpyHostToDevice, sm));
+            d_file[f] = d;
+            h2d += sf.size;
+        }
+    }
+    {
+        // device-resident files: bring the footers to the host (two small copies per file, two syncs per section)
+        std::vector<int> need;
+        for (int f = 0; f < nf; f++) {
+            if (files[f].meta) meta[f] = files[f].meta;
+            else if (files[f].mem == PG_MEM_DEVICE) need.push_back(f);
+        }
+        std::vector<uint8_t> tails(8 * need.size() + 8);
+        for (size_t i = 0; i < need.size(); i++)
+            PG_CUDA(cudaMemcpyAsync(tails.data() + 8 * i, files[need[i]].bytes + files[need[i]].size - 8, 8,
+                                    cudaMemcpyDeviceToHost, sm));
+        if (!need.empty()) PG_CUDA(cudaStreamSynchronize(sm));
+        std::vector<std::vector<uint8_t>> footers(need.size());
+        try {
+            for (size_t i = 0; i < need.size(); i++) {
+                const int64_t flen = pq::footer_length(tails.data() + 8 * i);
+                if (flen + 12 > files[need[i]].size) return fail(PG_ERR_FORMAT, "parquet: bad footer length");
+                footers[i].resize((size_t)flen + 8);
+                PG_CUDA(cudaMemcpyAsync(footers[i].data(), files[need[i]].bytes + files[need[i]].size - 8 - flen,
+                                        (size_t)flen, cudaMemcpyDeviceToHost, sm));
+            }
+            if (!need.empty()) PG_CUDA(cudaStreamSynchronize(sm));
+            for (size_t i = 0; i < need.size(); i++) {
+                own_meta[need[i]] = pq::parse_footer_thrift(footers[i].data(), (int64_t)footers[i].size() - 8);
+                meta[need[i]] = &own_meta[need[i]];
+            }
+            for (int f = 0; f < nf; f++)
+                if (!meta[f]) {
+                    own_meta[f] = pq::parse_footer(files[f].bytes, files[f].size);
+                    meta[f] = &own_meta[f];
+                }
+        } catch (const std::exception &e) {
+            return fail(PG_ERR_FORMAT, e.what());
+        }
+    }
+    std::vector<uint8_t> any_optional(nc, 0);
+    for (int f = 0; f < nf; f++) {
+        pg_status st = check_file_schema(s, *meta[f], names);
+        if (st) return st;
+        for (int c = 0; c < nc; c++)
+            if (meta[f]->schema[c + 1].repetition == pq::R_OPTIONAL) any_optional[c] = 1;
+    }
+
+    // ---- rows: a file's rows land behind the rows of the files in front of it in its run
+    std::vector<int64_t> run_rows(n_runs, 0), file_row0(nf, 0);
+    std::vector<std::vector<int>> run_files(n_runs);
+    for (int f = 0; f < nf; f++) {
+        file_row0[f] = run_rows[files[f].run];
+        run_rows[files[f].run] += meta[f]->num_rows;
+        run_files[files[f].run].push_back(f);
+    }
+    for (int r = 0; r < n_runs; r++)
+        if (run_rows[r] > 0x7fffffffLL) return fail(PG_ERR_UNSUPPORTED, "parquet: more than 2^31 rows in one run");
+
+    // ---- chunk table, ordered (run, column, file, row group): the pages of a (run, column) end up contiguous
+    std::vector<PqChunk> chunks;
+    std::vector<PqPair> pairs;
+    bool any_snappy = false, any_delta = false, any_zstd = false;
+    int64_t pair_rows = 0;
+    for (int r = 0; r < n_runs; r++) {
+        for (int c = 0; c < nc; c++) {
+            const int chunk0 = (int)chunks.size();
+            for (int f : run_files[r]) {
+                const pq::FileMetaData &m = *meta[f];
+                int64_t rg_row0 = 0;
+                int64_t rows = 0;
+                for (const pq::RowGroup &g : m.row_groups) {
+                    const pq::ColumnChunk &cc = g.columns[c];
+                    const int64_t start = cc.start();
+                    if (start < 4 || start >= files[f].size) return fail(PG_ERR_FORMAT, "parquet: page offset out of range");
+                    if (cc.num_values != g.num_rows) return fail(PG_ERR_FORMAT, "parquet: page row counts do not add up");
+                    PqChunk ch;
+                    memset(&ch, 0, sizeof(ch));
+                    ch.base = d_file[f] + start;
+                    ch.avail = std::min<int64_t>(cc.total_compressed_size > 0 ? cc.total_compressed_size : files[f].size,
+                                                 files[f].size - start);
+                    ch.num_values = cc.num_values;
+                    ch.row0 = file_row0[f] + rg_row0;
+                    ch.col = c; ch.run = r; ch.file = f; ch.codec = cc.codec;
+                    ch.max_def = m.schema[c + 1].repetition == pq::R_OPTIONAL ? 1 : 0;
+                    ch.phys = cc.type;
+                    ch.phys_width = phys_width_of(cc.type);
+                    if (cc.type != m.schema[c + 1].type) return fail(PG_ERR_FORMAT, "parquet: column chunk type differs from the schema");
+                    if (cc.codec == pq::C_SNAPPY) any_snappy = true;
+                    if (cc.codec == pq::C_ZSTD) any_zstd = true;
+                    for (int32_t e : cc.encodings) if (e == pq::E_DELTA_BINARY_PACKED) any_delta = true;
+                    if (cc.num_values > 0) chunks.push_back(ch);
+                    rg_row0 += g.num_rows;
+                    rows += g.num_rows;
+                }
+                if (rows != m.num_rows) return fail(PG_ERR_FORMAT, "parquet: row group row counts do not add up");
+            }
+            if (is_varlen(s->field(c).type)) {
+                PqPair pr{r, c, chunk0, (int)chunks.size(), pair_rows, (int)pairs.size(), 0};
+                pairs.push_back(pr);
+                pair_rows += run_rows[r];
+            }
+        }
+    }
+    const int n_chunks = (int)chunks.size(), n_pairs = (int)pairs.size();
+
+    // ---- output columns: one recycled buffer per run (validity bitmaps first and contiguous: one memset)
+    std::vector<std::unique_ptr<Run>> runs(n_runs);
+    std::vector<PqOut> outs((size_t)n_runs * nc);
+    int64_t decoded_bytes = 0;
+    bool any_empty = false;
+    struct RunGuard {                                   // buffers of runs that were not registered go back
+        std::vector<std::unique_ptr<Run>> &runs;
+        ~RunGuard() {
+            for (auto &r : runs)
+                if (r) for (size_t q = 0; q < r->owned.size(); q++) device_buffer_give(r->owned[q], r->owned_bytes[q]);
+        }
+    } run_guard{runs};
+    for (int r = 0; r < n_runs; r++) {
+        const int64_t n = run_rows[r];
+        if (n == 0) any_empty = true;
+        auto run = std::make_unique<Run>();
+        run->own_schema = *s;
+        run->schema = &run->own_schema;
+        run->n_rows = n;
+        run->cols.resize(nc);
+        run->varlen_bytes.assign(nc, 0);
+        run->varlen_base.assign(nc, 0);
+        run->bytes_h2d = 0;
+        size_t vbytes = 0, total = 0;
+        const size_t vb = pad((size_t)((n + 31) / 32) * 4 + 64);
+        for (int c = 0; c < nc; c++) if (any_optional[c]) vbytes += vb;
+        total = vbytes;
+        std::vector<size_t> o_main(nc);
+        for (int c = 0; c < nc; c++) {
+            const int ow = out_width_of(s->field(c).type);
+            o_main[c] = total;
+            total += ow ? pad((size_t)n * ow + 64) : pad(4 * (size_t)(n + 1) + 64);
+        }
+        size_t got = 0;
+        unsigned char *base = (unsigned char *)device_buffer_take(total + 256, &got);
+        if (!base) return fail(PG_ERR_CUDA, "parquet: out of device memory");
+        run->owned.push_back(base);
+        run->owned_bytes.push_back(got);
+        if (vbytes) PG_CUDA(cudaMemsetAsync(base, 0, vbytes, sm));
+        size_t vt = 0;
+        for (int c = 0; c < nc; c++) {
+            PqOut &o = outs[(size_t)r * nc + c];
+            memset(&o, 0, sizeof(o));
+            const int ow = out_width_of(s->field(c).type);
+            o.out_width = ow;
+            o.is_bool = s->field(c).type == PG_BOOL;
+            if (any_optional[c]) { o.validity = (uint32_t *)(base + vt); vt += vb; decoded_bytes += (n + 7) / 8; }
+            if (ow) { o.data = base + o_main[c]; decoded_bytes += n * ow; }
+            else { o.offsets = (int32_t *)(base + o_main[c]); decoded_bytes += 4 * (n + 1); }
+        }
+        runs[r] = std::move(run);
+    }
+
+    // ---- tables to the device, page count pass
+    const size_t tb_chunks = pad(sizeof(PqChunk) * (size_t)std::max(n_chunks, 1));
+    const size_t tb_outs = pad(sizeof(PqOut) * outs.size());
+    const size_t tb_pairs = pad(sizeof(PqPair) * (size_t)std::max(n_pairs, 1));
+    const size_t tb_tot = pad(sizeof(int64_t) * (size_t)(8 + n_pairs));
+    unsigned char *tb = (unsigned char *)scratch.take(tb_chunks + tb_outs + tb_pairs + tb_tot + 256);
+    if (!tb) return fail(PG_ERR_CUDA, "parquet: out of device memory");
+    PqChunk *d_chunks = (PqChunk *)tb;
+    PqOut *d_outs = (PqOut *)(tb + tb_chunks);
+    PqPair *d_pairs = (PqPair *)(tb + tb_chunks + tb_outs);
+    int64_t *d_totals = (int64_t *)(tb + tb_chunks + tb_outs + tb_pairs);      // [0..5] chunk totals, [8..] pair totals
+    int32_t *d_err = (int32_t *)(d_totals + 6);
+    PG_CUDA(cudaMemsetAsync(d_totals, 0, tb_tot, sm));
+    if (n_chunks) PG_CUDA(cudaMemcpyAsync(d_chunks, chunks.data(), sizeof(PqChunk) * n_chunks, cudaMemcpyHostToDevice, sm));
+    PG_CUDA(cudaMemcpyAsync(d_outs, outs.data(), sizeof(PqOut) * outs.size(), cudaMemcpyHostToDevice, sm));
+    if (n_pairs) PG_CUDA(cudaMemcpyAsync(d_pairs, pairs.data(), sizeof(PqPair) * n_pairs, cudaMemcpyHostToDevice, sm));
+    int64_t h_tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (n_chunks) {
+        k_pq_walk<false><<<(n_chunks + 63) / 64, 64, 0, sm>>>(d_chunks, n_chunks, nullptr, nullptr, nullptr, d_err);
+        k_pq_chunk_scan<<<1, kScanThreads, 0, sm>>>(d_chunks, n_chunks, d_totals);
+        launches += 2;
+        PG_CUDA(cudaMemcpyAsync(h_tot, d_totals, sizeof(int64_t) * 8, cudaMemcpyDeviceToHost, sm));
+        PG_CUDA(cudaStreamSynchronize(sm));              // read-back 1: how many pages the section has
+        const int herr = (int)(h_tot[6] & 0xffffffff);
+        if (herr != KERR_NONE) return kernel_error_status(herr);
+    }
+    const int64_t n_pages = h_tot[0], n_dicts = h_tot[1], sc_bytes = h_tot[2], dict_entries = h_tot[3],
+                  ids_entries = h_tot[4], page_bytes = h_tot[5];
+    if (n_pages > 0x7fffffffLL) return fail(PG_ERR_UNSUPPORTED, "parquet: too many pages in one section");
+
+    // ---- page table + scratch, fill pass, inflate
+    const size_t sb_pages = pad(sizeof(PqPage) * (size_t)std::max<int64_t>(n_pages, 1));
+    const size_t sb_dicts = pad(sizeof(PqPage) * (size_t)std::max<int64_t>(n_dicts, 1));
+    const size_t sb_sc = pad((size_t)sc_bytes + 64);
+    const size_t sb_de = pad(4 * (size_t)(dict_entries + 1));
+    const size_t sb_ids = pad(4 * (size_t)(ids_entries + 1));
+    const size_t sb_vs = pad(4 * (size_t)(pair_rows + n_pages + n_pairs + 2));
+    int zs_ctas = 0;
+    if (any_zstd) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        zs_ctas = (int)std::min<int64_t>((int64_t)sms * 4, (n_pages + n_dicts + kZsWarps - 1) / kZsWarps);
+    }
+    const size_t sb_zs = pad((size_t)zs_ctas * kZsWarps * (size_t)(zs::kMaxBlock + 64));
+    unsigned char *sbuf = (unsigned char *)scratch.take(sb_pages + sb_dicts + sb_sc + 2 * sb_de + sb_ids + sb_vs + sb_zs + 256);
+    if (!sbuf) return fail(PG_ERR_CUDA, "parquet: out of device memory");
+    PqPage *d_pages = (PqPage *)sbuf;
+    PqPage *d_dicts = (PqPage *)(sbuf + sb_pages);
+    uint8_t *d_sc = sbuf + sb_pages + sb_dicts;
+    int32_t *d_dict_off = (int32_t *)(d_sc + sb_sc);
+    int32_t *d_dict_len = (int32_t *)(d_sc + sb_sc + sb_de);
+    int32_t *d_ids = (int32_t *)(d_sc + sb_sc + 2 * sb_de);
+    int32_t *d_vstart = (int32_t *)(d_sc + sb_sc + 2 * sb_de + sb_ids);
+    uint8_t *d_zs_lit = (uint8_t *)d_vstart + sb_vs;
+    const int np = (int)n_pages, nd = (int)n_dicts;
+    std::vector<int64_t> pair_tot(std::max(n_pairs, 1), 0);
+    if (np > 0) {
+        k_pq_walk<true><<<(n_chunks + 63) / 64, 64, 0, sm>>>(d_chunks, n_chunks, d_pages, d_dicts, d_sc, d_err);
+        launches++;
+        if (any_snappy) {
+            const int64_t th = (int64_t)(np + nd) * 32;
+            k_pq_snappy<<<(unsigned)((th + 127) / 128), 128, 0, sm>>>(d_pages, np, d_dicts, nd, d_chunks, d_err);
+            launches++;
+        }
+        if (any_zstd && zs_ctas > 0) {
+            k_pq_zstd<<<zs_ctas, kZsWarps * 32, 0, sm>>>(d_pages, np, d_dicts, nd, d_chunks, d_zs_lit, (int32_t *)(d_totals + 7), d_err);
+            launches++;
+        }
+        if (any_delta) {
+            k_pq_delta<<<(unsigned)(((int64_t)np * 32 + 127) / 128), 128, 0, sm>>>(d_pages, np, d_chunks, d_err);
+            launches++;
+        }
+        if (dict_entries > 0) {
+            k_pq_walk_bytes<<<(nd + kWalkWarps - 1) / kWalkWarps, kWalkWarps * 32, 0, sm>>>(
+                d_pages, np, d_dicts, nd, d_chunks, 0, d_vstart, d_dict_off, d_dict_len, d_err);
+            launches++;
+        }
+        k_pq_levels<<<(unsigned)(((int64_t)np * 32 + 127) / 128), 128, 0, sm>>>(d_pages, np, d_dicts, d_chunks, d_outs, nc,
+                                                                            d_ids, d_dict_len, d_err);
+        launches++;
+        if (n_pairs) {
+            k_pq_scan_pages<<<(n_pairs * 32 + 127) / 128, 128, 0, sm>>>(d_pages, d_chunks, d_pairs, n_pairs, d_totals + 8, d_err);
+            launches++;
+            PG_CUDA(cudaMemcpyAsync(pair_tot.data(), d_totals + 8, sizeof(int64_t) * n_pairs, cudaMemcpyDeviceToHost, sm));
+            PG_CUDA(cudaMemcpyAsync(h_tot, d_totals, sizeof(int64_t) * 8, cudaMemcpyDeviceToHost, sm));
+            PG_CUDA(cudaStreamSynchronize(sm));          // read-back 2: exact payload sizes of the var-len columns
+            const int herr = (int)(h_tot[6] & 0xffffffff);
+            if (herr != KERR_NONE) return kernel_error_status(herr);
+        }
+    }
+
+    // ---- var-len payload buffers (one per run), then the value walk and the expansion
+    if (n_pairs) {
+        for (int r = 0; r < n_runs; r++) {
+            size_t sum = 256;
+            for (const PqPair &pr : pairs) if (pr.run == r) sum += pad((size_t)pair_tot[pr.idx] + 64);
+            size_t got = 0;
+            unsigned char *pl = (unsigned char *)device_buffer_take(sum, &got);
+            if (!pl) return fail(PG_ERR_CUDA, "parquet: out of device memory");
+            runs[r]->owned.push_back(pl);
+            runs[r]->owned_bytes.push_back(got);
+            size_t pt = 0;
+            for (const PqPair &pr : pairs) {
+                if (pr.run != r) continue;
+                outs[(size_t)r * nc + pr.col].data = pl + pt;
+                runs[r]->varlen_bytes[pr.col] = pair_tot[pr.idx];
+                decoded_bytes += pair_tot[pr.idx];
+                pt += pad((size_t)pair_tot[pr.idx] + 64);
+            }
+        }
+        PG_CUDA(cudaMemcpyAsync(d_outs, outs.data(), sizeof(PqOut) * outs.size(), cudaMemcpyHostToDevice, sm));
+    }
+    if (np > 0) {
+        if (n_pairs) {
+            k_pq_walk_bytes<<<(np + kWalkWarps - 1) / kWalkWarps, kWalkWarps * 32, 0, sm>>>(
+                d_pages, np, d_dicts, nd, d_chunks, 1, d_vstart, d_dict_off, d_dict_len, d_err);
+            launches++;
+        }
+        k_pq_expand<<<np, kExpThreads, 0, sm>>>(d_pages, d_dicts, d_chunks, d_outs, nc, d_ids, d_vstart, d_dict_off,
+                                                d_dict_len, d_err);
+        launches++;
+    }
+    if (any_empty && n_pairs) {
+        k_pq_zero_first_offset<<<(n_runs * nc + 127) / 128, 128, 0, sm>>>(d_outs, n_runs * nc);
+        launches++;
+    }
+    PG_CUDA(cudaEventRecord(e1, sm));
+    PG_CUDA(cudaMemcpyAsync(h_tot, d_totals, sizeof(int64_t) * 8, cudaMemcpyDeviceToHost, sm));
+    PG_CUDA(cudaStreamSynchronize(sm));
+    PG_CUDA(cudaGetLastError());
+    {
+        const int herr = (int)(h_tot[6] & 0xffffffff);
+        if (herr != KERR_NONE) return kernel_error_status(herr);
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+
+    for (int r = 0; r < n_runs; r++) {
+        for (int c = 0; c < nc; c++) {
+            const PqOut &o = outs[(size_t)r * nc + c];
+            DevColumn dc;
+            dc.data = o.data ? o.data : (const void *)runs[r]->owned[0];
+            dc.offsets = o.offsets;
+            dc.validity = (const uint8_t *)o.validity;
+            runs[r]->cols[c] = dc;
+        }
+        runs[r]->bytes_h2d = r == 0 ? h2d : 0;
+        out_runs[r] = register_run(std::move(runs[r]));
+    }
+    if (info) {
+        memset(info, 0, sizeof(*info));
+        for (int r = 0; r < n_runs; r++) info->n_rows += run_rows[r];
+        info->file_bytes = file_bytes;
+        info->page_bytes = page_bytes;
+        info->decoded_bytes = decoded_bytes;
+        info->n_files = nf;
+        info->n_runs = n_runs;
+        info->n_chunks = n_chunks;
+        info->n_data_pages = np;
+        info->n_dictionary_pages = nd;
+        info->launches = launches;
+        info->ms_decode = ms;
+    }
+    return PG_OK;
+}
+
+// ---- the single-file reader (FormatReaderFactory.createReader + readBatch): a section of one file
+
+struct PqReader {
+    const Schema *schema = nullptr;
+    Schema own_schema;
+    pq::FileMetaData meta;
+    std::vector<uint8_t> file;             // host copy: pg_parquet_open's caller may free its buffer
+    int64_t n_rows = 0;
+    int n_data_pages = 0, n_dict_pages = 0;
+    float ms_decode = 0;
+    int launches = 0;
+};
+
+static std::mutex g_pq_mu;
+static std::unordered_map<uint64_t, std::unique_ptr<PqReader>> g_pq;
+static uint64_t g_pq_next = 1;
+
+// open = footer + schema check + a host walk of the page headers, so that files the device would refuse are refused
+// here, before any device work (and on a box without a GPU)
+static pg_status pq_open(uint64_t schema_h, const uint8_t *bytes, int64_t size, uint64_t *out) {
+    Schema *s = schema_from_handle(schema_h);
+    if (!s || !bytes || !out) return fail(PG_ERR_INVALID, "bad schema handle or null argument");
+    auto rd = std::make_unique<PqReader>();
+    rd->own_schema = *s;
+    rd->schema = &rd->own_schema;
+    try {
+        rd->meta = pq::parse_footer(bytes, size);
+    } catch (const std::exception &e) {
+        return fail(PG_ERR_FORMAT, e.what());
+    }
+    const pq::FileMetaData &m = rd->meta;
+    pg_status st = check_file_schema(s, m, nullptr);
+    if (st) return st;
+    const int nc = s->n_cols();
+    rd->n_rows = m.num_rows;
+    int64_t row0 = 0;
+    for (const pq::RowGroup &g : m.row_groups) {
         for (int c = 0; c < nc; c++) {
             const pq::ColumnChunk &cc = g.columns[c];
-            if (cc.codec != pq::C_UNCOMPRESSED && cc.codec != pq::C_SNAPPY)
-                return fail(PG_ERR_UNSUPPORTED, "parquet: compression codec " + std::to_string(cc.codec) +
-                                                " is not decoded on device (UNCOMPRESSED and SNAPPY are); write with "
-                                                "'file.compression'='none' / 'snappy' or let the Java side decompress");
-            const bool snappy = cc.codec == pq::C_SNAPPY;
-            // returns the index of the decompression item of a page body, or -1 when it is stored as is
-            auto add_unc = [&](int64_t body, const pq::PageHeader &h, int32_t prefix, bool compressed) -> int32_t {
-                if (!snappy || !compressed) return -1;
-                PqReader::Unc u{body, h.compressed_size, h.uncompressed_size, prefix, rd->unc_bytes};
-                rd->unc_bytes += ((int64_t)h.uncompressed_size + 63) & ~(int64_t)63;
-                rd->unc.push_back(u);
-                return (int32_t)rd->unc.size() - 1;
-            };
             const int max_def = m.schema[c + 1].repetition == pq::R_OPTIONAL ? 1 : 0;
-            int64_t pos = cc.start(), vals = 0, page_row = row0;
-            int dict_index = -1;
+            int64_t pos = cc.start(), vals = 0;
+            bool have_dict = false;
             while (vals < cc.num_values) {
                 if (pos < 4 || pos >= size) return fail(PG_ERR_FORMAT, "parquet: page offset out of range");
-                pq::PageHeader h;
-                try {
-                    h = pq::parse_page_header(bytes + pos, size - pos);
-                } catch (const std::exception &e) {
-                    return fail(PG_ERR_FORMAT, e.what());
-                }
-                int64_t body = pos + h.header_size;
-                if (body + h.compressed_size > size) return fail(PG_ERR_FORMAT, "parquet: truncated page");
+                PqHeader h;
+                if (!pq_parse_header(bytes + pos, bytes + size, h)) return fail(PG_ERR_FORMAT, "parquet: malformed or truncated page header");
+                const int64_t body = pos + h.hdr;
+                if (h.comp < 0 || body + h.comp > size) return fail(PG_ERR_FORMAT, "parquet: truncated page");
                 if (h.type == pq::P_DICTIONARY) {
-                    if (h.encoding != pq::E_PLAIN && h.encoding != pq::E_PLAIN_DICTIONARY)
+                    if (h.enc != pq::E_PLAIN && h.enc != pq::E_PLAIN_DICTIONARY)
                         return fail(PG_ERR_UNSUPPORTED, "parquet: dictionary page encoding");
-                    PqDictJob dj{};
-                    dj.body = (const uint8_t *)(uintptr_t)body;
-                    dj.body_len = h.compressed_size;
-                    dj.num_values = h.num_values;
-                    dj.col = c;
-                    dj.entry_base = rd->dict_entries;
-                    if (cc.type == pq::T_BYTE_ARRAY) rd->dict_entries += h.num_values;
-                    dict_index = (int)rd->dicts.size();
-                    rd->dict_unc.push_back(add_unc(body, h, 0, true));
-                    if (rd->dict_unc.back() >= 0) dj.body_len = h.uncompressed_size;
-                    rd->dicts.push_back(dj);
+                    have_dict = true;
+                    rd->n_dict_pages++;
                 } else if (h.type == pq::P_DATA || h.type == pq::P_DATA_V2) {
-                    bool is_dict = h.encoding == pq::E_PLAIN_DICTIONARY || h.encoding == pq::E_RLE_DICTIONARY;
-                    const bool is_delta = h.encoding == pq::E_DELTA_BINARY_PACKED &&
-                                          (cc.type == pq::T_INT32 || cc.type == pq::T_INT64) && !snappy;
-                    if (!is_dict && !is_delta && h.encoding != pq::E_PLAIN)
-                        return fail(PG_ERR_UNSUPPORTED, "parquet: value encoding " + std::to_string(h.encoding) +
-                                                        " (PLAIN, dictionary and DELTA_BINARY_PACKED on uncompressed "
-                                                        "integer pages are decoded on device)");
-                    if (is_dict && dict_index < 0) return fail(PG_ERR_FORMAT, "parquet: dictionary-encoded page without dictionary");
-                    if (h.type == pq::P_DATA_V2 && h.rep_levels_byte_length != 0)
-                        return fail(PG_ERR_UNSUPPORTED, "parquet: repetition levels");
-                    PqPageJob pj{};
-                    pj.body = (const uint8_t *)(uintptr_t)body;
-                    pj.body_len = h.compressed_size;
-                    pj.num_values = h.num_values;
-                    pj.col = c;
-                    pj.page_type = h.type;
-                    pj.is_dict = is_dict;
-                    pj.max_def = max_def;
-                    pj.v2_def_len = h.def_levels_byte_length;
-                    pj.dict = is_dict ? dict_index : -1;
-                    pj.row0 = page_row;
-                    // V1: the whole body (levels + values) is one compressed block; V2: the levels stay as they
-                    // are in front of the (optionally) compressed values
-                    const int32_t prefix = h.type == pq::P_DATA_V2 ? h.def_levels_byte_length + h.rep_levels_byte_length : 0;
-                    rd->job_unc.push_back(add_unc(body, h, prefix, h.type == pq::P_DATA_V2 ? h.is_compressed : true));
-                    if (rd->job_unc.back() >= 0) pj.body_len = h.uncompressed_size;
-                    int32_t di = -1;
-                    if (is_delta) {
-                        // level bytes in front of the values: V1 = 4-byte length + RLE levels (OPTIONAL only)
-                        int32_t lv = prefix;
-                        if (h.type == pq::P_DATA && max_def > 0) {
-                            if (h.compressed_size < 4) return fail(PG_ERR_FORMAT, "parquet: truncated page");
-                            uint32_t l4;
-                            memcpy(&l4, bytes + body, 4);
-                            lv = 4 + (int32_t)l4;
-                        }
-                        if (lv < 0 || lv > h.compressed_size) return fail(PG_ERR_FORMAT, "parquet: bad level length");
-                        const int32_t width = cc.type == pq::T_INT32 ? 4 : 8;
-                        PqReader::Delta d{body, h.compressed_size, lv, width, h.num_values, rd->delta_bytes};
-                        rd->delta_bytes += ((int64_t)lv + (int64_t)h.num_values * width + 63) & ~(int64_t)63;
-                        rd->delta.push_back(d);
-                        di = (int32_t)rd->delta.size() - 1;
-                        pj.body_len = lv + h.num_values * width;
-                    }
-                    rd->job_delta.push_back(di);
-                    rd->jobs.push_back(pj);
-                    page_row += h.num_values;
-                    vals += h.num_values;
+                    const bool is_dict = h.enc == pq::E_PLAIN_DICTIONARY || h.enc == pq::E_RLE_DICTIONARY;
+                    const bool is_delta = h.enc == pq::E_DELTA_BINARY_PACKED && (cc.type == pq::T_INT32 || cc.type == pq::T_INT64);
+                    const bool is_rle_bool = h.enc == pq::E_RLE && cc.type == pq::T_BOOLEAN;
+                    if (!is_dict && !is_delta && !is_rle_bool && h.enc != pq::E_PLAIN)
+                        return fail(PG_ERR_UNSUPPORTED, "parquet: value encoding " + std::to_string(h.enc) +
+                                                        " (PLAIN, dictionary, DELTA_BINARY_PACKED integers and RLE booleans "
+                                                        "are decoded on device)");
+                    if (is_dict && !have_dict) return fail(PG_ERR_FORMAT, "parquet: dictionary-encoded page without dictionary");
+                    if (h.type == pq::P_DATA_V2 && h.rep_len != 0) return fail(PG_ERR_UNSUPPORTED, "parquet: repetition levels");
+                    if (h.type == pq::P_DATA && max_def > 0 && h.def_enc != pq::E_RLE)
+                        return fail(PG_ERR_UNSUPPORTED, "parquet: BIT_PACKED definition levels");
+                    rd->n_data_pages++;
+                    vals += h.nv;
                 }                                        // index pages are skipped
-                pos = body + h.compressed_size;
+                pos = body + h.comp;
             }
-            if (page_row - row0 != g.num_rows) return fail(PG_ERR_FORMAT, "parquet: page row counts do not add up");
+            if (vals != g.num_rows) return fail(PG_ERR_FORMAT, "parquet: page row counts do not add up");
         }
         row0 += g.num_rows;
     }
     if (row0 != m.num_rows) return fail(PG_ERR_FORMAT, "parquet: row group row counts do not add up");
+    rd->file.assign(bytes, bytes + size);
     std::lock_guard<std::mutex> lk(g_pq_mu);
     uint64_t h = (5ull << 56) | g_pq_next++;
     g_pq[h] = std::move(rd);
@@ -679,224 +1578,15 @@ static pg_status pq_open(uint64_t schema_h, const uint8_t *bytes, int64_t size, 
 }
 
 static pg_status pq_read_run(PqReader *rd, uint64_t *out_run) {
-    const Schema *s = rd->schema;
-    const int nc = s->n_cols();
-    const int64_t n = rd->n_rows;
-    auto run = std::make_unique<Run>();
-    run->own_schema = *s;
-    run->schema = &run->own_schema;
-    run->n_rows = n;
-    run->cols.resize(nc);
-    run->varlen_bytes.assign(nc, 0);
-    // every reader thread decodes on its own stream: the files of a section decode concurrently
-    cudaStream_t sm = thread_stream();
-    auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
-
-    // ---- device memory: file bytes + scratch (freed at the end) and the output columns (owned by the run)
-    size_t scratch = pad(rd->file.size() + 64) + pad(sizeof(PqPageJob) * rd->jobs.size() + 64) +
-                     pad(sizeof(PqDictJob) * rd->dicts.size() + 64) + pad(sizeof(PqCol) * nc) +
-                     pad(sizeof(PqPageState) * rd->jobs.size() + 64) + pad(sizeof(void *) * (rd->dict_entries + 1)) +
-                     pad(4 * (rd->dict_entries + 1)) + 4096 + pad((size_t)rd->unc_bytes + 64) +
-                     pad(sizeof(SnappyJob) * rd->unc.size() + 64) + 256 + pad((size_t)rd->delta_bytes + 64) +
-                     pad(sizeof(DeltaJob) * rd->delta.size() + 64) + 256;
-    size_t outb = 4096;
-    std::vector<PqCol> cols(nc);
-    for (int c = 0; c < nc; c++) {
-        pg_field f = s->field(c);
-        const pq::SchemaElement &e = rd->meta.schema[c + 1];
-        PqCol &pc = cols[c];
-        memset(&pc, 0, sizeof(pc));
-        pc.phys = e.type;
-        pc.phys_width = e.type == pq::T_INT32 || e.type == pq::T_FLOAT ? 4 : (e.type == pq::T_BYTE_ARRAY ? 0 : 8);
-        pc.out_width = out_width_of(f.type);
-        pc.nullable = e.repetition == pq::R_OPTIONAL;
-        if (pc.nullable) { scratch += pad((size_t)n + 64); outb += pad((size_t)((n + 31) / 32) * 4 + 64); }
-        scratch += pad(4 * (size_t)n + 64);                                        // ids
-        if (pc.phys == pq::T_BYTE_ARRAY) {
-            scratch += 2 * pad(8 * (size_t)n + 64) + pad(4 * (size_t)n + 64);       // vptr, rowsrc, vlen
-            scratch += pad(8 * ((size_t)n / 4096 + 2));                            // scan block sums
-            outb += pad(4 * (size_t)(n + 1) + 64);
-        } else {
-            outb += pad((size_t)n * pc.out_width + 64);
-        }
-    }
-    unsigned char *d_scratch = nullptr, *d_out = nullptr;
-    // recycled buffers (no cudaMalloc / cudaFree, which would serialise concurrent decodes)
-    size_t scratch_got = 0, out_got = 0;
-    d_scratch = (unsigned char *)device_buffer_take(scratch, &scratch_got);
-    if (!d_scratch) return fail(PG_ERR_CUDA, "parquet: out of device memory");
-    struct ScratchGuard { unsigned char *p; size_t n; ~ScratchGuard() { device_buffer_give(p, n); } } guard{d_scratch, scratch_got};
-    d_out = (unsigned char *)device_buffer_take(outb, &out_got);
-    if (!d_out) return fail(PG_ERR_CUDA, "parquet: out of device memory");
-    run->owned.push_back(d_out);
-    run->owned_bytes.push_back(out_got);
-    size_t st = 0, ot = 0;
-    auto stake = [&](size_t b) { unsigned char *p = d_scratch + st; st += pad(b); return p; };
-    auto otake = [&](size_t b) { unsigned char *p = d_out + ot; ot += pad(b); return p; };
-
-    uint8_t *d_file = stake(rd->file.size() + 64);
-    PG_CUDA(cudaMemcpyAsync(d_file, rd->file.data(), rd->file.size(), cudaMemcpyHostToDevice, sm));
-    run->bytes_h2d = (int64_t)rd->file.size();
-    std::vector<PqPageJob> jobs = rd->jobs;
-    std::vector<PqDictJob> dicts = rd->dicts;
-    for (auto &j : jobs) j.body = d_file + (uintptr_t)j.body;
-    for (auto &d : dicts) d.body = d_file + (uintptr_t)d.body;
-    cudaEvent_t e0, e1;
-    PG_CUDA(cudaEventCreate(&e0));
-    PG_CUDA(cudaEventCreate(&e1));
-    PG_CUDA(cudaEventRecord(e0, sm));
-    int32_t *d_err_early = nullptr;
-    if (!rd->unc.empty()) {
-        // Snappy pages: one warp per page decompresses into a scratch image the decode kernels then read
-        uint8_t *d_unc = stake((size_t)rd->unc_bytes + 64);
-        SnappyJob *d_sj = (SnappyJob *)stake(sizeof(SnappyJob) * rd->unc.size());
-        d_err_early = (int32_t *)stake(16);
-        std::vector<SnappyJob> sj(rd->unc.size());
-        for (size_t i = 0; i < sj.size(); i++) {
-            const PqReader::Unc &u = rd->unc[i];
-            sj[i] = SnappyJob{d_file + u.src_off, d_unc + u.dst_off, u.src_len, u.dst_len, u.prefix, 0};
-        }
-        PG_CUDA(cudaMemsetAsync(d_err_early, 0, 4, sm));
-        PG_CUDA(cudaMemcpyAsync(d_sj, sj.data(), sizeof(SnappyJob) * sj.size(), cudaMemcpyHostToDevice, sm));
-        PG_CUDA(cudaStreamSynchronize(sm));           // sj is a local vector
-        const int64_t threads = (int64_t)sj.size() * 32;
-        k_pq_snappy<<<(int)((threads + 127) / 128), 128, 0, sm>>>(d_sj, (int)sj.size(), d_err_early);
-        for (size_t i = 0; i < jobs.size(); i++)
-            if (rd->job_unc[i] >= 0) jobs[i].body = d_unc + rd->unc[rd->job_unc[i]].dst_off;
-        for (size_t i = 0; i < dicts.size(); i++)
-            if (rd->dict_unc[i] >= 0) dicts[i].body = d_unc + rd->unc[rd->dict_unc[i]].dst_off;
-    }
-    if (!rd->delta.empty()) {
-        uint8_t *d_delta = stake((size_t)rd->delta_bytes + 64);
-        DeltaJob *d_dj = (DeltaJob *)stake(sizeof(DeltaJob) * rd->delta.size());
-        if (!d_err_early) {
-            d_err_early = (int32_t *)stake(16);
-            PG_CUDA(cudaMemsetAsync(d_err_early, 0, 4, sm));
-        }
-        std::vector<DeltaJob> dj(rd->delta.size());
-        for (size_t i = 0; i < dj.size(); i++) {
-            const PqReader::Delta &d = rd->delta[i];
-            dj[i] = DeltaJob{d_file + d.src_off, d_delta + d.dst_off, d.src_len, d.prefix, d.width, d.max_values};
-        }
-        PG_CUDA(cudaMemcpyAsync(d_dj, dj.data(), sizeof(DeltaJob) * dj.size(), cudaMemcpyHostToDevice, sm));
-        PG_CUDA(cudaStreamSynchronize(sm));           // dj is a local vector
-        const int64_t threads = (int64_t)dj.size() * 32;
-        k_pq_delta<<<(int)((threads + 127) / 128), 128, 0, sm>>>(d_dj, (int)dj.size(), d_err_early);
-        for (size_t i = 0; i < jobs.size(); i++)
-            if (rd->job_delta[i] >= 0) jobs[i].body = d_delta + rd->delta[rd->job_delta[i]].dst_off;
-    }
-    PqPageJob *d_jobs = (PqPageJob *)stake(sizeof(PqPageJob) * jobs.size() + 64);
-    PqDictJob *d_dicts = (PqDictJob *)stake(sizeof(PqDictJob) * dicts.size() + 64);
-    PqCol *d_cols = (PqCol *)stake(sizeof(PqCol) * nc);
-    PqPageState *d_state = (PqPageState *)stake(sizeof(PqPageState) * jobs.size() + 64);
-    const uint8_t **d_dict_ptr = (const uint8_t **)stake(sizeof(void *) * (rd->dict_entries + 1));
-    int32_t *d_dict_len = (int32_t *)stake(4 * (rd->dict_entries + 1));
-    int32_t *d_err = (int32_t *)stake(64);
-    std::vector<int64_t *> block_sums(nc, nullptr);
-    for (int c = 0; c < nc; c++) {
-        PqCol &pc = cols[c];
-        if (pc.nullable) {
-            pc.defs = stake((size_t)n + 64);
-            size_t vb = (size_t)((n + 31) / 32) * 4 + 64;
-            pc.out_validity = (uint32_t *)otake(vb);
-            PG_CUDA(cudaMemsetAsync(pc.out_validity, 0, vb, sm));
-        }
-        pc.ids = (int32_t *)stake(4 * (size_t)n + 64);
-        if (pc.phys == pq::T_BYTE_ARRAY) {
-            pc.vptr = (const uint8_t **)stake(8 * (size_t)n + 64);
-            pc.rowsrc = (const uint8_t **)stake(8 * (size_t)n + 64);
-            pc.vlen = (int32_t *)stake(4 * (size_t)n + 64);
-            block_sums[c] = (int64_t *)stake(8 * ((size_t)n / 4096 + 2));
-            pc.out_offsets = (int32_t *)otake(4 * (size_t)(n + 1) + 64);
-            PG_CUDA(cudaMemsetAsync(pc.out_offsets, 0, 4, sm));
-        } else {
-            pc.out_data = otake((size_t)n * pc.out_width + 64);
-        }
-    }
-    PG_CUDA(cudaMemsetAsync(d_err, 0, 4, sm));
-    PG_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(PqPageJob) * jobs.size(), cudaMemcpyHostToDevice, sm));
-    if (!dicts.empty())
-        PG_CUDA(cudaMemcpyAsync(d_dicts, dicts.data(), sizeof(PqDictJob) * dicts.size(), cudaMemcpyHostToDevice, sm));
-    PG_CUDA(cudaMemcpyAsync(d_cols, cols.data(), sizeof(PqCol) * nc, cudaMemcpyHostToDevice, sm));
-
-    const int nj = (int)jobs.size(), nd = (int)dicts.size();
-    int launches = 0;
-    if (nj > 0) {
-        k_pq_hybrid<<<(nj * 32 + 127) / 128, 128, 0, sm>>>(d_jobs, nj, d_cols, d_state);
-        k_pq_walk_bytes<<<(nj + nd + kWalkWarps - 1) / kWalkWarps, kWalkWarps * 32, 0, sm>>>(
-            d_jobs, nj, d_dicts, nd, d_cols, d_state, d_dict_ptr, d_dict_len);
-        k_pq_assemble<<<nj, 256, 0, sm>>>(d_jobs, d_dicts, d_cols, d_state, d_dict_ptr, d_dict_len);
-        launches += 3;
-    }
-    // var-len columns: lengths -> offsets, then the payload (its size needs one read-back per column)
-    std::vector<unsigned char *> payload(nc, nullptr);
-    for (int c = 0; c < nc && n > 0; c++) {
-        if (cols[c].phys != pq::T_BYTE_ARRAY) continue;
-        int64_t nb = (n + 4095) / 4096;
-        k_scan_block_sums<<<(int)nb, 256, 0, sm>>>(cols[c].out_offsets + 1, n, block_sums[c]);
-        k_scan_block_prefix<<<1, 32, 0, sm>>>(block_sums[c], nb, d_err);
-        k_scan_apply<<<(int)nb, 256, 0, sm>>>(cols[c].out_offsets + 1, n, block_sums[c]);
-        launches += 3;
-    }
-    {
-        // one read-back for all var-len columns (their exact payload sizes), one allocation, then the copies
-        std::vector<int32_t> totals(nc, 0);
-        for (int c = 0; c < nc && n > 0; c++)
-            if (cols[c].phys == pq::T_BYTE_ARRAY)
-                PG_CUDA(cudaMemcpyAsync(&totals[c], cols[c].out_offsets + n, 4, cudaMemcpyDeviceToHost, sm));
-        PG_CUDA(cudaStreamSynchronize(sm));
-        size_t sum = 256;
-        for (int c = 0; c < nc; c++) if (cols[c].phys == pq::T_BYTE_ARRAY) sum += pad((size_t)totals[c] + 64);
-        unsigned char *pl = nullptr;
-        if (n > 0 && sum > 256) {
-            size_t pl_got = 0;
-            pl = (unsigned char *)device_buffer_take(sum, &pl_got);
-            if (!pl) return fail(PG_ERR_CUDA, "parquet: out of device memory");
-            run->owned_bytes.push_back(pl_got);
-            run->owned.push_back(pl);
-        }
-        size_t pt = 0;
-        for (int c = 0; c < nc && n > 0; c++) {
-            if (cols[c].phys != pq::T_BYTE_ARRAY) continue;
-            payload[c] = pl + pt;
-            pt += pad((size_t)totals[c] + 64);
-            run->varlen_bytes[c] = totals[c];
-            int64_t threads = n * 8;
-            k_pq_copy_bytes<<<(int)((threads + 255) / 256), 256, 0, sm>>>(cols[c].rowsrc, cols[c].out_offsets,
-                                                                        payload[c], n);
-            launches++;
-        }
-    }
-    PG_CUDA(cudaEventRecord(e1, sm));
-    int32_t herr = 0;
-    PG_CUDA(cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, sm));
-    int32_t herr_pages = 0;
-    if (d_err_early) PG_CUDA(cudaMemcpyAsync(&herr_pages, d_err_early, 4, cudaMemcpyDeviceToHost, sm));
-    PG_CUDA(cudaStreamSynchronize(sm));
-    PG_CUDA(cudaGetLastError());
-    cudaEventElapsedTime(&rd->ms_decode, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    rd->launches = launches;
-    if (herr_pages != KERR_NONE) {
-        for (size_t q = 0; q < run->owned.size(); q++) device_buffer_give(run->owned[q], run->owned_bytes[q]);
-        return fail(PG_ERR_FORMAT, "parquet: a Snappy / DELTA_BINARY_PACKED page does not expand to its declared size");
-    }
-    if (herr != KERR_NONE) {
-        for (size_t q = 0; q < run->owned.size(); q++) device_buffer_give(run->owned[q], run->owned_bytes[q]);
-        return fail(PG_ERR_INTERNAL, "parquet: a var-len column exceeds 2 GiB of payload");
-    }
-    for (int c = 0; c < nc; c++) {
-        DevColumn dc;
-        dc.data = cols[c].phys == pq::T_BYTE_ARRAY ? (const void *)payload[c] : cols[c].out_data;
-        if (cols[c].phys == pq::T_BYTE_ARRAY && n == 0) dc.data = d_out;
-        dc.offsets = cols[c].out_offsets;
-        dc.validity = (const uint8_t *)cols[c].out_validity;
-        run->cols[c] = dc;
-    }
-    *out_run = register_run(std::move(run));
+    std::vector<SectionFile> files{SectionFile{rd->file.data(), (int64_t)rd->file.size(), PG_MEM_HOST, 0, &rd->meta}};
+    pg_section_info info;
+    pg_status st = decode_section(rd->schema, files, 1, nullptr, out_run, &info);
+    if (st) return st;
+    rd->ms_decode = info.ms_decode;
+    rd->launches = info.launches;
     return PG_OK;
 }
+
 
 // ------------------------------------------------------------------ deletion vectors
 //
@@ -1068,6 +1758,7 @@ static pg_status apply_deletion_vector(uint64_t run_h, const uint8_t *deleted, i
     return PG_OK;
 }
 
+
 }  // namespace pg
 
 using namespace pg;
@@ -1086,8 +1777,8 @@ pg_status pg_parquet_describe(uint64_t reader, pg_parquet_info *out) {
     out->n_rows = rd->n_rows;
     out->n_row_groups = (int32_t)rd->meta.row_groups.size();
     out->n_columns = rd->schema->n_cols();
-    out->n_data_pages = (int32_t)rd->jobs.size();
-    out->n_dictionary_pages = (int32_t)rd->dicts.size();
+    out->n_data_pages = rd->n_data_pages;
+    out->n_dictionary_pages = rd->n_dict_pages;
     out->ms_decode = rd->ms_decode;
     out->launches = rd->launches;
     return PG_OK;
@@ -1104,6 +1795,23 @@ pg_status pg_parquet_read_run(uint64_t reader, uint64_t *out_run) {
     pg_status st = require_device();          // fails loudly without pg_init / a CUDA device: no CPU fallback
     if (st) return st;
     return pq_read_run(rd, out_run);
+}
+
+pg_status pg_parquet_read_section(uint64_t schema, const pg_file_desc *files, int32_t n_files, int32_t n_runs,
+                                  const char *const *column_names, uint64_t *out_runs, pg_section_info *info) {
+    Schema *s = schema_from_handle(schema);
+    if (!s || !out_runs || n_files < 0 || n_runs < 0 || (n_files > 0 && !files))
+        return fail(PG_ERR_INVALID, "bad schema handle or null argument");
+    if (n_runs == 0) return n_files == 0 ? PG_OK : fail(PG_ERR_INVALID, "files without runs");
+    pg_status st = require_device();
+    if (st) return st;
+    std::vector<SectionFile> fs(n_files);
+    for (int i = 0; i < n_files; i++) {
+        if (files[i].mem != PG_MEM_HOST && files[i].mem != PG_MEM_DEVICE) return fail(PG_ERR_INVALID, "bad memory kind");
+        fs[i] = SectionFile{files[i].bytes, files[i].size, files[i].mem, files[i].run, nullptr};
+    }
+    const Schema own = *s;                       // the schema handle may be freed while the runs live on
+    return decode_section(&own, fs, n_runs, column_names, out_runs, info);
 }
 
 pg_status pg_run_apply_deletion_vector(uint64_t run, const uint8_t *deleted_bitmap, int64_t n_bits, uint64_t *out_run) {

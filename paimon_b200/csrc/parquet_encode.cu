@@ -222,6 +222,15 @@ __global__ void k_pw_stats(const EncColumn *cols, const StatJob *jobs, int64_t *
     }
 }
 
+// host-built pieces of the file (page headers, level prefixes, footer) -> their places in the device image
+struct PatchJob { int64_t dst; int32_t src, len; };
+__global__ void k_pw_patch(const PatchJob *jobs, int n, const uint8_t *bytes, uint8_t *file) {
+    const int j = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (j >= n) return;
+    const PatchJob pj = jobs[j];
+    for (int i = lane; i < pj.len; i += 32) file[pj.dst + i] = bytes[pj.src + i];
+}
+
 // ------------------------------------------------------------------ Thrift compact protocol writer
 
 struct ThriftWriter {
@@ -259,6 +268,7 @@ struct EncodedFile {
     std::vector<std::pair<int64_t, std::vector<uint8_t>>> host_parts;   // (offset, bytes): headers, level prefixes, footer
     pg_file_meta meta{};
     std::vector<ColStats> stats;             // whole-file, per column
+    bool image_complete = false;             // host_parts have been patched into d_file
     ~EncodedFile() { if (d_file) cudaFree(d_file); }
 };
 static std::mutex g_enc_mu;
@@ -513,8 +523,8 @@ static pg_status encode(uint64_t source, const char *const *names, int64_t row0,
     ef->file_bytes = data_end + (int64_t)tail.size();
 
     // ---- page bodies on the device
-    PG_CUDA(cudaMalloc(&ef->d_file, (size_t)data_end + 64));
-    PG_CUDA(cudaMemsetAsync(ef->d_file, 0, (size_t)data_end + 64, 0));
+    PG_CUDA(cudaMalloc(&ef->d_file, (size_t)ef->file_bytes + 64));
+    PG_CUDA(cudaMemsetAsync(ef->d_file, 0, (size_t)ef->file_bytes + 64, 0));
     if (nj) {
         PG_CUDA(cudaMemcpy(d_jobs, jobs.data(), sizeof(EncJob) * nj, cudaMemcpyHostToDevice));
         k_pw_encode<<<(unsigned)nj, 256>>>(d_cols, d_jobs, ef->d_file);
@@ -592,6 +602,43 @@ pg_status pg_parquet_file_fetch(uint64_t file, void *host_buffer, int64_t capaci
     const auto &tail = ef->host_parts.back();
     PG_CUDA(cudaMemcpy(host_buffer, ef->d_file, (size_t)tail.first, cudaMemcpyDeviceToHost));
     for (const auto &p : ef->host_parts) memcpy((uint8_t *)host_buffer + p.first, p.second.data(), p.second.size());
+    return PG_OK;
+}
+
+pg_status pg_parquet_file_device_image(uint64_t file, const uint8_t **device_bytes, int64_t *size) {
+    EncodedFile *ef;
+    {
+        std::lock_guard<std::mutex> lk(g_enc_mu);
+        auto it = g_enc.find(file);
+        if (it == g_enc.end() || !device_bytes || !size) return fail(PG_ERR_INVALID, "unknown encoded file handle");
+        ef = it->second.get();
+    }
+    pg_status st = require_device();
+    if (st) return st;
+    if (!ef->image_complete) {
+        std::vector<PatchJob> jobs;
+        std::vector<uint8_t> bytes;
+        for (const auto &p : ef->host_parts) {
+            if (bytes.size() + p.second.size() > 0x7fffffffull) return fail(PG_ERR_UNSUPPORTED, "parquet encode: too many header bytes");
+            jobs.push_back(PatchJob{p.first, (int32_t)bytes.size(), (int32_t)p.second.size()});
+            bytes.insert(bytes.end(), p.second.begin(), p.second.end());
+        }
+        PatchJob *d_jobs = nullptr;
+        uint8_t *d_bytes = nullptr;
+        PG_CUDA(cudaMalloc(&d_jobs, sizeof(PatchJob) * jobs.size() + 16));
+        cudaError_t e = cudaMalloc(&d_bytes, bytes.size() + 16);
+        if (e != cudaSuccess) { cudaFree(d_jobs); return fail(PG_ERR_CUDA, cudaGetErrorString(e)); }
+        cudaMemcpy(d_jobs, jobs.data(), sizeof(PatchJob) * jobs.size(), cudaMemcpyHostToDevice);
+        cudaMemcpy(d_bytes, bytes.data(), bytes.size(), cudaMemcpyHostToDevice);
+        k_pw_patch<<<(unsigned)((jobs.size() * 32 + 127) / 128), 128>>>(d_jobs, (int)jobs.size(), d_bytes, ef->d_file);
+        e = cudaDeviceSynchronize();
+        cudaFree(d_jobs);
+        cudaFree(d_bytes);
+        if (e != cudaSuccess) return fail(PG_ERR_CUDA, std::string("parquet encode: ") + cudaGetErrorString(e));
+        ef->image_complete = true;
+    }
+    *device_bytes = ef->d_file;
+    *size = ef->file_bytes;
     return PG_OK;
 }
 

@@ -180,14 +180,8 @@ RowGroup read_row_group(Reader &r) {
 
 }  // namespace
 
-FileMetaData parse_footer(const uint8_t *file, int64_t size) {
-    if (size < 12 || file[0] != 'P' || file[1] != 'A' || file[2] != 'R' || file[3] != '1' ||
-        file[size - 4] != 'P' || file[size - 3] != 'A' || file[size - 2] != 'R' || file[size - 1] != '1')
-        throw std::runtime_error("parquet: missing PAR1 magic (encrypted or not a Parquet file)");
-    uint32_t flen = (uint32_t)file[size - 8] | ((uint32_t)file[size - 7] << 8) | ((uint32_t)file[size - 6] << 16) |
-                    ((uint32_t)file[size - 5] << 24);
-    if ((int64_t)flen + 12 > size) throw std::runtime_error("parquet: bad footer length");
-    Reader r(file + size - 8 - flen, flen);
+FileMetaData parse_footer_thrift(const uint8_t *footer, int64_t flen) {
+    Reader r(footer, flen);
     FileMetaData m;
     int16_t id = 0;
     int t;
@@ -212,6 +206,20 @@ FileMetaData parse_footer(const uint8_t *file, int64_t size) {
         }
     }
     return m;
+}
+
+int64_t footer_length(const uint8_t *tail8) {
+    if (tail8[4] != 'P' || tail8[5] != 'A' || tail8[6] != 'R' || tail8[7] != '1')
+        throw std::runtime_error("parquet: missing PAR1 magic (encrypted or not a Parquet file)");
+    return (int64_t)((uint32_t)tail8[0] | ((uint32_t)tail8[1] << 8) | ((uint32_t)tail8[2] << 16) | ((uint32_t)tail8[3] << 24));
+}
+
+FileMetaData parse_footer(const uint8_t *file, int64_t size) {
+    if (size < 12 || file[0] != 'P' || file[1] != 'A' || file[2] != 'R' || file[3] != '1')
+        throw std::runtime_error("parquet: missing PAR1 magic (encrypted or not a Parquet file)");
+    const int64_t flen = footer_length(file + size - 8);
+    if (flen + 12 > size) throw std::runtime_error("parquet: bad footer length");
+    return parse_footer_thrift(file + size - 8 - flen, flen);
 }
 
 PageHeader parse_page_header(const uint8_t *p, int64_t avail) {

@@ -76,6 +76,10 @@ struct PageHeader {
 
 // Throws std::runtime_error on malformed input.
 FileMetaData parse_footer(const uint8_t *file, int64_t size);
+// the pieces of parse_footer, for files whose bytes live on the device: the last 8 bytes of the file
+// ([footer length:4 LE]["PAR1"]) -> footer length; the Thrift FileMetaData bytes in front of them -> metadata
+int64_t footer_length(const uint8_t *tail8);
+FileMetaData parse_footer_thrift(const uint8_t *footer, int64_t flen);
 PageHeader parse_page_header(const uint8_t *p, int64_t avail);
 
 }  // namespace pq

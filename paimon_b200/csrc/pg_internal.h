@@ -36,7 +36,13 @@ enum : int {
     KERR_AGG_RETRACT = 4,            // FieldAggregator.java:47-54
     KERR_OFFSET_OVERFLOW = 5,        // a var-len output column exceeds int32 offsets
     KERR_DIV_ZERO = 6,               // FieldProductAgg retract: integer division by zero
-    KERR_BAD_PAGE = 7                // a compressed Parquet page does not decompress to its declared size
+    KERR_BAD_PAGE = 7,               // a compressed Parquet page does not decompress to its declared size
+    KERR_PQ_HEADER = 8,              // malformed / truncated Thrift page header, or page sizes that leave the chunk
+    KERR_PQ_ENCODING = 9,            // a page uses an encoding the device decoder does not implement
+    KERR_PQ_NO_DICT = 10,            // dictionary-encoded page in a chunk without dictionary page
+    KERR_PQ_ROWS = 11,               // the pages of a chunk do not add up to the chunk's value count
+    KERR_PQ_DICT_ID = 12,            // dictionary id outside the dictionary
+    KERR_PQ_LEVELS = 13              // repetition levels / unsupported level encoding
 };
 
 struct Schema {
@@ -230,7 +236,11 @@ struct EmitArgs {
     const uint32_t *gplan;             // sequence-group marks (see PlanArgs), NULL without groups
     const uint32_t *gagg;
     const ColDesc *cols;
-    const int32_t *col_order;          // device [n_cols]: order in which the emit kernel walks the columns
+    const int32_t *col_order;          // device [n_passes]: the emit kernel's pass list, column | phase << 16
+    int n_passes;
+    const int32_t *varlen_cols;        // device [n_varlen]: column of var-len index v
+    uint16_t *vsrc;                    // [n_varlen][vsrc_stride] scratch: source member of every var-len output cell
+    int64_t vsrc_stride;
     ColPtrs ptrs;
     const int64_t *run_rows;           // device [k] rows per run
     int n_cols;

@@ -110,6 +110,41 @@ class ParquetFileRecordReader(FileRecordReader):
             self._schema_h = None
 
 
+def read_section(schema: KeyValueSchema, files, n_runs: int, device: int = 0, check_names: bool = True):
+    """Decode every data file of a section with ONE batch of device launches (pg_parquet_read_section) and return
+    (one SortedRunReader per run, PgSectionInfo).  `files` = [(buffer, run index)], in key order inside a run; a
+    buffer is bytes / a numpy uint8 array (host memory) or a (device pointer, size) tuple (bytes already in HBM).
+    The files of a run are concatenated on the device, as MergeTreeReaders.readerForRun's ConcatRecordReader does
+    (MergeTreeReaders.java:94-101): the merge gets k = number of runs inputs."""
+    lib = N.init(device)
+    sh = _SchemaHandle(schema, device)
+    keep = []
+    descs = (N.PgFileDesc * max(len(files), 1))()
+    for i, (buf, run) in enumerate(files):
+        if isinstance(buf, tuple):
+            descs[i] = N.PgFileDesc(int(buf[0]), int(buf[1]), N.PG_MEM_DEVICE, int(run))
+        else:
+            arr = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else np.ascontiguousarray(buf, np.uint8)
+            keep.append(arr)
+            descs[i] = N.PgFileDesc(arr.ctypes.data, len(arr), N.PG_MEM_HOST, int(run))
+    names = None
+    if check_names:
+        nm = [f.name for f in schema.file_fields()]
+        names = (C.c_char_p * len(nm))(*[x.encode() for x in nm])
+    runs = (C.c_uint64 * max(n_runs, 1))()
+    info = N.PgSectionInfo()
+    try:
+        N.check(lib.pg_parquet_read_section(sh.handle, descs, len(files), n_runs, names, runs, C.byref(info)))
+    finally:
+        sh.close()
+    readers = []
+    for r in range(n_runs):
+        n_rows = C.c_int64(0)
+        N.check(lib.pg_run_layout(runs[r], C.byref(n_rows), None, None, schema.n_cols))
+        readers.append(SortedRunReader.from_native_run(schema, int(n_rows.value), runs[r]))
+    return readers, info
+
+
 class FormatReaderFactory:
     def create_reader(self, context: FormatReaderContext) -> FileRecordReader:
         raise NotImplementedError

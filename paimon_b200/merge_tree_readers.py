@@ -181,56 +181,73 @@ class KeyValueFileReaderFactory:
 
 class MergeTreeReaders:
     @staticmethod
-    def _open_file(meta: DataFileMeta, reader_factory: KeyValueFileReaderFactory):
-        """One data file -> (format reader, device-resident sorted run), deletion vector applied."""
-        fr = reader_factory.create_record_reader(meta)
-        rr = fr.as_sorted_run_reader()
-        deleted = reader_factory.dv_factory(meta.file_name) if reader_factory.dv_factory else None
-        if deleted is not None and len(deleted):
-            from .sort_merge_reader import apply_deletion_vector
-            filtered = apply_deletion_vector(reader_factory.schema, rr, deleted, device=reader_factory.device)
-            rr.close()
-            rr = filtered
-        return fr, rr
+    def _read_files(metas: Sequence[DataFileMeta], reader_factory: KeyValueFileReaderFactory) -> List[bytes]:
+        """FileIO reads of the section's files (concurrent: the device decode starts once all bytes are there)."""
+        for m in metas:                                   # format by file-name suffix (KeyValueFileReaderFactory.java:119-172)
+            FileFormat.from_identifier(m.file_name.rsplit(".", 1)[-1], reader_factory.device)
+        if len(metas) <= 1:
+            return [reader_factory.file_io.read_bytes(m.file_name) for m in metas]
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(8, len(metas))) as ex:
+            return list(ex.map(lambda m: reader_factory.file_io.read_bytes(m.file_name), metas))
 
     @staticmethod
-    def reader_for_run(run: SortedRun, reader_factory: KeyValueFileReaderFactory) -> List[SortedRunReader]:
-        """A run = its files in key order.  Each decoded file is handed to the merge as its own sorted input:
-        files of one run never share keys, so giving them to the k-way merge separately yields the same rows as
-        concatenating them first (MergeTreeReaders.java:94-101).  The files are read and decoded concurrently
-        (every worker thread has its own CUDA stream in the library): small files are latency-bound."""
-        if len(run.files) <= 1:
-            return [MergeTreeReaders._open_file(m, reader_factory) for m in run.files]
-        from concurrent.futures import ThreadPoolExecutor
-        with ThreadPoolExecutor(max_workers=min(8, len(run.files))) as ex:
-            return list(ex.map(lambda m: MergeTreeReaders._open_file(m, reader_factory), run.files))
+    def open_runs(section: Sequence[SortedRun], reader_factory: KeyValueFileReaderFactory) -> List[SortedRunReader]:
+        """The sorted runs of a section as device-resident merge inputs: ONE batch of decode launches for all files
+        (pg_parquet_read_section), and a run = the concatenation of its key-disjoint files, like readerForRun's
+        ConcatRecordReader (MergeTreeReaders.java:94-101) — so the merge fan-in is the number of RUNS, not files.
+        Deletion vectors (ApplyDeletionVectorReader) are applied per run with the files' positions shifted by the
+        file's row offset inside the run."""
+        from .format import read_section
+        metas, run_of = [], []
+        for r, run in enumerate(section):
+            for m in run.files:
+                metas.append(m)
+                run_of.append(r)
+        blobs = MergeTreeReaders._read_files(metas, reader_factory)
+        readers, _ = read_section(reader_factory.schema, list(zip(blobs, run_of)), len(section), reader_factory.device)
+        if reader_factory.dv_factory is not None:
+            from .sort_merge_reader import apply_deletion_vector
+            row0 = [0] * len(section)
+            deleted: List[List[int]] = [[] for _ in section]
+            for m, r in zip(metas, run_of):
+                d = reader_factory.dv_factory(m.file_name)
+                if d is not None and len(d):
+                    deleted[r] += [int(p) + row0[r] for p in d if 0 <= int(p) < m.row_count]
+                row0[r] += m.row_count
+            for r, d in enumerate(deleted):
+                if d:
+                    filtered = apply_deletion_vector(reader_factory.schema, readers[r], d, device=reader_factory.device)
+                    readers[r].close()
+                    readers[r] = filtered
+        return readers
+
+    @staticmethod
+    def reader_for_run(run: SortedRun, reader_factory: KeyValueFileReaderFactory) -> SortedRunReader:
+        """MergeTreeReaders.readerForRun (:94-101): the run's files, concatenated, as one merge input."""
+        return MergeTreeReaders.open_runs([run], reader_factory)[0]
 
     @staticmethod
     def reader_for_section(section: Sequence[SortedRun], reader_factory: KeyValueFileReaderFactory,
                            user_defined_seq_comparator, merge_function_wrapper: MergeSpec) -> RecordReader:
-        metas = [m for run in section for m in run.files]
-        if len(metas) > 32:
-            raise N.UnsupportedOnDevice(2, "more than 32 files in one section: merge in rounds is not implemented yet")
-        # all files of the section decode concurrently (order preserved: run by run, file by file)
-        from concurrent.futures import ThreadPoolExecutor
-        if len(metas) > 1:
-            with ThreadPoolExecutor(max_workers=min(8, len(metas))) as ex:
-                opened = list(ex.map(lambda m: MergeTreeReaders._open_file(m, reader_factory), metas))
-        else:
-            opened = [MergeTreeReaders._open_file(m, reader_factory) for m in metas]
-        if len(opened) > 32:
-            raise N.UnsupportedOnDevice(2, "more than 32 files in one section: merge in rounds is not implemented yet")
-        merge = SortMergeReader.create_sort_merge_reader([r for _, r in opened], None, user_defined_seq_comparator,
-                                                         merge_function_wrapper, device=reader_factory.device)
+        """MergeTreeReaders.readerForSection (:67-92)."""
+        if len(section) > 32:
+            raise N.UnsupportedOnDevice(2, "more than 32 sorted runs in one section: merge in rounds is not implemented yet")
+        runs = MergeTreeReaders.open_runs(section, reader_factory)
+        try:
+            merge = SortMergeReader.create_sort_merge_reader(runs, None, user_defined_seq_comparator,
+                                                             merge_function_wrapper, device=reader_factory.device)
+        except Exception:
+            for r in runs:
+                r.close()
+            raise
 
         class _Section(RecordReader):
             def read_batch(self_inner):
                 return merge.read_batch()
 
             def close(self_inner):
-                merge.close()
-                for fr, _ in opened:
-                    fr.close()
+                merge.close()                            # closes its run readers too
         return _Section()
 
     @staticmethod

@@ -192,7 +192,58 @@ def fetch_run(schema: KeyValueSchema, run_handle: int) -> KeyValueBatch:
             host[i] = N.PgOutColumn(_np_ptr(data), None, _np_ptr(valid), int(data_bytes[i]))
             cols.append(Column(t, data[:n], None, valid))
     N.check(lib.pg_run_fetch(run_handle, host, nc))
+    for col in cols:                                  # a view (pg_run_slice) keeps the source's absolute offsets
+        if col.offsets is not None and n > 0 and col.offsets[0] != 0:
+            col.offsets -= col.offsets[0]
     return KeyValueBatch(schema, cols)
+
+
+def slice_rows(batch: KeyValueBatch, lo: int, hi: int) -> KeyValueBatch:
+    """Rows [lo, hi) of a host batch (copies)."""
+    from .columnar import pack_validity, unpack_validity
+    cols = []
+    for col in batch.columns:
+        valid = None
+        if col.valid is not None:
+            valid = pack_validity(unpack_validity(col.valid, len(col))[lo:hi])
+        if col.offsets is not None:
+            o = np.asarray(col.offsets[lo:hi + 1], np.int64)
+            data = np.array(col.data[int(o[0]):int(o[-1])], copy=True) if hi > lo else np.zeros(0, np.uint8)
+            cols.append(Column(col.type, data, (o - (o[0] if hi > lo else 0)).astype(np.int32) if hi > lo
+                               else np.zeros(1, np.int32), valid))
+        else:
+            cols.append(Column(col.type, np.array(col.data[lo:hi], copy=True), None, valid))
+    return KeyValueBatch(batch.schema, cols)
+
+
+def export_arrow(schema: KeyValueSchema, source_handle: int, row0: int = 0, n_rows: int = -1):
+    """Rows of a merge handle's batch (or of a run) through the Arrow C Data Interface (pg_export_arrow), imported
+    with pyarrow exactly as the Java side imports them with org.apache.arrow.c.Data.importVectorSchemaRoot: a
+    pyarrow.RecordBatch whose columns carry the Paimon file field names.  The buffers are page-locked host memory
+    owned by the batch and released with it."""
+    import pyarrow as pa
+    from pyarrow.cffi import ffi
+    lib = N.load()
+    names = [f.name for f in schema.file_fields()]
+    arr = (C.c_char_p * len(names))(*[nm.encode() for nm in names])
+    c_schema = ffi.new("struct ArrowSchema*")
+    c_array = ffi.new("struct ArrowArray*")
+    N.check(lib.pg_export_arrow(source_handle, arr, row0, n_rows, int(ffi.cast("uintptr_t", c_array)),
+                                int(ffi.cast("uintptr_t", c_schema))))
+    return pa.RecordBatch._import_from_c(int(ffi.cast("uintptr_t", c_array)), int(ffi.cast("uintptr_t", c_schema)))
+
+
+def fetch_slice(schema: KeyValueSchema, source_handle: int, lo: int, hi: int) -> KeyValueBatch:
+    """Rows [lo, hi) of a device-resident run, or of a merge handle's current batch, as host columns
+    (pg_run_slice view + pg_run_fetch)."""
+    lib = N.load()
+    h, start = C.c_uint64(0), C.c_int64(0)
+    N.check(lib.pg_run_slice(source_handle, lo, hi, C.byref(h), C.byref(start)))
+    try:
+        view = fetch_run(schema, h.value)
+    finally:
+        lib.pg_run_free(h.value)
+    return slice_rows(view, int(start.value), int(start.value) + (hi - lo))
 
 
 @dataclass

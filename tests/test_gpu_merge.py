@@ -636,3 +636,36 @@ def test_device_matches_golden_file():
             assert from_batch(got) == records(want), (case["name"], name)
             n += 1
     assert n >= 100
+
+
+def test_arrow_c_data_export_matches_fetch():
+    """pg_export_arrow: the merged batch through the Arrow C Data Interface, imported by pyarrow the way the JVM
+    imports it (Data.importVectorSchemaRoot -> ArrowBatchReader, which maps columns by the Paimon field names);
+    whole batch and row ranges that do not start at byte boundaries of the validity bitmaps."""
+    import pyarrow as pa
+    from paimon_b200.sort_merge_reader import SortedRunReader, SortMergeReader, export_arrow
+    from parquet_util import arrow_to_batch
+    rng = random.Random(23)
+    schema, runs = random_all_types_runs(rng, 5, 400, 700, [0, 0, 2, 3])
+    spec = DeduplicateMergeFunction.factory().create()
+    rd = SortMergeReader.create_sort_merge_reader([SortedRunReader(schema, b) for b in runs], None, None, spec)
+    try:
+        rd.execute()
+        want = rd.fetch()
+        n = want.n_rows
+        full = export_arrow(schema, rd._merge_h)
+        assert full.schema.names == [f.name for f in schema.file_fields()]
+        assert full.schema.names[schema.n_key] == "_SEQUENCE_NUMBER" and full.schema.names[schema.n_key + 1] == "_VALUE_KIND"
+        got = arrow_to_batch(schema, pa.Table.from_batches([full]))
+        assert got.equals(want), got.first_difference(want)
+        from paimon_b200.sort_merge_reader import slice_rows
+        for lo, hi in ((0, 1), (3, 77), (129, n), (n - 1, n), (5, 5)):
+            part = export_arrow(schema, rd._merge_h, lo, hi - lo)
+            assert part.num_rows == hi - lo
+            if hi > lo:
+                g = arrow_to_batch(schema, pa.Table.from_batches([part]))
+                w = slice_rows(want, lo, hi)
+                assert g.equals(w), (lo, hi, g.first_difference(w))
+        del full, part
+    finally:
+        rd.close()

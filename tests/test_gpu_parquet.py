@@ -56,6 +56,9 @@ WRITER_OPTS = [
     dict(compression="snappy"),                                    # Snappy pages are decompressed on the device
     dict(compression="snappy", use_dictionary=False, data_page_version="2.0"),
     dict(compression="snappy", row_group_size=1000, data_page_size=512),
+    dict(compression="zstd"),                                      # Paimon's default 'file.compression'
+    dict(compression="zstd", compression_level=1, use_dictionary=False),
+    dict(compression="zstd", data_page_version="2.0", row_group_size=1000, data_page_size=512),
 ]
 
 
@@ -138,11 +141,11 @@ def test_unsupported_format_is_refused():
 
 
 def test_unsupported_codec_is_refused(tmp_path):
-    """zstd / gzip pages are not decoded on the device: refused when the file is opened, no CPU fallback."""
+    """gzip / lz4 pages are not decoded on the device: refused when the file is opened, no CPU fallback."""
     schema = datagen.schema_c2()
     run = datagen.make_runs(schema, 1, 200, seed=2)[0]
     path = str(tmp_path / "z.parquet")
-    write_kv_parquet(run, path, compression="zstd")
+    write_kv_parquet(run, path, compression="gzip")
     with pytest.raises(N.UnsupportedOnDevice):
         decode(schema, path)
 
@@ -158,7 +161,10 @@ def test_snappy_large_pages_and_long_matches(tmp_path):
     batch = KeyValueBatch.from_rows(schema, rows)
     for opts in (dict(compression="snappy", use_dictionary=False),
                  dict(compression="snappy", use_dictionary=False, data_page_version="2.0", data_page_size=1 << 16),
-                 dict(compression="snappy")):
+                 dict(compression="snappy"),
+                 dict(compression="zstd", use_dictionary=False),
+                 dict(compression="zstd", use_dictionary=False, data_page_version="2.0", data_page_size=1 << 16),
+                 dict(compression="zstd", compression_level=9)):
         check_file(schema, batch, str(tmp_path / "snappy.parquet"), **opts)
 
 
@@ -289,3 +295,176 @@ def test_delta_binary_packed_integers(tmp_path, opts):
                if f.physical.name in ("INT8", "INT16", "INT32", "INT64")}
         enc.update({f.name: "PLAIN" for f in schema.file_fields() if f.name not in enc})
         check_file(schema, batch, str(tmp_path / f"delta{n}.parquet"), use_dictionary=False, column_encoding=enc, **opts)
+
+
+# ------------------------------------------------------------------ section decode: runs are runs, one launch set
+
+def _fetch_and_close(readers):
+    out = []
+    for r in readers:
+        try:
+            out.append(r.read_batch())
+        finally:
+            r.close()
+    return out
+
+
+def test_section_runs_are_concatenations_of_their_files(tmp_path):
+    """pg_parquet_read_section: every file of a section in one batch of launches; the files of a run (key-disjoint,
+    in key order) come back as ONE run (MergeTreeReaders.readerForRun's ConcatRecordReader).  Files differ in page
+    version, dictionary use, page / row-group size and codec; row counts are not multiples of 32, so validity words
+    and var-len offsets continue across file boundaries."""
+    from paimon_b200.format import read_section
+    from paimon_b200.merge_tree_readers import concat_batches
+    schema = datagen.schema_c3(n_i64=2, n_f64=1, n_str=3)
+    opts = [dict(), dict(use_dictionary=False), dict(data_page_version="2.0"), dict(compression="snappy"),
+            dict(row_group_size=700, data_page_size=512), dict(use_dictionary=False, data_page_version="2.0", data_page_size=300),
+            dict(data_page_size=256, dictionary_pagesize_limit=512)]
+    rng = np.random.default_rng(5)
+    run_sizes = [[1237, 1, 3001, 33], [5], [], [64, 4099]]          # files per run; run 2 is empty
+    files, want, key0, fi = [], [], 0, 0
+    for r, sizes in enumerate(run_sizes):
+        parts = []
+        for n in sizes:
+            keys = np.arange(key0, key0 + 3 * n, 3, dtype=np.int64)
+            key0 += 3 * n + 10
+            part = datagen.make_run(schema, fi, keys, seed=3, null_prob=0.35, delete_prob=0.1)
+            path = str(tmp_path / f"f{fi}.parquet")
+            write_kv_parquet(part, path, **opts[fi % len(opts)])
+            files.append((open(path, "rb").read(), r))
+            parts.append(arrow_to_batch(schema, pq.read_table(path)))
+            fi += 1
+        want.append(concat_batches(schema, parts) if parts else None)
+    readers, info = read_section(schema, files, len(run_sizes))
+    assert info.n_files == len(files) and info.n_runs == len(run_sizes)
+    assert info.n_rows == sum(sum(s) for s in run_sizes)
+    assert info.launches <= 12                              # per SECTION, not per file
+    got = _fetch_and_close(readers)
+    for r, (g, w) in enumerate(zip(got, want)):
+        if w is None or w.n_rows == 0:
+            assert g is None or g.n_rows == 0
+        else:
+            assert g.equals(w), f"run {r}: " + g.first_difference(w)
+
+
+def test_section_of_empty_files(tmp_path):
+    from paimon_b200.format import read_section
+    schema = datagen.schema_c3(n_i64=1, n_f64=1, n_str=1)
+    path = str(tmp_path / "empty.parquet")
+    write_kv_parquet(KeyValueBatch.from_rows(schema, []), path)
+    blob = open(path, "rb").read()
+    readers, info = read_section(schema, [(blob, 0), (blob, 1)], 2)
+    assert info.n_rows == 0
+    for b in _fetch_and_close(readers):
+        assert b is None or b.n_rows == 0
+
+
+def test_boolean_columns_plain_and_rle(tmp_path):
+    """BOOLEAN: PLAIN pages are bit-packed LSB first (VectorizedPlainValuesReader.java:68-84); data page V2 writers
+    use RLE for booleans."""
+    vt = RowType((DataField("pk", "BIGINT", False), DataField("b", "BOOLEAN", True), DataField("c", "BOOLEAN", False),
+                  DataField("s", "STRING", True)))
+    schema = KeyValueSchema.of(vt, ["pk"])
+    rng = random.Random(8)
+    for n in (1, 7, 8, 9, 1000, 20001):
+        rows = [(k, k, 0, k, None if rng.random() < 0.3 else rng.random() < 0.5, (k // 37) % 2 == 0,
+                 None if k % 5 == 0 else "x" * (k % 9)) for k in range(n)]
+        batch = KeyValueBatch.from_rows(schema, rows)
+        for opts in (dict(), dict(data_page_version="2.0"), dict(use_dictionary=False, data_page_size=128),
+                     dict(data_page_version="2.0", compression="snappy", data_page_size=200)):
+            check_file(schema, batch, str(tmp_path / f"bool{n}.parquet"), **opts)
+
+
+def test_column_names_are_checked(tmp_path):
+    """The reference resolves file columns by NAME (ParquetReaderFactory.clipParquetSchema): a file whose columns
+    are named differently (written under another table schema) must not be decoded positionally."""
+    from paimon_b200.format import read_section
+    vt_a = RowType((DataField("pk", "BIGINT", False), DataField("a", "BIGINT", True), DataField("b", "BIGINT", True)))
+    vt_b = RowType((DataField("pk", "BIGINT", False), DataField("b", "BIGINT", True), DataField("a", "BIGINT", True)))
+    sa, sb = KeyValueSchema.of(vt_a, ["pk"]), KeyValueSchema.of(vt_b, ["pk"])
+    batch = KeyValueBatch.from_rows(sa, [(k, k, 0, k, k * 2, k * 3) for k in range(100)])
+    path = str(tmp_path / "a.parquet")
+    write_kv_parquet(batch, path)
+    blob = open(path, "rb").read()
+    readers, _ = read_section(sa, [(blob, 0)], 1)
+    assert _fetch_and_close(readers)[0].equals(batch)
+    with pytest.raises(N.UnsupportedOnDevice, match="expects"):
+        read_section(sb, [(blob, 0)], 1)
+
+
+def test_section_from_device_resident_file_images(tmp_path):
+    """Files whose bytes already sit in HBM (PG_MEM_DEVICE): the encoder's device image goes straight back into the
+    decoder — footers are fetched to the host, page headers are parsed on the device."""
+    import ctypes as C
+    from paimon_b200.compact_rewriter import file_column_names
+    from paimon_b200.format import read_section
+    from paimon_b200.merge_tree_readers import concat_batches
+    from paimon_b200.sort_merge_reader import SortedRunReader, _SchemaHandle
+    schema = datagen.schema_c3(n_i64=3, n_f64=2, n_str=3)
+    lib = N.init(0)
+    sh = _SchemaHandle(schema, 0)
+    names = file_column_names(schema)
+    arr = (C.c_char_p * len(names))(*[nm.encode() for nm in names])
+    parts, files, handles, rds = [], [], [], []
+    try:
+        for i, n in enumerate((40000, 1234, 70001)):
+            keys = np.arange(i * 1_000_000, i * 1_000_000 + n, dtype=np.int64)
+            part = datagen.make_run(schema, i, keys, seed=4, null_prob=0.5, delete_prob=0.05)
+            rd = SortedRunReader(schema, part)
+            rds.append(rd)
+            fh = C.c_uint64(0)
+            opts = N.PgParquetWriteOptions(16384, 2000)
+            N.check(lib.pg_parquet_encode(rd._open(sh.handle), arr, 0, -1, C.byref(opts), C.byref(fh)))
+            handles.append(fh.value)
+            ptr, size = C.c_void_p(0), C.c_int64(0)
+            N.check(lib.pg_parquet_file_device_image(fh.value, C.byref(ptr), C.byref(size)))
+            files.append(((ptr.value, size.value), 0))
+            parts.append(part)
+            # the patched device image is the same file pg_parquet_file_fetch assembles on the host
+            host = np.zeros(size.value, np.uint8)
+            N.check(lib.pg_parquet_file_fetch(fh.value, host.ctypes.data, size.value))
+            p = str(tmp_path / f"img{i}.parquet")
+            host.tofile(p)
+            assert arrow_to_batch(schema, pq.read_table(p)).equals(part)
+        readers, info = read_section(schema, files, 1)
+        got = _fetch_and_close(readers)[0]
+        want = concat_batches(schema, parts)
+        assert got.equals(want), got.first_difference(want)
+        assert info.n_data_pages >= sum(-(-p.n_rows // 2000) for p in parts) * schema.n_cols
+    finally:
+        for h in handles:
+            lib.pg_parquet_file_free(h)
+        for rd in rds:
+            rd.close()
+        sh.close()
+
+
+def test_wide_fan_in_of_files_is_few_runs(tmp_path):
+    """One wide level-0 file over a higher-level run made of 40 small files: 2 merge inputs for the reference
+    (IntervalPartition + ConcatRecordReader), and 2 here — not 41 (> PG_MAX_RUNS)."""
+    from paimon_b200.merge_tree_readers import DataFileMeta, MergeFileSplitRead, concat_batches
+    schema = datagen.schema_c3(n_i64=1, n_f64=1, n_str=1)
+    metas, file_runs = [], []
+    for j in range(40):
+        keys = np.arange(j * 1000, j * 1000 + 900, 2, dtype=np.int64)
+        file_runs.append(datagen.make_run(schema, 0, keys, seed=2, null_prob=0.3))
+    rng = np.random.default_rng(1)
+    keys = np.sort(rng.choice(40000, size=9000, replace=False)).astype(np.int64)
+    file_runs.append(datagen.make_run(schema, 1, keys, seed=2, null_prob=0.3, delete_prob=0.1))
+    for i, run in enumerate(file_runs):
+        path = str(tmp_path / f"d{i}.parquet")
+        write_kv_parquet(run, path)
+        k = run.columns[0].data
+        metas.append(DataFileMeta(path, 0, run.n_rows, int(k[0]), int(k[-1]), level=5 if i < 40 else 0))
+    spec = PartialUpdateMergeFunction.factory({"ignore-delete": "true"}, schema.value_type, ["pk"])
+    rd = MergeFileSplitRead(schema, spec).create_merge_reader(metas)
+    batches = []
+    while True:
+        b = rd.read_batch()
+        if b is None:
+            break
+        batches.append(b)
+    rd.close()
+    got = concat_batches(schema, batches)
+    want = pyoracle.merge(schema, spec.create().with_drop_delete(True), file_runs)
+    assert got.equals(want), got.first_difference(want)

@@ -150,3 +150,58 @@ def test_compact_rewriter_end_to_end(tmp_path, drop_delete):
     assert sum(m.delete_row_count for m in result.after) == int(np.isin(kinds, [1, 3]).sum())
     if drop_delete:
         assert sum(m.delete_row_count for m in result.after) == 0
+
+
+@pytest.mark.parametrize("key_kind", ["string", "composite"])
+def test_rewritten_files_carry_full_key_bounds(tmp_path, key_kind):
+    """min_key / max_key of a compaction's output are the key ROWS of the file's first and last record
+    (KeyValueDataFileWriter.java:116-118,166-167) — strings and every field of a composite key — so that the output
+    can be fed back into IntervalPartition / key-range pruning / another compaction."""
+    from paimon_b200.merge_tree_readers import MergeFileSplitRead, comparable_key
+    if key_kind == "string":
+        vt = RowType((DataField("pk", "VARCHAR(16)", False), DataField("v", "BIGINT", True), DataField("s", "STRING", True)))
+        schema = KeyValueSchema.of(vt, ["pk"])
+        def key_of(k): return ("user_%07d" % k,)
+    else:
+        vt = RowType((DataField("a", "INT", False), DataField("b", "VARCHAR(8)", False), DataField("v", "BIGINT", True),
+                      DataField("s", "STRING", True)))
+        schema = KeyValueSchema.of(vt, ["a", "b"])
+        def key_of(k): return (k // 50, "b%02d" % (k % 50))
+    rng = random.Random(3)
+    metas, file_runs = [], []
+    for f in range(6):
+        ks = sorted(rng.sample(range(3000), 900))
+        rows = [key_of(k) + (f * 10000 + i, 0) + key_of(k) + (k * 7 + f, None if k % 4 == 0 else "s%d" % k)
+                for i, k in enumerate(ks)]
+        batch = KeyValueBatch.from_rows(schema, rows)
+        path = str(tmp_path / f"in-{f}.parquet")
+        write_kv_parquet(batch, path)
+        first, last = key_of(ks[0]), key_of(ks[-1])
+        metas.append(DataFileMeta(path, 0, batch.n_rows, first[0] if len(first) == 1 else first,
+                                  last[0] if len(last) == 1 else last))
+        file_runs.append(batch)
+    factory = DeduplicateMergeFunction.factory()
+    rewriter = MergeTreeCompactRewriter(schema, factory, str(tmp_path), target_file_rows=700, page_rows=128)
+    result = rewriter.rewrite_compaction(3, False, IntervalPartition(metas).partition())
+    want = pyoracle.merge(schema, factory.create(), file_runs)
+    outs = [arrow_to_batch(schema, pq.read_table(m.file_name)) for m in result.after]
+    assert concat_batches(schema, outs).equals(want)
+    for m, b in zip(result.after, outs):
+        rows = b.to_rows()
+        lo, hi = rows[0][: schema.n_key], rows[-1][: schema.n_key]
+        assert m.min_key == (lo[0] if schema.n_key == 1 else tuple(lo))
+        assert m.max_key == (hi[0] if schema.n_key == 1 else tuple(hi))
+    for a, b in zip(result.after, result.after[1:]):
+        assert comparable_key(a.max_key) < comparable_key(b.min_key)
+    # the output re-partitions into ONE section of ONE run, and a key-range read prunes by the bounds
+    sections = IntervalPartition(result.after).partition()
+    assert len(sections) >= 1 and all(len(sec) == 1 for sec in sections)
+    read = MergeFileSplitRead(schema, factory).with_key_filter(result.after[1].min_key, result.after[1].max_key)
+    assert [f.file_name for f in read._prune(result.after)] == [result.after[1].file_name]
+    # and compacts again to the same rows
+    again = MergeTreeCompactRewriter(schema, factory, str(tmp_path / "x"), target_file_rows=100000)
+    import os
+    os.makedirs(str(tmp_path / "x"))
+    res2 = again.rewrite_compaction(4, False, IntervalPartition(result.after).partition())
+    got2 = concat_batches(schema, [arrow_to_batch(schema, pq.read_table(m.file_name)) for m in res2.after])
+    assert got2.equals(want)

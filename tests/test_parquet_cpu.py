@@ -63,9 +63,14 @@ def test_unsupported_files_are_refused(tmp_path):
     lib = N.load()
     sh = _schema_handle(schema)
     p = str(tmp_path / "z.parquet")
-    write_kv_parquet(run, p, compression="zstd")
+    write_kv_parquet(run, p, compression="gzip")
     st, _, _ = _open(sh, p)
     assert st == 2 and b"compression codec" in lib.pg_last_error()         # PG_ERR_UNSUPPORTED
+    p = str(tmp_path / "zstd.parquet")                  # Paimon's default codec is accepted
+    write_kv_parquet(run, p, compression="zstd")
+    st, h_z, _ = _open(sh, p)
+    assert st == 0
+    lib.pg_parquet_free(h_z)
     p = str(tmp_path / "delta.parquet")                 # DELTA_BINARY_PACKED integers are accepted ...
     write_kv_parquet(run, p, use_dictionary=False, column_encoding="DELTA_BINARY_PACKED")
     st, h_ok, _ = _open(sh, p)
