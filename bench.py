@@ -748,8 +748,7 @@ def main():
                     out = m_.fetch(allocator=alloc)                   # D2H of the merged batch
                     d2h_bytes[0] = m_.stats().bytes_d2h
                     rows_seen.append(out.n_rows)
-                    m_.release_batch()
-                    free_q.put(m_)
+                    free_q.put(m_)                                    # (the handle keeps its output arena for the next bucket)
             except BaseException as e:                                # surfaced below
                 errors.append(e)
                 free_q.put(None)
@@ -948,6 +947,41 @@ def main():
                     lib.pg_trim()
             except Exception as e:                                   # an extra must not take the headline line down
                 extra[f"{wl}_merge_only"] = {"error": repr(e)[:300]}
+
+    # ---------------- extra: C4's bucket scheduling on hardware — many buckets per GPU, longest-processing-time
+    # assignment by input bytes (paimon_b200/bucket_scheduler.py), every rank merging its own buckets back to back
+    if not args.no_extra and args.workload == "c3" and rows == w["rows"]:
+        try:
+            from paimon_b200.bucket_scheduler import assign_buckets, reduce_stats
+            n_buckets = 8 * world
+            rng_b = np.random.default_rng(7)
+            bucket_rows = [int(x) for x in rng_b.integers(1_000_000, 3_000_000, n_buckets)]     # skewed bucket sizes
+            mine = assign_buckets(n_buckets, world, weights=bucket_rows)[rank]
+            sc4 = make_schema("c4")
+            sp4 = make_spec("c4", sc4)
+            t_ms, r_in, r_out = 0.0, 0, 0
+            for b in mine:
+                rds4, keys4, _, kinds4 = device_runs("c4", sc4, bucket_rows[b], dev, seed=1000 + b)
+                r4 = SortMergeReader.create_sort_merge_reader(rds4, None, None, sp4, device=local_rank)
+                try:
+                    r4.execute()
+                    r4.execute()
+                    s4 = r4.stats()
+                    assert s4.rows_out == expected_rows(WORKLOADS["c4"], keys4, kinds4)
+                    t_ms += s4.ms_total; r_in += s4.rows_in; r_out += s4.rows_out
+                finally:
+                    r4.close()
+                    del rds4, keys4, kinds4
+                    torch.cuda.empty_cache()
+            agg = reduce_stats({"rows_in": float(r_in), "rows_out": float(r_out), "device_ms": t_ms}, device=dev)
+            extra["c4_bucket_schedule"] = {
+                "what": f"{n_buckets} C4-shaped buckets of 1-3 M rows (32 runs each) over {world} GPU(s), LPT assignment by "
+                        "input rows, device-timed merges back to back; device_ms is the slowest rank's sum",
+                "buckets_of_rank0": mine if rank == 0 else None, "rows_in": int(agg["rows_in"]), "rows_out": int(agg["rows_out"]),
+                "device_ms": agg["device_ms"], "rows_per_s": agg["rows_in"] / (agg["device_ms"] * 1e-3)}
+            lib.pg_trim()
+        except Exception as e:
+            extra["c4_bucket_schedule"] = {"error": repr(e)[:300]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -115,6 +115,11 @@ typedef struct {
     const int32_t *field_group;         /* [n_val] group protecting the field (its sequence fields included), -1 */
     const uint8_t *group_partial_delete;/* [n_val] sequence field listed in
                                            'partial-update.remove-record-on-sequence-group'; NULL = none */
+    /* read-type projection (MergeFunctionFactory.create(readType), MergeFileSplitRead.withReadType :133-163): value
+     * fields with 0 are not part of the merged batch (no output buffers, no emit work); the runs may come without
+     * buffers for them (pg_parquet_read_section's read_columns), except for fields the merge itself compares
+     * ('sequence.field', sequence-group fields: PartialUpdateMergeFunction.adjustReadType :576-606 keeps those) */
+    const uint8_t *read_fields;         /* [n_val]; NULL = every field */
 } pg_merge_spec;
 
 /* one column, Arrow buffer layout */
@@ -292,10 +297,17 @@ pg_status pg_parquet_free(uint64_t reader);
  * `files[i].run` names the output run of file i; files of a run must be listed in key order.  `bytes` is host memory
  * (copied to the device by the call) or device memory (PG_MEM_DEVICE: the bytes already sit in HBM, e.g. read by
  * GPUDirect storage or produced by pg_parquet_encode; must stay valid during the call only).  Only the footers are
- * parsed on the host; page headers are parsed on the device.  `column_names` (n_key + 2 + n_val entries, or NULL)
- * are the field names the read schema expects: a file whose column names differ is refused (the reference maps
- * columns by name, ParquetReaderFactory.java:113-148, and files of older schemas need the Java-side evolution
- * mapping).  out_runs[n_runs] receives run handles (pg_run_free each). */
+ * parsed on the host; page headers are parsed on the device.
+ * `column_names` (n_key + 2 + n_val entries, or NULL = positional) are the names the read schema's fields have in the
+ * files: columns are resolved BY NAME like the reference does (ParquetReaderFactory.java:113-148 clipParquetSchema):
+ * a nullable read field the file does not have decodes as all-NULL (file written before ADD COLUMN), file columns
+ * the read schema does not name are ignored (DROP COLUMN), and a file column that is narrower than the read field is
+ * widened on the fly (INT-family -> BIGINT, FLOAT -> DOUBLE: the casts of DataFileRecordReader.java:55-57 that need
+ * no rewrite).  Anything else (renames without the old name, other casts) is refused with PG_ERR_UNSUPPORTED.
+ * `read_columns` ([n_key + 2 + n_val] bytes, or NULL = all) is the read-type projection pushed into the decoder
+ * (MergeFileSplitRead.withReadType, operation/MergeFileSplitRead.java:133-163): columns with 0 are not decoded and the
+ * runs carry no buffers for them; key, sequence-number and kind columns are always read (keys are never projected
+ * before a merge, :276-277).  out_runs[n_runs] receives run handles (pg_run_free each). */
 typedef struct {
     const uint8_t *bytes;
     int64_t size;
@@ -314,7 +326,8 @@ typedef struct {
 } pg_section_info;
 
 pg_status pg_parquet_read_section(uint64_t schema, const pg_file_desc *files, int32_t n_files, int32_t n_runs,
-                                  const char *const *column_names, uint64_t *out_runs, pg_section_info *info);
+                                  const char *const *column_names, const uint8_t *read_columns, uint64_t *out_runs,
+                                  pg_section_info *info);
 
 /* ApplyDeletionVectorReader (paimon-core/.../deletionvectors/ApplyDeletionVectorReader.java:31-54): a new run holding
  * the rows of `run` whose file position is NOT set in the deletion vector.  `deleted_bitmap` is host memory, LSB

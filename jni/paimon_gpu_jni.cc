@@ -107,13 +107,14 @@ JNIEXPORT jint JNICALL Java_org_apache_paimon_gpu_NativeMerge_schemaFree(JNIEnv 
 JNIEXPORT jlong JNICALL Java_org_apache_paimon_gpu_NativeMerge_mergeSpecCreate(
     JNIEnv *env, jclass, jlong schema, jint engine, jboolean ignoreDelete, jboolean removeRecordOnDelete,
     jboolean dropDelete, jintArray seqFields, jboolean seqAscending, jintArray agg, jbooleanArray ignoreRetract,
-    jintArray groupSeqStart, jintArray groupSeqFields, jintArray fieldGroup, jbooleanArray groupPartialDelete) {
+    jintArray groupSeqStart, jintArray groupSeqFields, jintArray fieldGroup, jbooleanArray groupPartialDelete,
+    jbooleanArray readFields) {
     // every per-field array has one entry per VALUE field of the schema (pg_merge_spec_create reads n_val entries)
     int32_t n_key = 0, n_val = 0;
     PG_CHECK(pg_schema_info((uint64_t)schema, &n_key, &n_val));
     const jsize nv = n_val;
     auto bad_len = [&](jarray a) { return a != nullptr && env->GetArrayLength(a) != nv; };
-    if (bad_len(agg) || bad_len(ignoreRetract) || bad_len(fieldGroup) || bad_len(groupPartialDelete)) {
+    if (bad_len(agg) || bad_len(ignoreRetract) || bad_len(fieldGroup) || bad_len(groupPartialDelete) || bad_len(readFields)) {
         env->ThrowNew(env->FindClass("java/lang/IllegalArgumentException"),
                       "per-field arrays must have one entry per value field of the schema");
         return 0;
@@ -155,6 +156,14 @@ JNIEXPORT jlong JNICALL Java_org_apache_paimon_gpu_NativeMerge_mergeSpecCreate(
         sp.group_seq_fields = gf.data();
         sp.field_group = fg.data();
         sp.group_partial_delete = gpd8.empty() ? nullptr : gpd8.data();
+    }
+    // read-type projection (MergeFunctionFactory.create(readType)): null = every field
+    std::vector<uint8_t> rf8;
+    if (readFields) {
+        std::vector<jboolean> rf(nv);
+        if (nv) env->GetBooleanArrayRegion(readFields, 0, nv, rf.data());
+        rf8.assign(rf.begin(), rf.end());
+        sp.read_fields = rf8.data();
     }
     uint64_t h = 0;
     PG_CHECK(pg_merge_spec_create((uint64_t)schema, &sp, &h));
@@ -442,7 +451,7 @@ JNIEXPORT jlongArray JNICALL Java_org_apache_paimon_gpu_NativeMerge_parquetDescr
 // batch of device launches; runOf[i] = sorted run of file i; returns one run handle per sorted run
 JNIEXPORT jlongArray JNICALL Java_org_apache_paimon_gpu_NativeMerge_parquetReadSection(
     JNIEnv *env, jclass, jlong schema, jobjectArray fileBuffers, jlongArray sizes, jintArray runOf, jint nRuns,
-    jobjectArray columnNames) {
+    jobjectArray columnNames, jbooleanArray readColumns) {
     const jsize nf = env->GetArrayLength(fileBuffers);
     if (env->GetArrayLength(sizes) != nf || env->GetArrayLength(runOf) != nf) {
         env->ThrowNew(env->FindClass("java/lang/IllegalArgumentException"), "one size and one run index per file");
@@ -464,9 +473,24 @@ JNIEXPORT jlongArray JNICALL Java_org_apache_paimon_gpu_NativeMerge_parquetReadS
     std::vector<std::string> keep;
     std::vector<const char *> names = utf_names(env, columnNames, keep);
     std::vector<uint64_t> runs(nRuns > 0 ? nRuns : 1);
+    // read-type projection pushed into the decoder: one flag per file column, null = all
+    std::vector<uint8_t> rc8;
+    if (readColumns) {
+        int32_t n_key = 0, n_val = 0;
+        pg_status rs = pg_schema_info((uint64_t)schema, &n_key, &n_val);
+        if (rs != PG_OK) { throw_for(env, rs); return nullptr; }
+        const jsize ncol = env->GetArrayLength(readColumns);
+        if (ncol != n_key + 2 + n_val) {
+            env->ThrowNew(env->FindClass("java/lang/IllegalArgumentException"), "one read flag per file column");
+            return nullptr;
+        }
+        std::vector<jboolean> rcb(ncol);
+        env->GetBooleanArrayRegion(readColumns, 0, ncol, rcb.data());
+        rc8.assign(rcb.begin(), rcb.end());
+    }
     pg_section_info info{};
     pg_status rc = pg_parquet_read_section((uint64_t)schema, files.data(), nf, nRuns, columnNames ? names.data() : nullptr,
-                                           runs.data(), &info);
+                                           readColumns ? rc8.data() : nullptr, runs.data(), &info);
     if (rc != PG_OK) { throw_for(env, rc); return nullptr; }
     std::vector<jlong> out(runs.begin(), runs.begin() + (nRuns > 0 ? nRuns : 0));
     jlongArray arr = env->NewLongArray((jsize)out.size());

@@ -32,7 +32,7 @@ class PgMergeSpec(C.Structure):
                 ("seq_ascending", C.c_int32), ("agg", C.c_void_p), ("ignore_retract", C.c_void_p),
                 ("n_sequence_groups", C.c_int32), ("group_seq_start", C.c_void_p),
                 ("group_seq_fields", C.c_void_p), ("field_group", C.c_void_p),
-                ("group_partial_delete", C.c_void_p)]
+                ("group_partial_delete", C.c_void_p), ("read_fields", C.c_void_p)]
 
 
 class PgColumn(C.Structure):
@@ -137,7 +137,8 @@ _SIGNATURES = {
     "pg_parquet_read_run": (C.c_int32, [C.c_uint64, C.POINTER(C.c_uint64)]),
     "pg_parquet_free": (C.c_int32, [C.c_uint64]),
     "pg_parquet_read_section": (C.c_int32, [C.c_uint64, C.POINTER(PgFileDesc), C.c_int32, C.c_int32,
-                                            C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.POINTER(PgSectionInfo)]),
+                                            C.POINTER(C.c_char_p), C.c_void_p, C.POINTER(C.c_uint64),
+                                            C.POINTER(PgSectionInfo)]),
     "pg_parquet_file_device_image": (C.c_int32, [C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "pg_run_apply_deletion_vector": (C.c_int32, [C.c_uint64, C.c_void_p, C.c_int64, C.POINTER(C.c_uint64)]),
     "pg_parquet_encode": (C.c_int32, [C.c_uint64, C.POINTER(C.c_char_p), C.c_int64, C.c_int64,

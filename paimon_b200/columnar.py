@@ -132,17 +132,34 @@ class KeyValueBatch:
         return self.columns[self.schema.n_key + 2 + i]
 
     def to_rows(self) -> list:
-        cols = [c.to_pylist() for c in self.columns]
+        cols = [c.to_pylist() if c is not None else [None] * self.n_rows for c in self.columns]
         return [tuple(c[i] for c in cols) for i in range(self.n_rows)]
 
+    def project(self, keep: Sequence[bool]) -> "KeyValueBatch":
+        """The batch with the value columns of a read-type projection only (others become None, the way a projected
+        merge returns them); `keep` has one entry per VALUE field."""
+        nk = self.schema.n_key + 2
+        cols = [c if (i < nk or keep[i - nk]) else None for i, c in enumerate(self.columns)]
+        return KeyValueBatch(self.schema, cols)
+
     def equals(self, other: "KeyValueBatch") -> bool:
-        return (self.n_rows == other.n_rows and len(self.columns) == len(other.columns)
-                and all(a.equals(b) for a, b in zip(self.columns, other.columns)))
+        if self.n_rows != other.n_rows or len(self.columns) != len(other.columns):
+            return False
+        for a, b in zip(self.columns, other.columns):
+            if (a is None) != (b is None):
+                return False
+            if a is not None and not a.equals(b):
+                return False
+        return True
 
     def first_difference(self, other: "KeyValueBatch") -> str:
         if self.n_rows != other.n_rows:
             return f"row count {self.n_rows} != {other.n_rows}"
         for ci, (a, b) in enumerate(zip(self.columns, other.columns)):
+            if (a is None) != (b is None):
+                return f"column {ci}: present in one batch only"
+            if a is None:
+                continue
             if not a.equals(b):
                 la, lb = a.to_pylist(), b.to_pylist()
                 for i, (x, y) in enumerate(zip(la, lb)):

@@ -68,6 +68,7 @@ struct Merge {
     MergeFlags flags{};
     std::vector<ColDesc> cols;
     std::vector<int32_t> varlen_cols;
+    std::vector<uint8_t> emit;          // per column: part of the merged batch (read-type projection)
     // persistent device descriptors
     void *d_desc = nullptr;            // one allocation holding all descriptor arrays
     const void **d_key_ptrs = nullptr;
@@ -327,6 +328,19 @@ static pg_status build_descriptors(Merge *m) {
     const int nc = s->n_cols();
     m->cols.assign(nc, ColDesc{});
     m->varlen_cols.clear();
+    m->emit.assign(nc, 1);
+    for (int c = s->n_key + 2; c < nc; c++)
+        if (!sp->read_fields.empty() && !sp->read_fields[c - s->n_key - 2]) m->emit[c] = 0;
+    // columns the kernels read: everything that is emitted, plus what the plan kernel compares
+    std::vector<uint8_t> needed = m->emit;
+    for (int32_t vf : sp->seq_fields) if (vf >= 0 && vf < s->n_val) needed[s->n_key + 2 + vf] = 1;
+    for (int32_t vf : sp->group_seq_fields) if (vf >= 0 && vf < s->n_val) needed[s->n_key + 2 + vf] = 1;
+    for (int r = 0; r < m->k; r++)
+        for (int c = 0; c < nc; c++)
+            if (needed[c] && m->runs[r]->n_rows > 0 && !m->runs[r]->cols[c].data && !m->runs[r]->cols[c].offsets)
+                return fail(PG_ERR_INVALID, "run " + std::to_string(r) + " has no buffers for column " + std::to_string(c) +
+                                            ", which the merge reads (read-type projection dropped a field the merge "
+                                            "function compares or emits)");
     for (int c = 0; c < nc; c++) {
         pg_field f = s->field(c);
         ColDesc &cd = m->cols[c];
@@ -336,7 +350,7 @@ static pg_status build_descriptors(Merge *m) {
         cd.agg = PG_AGG_NONE;
         cd.retract = RT_OK;
         cd.varlen_index = -1;
-        if (is_varlen(f.type)) {
+        if (is_varlen(f.type) && m->emit[c]) {
             cd.varlen_index = (int)m->varlen_cols.size();
             m->varlen_cols.push_back(c);
         }
@@ -440,9 +454,9 @@ static pg_status build_descriptors(Merge *m) {
         int n = 0;
         auto plain = [&](int c) { return m->cols[c].mode == CM_SEQ || m->cols[c].mode == CM_KIND; };
         for (int c = 0; c < nc; c++) if (plain(c)) ord[n++] = c | (0 << 16);
-        for (int c = 0; c < nc; c++) if (m->cols[c].width == 0) ord[n++] = c | (1 << 16);
-        for (int c = 0; c < nc; c++) if (m->cols[c].width != 0 && !plain(c)) ord[n++] = c | (2 << 16);
-        for (int c = 0; c < nc; c++) if (m->cols[c].width == 0) ord[n++] = c | (3 << 16);
+        for (int c = 0; c < nc; c++) if (m->emit[c] && m->cols[c].width == 0) ord[n++] = c | (1 << 16);
+        for (int c = 0; c < nc; c++) if (m->emit[c] && m->cols[c].width != 0 && !plain(c)) ord[n++] = c | (2 << 16);
+        for (int c = 0; c < nc; c++) if (m->emit[c] && m->cols[c].width == 0) ord[n++] = c | (3 << 16);
         m->n_passes = n;
         for (int v = 0; v < nv; v++) vlc[v] = m->varlen_cols[v];
     }
@@ -679,6 +693,7 @@ static pg_status execute(Merge *m) {
         auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
         for (int c = 0; c < nc; c++) {
             const ColDesc &cd = m->cols[c];
+            if (!m->emit[c]) continue;
             if (cd.nullable) vbytes += pad((size_t)((n_out + 31) / 32) * 4 + 64);
             if (cd.width > 0) need += pad((size_t)n_out * cd.width + 64);
             else need += pad((size_t)m->varlen_bound[cd.varlen_index] + 64) + pad(4 * (size_t)(n_out + 1) + 64);
@@ -699,7 +714,7 @@ static pg_status execute(Merge *m) {
     };
     // pass 1: validity bitmaps (the zeroed region), pass 2: data + offsets
     for (int c = 0; c < nc; c++) {
-        if (m->cols[c].nullable) {
+        if (m->cols[c].nullable && m->emit[c]) {
             size_t vb = (size_t)((n_out + 31) / 32) * 4 + 64;
             PG_CUDA(oalloc(vb, (void **)&m->out_cols[c].validity));
             bytes_out += (n_out + 7) / 8;
@@ -708,6 +723,7 @@ static pg_status execute(Merge *m) {
     for (int c = 0; c < nc; c++) {
         const ColDesc &cd = m->cols[c];
         pg_out_column &oc = m->out_cols[c];
+        if (!m->emit[c]) continue;                       // not part of the read type: the batch has no such column
         if (cd.width > 0) {
             oc.data_bytes = n_out * cd.width;
             PG_CUDA(oalloc((size_t)oc.data_bytes + 64, &oc.data));
@@ -771,7 +787,7 @@ static pg_status execute(Merge *m) {
         return fail(PG_ERR_MERGE_FUNCTION, kernel_error_message(*m->h_err));
     }
     for (int c = 0; c < nc; c++)
-        if (m->cols[c].width == 0) {
+        if (m->cols[c].width == 0 && m->emit[c]) {
             m->out_cols[c].data_bytes = m->h_totals[1 + m->cols[c].varlen_index];
             m->stats.bytes_out += m->out_cols[c].data_bytes;
         }
@@ -885,6 +901,7 @@ pg_status pg_merge_spec_create(uint64_t schema, const pg_merge_spec *spec, uint6
     }
     if (spec->agg) sp->agg.assign(spec->agg, spec->agg + s->n_val);
     if (spec->ignore_retract) sp->ignore_retract.assign(spec->ignore_retract, spec->ignore_retract + s->n_val);
+    if (spec->read_fields) sp->read_fields.assign(spec->read_fields, spec->read_fields + s->n_val);
     if (spec->n_sequence_groups > 0) {
         const int ng = spec->n_sequence_groups;
         sp->group_seq_start.assign(spec->group_seq_start, spec->group_seq_start + ng + 1);
@@ -1050,7 +1067,8 @@ pg_status pg_run_layout(uint64_t run, int64_t *n_rows, int64_t *data_bytes, int3
     *n_rows = r->n_rows;
     for (int c = 0; c < nc; c++) {
         pg_field f = r->schema->field(c);
-        if (data_bytes) data_bytes[c] = is_varlen(f.type) ? r->varlen_bytes[c] : r->n_rows * type_width(f.type);
+        const bool absent = !r->cols[c].data && !r->cols[c].offsets;      // not decoded (read-type projection)
+        if (data_bytes) data_bytes[c] = absent ? -1 : (is_varlen(f.type) ? r->varlen_bytes[c] : r->n_rows * type_width(f.type));
         if (has_validity) has_validity[c] = r->cols[c].validity != nullptr;
     }
     return PG_OK;
@@ -1069,6 +1087,7 @@ pg_status pg_run_fetch(uint64_t run, const pg_out_column *host_cols, int32_t n_c
         const DevColumn &dc = r->cols[c];
         const pg_out_column &hc = host_cols[c];
         size_t db = is_varlen(f.type) ? (size_t)r->varlen_bytes[c] : (size_t)n * type_width(f.type);
+        if (!dc.data && !dc.offsets) continue;           // column not decoded (read-type projection)
         if (db && hc.data && (size_t)hc.data_bytes < db)
             return fail(PG_ERR_INVALID, "pg_run_fetch: data buffer of column " + std::to_string(c) + " is too small");
         if (db && hc.data)

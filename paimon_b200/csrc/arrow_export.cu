@@ -79,7 +79,17 @@ static pg_status export_arrow(uint64_t source, const char *const *names, int64_t
     if (st) return st;
     if (n_rows < 0) n_rows = total - row0;
     if (row0 < 0 || n_rows < 0 || row0 + n_rows > total) return fail(PG_ERR_INVALID, "arrow export: row range outside the batch");
-    const int nc = s->n_cols();
+    // columns a read-type projection left out of the batch are not exported
+    std::vector<int> present;
+    for (int c = 0; c < s->n_cols(); c++)
+        if (cols[c].data || cols[c].offsets || total == 0) present.push_back(c);
+    {
+        std::vector<DevColumn> pc;
+        for (int c : present) pc.push_back(cols[c]);
+        cols.swap(pc);
+    }
+    const int nc = (int)present.size();
+    auto field_of = [&](int i) { return s->field(present[i]); };
     const int64_t lo = row0 & ~(int64_t)7;              // validity bitmaps are byte-granular
     const int64_t delta = row0 - lo, m = n_rows + delta; // rows copied per column; children carry offset = delta
     auto pad = [](size_t b) { return (b + 63) & ~(size_t)63; };
@@ -87,14 +97,14 @@ static pg_status export_arrow(uint64_t source, const char *const *names, int64_t
     // ---- sizes: var-len payload ranges need the boundary offsets
     std::vector<int32_t> off_lo(nc, 0), off_hi(nc, 0);
     for (int c = 0; c < nc; c++) {
-        if (!is_varlen(s->field(c).type) || m == 0) continue;
+        if (!is_varlen(field_of(c).type) || m == 0) continue;
         PG_CUDA(cudaMemcpy(&off_lo[c], cols[c].offsets + lo, 4, cudaMemcpyDeviceToHost));
         PG_CUDA(cudaMemcpy(&off_hi[c], cols[c].offsets + lo + m, 4, cudaMemcpyDeviceToHost));
     }
     std::vector<size_t> o_val(nc), o_main(nc), o_data(nc);
     size_t bytes = 64;
     for (int c = 0; c < nc; c++) {
-        const pg_field f = s->field(c);
+        const pg_field f = field_of(c);
         o_val[c] = bytes;
         if (cols[c].validity) bytes += pad((size_t)((m + 7) / 8) + 8);
         o_main[c] = bytes;
@@ -115,7 +125,7 @@ static pg_status export_arrow(uint64_t source, const char *const *names, int64_t
     unsigned char *h = (unsigned char *)priv->pinned;
     // ---- device -> host
     for (int c = 0; c < nc && m > 0; c++) {
-        const pg_field f = s->field(c);
+        const pg_field f = field_of(c);
         const DevColumn &dc = cols[c];
         if (dc.validity) PG_CUDA(cudaMemcpyAsync(h + o_val[c], dc.validity + lo / 8, (size_t)((m + 7) / 8), cudaMemcpyDeviceToHost, 0));
         if (is_varlen(f.type)) {
@@ -135,7 +145,7 @@ static pg_status export_arrow(uint64_t source, const char *const *names, int64_t
     priv->child_ptrs.resize(nc);
     priv->buffers.resize(nc);
     for (int c = 0; c < nc; c++) {
-        const pg_field f = s->field(c);
+        const pg_field f = field_of(c);
         ArrowArray &a = priv->children[c];
         memset(&a, 0, sizeof(a));
         a.length = n_rows;
@@ -179,12 +189,12 @@ static pg_status export_arrow(uint64_t source, const char *const *names, int64_t
         sp->children.resize(nc);
         sp->child_ptrs.resize(nc);
         for (int c = 0; c < nc; c++) {
-            sp->names[c] = names && names[c] ? names[c] : ("c" + std::to_string(c));
+            sp->names[c] = names && names[present[c]] ? names[present[c]] : ("c" + std::to_string(present[c]));
             ArrowSchema &cs = sp->children[c];
             memset(&cs, 0, sizeof(cs));
-            cs.format = arrow_format(s->field(c).type);
+            cs.format = arrow_format(field_of(c).type);
             cs.name = sp->names[c].c_str();
-            cs.flags = (s->field(c).nullable || cols[c].validity) ? 2 : 0;      // ARROW_FLAG_NULLABLE
+            cs.flags = (field_of(c).nullable || cols[c].validity) ? 2 : 0;      // ARROW_FLAG_NULLABLE
             cs.release = release_child_schema;
             sp->child_ptrs[c] = &cs;
         }

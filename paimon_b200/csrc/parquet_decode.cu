@@ -48,7 +48,8 @@ struct PqChunk {
     int64_t num_values;
     int64_t row0;             // first row of the chunk inside its output run
     int32_t col, run, file, codec;
-    int32_t max_def, phys, phys_width, pad;
+    int32_t max_def, phys, phys_width;
+    int32_t cast;             // schema evolution: 0 none, 1 INT32 -> BIGINT (sign extension), 2 FLOAT -> DOUBLE
     // count pass
     int32_t n_pages, n_dicts;
     int64_t scratch_bytes;    // inflate / delta images this chunk needs
@@ -959,6 +960,10 @@ k_pq_expand(const PqPage *pages, const PqPage *dicts, const PqChunk *chunks, con
                         else if (ch.phys == pq::T_BOOLEAN) v = (values[rank >> 3] >> (rank & 7)) & 1;
                         else if (is_dict) v = pq_load_unaligned(dbody + (int64_t)pids[rank] * pw, pw);
                         else v = pq_load_unaligned(values + (int64_t)rank * pw, pw);
+                        // a file written before the column was widened (SchemaEvolutionUtil / CastExecutors on the
+                        // Java side, DataFileRecordReader.java:55-57): INT -> BIGINT, FLOAT -> DOUBLE are exact
+                        if (ch.cast == 1) v = (uint64_t)(int64_t)(int32_t)(uint32_t)v;
+                        else if (ch.cast == 2) v = (uint64_t)__double_as_longlong((double)__uint_as_float((uint32_t)v));
                     }
                     store_fixed(out.data, out.out_width, row, v);   // narrowing keeps the low bytes (INT32 -> TINYINT)
                 }
@@ -1050,45 +1055,73 @@ static int out_width_of(int t) {
     }
 }
 
-// ParquetSchemaConverter.java:76-160 — which physical type a Paimon column must have in the file
-static bool phys_compatible(int pg_t, int phys) {
+// ParquetSchemaConverter.java:76-160 — which physical type a Paimon column has in the file.  Returns the cast the
+// decoder applies (0 = none), or -1 when the file type does not map to the read type.  Besides the exact mapping, the
+// widenings Paimon's schema evolution allows without rewriting files are accepted: INT-family -> BIGINT, FLOAT -> DOUBLE.
+static int phys_cast(int pg_t, int phys) {
     switch (pg_t) {
-        case PG_INT8: case PG_INT16: case PG_INT32: return phys == pq::T_INT32;
-        case PG_INT64: return phys == pq::T_INT64;
-        case PG_FLOAT: return phys == pq::T_FLOAT;
-        case PG_DOUBLE: return phys == pq::T_DOUBLE;
-        case PG_BOOL: return phys == pq::T_BOOLEAN;
-        case PG_STRING: case PG_BINARY: return phys == pq::T_BYTE_ARRAY;
-        default: return false;
+        case PG_INT8: case PG_INT16: case PG_INT32: return phys == pq::T_INT32 ? 0 : -1;
+        case PG_INT64: return phys == pq::T_INT64 ? 0 : (phys == pq::T_INT32 ? 1 : -1);
+        case PG_FLOAT: return phys == pq::T_FLOAT ? 0 : -1;
+        case PG_DOUBLE: return phys == pq::T_DOUBLE ? 0 : (phys == pq::T_FLOAT ? 2 : -1);
+        case PG_BOOL: return phys == pq::T_BOOLEAN ? 0 : -1;
+        case PG_STRING: case PG_BINARY: return phys == pq::T_BYTE_ARRAY ? 0 : -1;
+        default: return -1;
     }
 }
 static int phys_width_of(int phys) {
     return phys == pq::T_INT32 || phys == pq::T_FLOAT ? 4 : (phys == pq::T_INT64 || phys == pq::T_DOUBLE ? 8 : 0);
 }
 
-// The file's columns against the KeyValue file schema [_KEY_*, _SEQUENCE_NUMBER, _VALUE_KIND, value...]: same
-// count, flat, compatible physical types and — when the caller passes the expected field names — the same names
-// in the same order (the reference resolves columns by name, ParquetReaderFactory.clipParquetSchema; a file written
-// under another table schema needs the schema-evolution mapping of the Java side and is refused here).
-static pg_status check_file_schema(const Schema *s, const pq::FileMetaData &m, const char *const *names) {
+// The file's columns against the read schema [_KEY_*, _SEQUENCE_NUMBER, _VALUE_KIND, value...].
+//   names == NULL: positional — same column count, compatible physical types (the single-file reader).
+//   names != NULL: BY NAME, as the reference resolves them (ParquetReaderFactory.clipParquetSchema -> containsField):
+//     a read column the file does not have becomes an all-NULL column (a file written before ADD COLUMN; the field
+//     must be nullable, key / sequence / kind columns must exist), extra file columns are ignored (DROP COLUMN), the
+//     order in the file does not matter.  Renames are resolved by field id above this layer (SchemaEvolutionUtil):
+//     the caller passes the names the field had in the file's schema.
+// file_col[c] = the file's leaf column of read column c, -1 = not in the file, -2 = not requested (read_cols[c] == 0)
+static pg_status map_file_schema(const Schema *s, const pq::FileMetaData &m, const char *const *names,
+                                 const uint8_t *read_cols, std::vector<int> *file_col) {
     const int nc = s->n_cols();
-    if (m.schema.empty() || m.schema[0].num_children != nc || (int)m.schema.size() != nc + 1)
-        return fail(PG_ERR_UNSUPPORTED, "parquet: only flat schemas whose columns match the KeyValue file schema "
-                                        "[_KEY_*, _SEQUENCE_NUMBER, _VALUE_KIND, value...] are decoded on device");
+    if (m.schema.empty()) return fail(PG_ERR_FORMAT, "parquet: empty schema");
+    const int nleaf = (int)m.schema.size() - 1;
+    if (m.schema[0].num_children != nleaf)
+        return fail(PG_ERR_UNSUPPORTED, "parquet: nested columns are not decoded on device (flat KeyValue file schemas are)");
+    for (int i = 1; i <= nleaf; i++)
+        if (m.schema[i].num_children != 0 || m.schema[i].repetition == pq::R_REPEATED)
+            return fail(PG_ERR_UNSUPPORTED, "parquet: nested / repeated column " + m.schema[i].name);
+    file_col->assign(nc, -1);
+    if (!names) {
+        if (nleaf != nc)
+            return fail(PG_ERR_UNSUPPORTED, "parquet: only flat schemas whose columns match the KeyValue file schema "
+                                            "[_KEY_*, _SEQUENCE_NUMBER, _VALUE_KIND, value...] are decoded on device");
+        for (int c = 0; c < nc; c++) (*file_col)[c] = c;
+    } else {
+        std::unordered_map<std::string, int> by_name;
+        for (int i = 0; i < nleaf; i++) by_name.emplace(m.schema[i + 1].name, i);
+        for (int c = 0; c < nc; c++) {
+            if (!names[c]) return fail(PG_ERR_INVALID, "parquet: null column name");
+            auto it = by_name.find(names[c]);
+            if (it != by_name.end()) { (*file_col)[c] = it->second; continue; }
+            if (read_cols && !read_cols[c]) continue;
+            if (c < s->n_key + 2 || !s->field(c).nullable)
+                return fail(PG_ERR_UNSUPPORTED, std::string("parquet: the file has no column '") + names[c] + "' and the read "
+                                                "schema does not allow NULL for it (a file written under another table "
+                                                "schema needs the Java-side schema-evolution mapping)");
+        }
+    }
     for (int c = 0; c < nc; c++) {
-        const pq::SchemaElement &e = m.schema[c + 1];
-        if (e.num_children != 0 || e.repetition == pq::R_REPEATED)
-            return fail(PG_ERR_UNSUPPORTED, "parquet: nested / repeated column " + e.name);
-        if (!phys_compatible(s->field(c).type, e.type))
+        if (read_cols && !read_cols[c]) { (*file_col)[c] = -2; continue; }
+        const int fc = (*file_col)[c];
+        if (fc < 0) continue;
+        const pq::SchemaElement &e = m.schema[fc + 1];
+        if (phys_cast(s->field(c).type, e.type) < 0)
             return fail(PG_ERR_UNSUPPORTED, "parquet: column " + e.name + " has a physical type the device decoder "
                                             "does not map to the table type");
-        if (names && names[c] && e.name != names[c])
-            return fail(PG_ERR_UNSUPPORTED, "parquet: file column " + std::to_string(c) + " is '" + e.name +
-                                            "' but the read schema expects '" + names[c] + "' (a file written under "
-                                            "another table schema needs the schema-evolution mapping; not on device)");
     }
     for (const pq::RowGroup &g : m.row_groups) {
-        if ((int)g.columns.size() != nc) return fail(PG_ERR_FORMAT, "parquet: row group with a different column count");
+        if ((int)g.columns.size() != nleaf) return fail(PG_ERR_FORMAT, "parquet: row group with a different column count");
         for (const pq::ColumnChunk &cc : g.columns)
             if (cc.codec != pq::C_UNCOMPRESSED && cc.codec != pq::C_SNAPPY && cc.codec != pq::C_ZSTD)
                 return fail(PG_ERR_UNSUPPORTED, "parquet: compression codec " + std::to_string(cc.codec) +
@@ -1140,7 +1173,8 @@ struct BufList {
 };
 
 static pg_status decode_section(const Schema *s, const std::vector<SectionFile> &files, int n_runs,
-                                const char *const *names, uint64_t *out_runs, pg_section_info *info) {
+                                const char *const *names, const uint8_t *read_cols, uint64_t *out_runs,
+                                pg_section_info *info) {
     const int nc = s->n_cols();
     const int nf = (int)files.size();
     cudaStream_t sm = thread_stream();
@@ -1208,12 +1242,19 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
             return fail(PG_ERR_FORMAT, e.what());
         }
     }
-    std::vector<uint8_t> any_optional(nc, 0);
+    if (read_cols)
+        for (int c = 0; c < s->n_key + 2; c++)
+            if (!read_cols[c]) return fail(PG_ERR_INVALID, "parquet: key, sequence number and kind columns are always read");
+    std::vector<uint8_t> any_optional(nc, 0), wanted(nc, 1);
+    std::vector<std::vector<int>> file_col(nf);
+    for (int c = 0; c < nc; c++) wanted[c] = !read_cols || read_cols[c];
     for (int f = 0; f < nf; f++) {
-        pg_status st = check_file_schema(s, *meta[f], names);
+        pg_status st = map_file_schema(s, *meta[f], names, read_cols, &file_col[f]);
         if (st) return st;
-        for (int c = 0; c < nc; c++)
-            if (meta[f]->schema[c + 1].repetition == pq::R_OPTIONAL) any_optional[c] = 1;
+        for (int c = 0; c < nc; c++) {
+            const int fc = file_col[f][c];
+            if (fc == -1 || (fc >= 0 && meta[f]->schema[fc + 1].repetition == pq::R_OPTIONAL)) any_optional[c] = 1;
+        }
     }
 
     // ---- rows: a file's rows land behind the rows of the files in front of it in its run
@@ -1232,15 +1273,28 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
     std::vector<PqPair> pairs;
     bool any_snappy = false, any_delta = false, any_zstd = false;
     int64_t pair_rows = 0;
+    // (run, column) pairs some / all of whose files lack the column: the rows of those files are NULL
+    std::vector<uint8_t> col_missing((size_t)n_runs * nc, 0);          // 1 = in some files, 2 = in every file of the run
     for (int r = 0; r < n_runs; r++) {
         for (int c = 0; c < nc; c++) {
+            if (!wanted[c]) continue;
             const int chunk0 = (int)chunks.size();
+            int n_missing = 0;
+            for (int f : run_files[r]) if (file_col[f][c] < 0) n_missing++;
+            if (n_missing > 0) {
+                col_missing[(size_t)r * nc + c] = n_missing == (int)run_files[r].size() ? 2 : 1;
+                if (n_missing != (int)run_files[r].size() && is_varlen(s->field(c).type))
+                    return fail(PG_ERR_UNSUPPORTED, "parquet: a var-len column exists in some files of a sorted run only "
+                                                    "(mixed table schemas inside one run: not decoded on device)");
+            }
             for (int f : run_files[r]) {
                 const pq::FileMetaData &m = *meta[f];
+                const int fc = file_col[f][c];
                 int64_t rg_row0 = 0;
                 int64_t rows = 0;
+                if (fc < 0) continue;
                 for (const pq::RowGroup &g : m.row_groups) {
-                    const pq::ColumnChunk &cc = g.columns[c];
+                    const pq::ColumnChunk &cc = g.columns[fc];
                     const int64_t start = cc.start();
                     if (start < 4 || start >= files[f].size) return fail(PG_ERR_FORMAT, "parquet: page offset out of range");
                     if (cc.num_values != g.num_rows) return fail(PG_ERR_FORMAT, "parquet: page row counts do not add up");
@@ -1252,10 +1306,11 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
                     ch.num_values = cc.num_values;
                     ch.row0 = file_row0[f] + rg_row0;
                     ch.col = c; ch.run = r; ch.file = f; ch.codec = cc.codec;
-                    ch.max_def = m.schema[c + 1].repetition == pq::R_OPTIONAL ? 1 : 0;
+                    ch.max_def = m.schema[fc + 1].repetition == pq::R_OPTIONAL ? 1 : 0;
                     ch.phys = cc.type;
                     ch.phys_width = phys_width_of(cc.type);
-                    if (cc.type != m.schema[c + 1].type) return fail(PG_ERR_FORMAT, "parquet: column chunk type differs from the schema");
+                    ch.cast = phys_cast(s->field(c).type, cc.type);
+                    if (cc.type != m.schema[fc + 1].type) return fail(PG_ERR_FORMAT, "parquet: column chunk type differs from the schema");
                     if (cc.codec == pq::C_SNAPPY) any_snappy = true;
                     if (cc.codec == pq::C_ZSTD) any_zstd = true;
                     for (int32_t e : cc.encodings) if (e == pq::E_DELTA_BINARY_PACKED) any_delta = true;
@@ -1299,13 +1354,13 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
         run->bytes_h2d = 0;
         size_t vbytes = 0, total = 0;
         const size_t vb = pad((size_t)((n + 31) / 32) * 4 + 64);
-        for (int c = 0; c < nc; c++) if (any_optional[c]) vbytes += vb;
+        for (int c = 0; c < nc; c++) if (wanted[c] && any_optional[c]) vbytes += vb;
         total = vbytes;
         std::vector<size_t> o_main(nc);
         for (int c = 0; c < nc; c++) {
             const int ow = out_width_of(s->field(c).type);
             o_main[c] = total;
-            total += ow ? pad((size_t)n * ow + 64) : pad(4 * (size_t)(n + 1) + 64);
+            if (wanted[c]) total += ow ? pad((size_t)n * ow + 64) : pad(4 * (size_t)(n + 1) + 64);
         }
         size_t got = 0;
         unsigned char *base = (unsigned char *)device_buffer_take(total + 256, &got);
@@ -1320,9 +1375,13 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
             const int ow = out_width_of(s->field(c).type);
             o.out_width = ow;
             o.is_bool = s->field(c).type == PG_BOOL;
+            if (!wanted[c]) continue;                    // not part of the read type: the run has no such column
             if (any_optional[c]) { o.validity = (uint32_t *)(base + vt); vt += vb; decoded_bytes += (n + 7) / 8; }
             if (ow) { o.data = base + o_main[c]; decoded_bytes += n * ow; }
             else { o.offsets = (int32_t *)(base + o_main[c]); decoded_bytes += 4 * (n + 1); }
+            // rows of files that lack the column stay NULL (validity is zeroed); give them defined contents
+            if (col_missing[(size_t)r * nc + c])
+                PG_CUDA(cudaMemsetAsync(base + o_main[c], 0, ow ? (size_t)n * ow : 4 * (size_t)(n + 1), sm));
         }
         runs[r] = std::move(run);
     }
@@ -1469,9 +1528,11 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
         for (int c = 0; c < nc; c++) {
             const PqOut &o = outs[(size_t)r * nc + c];
             DevColumn dc;
-            dc.data = o.data ? o.data : (const void *)runs[r]->owned[0];
-            dc.offsets = o.offsets;
-            dc.validity = (const uint8_t *)o.validity;
+            if (wanted[c]) {
+                dc.data = o.data ? o.data : (const void *)runs[r]->owned[0];
+                dc.offsets = o.offsets;
+                dc.validity = (const uint8_t *)o.validity;
+            }
             runs[r]->cols[c] = dc;
         }
         runs[r]->bytes_h2d = r == 0 ? h2d : 0;
@@ -1525,7 +1586,8 @@ static pg_status pq_open(uint64_t schema_h, const uint8_t *bytes, int64_t size, 
         return fail(PG_ERR_FORMAT, e.what());
     }
     const pq::FileMetaData &m = rd->meta;
-    pg_status st = check_file_schema(s, m, nullptr);
+    std::vector<int> file_col;
+    pg_status st = map_file_schema(s, m, nullptr, nullptr, &file_col);
     if (st) return st;
     const int nc = s->n_cols();
     rd->n_rows = m.num_rows;
@@ -1580,7 +1642,7 @@ static pg_status pq_open(uint64_t schema_h, const uint8_t *bytes, int64_t size, 
 static pg_status pq_read_run(PqReader *rd, uint64_t *out_run) {
     std::vector<SectionFile> files{SectionFile{rd->file.data(), (int64_t)rd->file.size(), PG_MEM_HOST, 0, &rd->meta}};
     pg_section_info info;
-    pg_status st = decode_section(rd->schema, files, 1, nullptr, out_run, &info);
+    pg_status st = decode_section(rd->schema, files, 1, nullptr, nullptr, out_run, &info);
     if (st) return st;
     rd->ms_decode = info.ms_decode;
     rd->launches = info.launches;
@@ -1798,7 +1860,8 @@ pg_status pg_parquet_read_run(uint64_t reader, uint64_t *out_run) {
 }
 
 pg_status pg_parquet_read_section(uint64_t schema, const pg_file_desc *files, int32_t n_files, int32_t n_runs,
-                                  const char *const *column_names, uint64_t *out_runs, pg_section_info *info) {
+                                  const char *const *column_names, const uint8_t *read_columns, uint64_t *out_runs,
+                                  pg_section_info *info) {
     Schema *s = schema_from_handle(schema);
     if (!s || !out_runs || n_files < 0 || n_runs < 0 || (n_files > 0 && !files))
         return fail(PG_ERR_INVALID, "bad schema handle or null argument");
@@ -1811,7 +1874,7 @@ pg_status pg_parquet_read_section(uint64_t schema, const pg_file_desc *files, in
         fs[i] = SectionFile{files[i].bytes, files[i].size, files[i].mem, files[i].run, nullptr};
     }
     const Schema own = *s;                       // the schema handle may be freed while the runs live on
-    return decode_section(&own, fs, n_runs, column_names, out_runs, info);
+    return decode_section(&own, fs, n_runs, column_names, read_columns, out_runs, info);
 }
 
 pg_status pg_run_apply_deletion_vector(uint64_t run, const uint8_t *deleted_bitmap, int64_t n_bits, uint64_t *out_run) {

@@ -308,6 +308,10 @@ static pg_status encode(uint64_t source, const char *const *names, int64_t row0,
     int64_t total_rows = 0;
     st = batch_columns(source, &s, &dcols, &total_rows);
     if (st) return st;
+    for (int c = 0; c < s->n_cols() && total_rows > 0; c++)
+        if (!dcols[c].data && !dcols[c].offsets)
+            return fail(PG_ERR_INVALID, "parquet encode: the batch was produced under a read-type projection and has no "
+                                        "column " + std::to_string(c) + "; a data file needs every column");
     if (n_rows < 0) n_rows = total_rows - row0;
     if (row0 < 0 || (row0 & 7) || row0 + n_rows > total_rows)
         return fail(PG_ERR_INVALID, "parquet encode: row range outside the batch or not starting at a multiple of 8");

@@ -68,6 +68,7 @@ struct Spec {
     // partial-update sequence groups
     std::vector<int32_t> group_seq_start, group_seq_fields, field_group;
     std::vector<uint8_t> group_partial_delete;      // per group
+    std::vector<uint8_t> read_fields;               // per value field: part of the read type (empty = all)
     int n_groups() const { return group_seq_start.empty() ? 0 : (int)group_seq_start.size() - 1; }
 };
 

@@ -110,12 +110,15 @@ class ParquetFileRecordReader(FileRecordReader):
             self._schema_h = None
 
 
-def read_section(schema: KeyValueSchema, files, n_runs: int, device: int = 0, check_names: bool = True):
+def read_section(schema: KeyValueSchema, files, n_runs: int, device: int = 0, check_names: bool = True,
+                 read_value_fields=None):
     """Decode every data file of a section with ONE batch of device launches (pg_parquet_read_section) and return
     (one SortedRunReader per run, PgSectionInfo).  `files` = [(buffer, run index)], in key order inside a run; a
     buffer is bytes / a numpy uint8 array (host memory) or a (device pointer, size) tuple (bytes already in HBM).
     The files of a run are concatenated on the device, as MergeTreeReaders.readerForRun's ConcatRecordReader does
-    (MergeTreeReaders.java:94-101): the merge gets k = number of runs inputs."""
+    (MergeTreeReaders.java:94-101): the merge gets k = number of runs inputs.  Columns are resolved by field name
+    (missing nullable fields decode as NULL, extra file columns are ignored, INT -> BIGINT / FLOAT -> DOUBLE widen);
+    `read_value_fields` (one bool per value field) is the read-type projection pushed into the decoder."""
     lib = N.init(device)
     sh = _SchemaHandle(schema, device)
     keep = []
@@ -133,8 +136,13 @@ def read_section(schema: KeyValueSchema, files, n_runs: int, device: int = 0, ch
         names = (C.c_char_p * len(nm))(*[x.encode() for x in nm])
     runs = (C.c_uint64 * max(n_runs, 1))()
     info = N.PgSectionInfo()
+    mask = None
+    if read_value_fields is not None:
+        mask = np.array([1] * (schema.n_key + 2) + [1 if b else 0 for b in read_value_fields], np.uint8)
+        keep.append(mask)
     try:
-        N.check(lib.pg_parquet_read_section(sh.handle, descs, len(files), n_runs, names, runs, C.byref(info)))
+        N.check(lib.pg_parquet_read_section(sh.handle, descs, len(files), n_runs, names,
+                                            None if mask is None else mask.ctypes.data, runs, C.byref(info)))
     finally:
         sh.close()
     readers = []

@@ -90,6 +90,27 @@ class MergeSpec:
     groups: List[List[int]] = field(default_factory=list)  # sequence fields of each sequence group
     field_group: List[int] = field(default_factory=list)   # per value field: protecting group or -1
     group_partial_delete: List[bool] = field(default_factory=list)
+    # read-type projection (MergeFunctionFactory.create(readType)): per value field, part of the merged batch;
+    # empty = every field.  Field indexes everywhere in the spec stay those of the table's row type.
+    read_fields: List[bool] = field(default_factory=list)
+
+    def with_read_fields(self, mask: Sequence[bool]) -> "MergeSpec":
+        import copy
+        s = copy.deepcopy(self)
+        s.read_fields = [bool(b) for b in mask]
+        return s
+
+    def fields_the_merge_reads(self, n_val: int) -> List[bool]:
+        """Value fields a reader has to decode for this spec: the read type plus what the merge function itself
+        compares — 'sequence.field' columns and every sequence-group field (PartialUpdateMergeFunction.adjustReadType,
+        PartialUpdateMergeFunction.java:576-606)."""
+        need = list(self.read_fields) if self.read_fields else [True] * n_val
+        for f in self.seq_fields:
+            need[f] = True
+        for g in self.groups:
+            for f in g:
+                need[f] = True
+        return need
 
     def with_drop_delete(self, drop: bool = True) -> "MergeSpec":
         import copy
@@ -261,13 +282,19 @@ class PartialUpdateMergeFunction:
 
         class _F(MergeFunctionFactory):
             def create(self, read_type=None) -> MergeSpec:
-                if read_type is not None and read_type.field_names() != names:
-                    raise UnsupportedMergeSpec("projected read types are resolved on the Java side "
-                                               "(PartialUpdateMergeFunction.java:492-573); pass the full row type")
-                return MergeSpec(engine=MergeEngine.PARTIAL_UPDATE, ignore_delete=ignore_delete,
+                spec = MergeSpec(engine=MergeEngine.PARTIAL_UPDATE, ignore_delete=ignore_delete,
                                  remove_record_on_delete=remove_on_delete, agg=list(aggs),
                                  ignore_retract=list(ign), groups=[list(g) for g in groups],
                                  field_group=list(field_group), group_partial_delete=list(partial_delete))
+                if read_type is not None and read_type.field_names() != names:
+                    # a projected read type (PartialUpdateMergeFunction.java:492-573 re-indexes the per-field
+                    # configuration; here the indexes stay those of the table and the projection is a mask)
+                    unknown = [n for n in read_type.field_names() if n not in names]
+                    if unknown:
+                        raise ValueError(f"read type has fields the table does not have: {unknown}")
+                    wanted = set(read_type.field_names())
+                    spec.read_fields = [n in wanted for n in names]
+                return spec
         return _F()
 
 

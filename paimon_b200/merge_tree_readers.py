@@ -192,7 +192,8 @@ class MergeTreeReaders:
             return list(ex.map(lambda m: reader_factory.file_io.read_bytes(m.file_name), metas))
 
     @staticmethod
-    def open_runs(section: Sequence[SortedRun], reader_factory: KeyValueFileReaderFactory) -> List[SortedRunReader]:
+    def open_runs(section: Sequence[SortedRun], reader_factory: KeyValueFileReaderFactory,
+                  read_value_fields=None) -> List[SortedRunReader]:
         """The sorted runs of a section as device-resident merge inputs: ONE batch of decode launches for all files
         (pg_parquet_read_section), and a run = the concatenation of its key-disjoint files, like readerForRun's
         ConcatRecordReader (MergeTreeReaders.java:94-101) — so the merge fan-in is the number of RUNS, not files.
@@ -205,7 +206,8 @@ class MergeTreeReaders:
                 metas.append(m)
                 run_of.append(r)
         blobs = MergeTreeReaders._read_files(metas, reader_factory)
-        readers, _ = read_section(reader_factory.schema, list(zip(blobs, run_of)), len(section), reader_factory.device)
+        readers, _ = read_section(reader_factory.schema, list(zip(blobs, run_of)), len(section), reader_factory.device,
+                                  read_value_fields=read_value_fields)
         if reader_factory.dv_factory is not None:
             from .sort_merge_reader import apply_deletion_vector
             row0 = [0] * len(section)
@@ -230,16 +232,26 @@ class MergeTreeReaders:
     @staticmethod
     def reader_for_section(section: Sequence[SortedRun], reader_factory: KeyValueFileReaderFactory,
                            user_defined_seq_comparator, merge_function_wrapper: MergeSpec) -> RecordReader:
-        """MergeTreeReaders.readerForSection (:67-92)."""
-        if len(section) > 32:
-            raise N.UnsupportedOnDevice(2, "more than 32 sorted runs in one section: merge in rounds is not implemented yet")
-        runs = MergeTreeReaders.open_runs(section, reader_factory)
+        """MergeTreeReaders.readerForSection (:67-92).  One device merge takes at most PG_MAX_RUNS = 32 sorted runs;
+        a section with more runs (the reference's MergeSorter, MergeSorter.java:112-198, spills the smallest ones and
+        still merges all of them at once) is merged in rounds when the merge function allows it exactly."""
+        spec_n = merge_function_wrapper.normalised(reader_factory.schema.n_val)
+        if user_defined_seq_comparator is not None and hasattr(user_defined_seq_comparator, "apply"):
+            spec_n = user_defined_seq_comparator.apply(spec_n)
+        decode_mask = spec_n.fields_the_merge_reads(reader_factory.schema.n_val) if spec_n.read_fields else None
+        runs = MergeTreeReaders.open_runs(section, reader_factory, read_value_fields=decode_mask)
+        inner: List[SortMergeReader] = []
         try:
+            if len(runs) > 32:
+                runs = MergeTreeReaders._merge_in_rounds(runs, user_defined_seq_comparator, merge_function_wrapper,
+                                                         reader_factory, inner)
             merge = SortMergeReader.create_sort_merge_reader(runs, None, user_defined_seq_comparator,
                                                              merge_function_wrapper, device=reader_factory.device)
         except Exception:
             for r in runs:
                 r.close()
+            for m in inner:
+                m.close()
             raise
 
         class _Section(RecordReader):
@@ -248,7 +260,44 @@ class MergeTreeReaders:
 
             def close(self_inner):
                 merge.close()                            # closes its run readers too
+                for m in inner:
+                    m.close()
         return _Section()
+
+    @staticmethod
+    def _merge_in_rounds(runs: List[SortedRunReader], udsc, spec: MergeSpec, reader_factory, inner: list):
+        """More than 32 sorted runs: groups of 32 are merged into intermediate runs (views of the group merges'
+        device batches, no copy), until at most 32 remain for the final merge.  Pre-reducing a group is exact only
+        when the merge function's result is one of the group's input records, chosen by an order that does not
+        depend on the other groups: deduplicate (the newest record, retracts skipped under 'ignore-delete') and
+        first-row.  partial-update and aggregation fold every record of a key in global sequence order (a column of
+        group A's result may be older than group B's value for it; floating-point sums are not associative), so
+        they are refused instead of being merged approximately."""
+        from .merge_function import MergeEngine
+        if spec.engine not in (MergeEngine.DEDUPLICATE, MergeEngine.FIRST_ROW) or spec.read_fields:
+            for r in runs:
+                r.close()
+            raise N.UnsupportedOnDevice(2, "more than 32 sorted runs in one section are merged in rounds for the "
+                                           "deduplicate and first-row merge engines only (without a read-type "
+                                           "projection); partial-update / aggregation need one pass over all runs")
+        lib = N.load()
+        step = spec.with_drop_delete(False)              # deletes must survive until the last round
+        while len(runs) > 32:
+            nxt: List[SortedRunReader] = []
+            for g in range(0, len(runs), 32):
+                group = runs[g:g + 32]
+                if len(group) == 1:
+                    nxt.append(group[0])
+                    continue
+                m = SortMergeReader.create_sort_merge_reader(group, None, udsc, step, device=reader_factory.device)
+                inner.append(m)                          # owns the group's runs and the intermediate batch
+                m.execute()
+                n_out = m.device_batch().n_rows
+                h, start = C.c_uint64(0), C.c_int64(0)
+                N.check(lib.pg_run_slice(m._merge_h, 0, n_out, C.byref(h), C.byref(start)))
+                nxt.append(SortedRunReader.from_native_run(reader_factory.schema, n_out, h.value))
+            runs = nxt
+        return runs
 
     @staticmethod
     def reader_for_merge_tree(sections: Sequence[Sequence[SortedRun]], reader_factory: KeyValueFileReaderFactory,
@@ -276,6 +325,19 @@ class MergeFileSplitRead:
         self.force_keep_delete = True
         return self
 
+    def with_read_type(self, field_names: Sequence[str]) -> "MergeFileSplitRead":
+        """withReadType (MergeFileSplitRead.java:133-163): the value fields the engine wants.  The projection is pushed
+        into the decoder (column chunks of other fields are not decoded) and into the merge (no output columns, no emit
+        work for them); keys are never projected before the merge (:276-277), and fields the merge function compares
+        ('sequence.field', sequence groups) are still decoded (adjustReadType)."""
+        names = self.schema.value_type.field_names()
+        unknown = [n for n in field_names if n not in names]
+        if unknown:
+            raise ValueError(f"read type has fields the table does not have: {unknown}")
+        wanted = set(field_names)
+        self.read_fields = [n in wanted for n in names]
+        return self
+
     def with_key_filter(self, lower=None, upper=None) -> "MergeFileSplitRead":
         """withFilter (MergeFileSplitRead.java:181-217): only KEY predicates may be pushed below the merge — a value
         predicate would drop the newer version of a row and resurrect an older one (comment :204-213).  Here the
@@ -296,5 +358,7 @@ class MergeFileSplitRead:
     def create_merge_reader(self, files: Sequence[DataFileMeta], keep_delete: Optional[bool] = None) -> RecordReader:
         keep = self.force_keep_delete if keep_delete is None else keep_delete
         spec = self.mf_factory.create().with_drop_delete(not keep)      # DropDeleteReader fused into the merge
+        if getattr(self, "read_fields", None) is not None:
+            spec = spec.with_read_fields(self.read_fields)
         sections = IntervalPartition(self._prune(files)).partition()
         return MergeTreeReaders.reader_for_merge_tree(sections, self.reader_factory, self.udsc, spec)

@@ -181,6 +181,10 @@ def fetch_run(schema: KeyValueSchema, run_handle: int) -> KeyValueBatch:
     host = (N.PgOutColumn * nc)()
     cols: List[Column] = []
     for i, t in enumerate(schema.physical_types()):
+        if data_bytes[i] < 0:                               # the run was decoded without this column (projection)
+            host[i] = N.PgOutColumn(None, None, None, 0)
+            cols.append(None)
+            continue
         valid = np.zeros((n + 7) // 8 + 8, np.uint8) if has_valid[i] else None
         if is_varlen(t):
             data = np.zeros(max(int(data_bytes[i]), 1), np.uint8)
@@ -193,7 +197,7 @@ def fetch_run(schema: KeyValueSchema, run_handle: int) -> KeyValueBatch:
             cols.append(Column(t, data[:n], None, valid))
     N.check(lib.pg_run_fetch(run_handle, host, nc))
     for col in cols:                                  # a view (pg_run_slice) keeps the source's absolute offsets
-        if col.offsets is not None and n > 0 and col.offsets[0] != 0:
+        if col is not None and col.offsets is not None and n > 0 and col.offsets[0] != 0:
             col.offsets -= col.offsets[0]
     return KeyValueBatch(schema, cols)
 
@@ -203,6 +207,9 @@ def slice_rows(batch: KeyValueBatch, lo: int, hi: int) -> KeyValueBatch:
     from .columnar import pack_validity, unpack_validity
     cols = []
     for col in batch.columns:
+        if col is None:
+            cols.append(None)
+            continue
         valid = None
         if col.valid is not None:
             valid = pack_validity(unpack_validity(col.valid, len(col))[lo:hi])
@@ -311,13 +318,16 @@ class SortMergeReader(RecordReader):
             gstart[i + 1] = gstart[i] + len(g)
         fgroup = np.array(sp.field_group, np.int32)
         gpd = np.array([1 if b else 0 for b in sp.group_partial_delete], np.uint8)
-        self._keep += [gstart, gfields, fgroup, gpd]
+        rf = np.array([1 if b else 0 for b in sp.read_fields], np.uint8) if sp.read_fields else None
+        self._read_fields = list(sp.read_fields) if sp.read_fields else None
+        self._keep += [gstart, gfields, fgroup, gpd, rf]
         has_groups = len(sp.groups) > 0
         cs = N.PgMergeSpec(int(sp.engine), int(sp.ignore_delete), int(sp.remove_record_on_delete),
                            int(sp.drop_delete), len(seq), _np_ptr(seq_arr) if len(seq) else None,
                            int(sp.seq_ascending), _np_ptr(agg), _np_ptr(ign), len(sp.groups),
                            _np_ptr(gstart) if has_groups else None, _np_ptr(gfields) if has_groups else None,
-                           _np_ptr(fgroup) if has_groups else None, _np_ptr(gpd) if has_groups else None)
+                           _np_ptr(fgroup) if has_groups else None, _np_ptr(gpd) if has_groups else None,
+                           _np_ptr(rf))
         h = C.c_uint64(0)
         try:
             N.check(self.lib.pg_merge_spec_create(self._schema_h.handle, C.byref(cs), C.byref(h)))
@@ -372,8 +382,13 @@ class SortMergeReader(RecordReader):
         types = self.schema.physical_types()
         host = (N.PgOutColumn * len(types))()
         cols: List[Column] = []
+        nk2 = self.schema.n_key + 2
         for i, t in enumerate(types):
             oc = db.columns[i]
+            if self._read_fields is not None and i >= nk2 and not self._read_fields[i - nk2]:
+                host[i] = N.PgOutColumn(None, None, None, 0)       # not part of the read type
+                cols.append(None)
+                continue
             valid = alloc((n + 7) // 8 + 8) if oc.validity else None
             if is_varlen(t):
                 data = alloc(max(int(oc.data_bytes), 1))

@@ -375,9 +375,9 @@ def test_boolean_columns_plain_and_rle(tmp_path):
             check_file(schema, batch, str(tmp_path / f"bool{n}.parquet"), **opts)
 
 
-def test_column_names_are_checked(tmp_path):
-    """The reference resolves file columns by NAME (ParquetReaderFactory.clipParquetSchema): a file whose columns
-    are named differently (written under another table schema) must not be decoded positionally."""
+def test_columns_are_resolved_by_name_not_position(tmp_path):
+    """The reference resolves file columns by NAME (ParquetReaderFactory.clipParquetSchema): a read schema that lists
+    the value fields in another order gets every field's own values — never the positional neighbour's."""
     from paimon_b200.format import read_section
     vt_a = RowType((DataField("pk", "BIGINT", False), DataField("a", "BIGINT", True), DataField("b", "BIGINT", True)))
     vt_b = RowType((DataField("pk", "BIGINT", False), DataField("b", "BIGINT", True), DataField("a", "BIGINT", True)))
@@ -388,8 +388,12 @@ def test_column_names_are_checked(tmp_path):
     blob = open(path, "rb").read()
     readers, _ = read_section(sa, [(blob, 0)], 1)
     assert _fetch_and_close(readers)[0].equals(batch)
-    with pytest.raises(N.UnsupportedOnDevice, match="expects"):
-        read_section(sb, [(blob, 0)], 1)
+    readers, _ = read_section(sb, [(blob, 0)], 1)
+    swapped = KeyValueBatch.from_rows(sb, [(k, k, 0, k, k * 3, k * 2) for k in range(100)])
+    assert _fetch_and_close(readers)[0].equals(swapped)
+    # positional reading (no names) of a file whose types line up is what the single-file reader does
+    readers, _ = read_section(sb, [(blob, 0)], 1, check_names=False)
+    assert _fetch_and_close(readers)[0].equals(KeyValueBatch.from_rows(sb, [(k, k, 0, k, k * 2, k * 3) for k in range(100)]))
 
 
 def test_section_from_device_resident_file_images(tmp_path):
@@ -467,4 +471,137 @@ def test_wide_fan_in_of_files_is_few_runs(tmp_path):
     rd.close()
     got = concat_batches(schema, batches)
     want = pyoracle.merge(schema, spec.create().with_drop_delete(True), file_runs)
+    assert got.equals(want), got.first_difference(want)
+
+
+# ------------------------------------------------------------------ read-type projection, schema evolution by name
+
+def _drain(rd):
+    from paimon_b200.merge_tree_readers import concat_batches
+    batches = []
+    while True:
+        b = rd.read_batch()
+        if b is None:
+            break
+        batches.append(b)
+    rd.close()
+    return batches
+
+
+@pytest.mark.parametrize("engine", ["dedup", "partial-update", "partial-update-seq", "aggregation"])
+def test_read_type_projection_is_pushed_into_decode_and_merge(tmp_path, engine):
+    """MergeFileSplitRead.withReadType (MergeFileSplitRead.java:133-163): only the wanted value fields are decoded
+    and merged; the result equals the full merge with the other columns removed.  With 'sequence.field' the sequence
+    column is still decoded (the merge compares it) although it is not part of the read type."""
+    from paimon_b200.merge_function import AggregateMergeFunction
+    from paimon_b200.merge_tree_readers import DataFileMeta, MergeFileSplitRead
+    schema = datagen.schema_c3(n_i64=4, n_f64=3, n_str=3)
+    runs = datagen.make_runs(schema, 5, 40000, seed=77, null_prob=0.4)
+    metas = []
+    for i, run in enumerate(runs):
+        path = str(tmp_path / f"p{i}.parquet")
+        write_kv_parquet(run, path, use_dictionary=(i % 2 == 0), compression="zstd" if i == 3 else "none")
+        k = run.columns[0].data
+        metas.append(DataFileMeta(path, 0, run.n_rows, int(k[0]), int(k[-1])))
+    vt = schema.value_type
+    if engine == "dedup":
+        factory, udsc = DeduplicateMergeFunction.factory(), None
+    elif engine == "partial-update":
+        factory, udsc = PartialUpdateMergeFunction.factory({}, vt, ["pk"]), None
+    elif engine == "partial-update-seq":
+        from paimon_b200.merge_function import UserDefinedSeqComparator
+        opts = {"sequence.field": "i0"}
+        factory, udsc = PartialUpdateMergeFunction.factory(opts, vt, ["pk"]), UserDefinedSeqComparator.create(vt, opts)
+    else:
+        factory, udsc = AggregateMergeFunction.factory({"fields.i1.aggregate-function": "sum",
+                                                        "fields.d2.aggregate-function": "max"}, vt, ["pk"]), None
+    wanted = ["pk", "i1", "d2", "s0"]
+    mask = [n in wanted for n in vt.field_names()]
+    read = MergeFileSplitRead(schema, factory, udsc).with_read_type(wanted)
+    batches = _drain(read.create_merge_reader(metas, keep_delete=True))
+    assert len(batches) == 1
+    got = batches[0]
+    spec = factory.create()
+    if udsc is not None:
+        spec = udsc.apply(spec.normalised(schema.n_val))
+    want = pyoracle.merge(schema, spec, runs).project(mask)
+    assert [c is None for c in got.columns] == [c is None for c in want.columns]
+    assert got.equals(want), got.first_difference(want)
+    # the projection alone, on host runs (no files): the merge emits the read type only
+    from paimon_b200.sort_merge_reader import merge_runs
+    got2 = merge_runs(schema, spec.with_read_fields(mask), runs)
+    assert got2.equals(want), got2.first_difference(want)
+
+
+def test_schema_evolution_columns_resolve_by_name(tmp_path):
+    """Files written under older table schemas (ParquetReaderFactory.clipParquetSchema resolves by NAME;
+    DataFileRecordReader.java:55-57 casts): an added column is NULL in old files, a dropped column is ignored, column
+    order does not matter, INT widened to BIGINT and FLOAT to DOUBLE are cast on the fly."""
+    from paimon_b200.format import read_section
+    from paimon_b200.merge_tree_readers import concat_batches
+    read_vt = RowType((DataField("pk", "BIGINT", False), DataField("a", "BIGINT", True), DataField("f", "DOUBLE", True),
+                       DataField("b", "STRING", True), DataField("c", "DOUBLE", True)))
+    read_schema = KeyValueSchema.of(read_vt, ["pk"])
+    # v1: a INT, f FLOAT, b, no c, plus a column z that was dropped later; v2: another column order
+    v1 = KeyValueSchema.of(RowType((DataField("pk", "BIGINT", False), DataField("z", "INT", True), DataField("a", "INT", True),
+                                    DataField("f", "FLOAT", True), DataField("b", "STRING", True))), ["pk"])
+    v2 = KeyValueSchema.of(RowType((DataField("pk", "BIGINT", False), DataField("c", "DOUBLE", True), DataField("b", "STRING", True),
+                                    DataField("a", "BIGINT", True), DataField("f", "DOUBLE", True))), ["pk"])
+    rng = random.Random(4)
+
+    def opt(v):
+        return None if rng.random() < 0.3 else v
+    rows1 = [(k, k, 0, k, opt(k * 3), opt(rng.randrange(-2 ** 31, 2 ** 31)), opt(np.float32(rng.uniform(-9, 9)).item()),
+              opt("s%d" % k)) for k in range(0, 3000)]
+    rows2 = [(k, k, 0, k, opt(k / 7.0), opt("t%d" % k), opt(rng.randrange(-2 ** 62, 2 ** 62)), opt(rng.uniform(-1e9, 1e9)))
+             for k in range(5000, 9001)]
+    p1, p2 = str(tmp_path / "v1.parquet"), str(tmp_path / "v2.parquet")
+    write_kv_parquet(KeyValueBatch.from_rows(v1, rows1), p1, data_page_size=2048)
+    write_kv_parquet(KeyValueBatch.from_rows(v2, rows2), p2, use_dictionary=False)
+    want1 = KeyValueBatch.from_rows(read_schema, [(r[0], r[1], r[2], r[3], r[5], r[6], r[7], None) for r in rows1])
+    want2 = KeyValueBatch.from_rows(read_schema, [(r[0], r[1], r[2], r[3], r[6], r[7], r[5], r[4]) for r in rows2])
+    # each file as its own run, and both files as ONE run (a fixed-width column that only some files have)
+    readers, _ = read_section(read_schema, [(open(p1, "rb").read(), 0), (open(p2, "rb").read(), 1)], 2)
+    g1, g2 = _fetch_and_close(readers)
+    assert g1.equals(want1), g1.first_difference(want1)
+    assert g2.equals(want2), g2.first_difference(want2)
+    # in ONE run: column c exists in the second file only — allowed for fixed-width columns
+    readers, _ = read_section(read_schema, [(open(p1, "rb").read(), 0), (open(p2, "rb").read(), 0)], 1)
+    both = _fetch_and_close(readers)[0]
+    want = concat_batches(read_schema, [want1, want2])
+    assert both.equals(want), both.first_difference(want)
+    # a NOT NULL read field the file lacks, or a narrowing, is refused
+    bad_vt = RowType((DataField("pk", "BIGINT", False), DataField("a", "INT", True), DataField("nn", "BIGINT", False)))
+    with pytest.raises(N.UnsupportedOnDevice):
+        read_section(KeyValueSchema.of(bad_vt, ["pk"]), [(open(p2, "rb").read(), 0)], 1)
+
+
+@pytest.mark.parametrize("engine", ["dedup", "dedup-ignore-delete", "first-row", "partial-update"])
+def test_section_with_more_than_32_sorted_runs(tmp_path, engine):
+    """70 overlapping files = 70 sorted runs in one section (MergeSorter.java:112-198 merges any number at once):
+    merged in rounds of 32 on the device where that is exact (deduplicate, first-row), refused for merge functions
+    that fold all records of a key in sequence order."""
+    from paimon_b200.merge_function import FirstRowMergeFunction
+    from paimon_b200.merge_tree_readers import DataFileMeta, MergeFileSplitRead, concat_batches
+    schema = datagen.schema_c3(n_i64=2, n_f64=1, n_str=1)
+    rng = np.random.default_rng(12)
+    metas, file_runs = [], []
+    for i in range(70):
+        keys = np.sort(rng.choice(20000, size=1500, replace=False)).astype(np.int64)
+        run = datagen.make_run(schema, i, keys, seed=8, null_prob=0.3, delete_prob=0.0 if engine == "first-row" else 0.1)
+        path = str(tmp_path / f"o{i}.parquet")
+        write_kv_parquet(run, path)
+        metas.append(DataFileMeta(path, 0, run.n_rows, int(keys[0]), int(keys[-1])))
+        file_runs.append(run)
+    factory = {"dedup": DeduplicateMergeFunction.factory(),
+               "dedup-ignore-delete": DeduplicateMergeFunction.factory({"ignore-delete": "true"}),
+               "first-row": FirstRowMergeFunction.factory({}),
+               "partial-update": PartialUpdateMergeFunction.factory({"ignore-delete": "true"}, schema.value_type, ["pk"])}[engine]
+    read = MergeFileSplitRead(schema, factory)
+    if engine == "partial-update":
+        with pytest.raises(N.UnsupportedOnDevice, match="32 sorted runs"):
+            read.create_merge_reader(metas).read_batch()
+        return
+    got = concat_batches(schema, _drain(read.create_merge_reader(metas)))
+    want = pyoracle.merge(schema, factory.create().with_drop_delete(True), file_runs)
     assert got.equals(want), got.first_difference(want)
