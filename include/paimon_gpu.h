@@ -329,6 +329,18 @@ pg_status pg_parquet_read_section(uint64_t schema, const pg_file_desc *files, in
                                   const char *const *column_names, const uint8_t *read_columns, uint64_t *out_runs,
                                   pg_section_info *info);
 
+/* The same for ORC data files ('file.format' = 'orc'; OrcReaderFactory.createReader, paimon-format/.../orc/
+ * OrcReaderFactory.java:98-163): every stripe of every file of a section, the files of a run concatenated.  Decoded:
+ * flat schemas, BOOLEAN / TINYINT / SMALLINT / INT / BIGINT / FLOAT / DOUBLE / DATE / DECIMAL(p <= 18) / STRING-family /
+ * BINARY, integer RLE v1 and v2, DIRECT and DICTIONARY string encodings, PRESENT streams, compression NONE / ZLIB /
+ * ZSTD; columns are resolved by field name (missing nullable fields -> NULL, integer / float widening).  Timestamps,
+ * DECIMAL(p > 18), nested types and the other codecs return PG_ERR_UNSUPPORTED.  The file bytes must be host memory
+ * (footers and compression-chunk headers are walked on the host); pg_section_info.n_chunks counts (stripe, column)
+ * tasks and n_data_pages counts streams. */
+pg_status pg_orc_read_section(uint64_t schema, const pg_file_desc *files, int32_t n_files, int32_t n_runs,
+                              const char *const *column_names, const uint8_t *read_columns, uint64_t *out_runs,
+                              pg_section_info *info);
+
 /* ApplyDeletionVectorReader (paimon-core/.../deletionvectors/ApplyDeletionVectorReader.java:31-54): a new run holding
  * the rows of `run` whose file position is NOT set in the deletion vector.  `deleted_bitmap` is host memory, LSB
  * first, bit i = row i of the file is deleted (the Java side expands its RoaringBitmap32; DeletionVector.java);

@@ -449,8 +449,8 @@ JNIEXPORT jlongArray JNICALL Java_org_apache_paimon_gpu_NativeMerge_parquetDescr
 
 // MergeTreeReaders.readerForSection: every file of a section (direct ByteBuffers filled by the Java FileIO) in one
 // batch of device launches; runOf[i] = sorted run of file i; returns one run handle per sorted run
-JNIEXPORT jlongArray JNICALL Java_org_apache_paimon_gpu_NativeMerge_parquetReadSection(
-    JNIEnv *env, jclass, jlong schema, jobjectArray fileBuffers, jlongArray sizes, jintArray runOf, jint nRuns,
+JNIEXPORT jlongArray JNICALL Java_org_apache_paimon_gpu_NativeMerge_readSection(
+    JNIEnv *env, jclass, jint format, jlong schema, jobjectArray fileBuffers, jlongArray sizes, jintArray runOf, jint nRuns,
     jobjectArray columnNames, jbooleanArray readColumns) {
     const jsize nf = env->GetArrayLength(fileBuffers);
     if (env->GetArrayLength(sizes) != nf || env->GetArrayLength(runOf) != nf) {
@@ -489,8 +489,12 @@ JNIEXPORT jlongArray JNICALL Java_org_apache_paimon_gpu_NativeMerge_parquetReadS
         rc8.assign(rcb.begin(), rcb.end());
     }
     pg_section_info info{};
-    pg_status rc = pg_parquet_read_section((uint64_t)schema, files.data(), nf, nRuns, columnNames ? names.data() : nullptr,
-                                           readColumns ? rc8.data() : nullptr, runs.data(), &info);
+    // 'file.format': 0 = parquet, 1 = orc (FileFormat.fromIdentifier picks the reader by the data file's suffix)
+    pg_status rc = format == 1
+        ? pg_orc_read_section((uint64_t)schema, files.data(), nf, nRuns, columnNames ? names.data() : nullptr,
+                              readColumns ? rc8.data() : nullptr, runs.data(), &info)
+        : pg_parquet_read_section((uint64_t)schema, files.data(), nf, nRuns, columnNames ? names.data() : nullptr,
+                                  readColumns ? rc8.data() : nullptr, runs.data(), &info);
     if (rc != PG_OK) { throw_for(env, rc); return nullptr; }
     std::vector<jlong> out(runs.begin(), runs.begin() + (nRuns > 0 ? nRuns : 0));
     jlongArray arr = env->NewLongArray((jsize)out.size());

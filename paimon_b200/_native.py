@@ -139,6 +139,9 @@ _SIGNATURES = {
     "pg_parquet_read_section": (C.c_int32, [C.c_uint64, C.POINTER(PgFileDesc), C.c_int32, C.c_int32,
                                             C.POINTER(C.c_char_p), C.c_void_p, C.POINTER(C.c_uint64),
                                             C.POINTER(PgSectionInfo)]),
+    "pg_orc_read_section": (C.c_int32, [C.c_uint64, C.POINTER(PgFileDesc), C.c_int32, C.c_int32,
+                                        C.POINTER(C.c_char_p), C.c_void_p, C.POINTER(C.c_uint64),
+                                        C.POINTER(PgSectionInfo)]),
     "pg_parquet_file_device_image": (C.c_int32, [C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "pg_run_apply_deletion_vector": (C.c_int32, [C.c_uint64, C.c_void_p, C.c_int64, C.POINTER(C.c_uint64)]),
     "pg_parquet_encode": (C.c_int32, [C.c_uint64, C.POINTER(C.c_char_p), C.c_int64, C.c_int64,

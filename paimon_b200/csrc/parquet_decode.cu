@@ -35,6 +35,7 @@
 
 #include "device_utils.cuh"
 #include "parquet_meta.h"
+#include "scan_kernels.cuh"
 #include "zstd_device.cuh"
 
 namespace pg {
@@ -696,8 +697,9 @@ __global__ void k_pq_levels(PqPage *pages, int n_pages, const PqPage *dicts, con
             if (vbytes < 4) bad = nnz > 0;
             else pq_hybrid_decode(vp + 4, end, 1, nnz, [&](int i, uint32_t v) { dst[i] = (int32_t)v; });
         } else if (ch.phys == pq::T_BYTE_ARRAY) {
-            payload = vbytes - 4 * (int64_t)nnz;
-            if (payload < 0) bad = true;
+            const int64_t pb = vbytes - 4 * (int64_t)nnz;
+            if (pb < 0) bad = true;
+            payload = lane == 0 ? pb : 0;                  // (summed over the lanes below)
         } else if (ch.phys == pq::T_BOOLEAN) {
             if (vbytes < ((int64_t)nnz + 7) / 8) bad = true;
         } else {
@@ -993,49 +995,6 @@ __global__ void k_pq_zero_first_offset(const PqOut *outs, int n) {
     if (i < n && outs[i].offsets) outs[i].offsets[0] = 0;
 }
 
-// ---- device-wide inclusive scan of int32 (three small kernels; used by the deletion-vector filter)
-__global__ void k_scan_block_sums(const int32_t *data, int64_t n, int64_t *block_sums) {
-    __shared__ int64_t sh[256];
-    int64_t b0 = (int64_t)blockIdx.x * 4096;
-    int64_t s = 0;
-    for (int i = threadIdx.x; i < 4096 && b0 + i < n; i += blockDim.x) s += data[b0 + i];
-    sh[threadIdx.x] = s;
-    __syncthreads();
-    for (int d = 128; d > 0; d >>= 1) { if (threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d]; __syncthreads(); }
-    if (threadIdx.x == 0) block_sums[blockIdx.x] = sh[0];
-}
-__global__ void __launch_bounds__(1024) k_scan_block_prefix(int64_t *block_sums, int64_t n_blocks, int32_t *err) {
-    // exclusive scan of the block sums by one CTA: every thread owns a contiguous slice
-    __shared__ int64_t part[1024];
-    const int64_t per = (n_blocks + blockDim.x - 1) / blockDim.x;
-    const int64_t b = threadIdx.x * per, e = min(b + per, n_blocks);
-    int64_t s = 0;
-    for (int64_t i = b; i < e; i++) s += block_sums[i];
-    part[threadIdx.x] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int64_t acc = 0;
-        for (int i = 0; i < (int)blockDim.x; i++) { const int64_t t = part[i]; part[i] = acc; acc += t; }
-        if (acc > 0x7fffffffLL) atomicCAS(err, KERR_NONE, KERR_OFFSET_OVERFLOW);
-    }
-    __syncthreads();
-    int64_t acc = part[threadIdx.x];
-    for (int64_t i = b; i < e; i++) { const int64_t t = block_sums[i]; block_sums[i] = acc; acc += t; }
-}
-__global__ void __launch_bounds__(256) k_scan_apply(int32_t *data, int64_t n, const int64_t *block_sums) {
-    __shared__ int ws[34];
-    int64_t b0 = (int64_t)blockIdx.x * 4096;
-    int carry = (int)block_sums[blockIdx.x];
-    for (int base = 0; base < 4096; base += 256) {
-        int64_t i = b0 + base + threadIdx.x;
-        int v = i < n ? data[i] : 0;
-        int tot = 0;
-        int ex = block_scan_excl(v, ws, &tot);
-        if (i < n) data[i] = carry + ex + v;
-        carry += tot;
-    }
-}
-
 // ------------------------------------------------------------------ host side
 
 Schema *schema_from_handle(uint64_t h);                 // api.cu
@@ -1148,6 +1107,14 @@ static pg_status kernel_error_status(int code) {
     }
 }
 
+static pg_status oom(const char *what, size_t bytes) {
+    size_t fr = 0, tot = 0;
+    cudaMemGetInfo(&fr, &tot);
+    cudaGetLastError();
+    return fail(PG_ERR_CUDA, std::string("parquet: out of device memory for ") + what + " (" + std::to_string(bytes >> 20) +
+                                 " MiB wanted, " + std::to_string(fr >> 20) + " of " + std::to_string(tot >> 20) + " MiB free)");
+}
+
 struct SectionFile {
     const uint8_t *bytes;
     int64_t size;
@@ -1201,7 +1168,7 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
         if (sf.mem == PG_MEM_DEVICE) d_file[f] = sf.bytes;
         else {
             uint8_t *d = (uint8_t *)scratch.take((size_t)sf.size + 64);
-            if (!d) return fail(PG_ERR_CUDA, "parquet: out of device memory");
+            if (!d) return oom("a file image", (size_t)sf.size);
             PG_CUDA(cudaMemcpyAsync(d, sf.bytes, (size_t)sf.size, cudaMemcpyHostToDevice, sm));
             d_file[f] = d;
             h2d += sf.size;
@@ -1296,8 +1263,9 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
                 for (const pq::RowGroup &g : m.row_groups) {
                     const pq::ColumnChunk &cc = g.columns[fc];
                     const int64_t start = cc.start();
-                    if (start < 4 || start >= files[f].size) return fail(PG_ERR_FORMAT, "parquet: page offset out of range");
                     if (cc.num_values != g.num_rows) return fail(PG_ERR_FORMAT, "parquet: page row counts do not add up");
+                    if (cc.num_values == 0) continue;            // an empty row group has no pages (and no valid offsets)
+                    if (start < 4 || start >= files[f].size) return fail(PG_ERR_FORMAT, "parquet: page offset out of range");
                     PqChunk ch;
                     memset(&ch, 0, sizeof(ch));
                     ch.base = d_file[f] + start;
@@ -1364,7 +1332,7 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
         }
         size_t got = 0;
         unsigned char *base = (unsigned char *)device_buffer_take(total + 256, &got);
-        if (!base) return fail(PG_ERR_CUDA, "parquet: out of device memory");
+        if (!base) return oom("the columns of a run", total);
         run->owned.push_back(base);
         run->owned_bytes.push_back(got);
         if (vbytes) PG_CUDA(cudaMemsetAsync(base, 0, vbytes, sm));
@@ -1392,7 +1360,7 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
     const size_t tb_pairs = pad(sizeof(PqPair) * (size_t)std::max(n_pairs, 1));
     const size_t tb_tot = pad(sizeof(int64_t) * (size_t)(8 + n_pairs));
     unsigned char *tb = (unsigned char *)scratch.take(tb_chunks + tb_outs + tb_pairs + tb_tot + 256);
-    if (!tb) return fail(PG_ERR_CUDA, "parquet: out of device memory");
+    if (!tb) return oom("the chunk tables", tb_chunks + tb_outs + tb_pairs + tb_tot);
     PqChunk *d_chunks = (PqChunk *)tb;
     PqOut *d_outs = (PqOut *)(tb + tb_chunks);
     PqPair *d_pairs = (PqPair *)(tb + tb_chunks + tb_outs);
@@ -1432,7 +1400,7 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
     }
     const size_t sb_zs = pad((size_t)zs_ctas * kZsWarps * (size_t)(zs::kMaxBlock + 64));
     unsigned char *sbuf = (unsigned char *)scratch.take(sb_pages + sb_dicts + sb_sc + 2 * sb_de + sb_ids + sb_vs + sb_zs + 256);
-    if (!sbuf) return fail(PG_ERR_CUDA, "parquet: out of device memory");
+    if (!sbuf) return oom("the page table and scratch", sb_pages + sb_dicts + sb_sc + 2 * sb_de + sb_ids + sb_vs + sb_zs);
     PqPage *d_pages = (PqPage *)sbuf;
     PqPage *d_dicts = (PqPage *)(sbuf + sb_pages);
     uint8_t *d_sc = sbuf + sb_pages + sb_dicts;
@@ -1485,7 +1453,7 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
             for (const PqPair &pr : pairs) if (pr.run == r) sum += pad((size_t)pair_tot[pr.idx] + 64);
             size_t got = 0;
             unsigned char *pl = (unsigned char *)device_buffer_take(sum, &got);
-            if (!pl) return fail(PG_ERR_CUDA, "parquet: out of device memory");
+            if (!pl) return oom("the var-len payload of a run", sum);
             runs[r]->owned.push_back(pl);
             runs[r]->owned_bytes.push_back(got);
             size_t pt = 0;

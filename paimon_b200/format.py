@@ -111,7 +111,7 @@ class ParquetFileRecordReader(FileRecordReader):
 
 
 def read_section(schema: KeyValueSchema, files, n_runs: int, device: int = 0, check_names: bool = True,
-                 read_value_fields=None):
+                 read_value_fields=None, file_format: str = "parquet"):
     """Decode every data file of a section with ONE batch of device launches (pg_parquet_read_section) and return
     (one SortedRunReader per run, PgSectionInfo).  `files` = [(buffer, run index)], in key order inside a run; a
     buffer is bytes / a numpy uint8 array (host memory) or a (device pointer, size) tuple (bytes already in HBM).
@@ -141,8 +141,11 @@ def read_section(schema: KeyValueSchema, files, n_runs: int, device: int = 0, ch
         mask = np.array([1] * (schema.n_key + 2) + [1 if b else 0 for b in read_value_fields], np.uint8)
         keep.append(mask)
     try:
-        N.check(lib.pg_parquet_read_section(sh.handle, descs, len(files), n_runs, names,
-                                            None if mask is None else mask.ctypes.data, runs, C.byref(info)))
+        fn = {"parquet": lib.pg_parquet_read_section, "orc": lib.pg_orc_read_section}.get(file_format.lower())
+        if fn is None:
+            raise N.UnsupportedOnDevice(2, f"file format '{file_format}' is not decoded on device (parquet and orc are)")
+        N.check(fn(sh.handle, descs, len(files), n_runs, names, None if mask is None else mask.ctypes.data, runs,
+                   C.byref(info)))
     finally:
         sh.close()
     readers = []
@@ -179,8 +182,10 @@ class FileFormat:
     def from_identifier(identifier: str, device: int = 0) -> "FileFormat":
         if identifier.lower() == "parquet":
             return ParquetFileFormat(device)
-        raise N.UnsupportedOnDevice(2, f"file format '{identifier}' is not decoded on device (parquet only; "
-                                       f"ORC is a later row of SURVEY §8f)")
+        if identifier.lower() == "orc":
+            return OrcFileFormat(device)
+        raise N.UnsupportedOnDevice(2, f"file format '{identifier}' is not decoded on device (parquet and orc are; "
+                                       f"avro data files stay on the Java side)")
 
     def create_reader_factory(self, data_schema: KeyValueSchema, projected=None, filters=None) -> FormatReaderFactory:
         raise NotImplementedError
@@ -198,3 +203,67 @@ class ParquetFileFormat(FileFormat):
         if projected is not None and projected != data_schema:
             raise N.UnsupportedOnDevice(2, "projection push-down is not applied on the merge path")
         return ParquetReaderFactory(data_schema, self.device)
+
+
+class OrcFileRecordReader(FileRecordReader):
+    """One ORC KeyValue data file, decoded on the device (pg_orc_read_section over a section of one file)."""
+
+    def __init__(self, schema: KeyValueSchema, file_bytes: bytes, device: int = 0):
+        self.schema = schema
+        self.device = device
+        self._bytes = file_bytes
+        self._reader: Optional[SortedRunReader] = None
+        self._info = None
+        self._done = False
+
+    def _decode(self) -> SortedRunReader:
+        if self._reader is None:
+            readers, self._info = read_section(self.schema, [(self._bytes, 0)], 1, self.device, file_format="orc")
+            self._reader = readers[0]
+        return self._reader
+
+    def info(self):
+        self._decode()
+        return self._info
+
+    def read_batch(self) -> Optional[KeyValueBatch]:
+        if self._done:
+            return None
+        self._done = True
+        batch = self._decode().read_batch()
+        return batch if batch is not None and batch.n_rows > 0 else None
+
+    def as_sorted_run_reader(self) -> SortedRunReader:
+        r = self._decode()
+        self._reader = None
+        return r
+
+    def close(self) -> None:
+        if self._reader is not None:
+            self._reader.close()
+            self._reader = None
+
+
+class OrcReaderFactory(FormatReaderFactory):
+    """OrcReaderFactory.createReader (paimon-format/.../orc/OrcReaderFactory.java:98-163)."""
+
+    def __init__(self, data_schema: KeyValueSchema, device: int = 0):
+        self.data_schema = data_schema
+        self.device = device
+
+    def create_reader(self, context: FormatReaderContext) -> OrcFileRecordReader:
+        if context.selection is not None:
+            raise N.UnsupportedOnDevice(2, "RoaringBitmap32 row selections are not pushed into the device decoder")
+        return OrcFileRecordReader(self.data_schema, context.file_io.read_bytes(context.file_path), self.device)
+
+
+class OrcFileFormat(FileFormat):
+    identifier = "orc"
+
+    def __init__(self, device: int = 0):
+        self.device = device
+
+    def create_reader_factory(self, data_schema: KeyValueSchema, projected=None, filters=None) -> OrcReaderFactory:
+        if projected is not None and projected != data_schema:
+            raise N.UnsupportedOnDevice(2, "pass the read-type projection to MergeFileSplitRead.with_read_type")
+        return OrcReaderFactory(data_schema, self.device)

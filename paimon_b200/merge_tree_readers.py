@@ -206,8 +206,11 @@ class MergeTreeReaders:
                 metas.append(m)
                 run_of.append(r)
         blobs = MergeTreeReaders._read_files(metas, reader_factory)
+        formats = {m.file_name.rsplit(".", 1)[-1].lower() for m in metas} or {"parquet"}
+        if len(formats) > 1:
+            raise N.UnsupportedOnDevice(2, f"a section mixes file formats {sorted(formats)}: decoded per format on the Java side")
         readers, _ = read_section(reader_factory.schema, list(zip(blobs, run_of)), len(section), reader_factory.device,
-                                  read_value_fields=read_value_fields)
+                                  read_value_fields=read_value_fields, file_format=formats.pop())
         if reader_factory.dv_factory is not None:
             from .sort_merge_reader import apply_deletion_vector
             row0 = [0] * len(section)
