@@ -12,8 +12,16 @@ LIB := paimon_b200/libpaimon_gpu.so
 
 all: $(LIB) oracle
 
-$(LIB): $(SRCS) $(HDRS)
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRCS)
+# one object per source (build/ is scratch), linked into the shared library
+OBJDIR ?= build
+OBJS := $(patsubst paimon_b200/csrc/%,$(OBJDIR)/%.o,$(SRCS))
+
+$(OBJDIR)/%.o: paimon_b200/csrc/% $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) $(EXTRA_DEFS) -x cu -c -o $@ $<
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS)
 
 ptxas-info: $(SRCS) $(HDRS)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c -o /dev/null paimon_b200/csrc/merge.cu
@@ -26,7 +34,7 @@ oracle:
 	$(MAKE) -C oracle -s
 
 clean:
-	rm -f $(LIB)
+	rm -rf $(LIB) $(OBJDIR)
 	$(MAKE) -C oracle clean
 
 .PHONY: all oracle clean ptxas-info jni-check

@@ -269,8 +269,8 @@ pg_status pg_thread_stream(void **out_cuda_stream);
  * 113-148, reader/VectorizedParquetRecordReader.java:178-241) for KeyValue data files: the file bytes (read by the
  * Java FileIO) are parsed on the host for footer + page headers and decoded on the device straight into the
  * columnar run the merge consumes.  Decoded: flat schemas, BOOLEAN/INT32/INT64/FLOAT/DOUBLE/BYTE_ARRAY, PLAIN and
- * dictionary encodings, RLE booleans, DELTA_BINARY_PACKED integers, data pages V1/V2, uncompressed and
- * Snappy-compressed pages (decompressed on the device); anything else (gzip, lz4, byte-array DELTA encodings,
+ * dictionary encodings, RLE booleans, DELTA_BINARY_PACKED integers, data pages V1/V2, uncompressed, Snappy-, zstd- and
+ * gzip-compressed pages (decompressed on the device); anything else (lz4, brotli, byte-array DELTA encodings,
  * INT96 / FIXED_LEN_BYTE_ARRAY, nested columns) returns PG_ERR_UNSUPPORTED.  pg_parquet_open walks the page headers
  * on the host once so that such files are refused before any device work. */
 typedef struct {

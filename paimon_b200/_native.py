@@ -12,7 +12,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpaimon_gpu.so")
+# PAIMON_GPU_LIB: another build of the same library (kernel A/B experiments; profiles/README.md)
+LIB_PATH = os.environ.get("PAIMON_GPU_LIB") or os.path.join(_HERE, "libpaimon_gpu.so")
 
 PG_MEM_HOST, PG_MEM_DEVICE = 0, 1
 

@@ -759,6 +759,7 @@ static pg_status execute(Merge *m) {
     ea.cols = m->d_cols;
     ea.col_order = m->d_col_order;
     ea.n_passes = m->n_passes;
+    ea.single_winner = (m->flags.engine == PG_ENGINE_DEDUPLICATE || m->flags.engine == PG_ENGINE_FIRST_ROW) ? 1 : 0;
     ea.varlen_cols = m->d_varlen_cols;
     ea.vsrc = vsrc;
     ea.vsrc_stride = n_out + 64;

@@ -284,6 +284,7 @@ struct TileView {
     const uint8_t *gcnt;
     const uint32_t *aebits;
     int n;                       // merged positions (input rows) of the tile
+    int single;                  // deduplicate / first-row: glast[] = the group's ONE eligible member
     int n_out;
     int o_shift;
     int64_t out_base;
@@ -296,14 +297,24 @@ __device__ __forceinline__ int64_t result_index(const TileView &tv, int ob) {
     return tv.in_base + ob + (ob >= tv.n_out_a ? tv.seq_shift : 0);
 }
 
-// Select for 32 consecutive output rows at once (one per lane; `active` lanes hold a row).  The members of these rows
-// are a contiguous range of merged positions: the warp ballots the staged validity of every position in the range,
-// ANDs it with the tile's eligibility bitmap (members that may provide the value: op != NOOP and not older than the
-// group's newest SET member), and each lane takes the highest set bit inside its group's window: the newest
-// eligible member with a non-null cell (PartialUpdateMergeFunction.updateNonNullFields :177-188; for deduplicate /
-// first-row the bitmap holds the single winner).  Returns the merged position of the winner or -1 (NULL).
+// Select for 32 consecutive output rows at once (one per lane; `active` lanes hold a row): the newest eligible member
+// with a non-null cell (PartialUpdateMergeFunction.updateNonNullFields :177-188; deduplicate / first-row have ONE
+// eligible member per group, found in the prologue: tv.single).  Returns the winner's merged position or -1 (NULL).
 // Must be called by all 32 lanes.
+//   default: newest-first walk over the group's members — UPD members with a NULL cell are skipped, a SET member ends
+//     the walk.  Short (the newest member usually has the value) and measured faster than the variant below.
+//   -DPG_EMIT_BITMAP_SELECT: the warp ballots the staged validity of every merged position its 32 rows span, ANDs it
+//     with the tile's eligibility bitmap and every lane takes the highest set bit of its group's window.  No
+//     divergence, but ~3 ballot rounds per 32 rows cost more than the walks they replace (profiles/README.md).
+template <bool GAGG>
 __device__ __forceinline__ int select_idx_warp(const TileView &tv, const uint32_t *vw, bool active, int last, int cnt) {
+    if (tv.single) {
+        // glast[] holds the group's only eligible member (or a member without an op: no value)
+        if (!active) return -1;
+        const uint32_t e = tv.pm[last];
+        return (((e >> kPmOpShift) & 3) != OP_NOOP && staged_valid(vw, e & kPmPosMask)) ? last : -1;
+    }
+#ifdef PG_EMIT_BITMAP_SELECT
     const int lane = threadIdx.x & 31;
     const unsigned act = __ballot_sync(0xffffffffu, active);
     if (act == 0) return -1;
@@ -324,6 +335,23 @@ __device__ __forceinline__ int select_idx_warp(const TileView &tv, const uint32_
     if (cnt < 32) win &= (1u << cnt) - 1;
     if (!active || win == 0) return -1;
     return first + 31 - __clz(win);
+#else
+    if (!active) return -1;
+    int j = last;
+    while (true) {
+        const uint32_t e = tv.pm[j];
+        uint32_t op = (e >> kPmOpShift) & 3;
+        // (only with aggregates inside sequence groups does the plan mark retracts on a partial-update merge) a
+        // RETRACT member leaves select columns alone, unless it is the group's first record (initRow: verbatim)
+        if (GAGG && op == OP_RETRACT) op = (e & kPmHead) ? OP_SET : OP_NOOP;
+        if (op != OP_NOOP) {
+            if (staged_valid(vw, e & kPmPosMask)) return j;
+            if (op == OP_SET) return -1;
+        }
+        if (e & kPmHead) return -1;
+        --j;
+    }
+#endif
 }
 
 // one output validity word per warp iteration: interior words are plain stores, tile-boundary words OR
@@ -350,7 +378,7 @@ __device__ __forceinline__ void emit_fixed_column(const EmitArgs &ea, const ColD
         uint64_t val = 0;
         const int last = active ? tv.glast[ob] : 0;
         if (cd.mode == CM_SELECT) {
-            const int j = select_idx_warp(tv, vw, active, last, active ? tv.gcnt[ob] : 1);
+            const int j = select_idx_warp<GAGG>(tv, vw, active, last, active ? tv.gcnt[ob] : 1);
             if (j >= 0) { val = lds_fixed<W>(vals, tv.pm[j] & kPmPosMask); is_valid = true; }
         } else if (active) {
             if (cd.mode == CM_GVAL || cd.mode == CM_GSEQ) {
@@ -392,6 +420,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+#ifdef PG_EMIT_TIMING
+// per-pass cycle stamps of a few tiles in the middle of the grid (experiments; profiles/README.md):
+// slot 0 = kernel entry, 1 = prologue done, then per pipelined pass u: 2+3u = top, 3+3u = stage full, 4+3u = pass done
+constexpr int kTsTiles = 64, kTsSlots = 256;
+__device__ long long g_emit_ts[2 * kTsTiles * kTsSlots];
+#define TS(slot) do { if (ts_on && lane == 0 && (slot) < kTsSlots) g_emit_ts[(ts_w * kTsTiles + ts_tile) * kTsSlots + (slot)] = clock64(); } while (0)
+#else
+#define TS(slot) do { } while (0)
+#endif
+
 // GAGG: the merge has aggregate functions inside sequence groups (the fold for them is compiled into its own
 // kernel variant: inlined into the common one it costs every workload registers and spills)
 template <bool GAGG>
@@ -432,32 +470,39 @@ k_emit(EmitArgs ea) {
     // ---- tile ticket (tiles are started in order => look-back never waits on an unscheduled tile)
     if (tid == 0) {
         s_i32[0] = atomicAdd(ea.tile_counter, 1);
-        for (int s = 0; s < kStages; s++) { mbar_init(&mbar_full[s], 2); mbar_init(&mbar_empty[s], kEmitWarps); }
+        for (int s = 0; s < kStages; s++) { mbar_init(&mbar_full[s], 1 + kEmitWarps); mbar_init(&mbar_empty[s], kEmitWarps); }
         mbar_fence_init();
     }
     for (int i = tid; i < kTileMax / 32; i += kEmitThreads) aebits[i] = 0;
     for (int i = tid; i < nv; i += kEmitThreads) { s_tot[i] = 0; s_cnt[i] = 0; }
     __syncthreads();
     const int tile = s_i32[0];
+#ifdef PG_EMIT_TIMING
+    const int ts_tile = tile - ea.n_tiles / 2;
+    const bool ts_on = ts_tile >= 0 && ts_tile < kTsTiles && (warp == 0 || warp == kEmitWarps - 1);
+    const int ts_w = warp == 0 ? 0 : 1;
+#endif
+    TS(0);
     // an emit tile is two consecutive plan tiles (the last one may be single)
     const int plan_a = 2 * tile, plan_end = min(plan_a + 2, ea.n_plan_tiles);
-    if (tid == 0) {
-        int acc = 0, racc = 0, acc_a = 0;
-        for (int r = 0; r < k; r++) {
-            int64_t b0 = ea.bounds[(int64_t)plan_a * k + r], bm = ea.bounds[(int64_t)(plan_a + 1) * k + r],
-                    b1 = ea.bounds[(int64_t)plan_end * k + r];
-            rstart[r] = b0;
-            seg[r] = acc;
-            seg_a[r] = acc_a;
-            rr[r] = racc;
-            int len = (int)(b1 - b0);
-            acc += len;
-            acc_a += (int)(bm - b0);
-            racc += (((int)(b0 & 31) + len + 1) + 31) & ~31;
+    if (warp == 0) {
+        // lane r = run r (its three bounds in flight together); slot / staged-row bases by warp scans
+        int64_t b0 = 0, bm = 0, b1 = 0;
+        if (lane < k) {
+            b0 = ea.bounds[(int64_t)plan_a * k + lane];
+            bm = ea.bounds[(int64_t)(plan_a + 1) * k + lane];
+            b1 = ea.bounds[(int64_t)plan_end * k + lane];
         }
-        seg[k] = acc;
-        seg_a[k] = acc_a;
-        rr[k] = racc;
+        const int len = (int)(b1 - b0), len_a = (int)(bm - b0);
+        const int rlen = lane < k ? (((int)(b0 & 31) + len + 1) + 31) & ~31 : 0;
+        const int i_len = warp_scan_incl(len), i_a = warp_scan_incl(len_a), i_r = warp_scan_incl(rlen);
+        if (lane < k) {
+            rstart[lane] = b0;
+            seg[lane] = i_len - len;
+            seg_a[lane] = i_a - len_a;
+            rr[lane] = i_r - rlen;
+        }
+        if (lane == 31) { seg[k] = i_len; seg_a[k] = i_a; rr[k] = i_r; }
     }
     __syncthreads();
     const int n = seg[k];
@@ -470,6 +515,7 @@ k_emit(EmitArgs ea) {
     const int p0 = tid * VT, p1 = min(p0 + VT, n);
     int my = 0;
     uint32_t emit_bits = 0;
+    const bool single = ea.single_winner != 0;
     // slot -> (staged position, run) tables, built per run segment (no searches); they live in memory that
     // is not in use yet (glast, stage 1)
     uint16_t *spos = glast;
@@ -509,12 +555,17 @@ k_emit(EmitArgs ea) {
         if (emit_bits & (1u << (i - p0))) {
             int e = i + 1;
             while (e < n && !(pm[e] & kPmHead)) e++;
-            glast[o] = (uint16_t)(e - 1);
+            int gl = e - 1;
+            if (single) {
+                // deduplicate / first-row: exactly one member of an emitted group has an op (its cells are the row)
+                for (int j = e - 1; j >= i; j--)
+                    if (((pm[j] >> kPmOpShift) & 3) != OP_NOOP) { gl = j; break; }
+            }
+            glast[o] = (uint16_t)gl;
             gcnt[o] = (uint8_t)(e - i);
             o++;
-            // eligibility: newest first, every member with an op until (and including) the newest SET.
-            // (only with aggregates inside sequence groups does the plan mark retracts on a partial-update merge: a
-            // RETRACT member leaves select columns alone, unless it is the group's first record — initRow: verbatim)
+#ifdef PG_EMIT_BITMAP_SELECT
+            // eligibility: newest first, every member with an op until (and including) the newest SET
             for (int j = e - 1; j >= i; j--) {
                 uint32_t ej = pm[j];
                 uint32_t op = (ej >> kPmOpShift) & 3;
@@ -522,6 +573,7 @@ k_emit(EmitArgs ea) {
                 if (op != OP_NOOP) atomicOr(&aebits[j >> 5], 1u << (j & 31));
                 if (op == OP_SET) break;
             }
+#endif
         }
     }
     __syncthreads();
@@ -532,6 +584,7 @@ k_emit(EmitArgs ea) {
     tv.gcnt = gcnt;
     tv.aebits = aebits;
     tv.n = n;
+    tv.single = single;
     tv.n_out = n_out;
     tv.out_base = ea.row_base[plan_a];
     tv.o_shift = (int)(tv.out_base & 31);
@@ -539,7 +592,7 @@ k_emit(EmitArgs ea) {
     tv.n_out_a = ea.tile_rows[plan_a];
     tv.seq_shift = n_a - tv.n_out_a;
 
-    // issue the bulk copies of column c into stage s and bring its validity words (warp 0; lane r = run r)
+    // issue the bulk copies of column c into stage s (warp 0; lane r = run r)
     auto issue = [&](int c, int s) {
         const ColDesc cd = ea.cols[c];
         // the stage was last touched through the generic proxy (scratch + validity words)
@@ -573,43 +626,38 @@ k_emit(EmitArgs ea) {
         if (lane == 0) mbar_arrive_expect_tx(&mbar_full[s], total);
         __syncwarp();
         if (bytes) bulk_g2s(dst, src, bytes, &mbar_full[s]);
-        // validity words of the column: global -> registers -> shared (all loads in flight before the stores)
-        uint32_t *dvw = stage_vw[s];
-        for (int j0 = 0; j0 < n_vw; j0 += 128) {
-            uint32_t x[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int j = j0 + q * 32 + lane;
-                x[q] = 0xffffffffu;
-                if (j < n_vw) {
-                    const int g = vwg[j];
-                    if (g >= 0) {
-                        const uint32_t *vp = ea.ptrs.validity[(int64_t)c * k + (g & 31)];
-                        if (vp) x[q] = vp[g >> 5];
-                    }
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int j = j0 + q * 32 + lane;
-                if (j < n_vw) dvw[j] = x[q];
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&mbar_full[s]);           // second arrival: validity words + payload bases are in place
     };
 
     const int n_pass = ea.n_passes;
-    // ---- passes without staged data first (sequence number, kind): they do not take part in the pipeline
+    // passes without staged data (sequence number, kind) come first in the list and do not take part in the pipeline
     int pp = 0;
-    for (; pp < n_pass; pp++) {
-        const int ent = ea.col_order[pp];
-        if ((ent >> 16) != PH_PLAIN) break;
-        const int c = ent & 0xffff;
+    while (pp < n_pass && (ea.col_order[pp] >> 16) == PH_PLAIN) pp++;
+    const int pbase = pp;                              // first pipelined pass
+    // validity words of a column: every thread brings (at most) one staged word, global -> register -> shared.  The
+    // load for pass pp + 1 is issued at the top of pass pp and stored at its end, so its latency hides behind the pass.
+    const int my_vwg = tid < n_vw ? vwg[tid] : -1;
+    auto load_vw = [&](int c) -> uint32_t {
+        uint32_t x = 0xffffffffu;
+        if (my_vwg >= 0) {
+            const uint32_t *vp = ea.ptrs.validity[(int64_t)c * k + (my_vwg & 31)];
+            if (vp) x = __ldg(vp + (my_vwg >> 5));
+        }
+        return x;
+    };
+    const bool vw_warp = warp == 0 || warp * 32 < n_vw;   // this warp stores validity words (warp 0: always, it issues)
+    if (pbase < n_pass) {
+        // the first staged column is in flight while the unstaged passes run
+        const int c0 = ea.col_order[pbase] & 0xffff;
+        if (warp == 0) issue(c0, 0);
+        const uint32_t x = load_vw(c0);
+        if (tid < n_vw) stage_vw[0][tid] = x;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&mbar_full[0]);
+    }
+    for (int q = 0; q < pbase; q++) {
+        const int c = ea.col_order[q] & 0xffff;
         emit_fixed_dispatch<GAGG>(ea, ea.cols[c], ea.out_cols[c], tv, nullptr, nullptr);
     }
-    const int pbase = pp;                              // first pipelined pass
-    if (warp == 0 && pbase < n_pass) issue(ea.col_order[pbase] & 0xffff, 0);
 
     // rows of a var-len column are dealt to warps in contiguous chunks of RW rows (RW a multiple of 32, aligned to
     // the output's 32-row validity words): offsets come from warp-level scans
@@ -617,17 +665,27 @@ k_emit(EmitArgs ea) {
     const int RW = (((span + kEmitWarps - 1) / kEmitWarps) + 31) & ~31;
     const int wbeg = -tv.o_shift + warp * RW;
 
+    TS(1);
     for (pp = pbase; pp < n_pass; pp++) {
         const int u = pp - pbase;                      // pipelined pass number: stage u & 1, use u >> 1 of that stage
+        TS(2 + 3 * u);
         const int s = u & 1;
         const int ent = ea.col_order[pp];
         const int c = ent & 0xffff, phase = ent >> 16;
         const ColDesc cd = ea.cols[c];
         const pg_out_column oc = ea.out_cols[c];
-        if (warp == 0 && pp + 1 < n_pass) {
-            // refill the other stage for the next pass, once every warp has released its previous use
-            if (u >= 1) mbar_wait(&mbar_empty[s ^ 1], (uint32_t)(((u - 1) >> 1) & 1));
-            issue(ea.col_order[pp + 1] & 0xffff, s ^ 1);
+        const bool more = pp + 1 < n_pass;
+        uint32_t next_vw = 0;
+        if (more) {
+            const int cn = ea.col_order[pp + 1] & 0xffff;
+            next_vw = load_vw(cn);
+            if (warp == 0) {
+                // refill the other stage for the next pass, once every warp has released its previous use
+                if (u >= 1) mbar_wait(&mbar_empty[s ^ 1], (uint32_t)(((u - 1) >> 1) & 1));
+                issue(cn, s ^ 1);
+            } else if (!vw_warp && lane == 0) {
+                mbar_arrive(&mbar_full[s ^ 1]);        // nothing to store: arrive right away
+            }
         }
         if (phase == PH_COPY && (ea.col_order[pp - 1] >> 16) != PH_COPY) {
             // ---- every var-len column's byte base: decoupled look-back over earlier tiles, one warp per column.
@@ -686,6 +744,7 @@ k_emit(EmitArgs ea) {
             __syncthreads();
         }
         mbar_wait(&mbar_full[s], (uint32_t)((u >> 1) & 1));
+        TS(3 + 3 * u);
         const unsigned char *vals = stage_vals[s];
         const uint32_t *vw = stage_vw[s];
 
@@ -704,7 +763,7 @@ k_emit(EmitArgs ea) {
                 const bool active = ob >= 0 && ob < n_out;
                 const int last = active ? glast[ob] : 0;
                 int src = -1;
-                if (cd.mode == CM_SELECT) src = select_idx_warp(tv, vw, active, last, active ? gcnt[ob] : 1);
+                if (cd.mode == CM_SELECT) src = select_idx_warp<GAGG>(tv, vw, active, last, active ? gcnt[ob] : 1);
                 else if (active) {
                     if (cd.mode == CM_KEY) src = last;
                     else if (cd.mode == CM_FOLD) src = fold_member_idx(cd, pm, mrun, vw, offs, cd_data, last, ea.err);
@@ -810,10 +869,59 @@ k_emit(EmitArgs ea) {
             }
         }
         // release the stage: this warp is done with its rows of the pass
+        TS(4 + 3 * u);
         __syncwarp();
         if (lane == 0) mbar_arrive(&mbar_empty[s]);
+        if (more && vw_warp) {
+            // the next pass's validity words go into the other stage once its previous use (pass pp - 1) is released
+            if (u >= 1 && warp != 0) mbar_wait(&mbar_empty[s ^ 1], (uint32_t)(((u - 1) >> 1) & 1));
+            if (tid < n_vw) stage_vw[s ^ 1][tid] = next_vw;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&mbar_full[s ^ 1]);
+        }
     }
 }
+
+#ifdef PG_EMIT_TIMING
+static void emit_timing_dump(const EmitArgs &ea) {
+    static long long h[2 * kTsTiles * kTsSlots];
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(h, g_emit_ts, sizeof(h));
+    std::vector<int32_t> order(ea.n_passes);
+    cudaMemcpy(order.data(), ea.col_order, 4 * (size_t)ea.n_passes, cudaMemcpyDeviceToHost);
+    int pbase = 0;
+    while (pbase < ea.n_passes && (order[pbase] >> 16) == PH_PLAIN) pbase++;
+    for (int w = 0; w < 2; w++) {
+        // per phase kind: wait for the stage, compute; plus the prologue and the whole tile
+        double wait[4] = {0}, comp[4] = {0}, gap[4] = {0}, pro = 0, whole = 0;
+        int cnt[4] = {0}, tiles = 0;
+        for (int t = 0; t < kTsTiles; t++) {
+            const long long *x = h + (size_t)(w * kTsTiles + t) * kTsSlots;
+            if (!x[0] || !x[1]) continue;
+            tiles++;
+            pro += (double)(x[1] - x[0]);
+            long long last = x[1];
+            for (int u = 0; pbase + u < ea.n_passes && 4 + 3 * u < kTsSlots; u++) {
+                const int ph = order[pbase + u] >> 16;
+                const long long a = x[2 + 3 * u], b = x[3 + 3 * u], c = x[4 + 3 * u];
+                if (!a || !b || !c) break;
+                wait[ph] += (double)(b - a); comp[ph] += (double)(c - b); gap[ph] += (double)(a - last); cnt[ph]++;
+                last = c;
+            }
+            whole += (double)(last - x[0]);
+        }
+        if (!tiles) continue;
+        fprintf(stderr, "[emit timing] warp %s, %d tiles: prologue %.0f, tile %.0f cycles;", w ? "15" : "0", tiles, pro / tiles, whole / tiles);
+        const char *nm[4] = {"plain", "size", "fixed", "copy"};
+        for (int ph = 1; ph < 4; ph++)
+            if (cnt[ph]) fprintf(stderr, " %s x%.1f: wait %.0f compute %.0f tail %.0f;", nm[ph], (double)cnt[ph] / tiles,
+                                 wait[ph] / cnt[ph], comp[ph] / cnt[ph], gap[ph] / cnt[ph]);
+        fprintf(stderr, "\n");
+    }
+    static long long z[2 * kTsTiles * kTsSlots];
+    cudaMemcpyToSymbol(g_emit_ts, z, sizeof(z));
+}
+#endif
 
 static bool g_emit_attr = false;
 void launch_emit(const EmitArgs &ea) {
@@ -825,6 +933,9 @@ void launch_emit(const EmitArgs &ea) {
     }
     if (ea.gagg) k_emit<true><<<ea.n_tiles, kEmitThreads, L.total, ea.stream>>>(ea);
     else k_emit<false><<<ea.n_tiles, kEmitThreads, L.total, ea.stream>>>(ea);
+#ifdef PG_EMIT_TIMING
+    emit_timing_dump(ea);
+#endif
 }
 
 }  // namespace pg

@@ -179,19 +179,25 @@ __device__ bool merge_tile(TileCtx &tc, int k, const KeyDesc &kd, const KeySrc &
                            int skip, bool refine) {
     const int tid = threadIdx.x;
     __shared__ int s_skip, s_len0;
-    if (tid == 0) {
-        int acc = 0;
-        for (int r = 0; r < k; r++) {
-            int64_t b0 = bounds[(int64_t)tile * k + r], b1 = bounds[(int64_t)(tile + 1) * k + r];
-            tc.rstart[r] = b0;
-            tc.seg[r] = acc;
-            tc.lb[0][r] = acc;
-            int64_t len = b1 - b0;
-            if (len < 0 || acc + len > kPlanTile) { len = 0; acc = kPlanTile + 1; }
-            else acc += (int)len;
+    if (tid < 32) {
+        // lane r = run r: both loads of every run in flight at once, slot bases by a warp scan
+        int64_t b0 = 0, b1 = 0;
+        if (tid < k) { b0 = bounds[(int64_t)tile * k + tid]; b1 = bounds[(int64_t)(tile + 1) * k + tid]; }
+        const int64_t len = b1 - b0;
+        const bool odd = len < 0 || len > kPlanTile;
+        const int l = odd ? 0 : (int)len;
+        const int incl = warp_scan_incl(l);
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const bool over = __any_sync(0xffffffffu, odd) || total > kPlanTile;
+        if (tid < k) {
+            tc.rstart[tid] = b0;
+            tc.seg[tid] = incl - l;
+            tc.lb[0][tid] = incl - l;
         }
-        tc.seg[k] = acc;
-        tc.lb[0][k] = acc;
+        if (tid == 0) {
+            tc.seg[k] = over ? kPlanTile + 1 : total;
+            tc.lb[0][k] = over ? kPlanTile + 1 : total;
+        }
     }
     __syncthreads();
     tc.n = tc.seg[k];
@@ -227,15 +233,28 @@ __device__ bool merge_tile(TileCtx &tc, int k, const KeyDesc &kd, const KeySrc &
         len0 = key_stream_len(ks, kd, ref_r, tc.rstart[ref_r]);
         if (len0 < 0 || len0 > skip + 8) odd_len = true;
     }
-    for (int r = 0; r < k; r++) {                    // coalesced per run segment
-        const int s0 = tc.seg[r], s1 = tc.seg[r + 1];
-        const int64_t j0 = tc.rstart[r] - s0;
-        const int64_t rb = row0 ? row0[r] : 0;           // (level 0 bounds are absolute rows already)
-        for (int i = s0 + tid; i < s1; i += blockDim.x) {
-            const int64_t row = rb + (j0 + i + 1) * stride - 1;
-            tc.key[0][PADI(i)] = load_key(ks, kd, r, row, skip);
-            tc.idx[0][PADI(i)] = (uint16_t)i;
-            if (!EXACT && refine && !odd_len && key_stream_len(ks, kd, r, row) != len0) odd_len = true;
+    {
+        // slots tid, tid + blockDim, ...: neighbours in a warp are neighbours in a run (coalesced), and all of a
+        // thread's loads are in flight before the first one is stored (a loop over the runs with the store inside
+        // serialises k memory latencies per tile)
+        constexpr int VTL = kPlanTile / kThreads;
+        uint64_t kv[VTL];
+#pragma unroll
+        for (int u = 0; u < VTL; u++) {
+            const int i = tid + u * kThreads;
+            kv[u] = 0;
+            if (i < n) {
+                const int r = run_of_slot(tc.seg, k, i);
+                const int64_t rb = row0 ? row0[r] : 0;       // (level 0 bounds are absolute rows already)
+                const int64_t row = rb + (tc.rstart[r] + (i - tc.seg[r]) + 1) * stride - 1;
+                kv[u] = load_key(ks, kd, r, row, skip);
+                if (!EXACT && refine && !odd_len && key_stream_len(ks, kd, r, row) != len0) odd_len = true;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < VTL; u++) {
+            const int i = tid + u * kThreads;
+            if (i < n) { tc.key[0][PADI(i)] = kv[u]; tc.idx[0][PADI(i)] = (uint16_t)i; }
         }
     }
     if (!EXACT && refine) tc.exact = !__syncthreads_or(odd_len);
@@ -491,14 +510,26 @@ k_plan(int k, KeyDesc kd, KeySrc ks, PlanArgs pa, int32_t *err) {
         return full_key_compare(ks, kd, ra, tc.rstart[ra] + (sa - tc.seg[ra]), rb, tc.rstart[rb] + (sb - tc.seg[rb])) == 0;
     };
 
-    // stage sequence numbers and kinds (coalesced per run segment)
-    for (int r = 0; r < k; r++) {
-        const int s0 = tc.seg[r], s1 = tc.seg[r + 1];
-        const int64_t *sq = pa.seq_ptrs[r] + (tc.rstart[r] - s0);
-        const int8_t *kd8 = pa.kind_ptrs[r] + (tc.rstart[r] - s0);
-        for (int s = s0 + tid; s < s1; s += blockDim.x) {
-            seq_s[s] = sq[s];
-            kind_s[s] = (uint8_t)kd8[s];
+    // stage sequence numbers and kinds (slot order: coalesced inside a run; all loads before the stores)
+    {
+        constexpr int VTL = kPlanTile / kThreads;
+        int64_t sq[VTL];
+        uint8_t kn[VTL];
+#pragma unroll
+        for (int u = 0; u < VTL; u++) {
+            const int sl = tid + u * kThreads;
+            sq[u] = 0; kn[u] = 0;
+            if (sl < n) {
+                const int r = run_of_slot(tc.seg, k, sl);
+                const int64_t row = tc.rstart[r] + (sl - tc.seg[r]);
+                sq[u] = pa.seq_ptrs[r][row];
+                kn[u] = (uint8_t)pa.kind_ptrs[r][row];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < VTL; u++) {
+            const int sl = tid + u * kThreads;
+            if (sl < n) { seq_s[sl] = sq[u]; kind_s[sl] = kn[u]; }
         }
     }
     __syncthreads();

@@ -36,6 +36,8 @@ struct OrcStream {
     const uint8_t *src;        // device: the stream as stored in the file
     uint8_t *dst;              // scratch image (compressed files)
     int64_t length, bound;
+    int32_t codec;             // orc::Compression of the stream's file (files of a section may differ)
+    int32_t block_size;        // compression block size of that file
     const uint8_t *bytes;      // result: contiguous decoded bytes
     int64_t n;
 };
@@ -46,8 +48,7 @@ struct OrcTaskRef {            // stream table indexes of a task (-1 = absent)
 
 constexpr int kOrcWarps = 4;
 __global__ void __launch_bounds__(kOrcWarps * 32)
-k_orc_inflate(OrcStream *streams, int n_streams, int codec, int64_t block_size, uint8_t *lit_scratch, int32_t *counter,
-              int32_t *err) {
+k_orc_inflate(OrcStream *streams, int n_streams, uint8_t *lit_scratch, int32_t *counter, int32_t *err) {
     __shared__ zs::Tables ZT[kOrcWarps];               // (the DEFLATE tables are smaller and overlay them)
     static_assert(sizeof(inflate::Tables) <= sizeof(zs::Tables), "tables overlay");
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -58,6 +59,8 @@ k_orc_inflate(OrcStream *streams, int n_streams, int codec, int64_t block_size, 
         j = __shfl_sync(0xffffffffu, j, 0);
         if (j >= n_streams) return;
         OrcStream st = streams[j];
+        const int codec = st.codec;
+        const int64_t block_size = st.block_size;
         if (codec == orc::C_NONE) {
             if (lane == 0) { streams[j].bytes = st.src; streams[j].n = st.length; }
             continue;
@@ -192,8 +195,7 @@ static pg_status orc_decode_section(const Schema *s, const pg_file_desc *files, 
     std::vector<const uint8_t *> d_file(nf, nullptr);
     std::vector<int64_t> run_rows(n_runs, 0), file_row0(nf, 0);
     int64_t file_bytes = 0, page_bytes = 0;
-    int codec = -1;
-    int64_t block_size = 0;
+    bool any_compressed = false, any_zstd = false;
     std::vector<uint8_t> col_missing((size_t)n_runs * nc, 0);
     std::vector<int> files_of_run(n_runs, 0);
     for (int f = 0; f < nf; f++) {
@@ -208,10 +210,9 @@ static pg_status orc_decode_section(const Schema *s, const pg_file_desc *files, 
             if (t.compression != orc::C_NONE && t.compression != orc::C_ZLIB && t.compression != orc::C_ZSTD)
                 return fail(PG_ERR_UNSUPPORTED, "orc: compression kind " + std::to_string(t.compression) +
                                                 " is not decoded on device (NONE, ZLIB and ZSTD are)");
-            if (codec >= 0 && (codec != t.compression || block_size != (int64_t)t.block_size))
-                return fail(PG_ERR_UNSUPPORTED, "orc: the files of a section use different compression settings");
-            codec = t.compression;
-            block_size = (int64_t)t.block_size;
+            if (t.compression != orc::C_NONE) any_compressed = true;
+            if (t.compression == orc::C_ZSTD) any_zstd = true;
+            if (t.block_size > (1u << 30)) return fail(PG_ERR_UNSUPPORTED, "orc: compression block size above 1 GiB");
             const orc::Type &root = t.types[0];
             std::unordered_map<std::string, int> by_name;
             for (size_t i = 0; i < root.field_names.size() && i < root.subtypes.size(); i++) by_name.emplace(root.field_names[i], (int)i);
@@ -239,7 +240,9 @@ static pg_status orc_decode_section(const Schema *s, const pg_file_desc *files, 
                 return fail(PG_ERR_UNSUPPORTED, "orc: the file's column count differs from the read schema (pass the field names)");
             plans[f] = orc::plan_file(t, files[f].bytes, files[f].size, file_col);
         } catch (const std::exception &e) {
-            return fail(PG_ERR_FORMAT, e.what());
+            // (a codec or type this decoder does not cover is a refusal, not a malformed file)
+            const bool refusal = strstr(e.what(), "is not decoded") != nullptr || strstr(e.what(), "not supported") != nullptr;
+            return fail(refusal ? PG_ERR_UNSUPPORTED : PG_ERR_FORMAT, e.what());
         }
         file_row0[f] = run_rows[files[f].run];
         run_rows[files[f].run] += (int64_t)tails[f].rows;
@@ -328,8 +331,8 @@ static pg_status orc_decode_section(const Schema *s, const pg_file_desc *files, 
     std::vector<int32_t> h_task_out;
     uint64_t sc_bytes = 0, dict_entries = 0;
     for (int f = 0; f < nf; f++) { sc_bytes += plans[f].scratch_bytes; dict_entries += plans[f].dict_entries; }
-    uint8_t *d_sc = codec == orc::C_NONE ? nullptr : (uint8_t *)scratch.take((size_t)sc_bytes + 256);
-    if (codec != orc::C_NONE && !d_sc) return fail(PG_ERR_CUDA, "orc: out of device memory");
+    uint8_t *d_sc = !any_compressed ? nullptr : (uint8_t *)scratch.take((size_t)sc_bytes + 256);
+    if (any_compressed && !d_sc) return fail(PG_ERR_CUDA, "orc: out of device memory");
     int32_t *d_dict_off = (int32_t *)scratch.take(4 * (size_t)(dict_entries + 1) + 256);
     if (!d_dict_off) return fail(PG_ERR_CUDA, "orc: out of device memory");
     uint64_t sc_base = 0, dict_base = 0;
@@ -340,6 +343,8 @@ static pg_status orc_decode_section(const Schema *s, const pg_file_desc *files, 
             st.src = d_file[f] + ps.offset;
             st.length = (int64_t)ps.length;
             st.bound = (int64_t)ps.out_bound;
+            st.codec = tails[f].compression;
+            st.block_size = (int32_t)tails[f].block_size;
             st.dst = d_sc ? d_sc + sc_base + ps.out_off : nullptr;
             h_streams.push_back(st);
             page_bytes += (int64_t)ps.length;
@@ -372,9 +377,9 @@ static pg_status orc_decode_section(const Schema *s, const pg_file_desc *files, 
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int inflate_ctas = codec == orc::C_NONE ? std::max(1, std::min(sms, (n_streams + kOrcWarps - 1) / kOrcWarps))
+    const int inflate_ctas = !any_compressed ? std::max(1, std::min(sms, (n_streams + kOrcWarps - 1) / kOrcWarps))
                                                   : std::max(1, std::min(sms * 4, (n_streams + kOrcWarps - 1) / kOrcWarps));
-    const size_t tb_lit = codec == orc::C_ZSTD ? pad((size_t)inflate_ctas * kOrcWarps * (size_t)(zs::kMaxBlock + 64)) : 256;
+    const size_t tb_lit = any_zstd ? pad((size_t)inflate_ctas * kOrcWarps * (size_t)(zs::kMaxBlock + 64)) : 256;
     unsigned char *tb = (unsigned char *)scratch.take(tb_s + tb_t + tb_r + tb_o + tb_p + tb_lit + 1024);
     if (!tb) return fail(PG_ERR_CUDA, "orc: out of device memory");
     OrcStream *d_streams = (OrcStream *)tb;
@@ -394,7 +399,7 @@ static pg_status orc_decode_section(const Schema *s, const pg_file_desc *files, 
         PG_CUDA(cudaMemcpyAsync(d_task_out, h_task_out.data(), 4 * (size_t)n_tasks, cudaMemcpyHostToDevice, sm));
     }
     if (n_streams) {
-        k_orc_inflate<<<inflate_ctas, kOrcWarps * 32, 0, sm>>>(d_streams, n_streams, codec, block_size, d_lit, d_counter, d_err);
+        k_orc_inflate<<<inflate_ctas, kOrcWarps * 32, 0, sm>>>(d_streams, n_streams, d_lit, d_counter, d_err);
         launches++;
     }
     if (n_tasks) {

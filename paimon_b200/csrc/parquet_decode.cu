@@ -35,6 +35,7 @@
 
 #include "device_utils.cuh"
 #include "parquet_meta.h"
+#include "inflate_device.cuh"
 #include "scan_kernels.cuh"
 #include "zstd_device.cuh"
 
@@ -413,18 +414,20 @@ __global__ void k_pq_snappy(const PqPage *pages, int n_pages, const PqPage *dict
     if ((bad || out != n_dst) && lane == 0) pq_err(err, KERR_BAD_PAGE);
 }
 
-// ------------------------------------------------------------------ Zstandard page decompression
+// ------------------------------------------------------------------ Zstandard / GZIP page decompression
 //
-// Paimon's default codec (CoreOptions.java:318-321).  The decoder is zstd_device.cuh (RFC 8878, written once for host
-// and device; the host build is pinned against libzstd-compressed buffers by tests/test_zstd_cpu.py).  A fixed grid of
-// warps pulls pages off a counter: every warp owns one set of FSE / Huffman tables in shared memory and one
-// 128 KiB literals buffer in global scratch; the lanes run the block decoder in lock step and move the bytes of
+// zstd is Paimon's default codec (CoreOptions.java:318-321); gzip is parquet-mr's other general-purpose codec.  The
+// decoders are zstd_device.cuh (RFC 8878) and inflate_device.cuh (RFC 1951 / 1952), written once for host and device;
+// their host builds are pinned against libzstd / zlib by tests/test_zstd_cpu.py and tests/test_inflate_cpu.py.  A
+// fixed grid of warps pulls pages off a counter: every warp owns one set of FSE / Huffman tables in shared memory and
+// one 128 KiB literals buffer in global scratch; the lanes run the block decoder in lock step and move the bytes of
 // literal / match copies lane-parallel.
 constexpr int kZsWarps = 4;
 __global__ void __launch_bounds__(kZsWarps * 32)
 k_pq_zstd(const PqPage *pages, int n_pages, const PqPage *dicts, int n_dicts, const PqChunk *chunks, uint8_t *lit_scratch,
           int32_t *counter, int32_t *err) {
-    __shared__ zs::Tables T[kZsWarps];
+    __shared__ zs::Tables T[kZsWarps];                     // (the DEFLATE tables are smaller and overlay them)
+    static_assert(sizeof(inflate::Tables) <= sizeof(zs::Tables), "tables overlay");
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t *lit = lit_scratch + ((size_t)blockIdx.x * kZsWarps + w) * (size_t)(zs::kMaxBlock + 64);
     while (true) {
@@ -433,13 +436,16 @@ k_pq_zstd(const PqPage *pages, int n_pages, const PqPage *dicts, int n_dicts, co
         j = __shfl_sync(0xffffffffu, j, 0);
         if (j >= n_pages + n_dicts) return;
         const PqPage &pg = j < n_pages ? pages[j] : dicts[j - n_pages];
-        if (!pg.compressed || chunks[pg.chunk].codec != pq::C_ZSTD) continue;
+        const int codec = chunks[pg.chunk].codec;
+        if (!pg.compressed || (codec != pq::C_ZSTD && codec != pq::C_GZIP)) continue;
         const int prefix = pg.type == pq::P_DATA_V2 ? pg.def_len : 0;
         uint8_t *out0 = const_cast<uint8_t *>(pg.body);
         if (prefix > pg.src_len || prefix > pg.body_len) { if (lane == 0) pq_err(err, KERR_BAD_PAGE); continue; }
         for (int i = lane; i < prefix; i += 32) out0[i] = pg.src[i];
         const int64_t want = pg.body_len - prefix;
-        const int64_t got = zs::decode(pg.src + prefix, pg.src_len - prefix, out0 + prefix, want, lit, T[w]);
+        const int64_t got = codec == pq::C_ZSTD
+            ? zs::decode(pg.src + prefix, pg.src_len - prefix, out0 + prefix, want, lit, T[w])
+            : inflate::inflate_gzip(pg.src + prefix, pg.src_len - prefix, out0 + prefix, want, *(inflate::Tables *)&T[w]);
         if (got != want && lane == 0) pq_err(err, KERR_BAD_PAGE);
         __syncwarp();
     }
@@ -804,39 +810,78 @@ __device__ int64_t pq_walk_stream(const uint8_t *stream, int64_t stream_len, int
     return pos;
 }
 
-// warps [0, n_pages): PLAIN BYTE_ARRAY data pages -> value start offsets in the OUTPUT payload;
-// warps [n_pages, n_pages + n_dicts): BYTE_ARRAY dictionary pages -> entry offsets / lengths.
-// `which`: 0 = dictionaries only (before the levels pass), 1 = data pages only (after the page scan)
+// BYTE_ARRAY dictionary pages -> entry offsets / lengths: one warp per dictionary page (few, large pages).
 __global__ void __launch_bounds__(kWalkWarps * 32)
-k_pq_walk_bytes(PqPage *pages, int n_pages, const PqPage *dicts, int n_dicts, const PqChunk *chunks, int which,
-                int32_t *vstart, int32_t *dict_off, int32_t *dict_len, int32_t *err) {
+k_pq_walk_dicts(const PqPage *dicts, int n_dicts, const PqChunk *chunks, int32_t *dict_off, int32_t *dict_len, int32_t *err) {
     __shared__ __align__(16) uint8_t s_win[kWalkWarps][kWalkWindow + 32];
     __shared__ uint32_t s_off[kWalkWarps][256];
     __shared__ int32_t s_len[kWalkWarps][256];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = blockIdx.x * kWalkWarps + w;
-    if (which == 1) {
-        if (t >= n_pages) return;
-        const PqPage pg = pages[t];
-        if (pg.bad || pg.enc != ENC_PLAIN || chunks[pg.chunk].phys != pq::T_BYTE_ARRAY) return;
-        int32_t *vs = vstart + pg.vs_base;
-        const int64_t pb = pg.payload_base;
-        const int64_t slen = pg.body_len - pg.values_off;
-        const int64_t endq = pq_walk_stream(pg.body + pg.values_off, slen, pg.nnz, s_win[w], s_off[w], s_len[w],
-                                            [&](int j, int64_t q, int32_t) { vs[j] = (int32_t)(pb + q - 4 * (int64_t)j); });
-        if (lane == 0) {
-            if (endq != slen) { pq_err(err, KERR_BAD_PAGE); pages[t].bad = 1; }
-            vs[pg.nnz] = (int32_t)(pb + slen - 4 * (int64_t)pg.nnz);
+    if (t >= n_dicts) return;
+    const PqPage dj = dicts[t];
+    if (chunks[dj.chunk].phys != pq::T_BYTE_ARRAY) return;
+    int32_t *doff = dict_off + dj.entry_base, *dlen = dict_len + dj.entry_base;
+    const int64_t endq = pq_walk_stream(dj.body, dj.body_len, dj.num_values, s_win[w], s_off[w], s_len[w],
+                                        [&](int j, int64_t q, int32_t len) { doff[j] = (int32_t)(q + 4); dlen[j] = len; });
+    if (lane == 0 && endq < 0) pq_err(err, KERR_BAD_PAGE);
+}
+
+// PLAIN BYTE_ARRAY data pages -> value start offsets in the OUTPUT payload (vstart[vs_base + j], j <= nnz).
+// The walk of one page is a dependent chain (every length word says where the next one is), so a page cannot be
+// split; a section has tens of thousands of such pages, though, so every LANE walks its own page: 32 independent
+// chains per warp instead of one lane working while 31 idle (the warp-per-page version spent ~38 issue slots per
+// value and was issue-bound at 24 ms per 700 M values; profiles/README.md).  Pages of a column chunk are neighbours in
+// the page table, so the lanes of a warp walk streams of similar length.  Length words are read through L1 (a 128-byte
+// line serves ~6 values) with the lines ahead prefetched; the offsets go out four at a time as 16-byte stores.
+__device__ __forceinline__ uint32_t pq_ld32_unaligned(const uint8_t *p) {
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
+    const uint32_t lo = __ldg(q), hi = __ldg(q + 1);          // (streams are followed by >= 8 readable bytes)
+    return __funnelshift_r(lo, hi, (int)(a & 3) * 8);
+}
+
+constexpr int kWalkLaneThreads = 128;
+__global__ void __launch_bounds__(kWalkLaneThreads)
+k_pq_walk_values(PqPage *pages, int n_pages, const PqChunk *chunks, int32_t *vstart, int32_t *err) {
+    const int t = blockIdx.x * kWalkLaneThreads + threadIdx.x;
+    if (t >= n_pages) return;
+    const PqPage pg = pages[t];
+    if (pg.bad || pg.enc != ENC_PLAIN || chunks[pg.chunk].phys != pq::T_BYTE_ARRAY) return;
+    int32_t *vs = vstart + pg.vs_base;
+    const uint8_t *stream = pg.body + pg.values_off;
+    const int64_t slen = pg.body_len - pg.values_off;
+    const int nnz = pg.nnz;
+    // out(j) = payload_base + (stream offset of value j's length word) - 4 j
+    int64_t q = 0, bias = pg.payload_base;
+    bool bad = false;
+    auto step = [&]() -> int32_t {
+        // value at stream offset q: returns its output start, advances q behind it
+        if (q + 4 > slen) { bad = true; return 0; }
+        const uint32_t len = pq_ld32_unaligned(stream + q);
+        if ((int64_t)len > slen - q - 4) { bad = true; return 0; }
+        const int32_t o = (int32_t)(q + bias);
+        const int64_t qn = q + 4 + len;
+        if ((q ^ qn) >> 7) {
+            // entering a new 128-byte line: ask for the lines ahead
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(stream + min(qn + 256, slen)));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(stream + min(qn + 2048, slen)));
         }
-    } else {
-        if (t >= n_dicts) return;
-        const PqPage dj = dicts[t];
-        if (chunks[dj.chunk].phys != pq::T_BYTE_ARRAY) return;
-        int32_t *doff = dict_off + dj.entry_base, *dlen = dict_len + dj.entry_base;
-        const int64_t endq = pq_walk_stream(dj.body, dj.body_len, dj.num_values, s_win[w], s_off[w], s_len[w],
-                                            [&](int j, int64_t q, int32_t len) { doff[j] = (int32_t)(q + 4); dlen[j] = len; });
-        if (lane == 0 && endq < 0) pq_err(err, KERR_BAD_PAGE);
+        q = qn;
+        bias -= 4;
+        return o;
+    };
+    int j = 0;
+    while (j < nnz && !bad && ((uintptr_t)(vs + j) & 15)) { const int32_t o = step(); if (!bad) vs[j] = o; j++; }
+    while (j + 4 <= nnz && !bad) {
+        int4 o;
+        o.x = step(); o.y = step(); o.z = step(); o.w = step();
+        if (!bad) *(int4 *)(vs + j) = o;
+        j += 4;
     }
+    while (j < nnz && !bad) { const int32_t o = step(); if (!bad) vs[j] = o; j++; }
+    if (bad || q != slen) { pq_err(err, KERR_BAD_PAGE); pages[t].bad = 1; return; }
+    vs[nnz] = (int32_t)(q + bias);
 }
 
 // ------------------------------------------------------------------ expand: one CTA per data page
@@ -862,7 +907,7 @@ __device__ __forceinline__ uint64_t pq_load_unaligned(const uint8_t *p, int w) {
     return sh ? (uint64_t)((lo >> sh) | (q[1] << (32 - sh))) : (uint64_t)lo;
 }
 
-__global__ void __launch_bounds__(kExpThreads)
+__global__ void __launch_bounds__(kExpThreads, 6)
 k_pq_expand(const PqPage *pages, const PqPage *dicts, const PqChunk *chunks, const PqOut *outs, int n_cols,
             const int32_t *ids, const int32_t *vstart, const int32_t *dict_off, const int32_t *dict_len, int32_t *err) {
     __shared__ uint32_t s_bits[kExpThreads];
@@ -947,27 +992,84 @@ k_pq_expand(const PqPage *pages, const PqPage *dicts, const PqChunk *chunks, con
             }
             carry_bytes += wtot;
         } else {
-            for (int jj = warp; jj < nw; jj += kExpThreads / 32) {
-                const uint32_t b = s_bits[jj];
-                const int64_t row = g0 + 32 * (int64_t)(w0 + jj) + lane;
-                if (row < row0 || row >= row1) continue;
-                const bool valid = (b >> lane) & 1;
-                const int rank = s_rank[jj] + __popc(b & ((1u << lane) - 1));
-                if (varlen) {
-                    out.offsets[row] = vs[rank];                      // a NULL row starts where the next value starts
-                } else {
-                    uint64_t v = 0;
-                    if (valid) {
-                        if (pg.enc == ENC_RLE_BOOL) v = (uint64_t)(pids[rank] & 1);
-                        else if (ch.phys == pq::T_BOOLEAN) v = (values[rank >> 3] >> (rank & 7)) & 1;
-                        else if (is_dict) v = pq_load_unaligned(dbody + (int64_t)pids[rank] * pw, pw);
-                        else v = pq_load_unaligned(values + (int64_t)rank * pw, pw);
-                        // a file written before the column was widened (SchemaEvolutionUtil / CastExecutors on the
-                        // Java side, DataFileRecordReader.java:55-57): INT -> BIGINT, FLOAT -> DOUBLE are exact
-                        if (ch.cast == 1) v = (uint64_t)(int64_t)(int32_t)(uint32_t)v;
-                        else if (ch.cast == 2) v = (uint64_t)__double_as_longlong((double)__uint_as_float((uint32_t)v));
+            // every thread keeps kExpUnroll independent loads in flight (one validity word = one warp step; a warp
+            // takes words warp, warp + 8, ...): with a single load per thread the 64 resident warps of an SM cover
+            // ~8 KB of the ~40 KB that have to be in flight per SM to fill the HBM pipe.
+            constexpr int kExpUnroll = 4, kStep = kExpThreads / 32;
+            const int fmode = varlen ? 0 : pg.enc == ENC_RLE_BOOL ? 1 : ch.phys == pq::T_BOOLEAN ? 2 : is_dict ? 3 : 4;
+            for (int j0 = warp; j0 < nw; j0 += kStep * kExpUnroll) {
+                int64_t row[kExpUnroll];
+                int rank[kExpUnroll];
+                bool inpage[kExpUnroll], valid[kExpUnroll];
+#pragma unroll
+                for (int u = 0; u < kExpUnroll; u++) {
+                    const int jj = j0 + u * kStep;
+                    const uint32_t b = jj < nw ? s_bits[jj] : 0;
+                    row[u] = g0 + 32 * (int64_t)(w0 + jj) + lane;
+                    inpage[u] = jj < nw && row[u] >= row0 && row[u] < row1;
+                    valid[u] = (b >> lane) & 1;
+                    rank[u] = jj < nw ? s_rank[jj] + __popc(b & ((1u << lane) - 1)) : 0;
+                }
+                if (fmode == 0) {
+                    int32_t o[kExpUnroll];
+#pragma unroll
+                    for (int u = 0; u < kExpUnroll; u++) o[u] = inpage[u] ? vs[rank[u]] : 0;   // a NULL row starts where the next value starts
+#pragma unroll
+                    for (int u = 0; u < kExpUnroll; u++) if (inpage[u]) out.offsets[row[u]] = o[u];
+                    continue;
+                }
+                uint64_t v[kExpUnroll];
+                if (fmode == 4) {
+                    if (pw == 8) {
+                        const uintptr_t a0 = (uintptr_t)values;
+                        const int sh = (int)(a0 & 7) * 8;
+                        const uint64_t *q0 = (const uint64_t *)(a0 & ~(uintptr_t)7);
+                        uint64_t lo[kExpUnroll], hi[kExpUnroll];
+#pragma unroll
+                        for (int u = 0; u < kExpUnroll; u++) {
+                            const bool ld = inpage[u] && valid[u];
+                            lo[u] = ld ? q0[rank[u]] : 0;
+                            hi[u] = (ld && sh) ? q0[rank[u] + 1] : 0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < kExpUnroll; u++) v[u] = sh ? (lo[u] >> sh) | (hi[u] << (64 - sh)) : lo[u];
+                    } else {
+                        const uintptr_t a0 = (uintptr_t)values;
+                        const int sh = (int)(a0 & 3) * 8;
+                        const uint32_t *q0 = (const uint32_t *)(a0 & ~(uintptr_t)3);
+                        uint32_t lo[kExpUnroll], hi[kExpUnroll];
+#pragma unroll
+                        for (int u = 0; u < kExpUnroll; u++) {
+                            const bool ld = inpage[u] && valid[u];
+                            lo[u] = ld ? q0[rank[u]] : 0;
+                            hi[u] = (ld && sh) ? q0[rank[u] + 1] : 0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < kExpUnroll; u++) v[u] = __funnelshift_r(lo[u], hi[u], sh);
                     }
-                    store_fixed(out.data, out.out_width, row, v);   // narrowing keeps the low bytes (INT32 -> TINYINT)
+                } else if (fmode == 3) {
+                    int32_t id[kExpUnroll];
+#pragma unroll
+                    for (int u = 0; u < kExpUnroll; u++) id[u] = (inpage[u] && valid[u]) ? pids[rank[u]] : -1;
+#pragma unroll
+                    for (int u = 0; u < kExpUnroll; u++) v[u] = id[u] >= 0 ? pq_load_unaligned(dbody + (int64_t)id[u] * pw, pw) : 0;
+                } else {
+#pragma unroll
+                    for (int u = 0; u < kExpUnroll; u++) {
+                        v[u] = 0;
+                        if (inpage[u] && valid[u])
+                            v[u] = fmode == 1 ? (uint64_t)(pids[rank[u]] & 1) : (uint64_t)((values[rank[u] >> 3] >> (rank[u] & 7)) & 1);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kExpUnroll; u++) {
+                    if (!inpage[u]) continue;
+                    uint64_t x = valid[u] ? v[u] : 0;
+                    // a file written before the column was widened (SchemaEvolutionUtil / CastExecutors on the
+                    // Java side, DataFileRecordReader.java:55-57): INT -> BIGINT, FLOAT -> DOUBLE are exact
+                    if (valid[u] && ch.cast == 1) x = (uint64_t)(int64_t)(int32_t)(uint32_t)x;
+                    else if (valid[u] && ch.cast == 2) x = (uint64_t)__double_as_longlong((double)__uint_as_float((uint32_t)x));
+                    store_fixed(out.data, out.out_width, row[u], x);    // narrowing keeps the low bytes (INT32 -> TINYINT)
                 }
             }
         }
@@ -976,13 +1078,35 @@ k_pq_expand(const PqPage *pages, const PqPage *dicts, const PqChunk *chunks, con
     }
     if (varlen) {
         if (!is_dict) {
-            // PLAIN: the page's payload is its value stream without the 4-byte length words; 8 lanes per value
+            // PLAIN: the page's payload is its value stream without the 4-byte length words.  8 lanes per value, two
+            // values per lane group and three bytes per lane in flight (all loads before the stores); longer
+            // values finish in a byte loop.
             const int nnz = pg.nnz;
             const int64_t pb = pg.payload_base;
-            for (int j = tid >> 3; j < nnz; j += kExpThreads / 8) {
-                const int s = vs[j], e = vs[j + 1];
-                const uint8_t *src = values + ((int64_t)s - pb) + 4 * (int64_t)(j + 1);
-                for (int bb = tid & 7; bb < e - s; bb += 8) payload[(int64_t)s + bb] = src[bb];
+            const int l8 = tid & 7;
+            for (int j = tid >> 3; j < nnz; j += 2 * (kExpThreads / 8)) {
+                const int jb = j + kExpThreads / 8;
+                const int sa = vs[j], ea = vs[j + 1];
+                int sb = 0, eb = 0;
+                if (jb < nnz) { sb = vs[jb]; eb = vs[jb + 1]; }
+                const uint8_t *pa = values + (4 * (int64_t)(j + 1) - pb);      // pa[o] = source of output byte o
+                const uint8_t *pbb = values + (4 * (int64_t)(jb + 1) - pb);
+                const int ia = sa + l8, ib = sb + l8;
+                uint8_t xa0 = 0, xa1 = 0, xa2 = 0, xb0 = 0, xb1 = 0, xb2 = 0;
+                if (ia < ea) xa0 = pa[ia];
+                if (ia + 8 < ea) xa1 = pa[ia + 8];
+                if (ia + 16 < ea) xa2 = pa[ia + 16];
+                if (ib < eb) xb0 = pbb[ib];
+                if (ib + 8 < eb) xb1 = pbb[ib + 8];
+                if (ib + 16 < eb) xb2 = pbb[ib + 16];
+                if (ia < ea) payload[ia] = xa0;
+                if (ia + 8 < ea) payload[ia + 8] = xa1;
+                if (ia + 16 < ea) payload[ia + 16] = xa2;
+                if (ib < eb) payload[ib] = xb0;
+                if (ib + 8 < eb) payload[ib + 8] = xb1;
+                if (ib + 16 < eb) payload[ib + 16] = xb2;
+                for (int b = ia + 24; b < ea; b += 8) payload[b] = pa[b];
+                for (int b = ib + 24; b < eb; b += 8) payload[b] = pbb[b];
             }
         }
         if (pg.is_last && tid == 0) out.offsets[row1] = (int32_t)(pg.payload_base + pg.payload_bytes);
@@ -1082,10 +1206,10 @@ static pg_status map_file_schema(const Schema *s, const pq::FileMetaData &m, con
     for (const pq::RowGroup &g : m.row_groups) {
         if ((int)g.columns.size() != nleaf) return fail(PG_ERR_FORMAT, "parquet: row group with a different column count");
         for (const pq::ColumnChunk &cc : g.columns)
-            if (cc.codec != pq::C_UNCOMPRESSED && cc.codec != pq::C_SNAPPY && cc.codec != pq::C_ZSTD)
+            if (cc.codec != pq::C_UNCOMPRESSED && cc.codec != pq::C_SNAPPY && cc.codec != pq::C_ZSTD && cc.codec != pq::C_GZIP)
                 return fail(PG_ERR_UNSUPPORTED, "parquet: compression codec " + std::to_string(cc.codec) +
-                                                " is not decoded on device (UNCOMPRESSED, SNAPPY and ZSTD are); write with "
-                                                "'file.compression'='zstd' / 'snappy' / 'none' or let the Java side decompress");
+                                                " is not decoded on device (UNCOMPRESSED, SNAPPY, ZSTD and GZIP are); write with "
+                                                "'file.compression'='zstd' / 'snappy' / 'gzip' / 'none' or let the Java side decompress");
     }
     return PG_OK;
 }
@@ -1280,7 +1404,7 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
                     ch.cast = phys_cast(s->field(c).type, cc.type);
                     if (cc.type != m.schema[fc + 1].type) return fail(PG_ERR_FORMAT, "parquet: column chunk type differs from the schema");
                     if (cc.codec == pq::C_SNAPPY) any_snappy = true;
-                    if (cc.codec == pq::C_ZSTD) any_zstd = true;
+                    if (cc.codec == pq::C_ZSTD || cc.codec == pq::C_GZIP) any_zstd = true;
                     for (int32_t e : cc.encodings) if (e == pq::E_DELTA_BINARY_PACKED) any_delta = true;
                     if (cc.num_values > 0) chunks.push_back(ch);
                     rg_row0 += g.num_rows;
@@ -1428,8 +1552,8 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
             launches++;
         }
         if (dict_entries > 0) {
-            k_pq_walk_bytes<<<(nd + kWalkWarps - 1) / kWalkWarps, kWalkWarps * 32, 0, sm>>>(
-                d_pages, np, d_dicts, nd, d_chunks, 0, d_vstart, d_dict_off, d_dict_len, d_err);
+            k_pq_walk_dicts<<<(nd + kWalkWarps - 1) / kWalkWarps, kWalkWarps * 32, 0, sm>>>(
+                d_dicts, nd, d_chunks, d_dict_off, d_dict_len, d_err);
             launches++;
         }
         k_pq_levels<<<(unsigned)(((int64_t)np * 32 + 127) / 128), 128, 0, sm>>>(d_pages, np, d_dicts, d_chunks, d_outs, nc,
@@ -1469,8 +1593,8 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
     }
     if (np > 0) {
         if (n_pairs) {
-            k_pq_walk_bytes<<<(np + kWalkWarps - 1) / kWalkWarps, kWalkWarps * 32, 0, sm>>>(
-                d_pages, np, d_dicts, nd, d_chunks, 1, d_vstart, d_dict_off, d_dict_len, d_err);
+            k_pq_walk_values<<<(np + kWalkLaneThreads - 1) / kWalkLaneThreads, kWalkLaneThreads, 0, sm>>>(
+                d_pages, np, d_chunks, d_vstart, d_err);
             launches++;
         }
         k_pq_expand<<<np, kExpThreads, 0, sm>>>(d_pages, d_dicts, d_chunks, d_outs, nc, d_ids, d_vstart, d_dict_off,

@@ -59,6 +59,8 @@ WRITER_OPTS = [
     dict(compression="zstd"),                                      # Paimon's default 'file.compression'
     dict(compression="zstd", compression_level=1, use_dictionary=False),
     dict(compression="zstd", data_page_version="2.0", row_group_size=1000, data_page_size=512),
+    dict(compression="gzip"),
+    dict(compression="gzip", use_dictionary=False, data_page_version="2.0", data_page_size=4096),
 ]
 
 
@@ -137,15 +139,15 @@ def test_fused_decode_then_merge_matches_oracle(tmp_path, engine):
 
 def test_unsupported_format_is_refused():
     with pytest.raises(N.UnsupportedOnDevice):
-        FileFormat.from_identifier("orc")
+        FileFormat.from_identifier("avro")
 
 
 def test_unsupported_codec_is_refused(tmp_path):
-    """gzip / lz4 pages are not decoded on the device: refused when the file is opened, no CPU fallback."""
+    """lz4 / brotli pages are not decoded on the device: refused when the file is opened, no CPU fallback."""
     schema = datagen.schema_c2()
     run = datagen.make_runs(schema, 1, 200, seed=2)[0]
     path = str(tmp_path / "z.parquet")
-    write_kv_parquet(run, path, compression="gzip")
+    write_kv_parquet(run, path, compression="lz4")
     with pytest.raises(N.UnsupportedOnDevice):
         decode(schema, path)
 
