@@ -341,6 +341,21 @@ pg_status pg_orc_read_section(uint64_t schema, const pg_file_desc *files, int32_
                               const char *const *column_names, const uint8_t *read_columns, uint64_t *out_runs,
                               pg_section_info *info);
 
+/* Asynchronous host -> device copy of a section's data files, so that the NEXT section's bytes move while the current
+ * one decodes and merges (the copy of the encoded files is the longest leg of an end-to-end step).
+ *   pg_files_upload_begin: starts the copies on the library's upload stream and returns at once (host buffers should be
+ *     page-locked; descriptors that are already PG_MEM_DEVICE pass through untouched);
+ *   pg_files_upload_wait:  blocks until the bytes are resident and fills out_files[n_files] with PG_MEM_DEVICE
+ *     descriptors (same order, same run indexes) for pg_parquet_read_section;
+ *   pg_files_upload_free:  releases the device copies; call it from the thread that decoded them, after
+ *     pg_parquet_read_section returned (it waits for that thread's decode launches).
+ * Replaces: the blocking file read in front of FormatReaderFactory.createReader
+ * (paimon-core/.../io/KeyValueFileReaderFactory.java:104-140) for the device path. */
+pg_status pg_files_upload_begin(const pg_file_desc *files, int32_t n_files, uint64_t *out_upload);
+pg_status pg_files_upload_wait(uint64_t upload, pg_file_desc *out_files, int32_t n_files);
+pg_status pg_files_upload_free(uint64_t upload);
+
+
 /* ApplyDeletionVectorReader (paimon-core/.../deletionvectors/ApplyDeletionVectorReader.java:31-54): a new run holding
  * the rows of `run` whose file position is NOT set in the deletion vector.  `deleted_bitmap` is host memory, LSB
  * first, bit i = row i of the file is deleted (the Java side expands its RoaringBitmap32; DeletionVector.java);

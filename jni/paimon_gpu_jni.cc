@@ -389,6 +389,41 @@ JNIEXPORT jlong JNICALL Java_org_apache_paimon_gpu_NativeMerge_threadStream(JNIE
     return (jlong)(uintptr_t)s;
 }
 
+// asynchronous upload of the next section's files (direct ByteBuffers): begin -> handle; wait -> long[2 * n]
+// {devicePointer, size} per file, to be passed to readSectionDevice; free
+JNIEXPORT jlong JNICALL Java_org_apache_paimon_gpu_NativeMerge_uploadBegin(JNIEnv *env, jclass, jobjectArray fileBuffers,
+                                                                           jlongArray sizes) {
+    const jsize nf = env->GetArrayLength(fileBuffers);
+    std::vector<jlong> sz(nf);
+    env->GetLongArrayRegion(sizes, 0, nf, sz.data());
+    std::vector<pg_file_desc> files(nf);
+    for (jsize i = 0; i < nf; i++) {
+        jobject b = env->GetObjectArrayElement(fileBuffers, i);
+        if (!b || env->GetDirectBufferCapacity(b) < sz[i]) {
+            env->ThrowNew(env->FindClass("java/lang/IllegalArgumentException"), "file buffer smaller than its size");
+            return 0;
+        }
+        files[i] = pg_file_desc{(const uint8_t *)env->GetDirectBufferAddress(b), sz[i], PG_MEM_HOST, 0};
+    }
+    uint64_t up = 0;
+    PG_CHECK(pg_files_upload_begin(files.data(), (int32_t)nf, &up));
+    return (jlong)up;
+}
+JNIEXPORT jlongArray JNICALL Java_org_apache_paimon_gpu_NativeMerge_uploadWait(JNIEnv *env, jclass, jlong upload, jint nFiles) {
+    std::vector<pg_file_desc> d(nFiles > 0 ? nFiles : 1);
+    pg_status rc = pg_files_upload_wait((uint64_t)upload, d.data(), nFiles);
+    if (rc != PG_OK) { throw_for(env, rc); return nullptr; }
+    std::vector<jlong> out(2 * (size_t)nFiles);
+    for (jint i = 0; i < nFiles; i++) { out[2 * i] = (jlong)(uintptr_t)d[i].bytes; out[2 * i + 1] = d[i].size; }
+    jlongArray a = env->NewLongArray(2 * nFiles);
+    env->SetLongArrayRegion(a, 0, 2 * nFiles, out.data());
+    return a;
+}
+JNIEXPORT void JNICALL Java_org_apache_paimon_gpu_NativeMerge_uploadFree(JNIEnv *env, jclass, jlong upload) {
+    pg_status rc = pg_files_upload_free((uint64_t)upload);
+    if (rc != PG_OK) throw_for(env, rc);
+}
+
 // long[2 + 2 * nCols]: {nRows, nCols, then per column dataBytes, hasValidity}
 JNIEXPORT jlongArray JNICALL Java_org_apache_paimon_gpu_NativeMerge_runLayout(JNIEnv *env, jclass, jlong run, jint nCols) {
     std::vector<int64_t> bytes(nCols);

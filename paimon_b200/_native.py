@@ -132,6 +132,9 @@ _SIGNATURES = {
     "pg_run_fetch": (C.c_int32, [C.c_uint64, C.POINTER(PgOutColumn), C.c_int32]),
     "pg_run_slice": (C.c_int32, [C.c_uint64, C.c_int64, C.c_int64, C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]),
     "pg_thread_stream": (C.c_int32, [C.POINTER(C.c_void_p)]),
+    "pg_files_upload_begin": (C.c_int32, [C.POINTER(PgFileDesc), C.c_int32, C.POINTER(C.c_uint64)]),
+    "pg_files_upload_wait": (C.c_int32, [C.c_uint64, C.POINTER(PgFileDesc), C.c_int32]),
+    "pg_files_upload_free": (C.c_int32, [C.c_uint64]),
     "pg_export_arrow": (C.c_int32, [C.c_uint64, C.POINTER(C.c_char_p), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "pg_parquet_open": (C.c_int32, [C.c_uint64, C.c_void_p, C.c_int64, C.POINTER(C.c_uint64)]),
     "pg_parquet_describe": (C.c_int32, [C.c_uint64, C.POINTER(PgParquetInfo)]),

@@ -65,11 +65,14 @@ template <> __device__ __forceinline__ uint64_t lds_fixed<1>(const unsigned char
 template <> __device__ __forceinline__ uint64_t lds_fixed<2>(const unsigned char *v, int p) { return ((const uint16_t *)v)[p]; }
 template <> __device__ __forceinline__ uint64_t lds_fixed<4>(const unsigned char *v, int p) { return ((const uint32_t *)v)[p]; }
 template <> __device__ __forceinline__ uint64_t lds_fixed<8>(const unsigned char *v, int p) { return ((const uint64_t *)v)[p]; }
+// output / run column pointers come out of device tables as generic pointers: tell the compiler they are global
+// (STG / LDG instead of generic ST / LD).  Only for non-null pointers.
+template <typename T> __device__ __forceinline__ T *as_global(T *p) { __builtin_assume(__isGlobal(p)); return p; }
 template <int W> __device__ __forceinline__ void stg_fixed(void *d, int64_t row, uint64_t v);
-template <> __device__ __forceinline__ void stg_fixed<1>(void *d, int64_t r, uint64_t v) { ((uint8_t *)d)[r] = (uint8_t)v; }
-template <> __device__ __forceinline__ void stg_fixed<2>(void *d, int64_t r, uint64_t v) { ((uint16_t *)d)[r] = (uint16_t)v; }
-template <> __device__ __forceinline__ void stg_fixed<4>(void *d, int64_t r, uint64_t v) { ((uint32_t *)d)[r] = (uint32_t)v; }
-template <> __device__ __forceinline__ void stg_fixed<8>(void *d, int64_t r, uint64_t v) { ((uint64_t *)d)[r] = v; }
+template <> __device__ __forceinline__ void stg_fixed<1>(void *d, int64_t r, uint64_t v) { as_global((uint8_t *)d)[r] = (uint8_t)v; }
+template <> __device__ __forceinline__ void stg_fixed<2>(void *d, int64_t r, uint64_t v) { as_global((uint16_t *)d)[r] = (uint16_t)v; }
+template <> __device__ __forceinline__ void stg_fixed<4>(void *d, int64_t r, uint64_t v) { as_global((uint32_t *)d)[r] = (uint32_t)v; }
+template <> __device__ __forceinline__ void stg_fixed<8>(void *d, int64_t r, uint64_t v) { as_global((uint64_t *)d)[r] = v; }
 
 // partial-update sequence group column: the member the plan kernel marked (merged position), or -1
 __device__ __forceinline__ int select_marked_idx(const uint16_t *pm, const uint32_t *gplan, uint32_t bit, int last) {
@@ -361,7 +364,7 @@ __device__ __forceinline__ void put_validity_word(uint8_t *validity, int64_t out
     if ((threadIdx.x & 31) == 0) {
         int64_t word = (out_base + wb) >> 5;
         bool full = wb >= 0 && wb + 32 <= n_out;
-        uint32_t *bm = (uint32_t *)validity;
+        uint32_t *bm = as_global((uint32_t *)validity);
         if (full) bm[word] = mask;
         else if (mask) atomicOr(&bm[word], mask);
     }
@@ -439,12 +442,10 @@ k_emit(EmitArgs ea) {
     const int k = ea.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nv = ea.n_varlen;
     const EmitLayout L = emit_layout(k, nv);
-    unsigned char *stage_vals[kStages];
-    uint32_t *stage_vw[kStages];
-    for (int s = 0; s < kStages; s++) {
-        stage_vals[s] = smem + s * L.stage_bytes;
-        stage_vw[s] = (uint32_t *)(stage_vals[s] + (size_t)L.rt * 8);
-    }
+    // (computed from `smem` at every use: pointers picked out of a local array lose their address space, and every
+    // read of staged data becomes a generic LD through L1TEX instead of an LDS — ncu: long-scoreboard stalls)
+    auto stage_vals = [&](int s) -> unsigned char * { return smem + (size_t)s * L.stage_bytes; };
+    auto stage_vw = [&](int s) -> uint32_t * { return (uint32_t *)(smem + (size_t)s * L.stage_bytes + (size_t)L.rt * 8); };
     unsigned char *p = smem + kStages * L.stage_bytes;
     int64_t *rstart = (int64_t *)p;            p += PG_MAX_RUNS * 8;
     const uint8_t **cdata = (const uint8_t **)p; p += kStages * PG_MAX_RUNS * 8;   // payload base per run (var-len)
@@ -519,7 +520,7 @@ k_emit(EmitArgs ea) {
     // slot -> (staged position, run) tables, built per run segment (no searches); they live in memory that
     // is not in use yet (glast, stage 1)
     uint16_t *spos = glast;
-    uint8_t *srun = stage_vals[1];
+    uint8_t *srun = stage_vals(1);
     // plan slots are run-major inside their plan tile: table index = slot (first tile) or n_a + slot (second)
     const int n_a = seg_a[k];
     for (int r = 0; r < k; r++) {
@@ -609,13 +610,13 @@ k_emit(EmitArgs ea) {
                 if (len > 0) {
                     bytes = (uint32_t)(((head + len) * cd.width + 15) & ~15);
                     src = (const unsigned char *)ea.ptrs.data[(int64_t)c * k + r] + row0 * cd.width;
-                    dst = stage_vals[s] + (size_t)rr[r] * cd.width;
+                    dst = stage_vals(s) + (size_t)rr[r] * cd.width;
                 }
             } else {
                 if (len > 0) {
                     bytes = (uint32_t)(((head + len + 1) * 4 + 15) & ~15);
                     src = (const unsigned char *)(ea.ptrs.offsets[(int64_t)c * k + r] + row0);
-                    dst = stage_vals[s] + (size_t)rr[r] * 4;
+                    dst = stage_vals(s) + (size_t)rr[r] * 4;
                 }
                 cdata[s * PG_MAX_RUNS + r] = (const uint8_t *)ea.ptrs.data[(int64_t)c * k + r];
             }
@@ -650,7 +651,7 @@ k_emit(EmitArgs ea) {
         const int c0 = ea.col_order[pbase] & 0xffff;
         if (warp == 0) issue(c0, 0);
         const uint32_t x = load_vw(c0);
-        if (tid < n_vw) stage_vw[0][tid] = x;
+        if (tid < n_vw) stage_vw(0)[tid] = x;
         __syncwarp();
         if (lane == 0) mbar_arrive(&mbar_full[0]);
     }
@@ -745,8 +746,8 @@ k_emit(EmitArgs ea) {
         }
         mbar_wait(&mbar_full[s], (uint32_t)((u >> 1) & 1));
         TS(3 + 3 * u);
-        const unsigned char *vals = stage_vals[s];
-        const uint32_t *vw = stage_vw[s];
+        const unsigned char *vals = stage_vals(s);
+        const uint32_t *vw = stage_vw(s);
 
         if (phase == PH_FIXED) {
             emit_fixed_dispatch<GAGG>(ea, cd, oc, tv, vals, vw);
@@ -802,7 +803,8 @@ k_emit(EmitArgs ea) {
             const uint8_t *const *cd_data = cdata + s * PG_MAX_RUNS;
             const uint16_t *vsrc = ea.vsrc + (int64_t)vi * ea.vsrc_stride + tv.out_base;
             const int64_t byte_base = s_base[vi];
-            uint8_t *dbase = (uint8_t *)oc.data + byte_base;
+            uint8_t *dbase = as_global((uint8_t *)oc.data) + byte_base;
+            int32_t *out_offs = as_global(oc.offsets);
             int carry = 0;
             for (int w2 = 0; w2 < warp; w2++) carry += wtot[vi * kEmitWarps + w2];
             int *my_pre = wpre + warp * 33;
@@ -820,14 +822,14 @@ k_emit(EmitArgs ea) {
                         int ps = pm[src] & kPmPosMask;
                         int st = offs[ps];
                         len = offs[ps + 1] - st;
-                        sp = cd_data[mrun[src]] + st;
+                        sp = as_global(cd_data[mrun[src]]) + st;
                         has = true;
                     }
                 }
                 const int incl = warp_scan_incl(len);
                 const int off = carry + incl - len;
                 carry += __shfl_sync(0xffffffffu, incl, 31);
-                if (active) oc.offsets[tv.out_base + ob] = (int32_t)(byte_base + off);
+                if (active) out_offs[tv.out_base + ob] = (int32_t)(byte_base + off);
                 if (oc.validity != nullptr) put_validity_word(oc.validity, tv.out_base, ob0, n_out, has);
                 // warp-cooperative payload copy: the warp's 32 rows form one contiguous destination range;
                 // rows without payload (NULL / empty) are squeezed out first, then 8 lanes serve one row (so
@@ -843,27 +845,27 @@ k_emit(EmitArgs ea) {
                 }
                 __syncwarp();
                 for (int rg = 0; rg < n_pay; rg += 8) {
-                    const int ra = rg + (lane >> 3), rb = ra + 4;
-                    int a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+                    const int ra = rg + (lane >> 3), rb = ra + 4, l8 = lane & 7;
+                    int a0 = 0, la = 0, b0 = 0, lb = 0;                   // destination offset, bytes
                     const uint8_t *pa = nullptr, *pb = nullptr;
-                    if (ra < n_pay) { a0 = my_pre[ra]; a1 = my_end[ra]; pa = my_src[ra] - a0; }
-                    if (rb < n_pay) { b0 = my_pre[rb]; b1 = my_end[rb]; pb = my_src[rb] - b0; }
-                    const int ia = a0 + (lane & 7), ib = b0 + (lane & 7);
+                    if (ra < n_pay) { a0 = my_pre[ra]; la = my_end[ra] - a0; pa = my_src[ra]; }
+                    if (rb < n_pay) { b0 = my_pre[rb]; lb = my_end[rb] - b0; pb = my_src[rb]; }
+                    uint8_t *da = dbase + a0, *db = dbase + b0;
                     uint8_t xa0 = 0, xa1 = 0, xa2 = 0, xb0 = 0, xb1 = 0, xb2 = 0;
-                    if (ia < a1) xa0 = pa[ia];
-                    if (ia + 8 < a1) xa1 = pa[ia + 8];
-                    if (ia + 16 < a1) xa2 = pa[ia + 16];
-                    if (ib < b1) xb0 = pb[ib];
-                    if (ib + 8 < b1) xb1 = pb[ib + 8];
-                    if (ib + 16 < b1) xb2 = pb[ib + 16];
-                    if (ia < a1) dbase[ia] = xa0;
-                    if (ia + 8 < a1) dbase[ia + 8] = xa1;
-                    if (ia + 16 < a1) dbase[ia + 16] = xa2;
-                    if (ib < b1) dbase[ib] = xb0;
-                    if (ib + 8 < b1) dbase[ib + 8] = xb1;
-                    if (ib + 16 < b1) dbase[ib + 16] = xb2;
-                    for (int b = ia + 24; b < a1; b += 8) dbase[b] = pa[b];
-                    for (int b = ib + 24; b < b1; b += 8) dbase[b] = pb[b];
+                    if (l8 < la) xa0 = __ldg(&pa[l8]);
+                    if (l8 + 8 < la) xa1 = __ldg(&pa[l8 + 8]);
+                    if (l8 + 16 < la) xa2 = __ldg(&pa[l8 + 16]);
+                    if (l8 < lb) xb0 = __ldg(&pb[l8]);
+                    if (l8 + 8 < lb) xb1 = __ldg(&pb[l8 + 8]);
+                    if (l8 + 16 < lb) xb2 = __ldg(&pb[l8 + 16]);
+                    if (l8 < la) da[l8] = xa0;
+                    if (l8 + 8 < la) da[l8 + 8] = xa1;
+                    if (l8 + 16 < la) da[l8 + 16] = xa2;
+                    if (l8 < lb) db[l8] = xb0;
+                    if (l8 + 8 < lb) db[l8 + 8] = xb1;
+                    if (l8 + 16 < lb) db[l8 + 16] = xb2;
+                    for (int b = l8 + 24; b < la; b += 8) da[b] = __ldg(&pa[b]);
+                    for (int b = l8 + 24; b < lb; b += 8) db[b] = __ldg(&pb[b]);
                 }
                 __syncwarp();
             }
@@ -875,7 +877,7 @@ k_emit(EmitArgs ea) {
         if (more && vw_warp) {
             // the next pass's validity words go into the other stage once its previous use (pass pp - 1) is released
             if (u >= 1 && warp != 0) mbar_wait(&mbar_empty[s ^ 1], (uint32_t)(((u - 1) >> 1) & 1));
-            if (tid < n_vw) stage_vw[s ^ 1][tid] = next_vw;
+            if (tid < n_vw) stage_vw(s ^ 1)[tid] = next_vw;
             __syncwarp();
             if (lane == 0) mbar_arrive(&mbar_full[s ^ 1]);
         }

@@ -156,6 +156,41 @@ def read_section(schema: KeyValueSchema, files, n_runs: int, device: int = 0, ch
     return readers, info
 
 
+class FileUpload:
+    """The data files of one section on their way to the device (pg_files_upload_begin): start it for section i + 1
+    before decoding section i, and the host -> device copy of the encoded bytes — the longest leg of an end-to-end
+    step — overlaps the decode, the merge and the read-back.  `files` = [(buffer, run index)] with page-locked host
+    buffers (bytes / numpy uint8); wait() returns [((device pointer, size), run index)] for read_section()."""
+
+    def __init__(self, files, device: int = 0):
+        self._lib = N.init(device)
+        self._keep = []
+        self._runs = [int(r) for _, r in files]
+        descs = (N.PgFileDesc * max(len(files), 1))()
+        for i, (buf, run) in enumerate(files):
+            if isinstance(buf, tuple):
+                descs[i] = N.PgFileDesc(int(buf[0]), int(buf[1]), N.PG_MEM_DEVICE, int(run))
+            else:
+                arr = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else np.ascontiguousarray(buf, np.uint8)
+                self._keep.append(arr)
+                descs[i] = N.PgFileDesc(arr.ctypes.data, len(arr), N.PG_MEM_HOST, int(run))
+        h = C.c_uint64(0)
+        N.check(self._lib.pg_files_upload_begin(descs, len(files), C.byref(h)))
+        self._handle = h.value
+        self._n = len(files)
+
+    def wait(self):
+        out = (N.PgFileDesc * max(self._n, 1))()
+        N.check(self._lib.pg_files_upload_wait(self._handle, out, self._n))
+        return [((int(out[i].bytes), int(out[i].size)), self._runs[i]) for i in range(self._n)]
+
+    def close(self):
+        if self._handle:
+            N.check(self._lib.pg_files_upload_free(self._handle))
+            self._handle = 0
+            self._keep = []
+
+
 class FormatReaderFactory:
     def create_reader(self, context: FormatReaderContext) -> FileRecordReader:
         raise NotImplementedError

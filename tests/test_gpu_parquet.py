@@ -349,6 +349,36 @@ def test_section_runs_are_concatenations_of_their_files(tmp_path):
             assert g.equals(w), f"run {r}: " + g.first_difference(w)
 
 
+def test_section_from_an_asynchronous_upload(tmp_path):
+    """pg_files_upload_begin / wait / free: the files of the next section travel to the device on the library's upload
+    stream; the descriptors wait() hands back decode to the same runs as the host bytes do."""
+    from paimon_b200.format import FileUpload, read_section
+    schema = datagen.schema_c3(n_i64=2, n_f64=1, n_str=2)
+    files, uploads = [], []
+    for i, n in enumerate((3001, 17, 1200)):
+        keys = np.arange(i * 100_000, i * 100_000 + n, dtype=np.int64)
+        part = datagen.make_run(schema, i, keys, seed=9, null_prob=0.4, delete_prob=0.1)
+        path = str(tmp_path / f"u{i}.parquet")
+        write_kv_parquet(part, path, compression=["zstd", "snappy", "none"][i])
+        files.append((open(path, "rb").read(), i % 2))
+    files.sort(key=lambda f: f[1])
+    want = _fetch_and_close(read_section(schema, files, 2)[0])
+    # two uploads in flight, consumed in order
+    uploads = [FileUpload(files), FileUpload(files)]
+    try:
+        for up in uploads:
+            dev_files = up.wait()
+            assert [r for _, r in dev_files] == [r for _, r in files]
+            got = _fetch_and_close(read_section(schema, dev_files, 2)[0])
+            for g, w in zip(got, want):
+                assert g.equals(w), g.first_difference(w)
+    finally:
+        for up in uploads:
+            up.close()
+    with pytest.raises(N.PaimonGpuError):
+        N.check(N.load().pg_files_upload_free(12345))
+
+
 def test_section_of_empty_files(tmp_path):
     from paimon_b200.format import read_section
     schema = datagen.schema_c3(n_i64=1, n_f64=1, n_str=1)
