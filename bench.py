@@ -285,6 +285,127 @@ def device_parquet_files(workload, schema, rows, dev, seed, lib):
     return handles, images, all_keys, all_kinds
 
 
+# ------------------------------------------------------------------ C5: lineitem-shaped Parquet decode + merge
+
+def schema_c5():
+    """pk (l_orderkey BIGINT, l_linenumber INT), 16 columns."""
+    from paimon_b200.types import DataField, KeyValueSchema, RowType
+    fields = [DataField("l_orderkey", "BIGINT", False), DataField("l_linenumber", "INT", False),
+              DataField("l_partkey", "BIGINT", True), DataField("l_suppkey", "BIGINT", True),
+              DataField("l_quantity", "DECIMAL(15,2)", True), DataField("l_extendedprice", "DECIMAL(15,2)", True),
+              DataField("l_discount", "DECIMAL(15,2)", True), DataField("l_tax", "DECIMAL(15,2)", True),
+              DataField("l_returnflag", "CHAR(1)", True), DataField("l_linestatus", "CHAR(1)", True),
+              DataField("l_shipdate", "DATE", True), DataField("l_commitdate", "DATE", True),
+              DataField("l_receiptdate", "DATE", True), DataField("l_shipinstruct", "CHAR(25)", True),
+              DataField("l_shipmode", "CHAR(10)", True), DataField("l_comment", "VARCHAR(44)", True)]
+    return KeyValueSchema.of(RowType(tuple(fields)), ["l_orderkey", "l_linenumber"])
+
+
+def c5_bucket(schema, codec, seed=5):
+    """One C5 bucket as parquet-mr-style files written by pyarrow on the host (dictionary on, data page V1, 1 MiB
+    pages, ~128 MiB row groups; DECIMAL(15,2) / DATE in their physical INT64 / INT32 form): 1 base run (83.3 %) + 4
+    update runs whose keys are resampled from the base.  Returns ([(file bytes, run)], rows in, expected columns)."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    rng = np.random.default_rng(seed)
+    total = 1_000_000_000 // 64
+    n_base = int(total * 5 / 6)
+    n_upd = (total - n_base) // 4
+    names = [f.name for f in schema.file_fields()]
+    flags = [np.array([b"A", b"N", b"R"]), np.array([b"F", b"O"])]
+    instr = np.array([b"DELIVER IN PERSON", b"COLLECT COD", b"NONE", b"TAKE BACK RETURN"])
+    modes = np.array([b"REG AIR", b"AIR", b"RAIL", b"SHIP", b"TRUCK", b"MAIL", b"FOB"])
+
+    def run_table(idx, seq0):
+        n = len(idx)
+        ok_, ln_ = pa.array(idx // 4), pa.array((idx % 4 + 1).astype(np.int32))
+        # (a Paimon value row carries the primary-key fields too: _KEY_* copies + the table's own columns)
+        cols = [ok_, ln_, pa.array(seq0 + np.arange(n, dtype=np.int64)), pa.array(np.zeros(n, np.int8)), ok_, ln_]
+        part = rng.integers(1, 20_000_000, n)
+        cols += [pa.array(part), pa.array(rng.integers(1, 1_000_000, n))]
+        cols += [pa.array(rng.integers(100, 5_000_000, n)) for _ in range(4)]
+        cols += [pa.array(flags[0][rng.integers(0, 3, n)]).cast(pa.string()), pa.array(flags[1][rng.integers(0, 2, n)]).cast(pa.string())]
+        ship = rng.integers(8000, 10600, n).astype(np.int32)
+        cols += [pa.array(ship), pa.array(ship + 30), pa.array(ship + 45)]
+        cols += [pa.array(instr[rng.integers(0, 4, n)]).cast(pa.string()), pa.array(modes[rng.integers(0, 7, n)]).cast(pa.string())]
+        import pyarrow.compute as pc
+        cols.append(pc.binary_join_element_wise(pa.array(rng.integers(0, 1 << 40, n)).cast(pa.string()),
+                                                pa.array(rng.integers(0, 1 << 30, n)).cast(pa.string()), " carefully final "))
+        fields = [pa.field(nm, c.type, nullable=i >= schema.n_key + 2) for i, (nm, c) in enumerate(zip(names, cols))]
+        return pa.Table.from_arrays(cols, schema=pa.schema(fields)), part, ship
+
+    files = []
+    exp_part = exp_ship = exp_seq = None
+    for r in range(5):
+        idx = np.arange(n_base, dtype=np.int64) if r == 0 else np.sort(rng.choice(n_base, n_upd, replace=False))
+        seq0 = 0 if r == 0 else n_base + (r - 1) * n_upd
+        tb, part, ship = run_table(idx, seq0)
+        if r == 0:
+            exp_part, exp_ship, exp_seq = part.copy(), ship.copy(), np.arange(n_base, dtype=np.int64)
+        else:
+            exp_part[idx] = part; exp_ship[idx] = ship; exp_seq[idx] = seq0 + np.arange(n_upd, dtype=np.int64)
+        sink = pa.BufferOutputStream()
+        pq.write_table(tb, sink, compression=codec, use_dictionary=True, data_page_version="1.0", data_page_size=1 << 20,
+                       row_group_size=800_000, write_statistics=False, **({"compression_level": 1} if codec == "zstd" else {}))
+        files.append((np.frombuffer(sink.getvalue(), np.uint8), r))
+    return files, n_base + 4 * n_upd, {"l_partkey": exp_part, "l_shipdate": exp_ship, "_SEQUENCE_NUMBER": exp_seq}
+
+
+def extra_c5(local_rank, peak, steps=3):
+    """Decode + merge of a C5 bucket from file bytes resident in HBM, `none` and zstd-1 (run A / run B)."""
+    from paimon_b200.format import FileUpload, read_section
+    from paimon_b200.merge_function import DeduplicateMergeFunction
+    from paimon_b200.sort_merge_reader import SortMergeReader
+    schema = schema_c5()
+    spec = DeduplicateMergeFunction.factory().create()
+    out = {"what": "SURVEY C5: one bucket of lineitem-shaped Parquet (15.6 M rows: base run + 4 update runs; dictionary on, "
+                   "page V1, 1 MiB pages) -> device decode -> 5-run deduplicate, timed from file bytes in HBM"}
+    for codec in ("none", "zstd"):
+        t0 = time.perf_counter()
+        files, n_in, expect = c5_bucket(schema, codec)
+        gen_s = time.perf_counter() - t0
+        up = FileUpload(files, local_rank)
+        rd = SortMergeReader([], spec, None, local_rank, schema=schema)
+        try:
+            dev_files = up.wait()
+            ms_dec = ms_mrg = 0.0
+            for it in range(2 + steps):
+                readers, info = read_section(schema, dev_files, 5, local_rank)
+                rd.rebind(readers)
+                rd.execute()
+                st = rd.stats()
+                if it >= 2:
+                    ms_dec += info.ms_decode / steps; ms_mrg += st.ms_total / steps
+                if it < 1 + steps:
+                    for r_ in readers:
+                        r_.close()
+                    rd.readers = []
+            got = rd.fetch()
+            names = [f.name for f in schema.file_fields()]
+            ok = got.n_rows == len(expect["l_partkey"])
+            for nm, want in expect.items():
+                col = got.columns[names.index(nm)]
+                n_ = got.n_rows
+                ok = ok and bool(np.array_equal(np.asarray(col.data)[:n_], want))
+                ok = ok and (col.valid is None or bool(np.unpackbits(np.asarray(col.valid, np.uint8), bitorder="little")[:n_].all()))
+            for r_ in readers:
+                r_.close()
+            rd.readers = []
+            step = ms_dec + ms_mrg
+            out["run_A_none" if codec == "none" else "run_B_zstd1"] = {
+                "rows_per_s": n_in / (step * 1e-3), "ms_per_step": step, "decode_ms": ms_dec, "merge_ms": ms_mrg,
+                "rows_in": int(n_in), "rows_out": int(got.n_rows), "file_bytes": int(info.file_bytes),
+                "encoded_page_bytes": int(info.page_bytes), "decoded_bytes": int(info.decoded_bytes),
+                "dictionary_pages": int(info.n_dictionary_pages), "data_pages": int(info.n_data_pages),
+                "decode_frac_of_hbm_peak": (info.page_bytes + info.decoded_bytes) / (ms_dec * 1e-3) / 1e9 / peak,
+                "parity": "ok" if ok else "MISMATCH", "parity_what": "rows out, l_partkey, l_shipdate and _SEQUENCE_NUMBER of "
+                "all merged rows against the generator's last-writer-wins arrays", "host_generation_s": round(gen_s, 1)}
+        finally:
+            rd.close()
+            up.close()
+    return out
+
+
 # ------------------------------------------------------------------ clocks sampling
 
 class ClockSampler:
@@ -796,6 +917,12 @@ def main():
                 raise errors[0]
             return time.perf_counter() - t0
 
+        # what the link gives on this box: the file upload alone (the read-back alone is timed after the loop)
+        t0u = time.perf_counter()
+        up0 = FileUpload(hfiles, local_rank)
+        up0.wait()
+        h2d_only_ms = 1e3 * (time.perf_counter() - t0u)
+        up0.close()
         overlap = True
         try:
             run_buckets(1, True)
@@ -812,6 +939,28 @@ def main():
             lib.pg_trim()
             run_buckets(1, False)
         dt = run_buckets(n_e2e, overlap)
+        # what the link gives on this box: the read-back alone, and one upload + one read-back issued together
+        link = {}
+        try:
+            def fetch_again():
+                top_ = [0]
+
+                def alloc_(nbytes):
+                    a = (top_[0] + 63) & ~63
+                    top_[0] = a + nbytes
+                    return arena_np[a:a + nbytes]
+                mrs[0].fetch(allocator=alloc_)
+            t0l = time.perf_counter()
+            fetch_again()
+            link["d2h_alone_ms"] = 1e3 * (time.perf_counter() - t0l)
+            t0l = time.perf_counter()
+            upl = FileUpload(hfiles, local_rank)
+            fetch_again()
+            upl.wait()
+            link["h2d_and_d2h_together_ms"] = 1e3 * (time.perf_counter() - t0l)
+            upl.close()
+        except Exception as ex:                                          # a probe must not take the line down
+            link["error"] = repr(ex)[:200]
         assert all(x == n_out for x in rows_seen), (rows_seen, n_out)
         tt = torch.tensor([dt / n_e2e], device=dev, dtype=torch.float64)
         if world > 1:
@@ -825,7 +974,8 @@ def main():
                       "fetch() over the C ABI; wall clock of K consecutive buckets / K; the H2D of bucket i+1's files "
                       "(library upload stream) and the D2H of bucket i-1's batch (second merge handle) overlap the decode + "
                       "merge of bucket i; pinned buffers bound to the GPU's NUMA node",
-               "upload_overlapped": overlap,
+               "upload_overlapped": overlap, "h2d_alone_ms": h2d_only_ms, "link_probes": link,
+               "h2d_alone_gbs": sum(len(hf) for hf in host_files) / (h2d_only_ms * 1e-3) / 1e9,
                "pcie_floor_ms": 1e3 * max(h2d, int(d2h_bytes[0])) / 55e9}
         for m_ in mrs:
             m_.close()
@@ -985,6 +1135,13 @@ def main():
                     lib.pg_trim()
             except Exception as e:                                   # an extra must not take the headline line down
                 extra[f"{wl}_merge_only"] = {"error": repr(e)[:300]}
+
+    if world == 1 and not args.no_extra and args.workload == "c3" and rows == w["rows"]:
+        try:
+            extra["c5"] = extra_c5(local_rank, peak)
+        except Exception as e:
+            extra["c5"] = {"error": repr(e)[:300]}
+        lib.pg_trim()
 
     # ---------------- extra: C4's bucket scheduling on hardware — many buckets per GPU, longest-processing-time
     # assignment by input bytes (paimon_b200/bucket_scheduler.py), every rank merging its own buckets back to back

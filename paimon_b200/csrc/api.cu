@@ -447,16 +447,13 @@ static pg_status build_descriptors(Merge *m) {
     }
     memcpy(host.data() + o_cols, m->cols.data(), sizeof(ColDesc) * nc);
     {
-        // the emit kernel's pass list (see k_emit): columns without staged data, the size pass of every var-len
-        // column, the fixed-width columns, the copy pass of every var-len column.  phase ids = emit.cu PH_*
+        // the emit kernel's pass list: var-len columns first (their cross-tile look-back then happens while the CTAs of
+        // a wave are still close together in time), then everything else; columns the read type leaves out are skipped
         int32_t *ord = (int32_t *)(host.data() + o_ord);
         int32_t *vlc = (int32_t *)(host.data() + o_vlc);
         int n = 0;
-        auto plain = [&](int c) { return m->cols[c].mode == CM_SEQ || m->cols[c].mode == CM_KIND; };
-        for (int c = 0; c < nc; c++) if (plain(c)) ord[n++] = c | (0 << 16);
-        for (int c = 0; c < nc; c++) if (m->emit[c] && m->cols[c].width == 0) ord[n++] = c | (1 << 16);
-        for (int c = 0; c < nc; c++) if (m->emit[c] && m->cols[c].width != 0 && !plain(c)) ord[n++] = c | (2 << 16);
-        for (int c = 0; c < nc; c++) if (m->emit[c] && m->cols[c].width == 0) ord[n++] = c | (3 << 16);
+        for (int c = 0; c < nc; c++) if (m->emit[c] && m->cols[c].width == 0) ord[n++] = c;
+        for (int c = 0; c < nc; c++) if (m->emit[c] && m->cols[c].width != 0) ord[n++] = c;
         m->n_passes = n;
         for (int v = 0; v < nv; v++) vlc[v] = m->varlen_cols[v];
     }
@@ -738,8 +735,6 @@ static pg_status execute(Merge *m) {
         if (cd.width > 0) bytes_out += oc.data_bytes;
     }
     m->stats.bytes_out = bytes_out;
-    uint16_t *vsrc = nullptr;
-    if (nv > 0) PG_CUDA(oalloc(sizeof(uint16_t) * (size_t)nv * (size_t)(n_out + 64) + 64, (void **)&vsrc));
     PG_CUDA(cudaMemcpyAsync(m->d_out_cols, m->out_cols.data(), sizeof(pg_out_column) * nc,
                             cudaMemcpyHostToDevice, sm));
 
@@ -759,10 +754,7 @@ static pg_status execute(Merge *m) {
     ea.cols = m->d_cols;
     ea.col_order = m->d_col_order;
     ea.n_passes = m->n_passes;
-    ea.single_winner = (m->flags.engine == PG_ENGINE_DEDUPLICATE || m->flags.engine == PG_ENGINE_FIRST_ROW) ? 1 : 0;
     ea.varlen_cols = m->d_varlen_cols;
-    ea.vsrc = vsrc;
-    ea.vsrc_stride = n_out + 64;
     ea.ptrs = m->d_ptrs;
     ea.run_rows = m->d_run_rows;
     ea.n_cols = nc;

@@ -831,57 +831,88 @@ k_pq_walk_dicts(const PqPage *dicts, int n_dicts, const PqChunk *chunks, int32_t
 // The walk of one page is a dependent chain (every length word says where the next one is), so a page cannot be
 // split; a section has tens of thousands of such pages, though, so every LANE walks its own page: 32 independent
 // chains per warp instead of one lane working while 31 idle (the warp-per-page version spent ~38 issue slots per
-// value and was issue-bound at 24 ms per 700 M values; profiles/README.md).  Pages of a column chunk are neighbours in
-// the page table, so the lanes of a warp walk streams of similar length.  Length words are read through L1 (a 128-byte
-// line serves ~6 values) with the lines ahead prefetched; the offsets go out four at a time as 16-byte stores.
-__device__ __forceinline__ uint32_t pq_ld32_unaligned(const uint8_t *p) {
-    const uintptr_t a = (uintptr_t)p;
-    const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
-    const uint32_t lo = __ldg(q), hi = __ldg(q + 1);          // (streams are followed by >= 8 readable bytes)
-    return __funnelshift_r(lo, hi, (int)(a & 3) * 8);
-}
-
-constexpr int kWalkLaneThreads = 128;
-__global__ void __launch_bounds__(kWalkLaneThreads)
+// value and was issue-bound: 24 ms per 700 M values).  Pages of a column chunk are neighbours in the page table, so the
+// lanes of a warp walk streams of similar length.
+// Reading the length words straight from global memory makes every lane miss a 32-byte sector on nearly every value
+// (23 ms again: 32 scattered sector fetches per warp step, one round trip each), so the warp works in ROUNDS: it
+// loads the next kWvWin bytes of all 32 streams into shared memory with coalesced 16-byte loads (16 lanes per stream,
+// 8 KiB in flight per warp), then every lane walks the values whose length word lies inside its window at
+// shared-memory latency.  Rows of the window buffer are XOR-swizzled per 16-byte chunk (lanes walk their rows at
+// similar offsets: without it every access is a 32-way bank conflict).
+constexpr int kWvWarps = 4, kWvWin = 256;
+__global__ void __launch_bounds__(kWvWarps * 32)
 k_pq_walk_values(PqPage *pages, int n_pages, const PqChunk *chunks, int32_t *vstart, int32_t *err) {
-    const int t = blockIdx.x * kWalkLaneThreads + threadIdx.x;
-    if (t >= n_pages) return;
-    const PqPage pg = pages[t];
-    if (pg.bad || pg.enc != ENC_PLAIN || chunks[pg.chunk].phys != pq::T_BYTE_ARRAY) return;
-    int32_t *vs = vstart + pg.vs_base;
-    const uint8_t *stream = pg.body + pg.values_off;
-    const int64_t slen = pg.body_len - pg.values_off;
-    const int nnz = pg.nnz;
-    // out(j) = payload_base + (stream offset of value j's length word) - 4 j
-    int64_t q = 0, bias = pg.payload_base;
-    bool bad = false;
-    auto step = [&]() -> int32_t {
-        // value at stream offset q: returns its output start, advances q behind it
-        if (q + 4 > slen) { bad = true; return 0; }
-        const uint32_t len = pq_ld32_unaligned(stream + q);
-        if ((int64_t)len > slen - q - 4) { bad = true; return 0; }
-        const int32_t o = (int32_t)(q + bias);
-        const int64_t qn = q + 4 + len;
-        if ((q ^ qn) >> 7) {
-            // entering a new 128-byte line: ask for the lines ahead
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(stream + min(qn + 256, slen)));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(stream + min(qn + 2048, slen)));
-        }
-        q = qn;
-        bias -= 4;
-        return o;
-    };
-    int j = 0;
-    while (j < nnz && !bad && ((uintptr_t)(vs + j) & 15)) { const int32_t o = step(); if (!bad) vs[j] = o; j++; }
-    while (j + 4 <= nnz && !bad) {
-        int4 o;
-        o.x = step(); o.y = step(); o.z = step(); o.w = step();
-        if (!bad) *(int4 *)(vs + j) = o;
-        j += 4;
+    __shared__ __align__(16) uint8_t s_win[kWvWarps][32][kWvWin];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = blockIdx.x * (kWvWarps * 32) + threadIdx.x;
+    bool done = true;
+    PqPage pg;
+    pg.nnz = 0;
+    if (t < n_pages) {
+        pg = pages[t];
+        done = pg.bad || pg.enc != ENC_PLAIN || chunks[pg.chunk].phys != pq::T_BYTE_ARRAY;
     }
-    while (j < nnz && !bad) { const int32_t o = step(); if (!bad) vs[j] = o; j++; }
-    if (bad || q != slen) { pq_err(err, KERR_BAD_PAGE); pages[t].bad = 1; return; }
-    vs[nnz] = (int32_t)(q + bias);
+    const bool mine = !done;
+    int32_t *vs = mine ? vstart + pg.vs_base : nullptr;
+    const uint8_t *stream = mine ? pg.body + pg.values_off : nullptr;
+    const int64_t slen = mine ? pg.body_len - pg.values_off : 0;
+    const int nnz = mine ? pg.nnz : 0;
+    int64_t q = 0, bias = mine ? pg.payload_base : 0;     // out(j) = payload_base + (offset of value j's length word) - 4 j
+    int j = 0;
+    bool bad = false;
+    if (nnz == 0) done = true;
+    uint8_t (*rows)[kWvWin] = s_win[warp];
+    while (!__all_sync(0xffffffffu, done)) {
+        // ---- load every live lane's window [wb, wb + kWvWin): wb = the 16-byte boundary at or below its position
+        const uint8_t *wb = done ? nullptr : (const uint8_t *)((uintptr_t)(stream + q) & ~(uintptr_t)15);
+        const uint8_t *wend = done ? nullptr : stream + slen;
+#pragma unroll
+        for (int i0 = 0; i0 < 16; i0 += 4) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int w = 2 * (i0 + u) + (lane >> 4), c = lane & 15;
+                const uint8_t *wbw = (const uint8_t *)__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)wb, w);
+                const uint8_t *wew = (const uint8_t *)__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)wend, w);
+                v[u] = make_uint4(0, 0, 0, 0);
+                if (wbw != nullptr && wbw + 16 * c < wew) v[u] = __ldg((const uint4 *)(wbw + 16 * c));   // (<= 15 bytes past the page)
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int w = 2 * (i0 + u) + (lane >> 4), c = lane & 15;
+                *(uint4 *)&rows[w][((c ^ (w & 15)) << 4)] = v[u];
+            }
+        }
+        __syncwarp();
+        // ---- walk the values whose length word lies inside the window
+        if (!done) {
+            int rel = (int)((stream + q) - wb);
+            const uint8_t *row = rows[lane];
+            const int sw = lane & 15;
+            while (j < nnz && rel + 4 <= kWvWin) {
+                if (q + 4 > slen) { bad = true; break; }
+                uint32_t len = 0;
+#pragma unroll
+                for (int b2 = 0; b2 < 4; b2++) {
+                    const int a2 = rel + b2;
+                    len |= (uint32_t)row[(((a2 >> 4) ^ sw) << 4) | (a2 & 15)] << (8 * b2);
+                }
+                if ((int64_t)len > slen - q - 4) { bad = true; break; }
+                vs[j] = (int32_t)(q + bias);
+                bias -= 4;
+                j++;
+                q += 4 + (int64_t)len;
+                // (a long value ends the round: rel leaves the window)
+                rel = len > (uint32_t)kWvWin ? kWvWin : rel + 4 + (int)len;
+            }
+            if (bad || j >= nnz) done = true;
+        }
+        __syncwarp();
+    }
+    if (mine) {
+        if (bad || (nnz > 0 && q != slen) || (nnz == 0 && slen != 0)) { pq_err(err, KERR_BAD_PAGE); pages[t].bad = 1; return; }
+        vs[nnz] = (int32_t)(q + bias);
+    }
 }
 
 // ------------------------------------------------------------------ expand: one CTA per data page
@@ -891,6 +922,17 @@ k_pq_walk_values(PqPage *pages, int n_pages, const PqChunk *chunks, int32_t *vst
 // walked in windows of 256 validity words (aligned to the run's 32-row words, so pages that start in the middle of a
 // word mask their neighbours' bits out); a block scan of the word popcounts gives every word its rank base.
 constexpr int kExpThreads = 256;
+constexpr int kPayIn = 8 * 1024, kPayOut = 7 * 1024;      // staging of a batch of kExpThreads PLAIN BYTE_ARRAY values
+constexpr int kPayBatches = 1023;                          // batch boundaries kept per page (pages beyond: direct path)
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ uint64_t pq_load_unaligned(const uint8_t *p, int w) {
     if (w == 8) {
@@ -909,14 +951,21 @@ __device__ __forceinline__ uint64_t pq_load_unaligned(const uint8_t *p, int w) {
 
 __global__ void __launch_bounds__(kExpThreads, 6)
 k_pq_expand(const PqPage *pages, const PqPage *dicts, const PqChunk *chunks, const PqOut *outs, int n_cols,
-            const int32_t *ids, const int32_t *vstart, const int32_t *dict_off, const int32_t *dict_len, int32_t *err) {
+            const int32_t *ids, const int32_t *vstart, const int32_t *dict_off, const int32_t *dict_len, int32_t *err,
+            int kind) {
     __shared__ uint32_t s_bits[kExpThreads];
     __shared__ int s_rank[kExpThreads];
     __shared__ int s_wlen[kExpThreads];
     __shared__ int s_ws[34];
+    __shared__ int s_vs[2][kExpThreads + 4];
+    __shared__ int s_bnd[kPayBatches + 1];
+    __shared__ __align__(16) uint8_t s_in[2][kPayIn];
+    __shared__ __align__(16) uint8_t s_out[kPayOut];
     const PqPage pg = pages[blockIdx.x];
     if (pg.bad || pg.num_values == 0) return;
     const PqChunk ch = chunks[pg.chunk];
+    // kind 1: pages that do not need the value walk's offsets; kind 2: PLAIN BYTE_ARRAY pages (they do); 0: all
+    if (kind != 0 && (kind == 2) != (ch.phys == pq::T_BYTE_ARRAY && pg.enc == ENC_PLAIN)) return;
     const PqOut out = outs[ch.run * n_cols + ch.col];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t row0 = pg.row0, row1 = pg.row0 + pg.num_values;
@@ -997,6 +1046,44 @@ k_pq_expand(const PqPage *pages, const PqPage *dicts, const PqChunk *chunks, con
             // ~8 KB of the ~40 KB that have to be in flight per SM to fill the HBM pipe.
             constexpr int kExpUnroll = 4, kStep = kExpThreads / 32;
             const int fmode = varlen ? 0 : pg.enc == ENC_RLE_BOOL ? 1 : ch.phys == pq::T_BOOLEAN ? 2 : is_dict ? 3 : 4;
+            if (fmode == 4 && pw == 8 && out.out_width == 8 && ch.cast == 0) {
+                // the common case (PLAIN INT64 / DOUBLE into an 8-byte column): two rows per lane and one 16-byte store,
+                // a warp step covers two validity words; kPairUnroll steps in flight
+                constexpr int kPairUnroll = 2;
+                const int half = lane >> 4, p0 = 2 * (lane & 15);
+                const uintptr_t a0 = (uintptr_t)values;
+                const int sh = (int)(a0 & 7) * 8;
+                const uint64_t *q0 = (const uint64_t *)(a0 & ~(uintptr_t)7);
+                uint64_t *od = (uint64_t *)out.data;
+                for (int j0 = 2 * warp; j0 < nw; j0 += 2 * kStep * kPairUnroll) {
+                    int64_t row[kPairUnroll];
+                    bool in0[kPairUnroll], in1[kPairUnroll];
+                    uint64_t l0[kPairUnroll], h0[kPairUnroll], l1[kPairUnroll], h1[kPairUnroll];
+#pragma unroll
+                    for (int u = 0; u < kPairUnroll; u++) {
+                        const int jj = j0 + 2 * kStep * u + half;
+                        const uint32_t b = jj < nw ? s_bits[jj] : 0;
+                        const int rk = jj < nw ? s_rank[jj] + __popc(b & ((1u << p0) - 1)) : 0;
+                        const bool v0 = (b >> p0) & 1, v1 = (b >> (p0 + 1)) & 1;
+                        row[u] = g0 + 32 * (int64_t)(w0 + jj) + p0;
+                        in0[u] = jj < nw && row[u] >= row0 && row[u] < row1;
+                        in1[u] = jj < nw && row[u] + 1 >= row0 && row[u] + 1 < row1;
+                        const int r1 = rk + (v0 ? 1 : 0);
+                        l0[u] = v0 ? q0[rk] : 0;                        // (bits outside the page are masked out above)
+                        h0[u] = (v0 && sh) ? q0[rk + 1] : 0;
+                        l1[u] = v1 ? q0[r1] : 0;
+                        h1[u] = (v1 && sh) ? q0[r1 + 1] : 0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < kPairUnroll; u++) {
+                        const uint64_t x0 = sh ? (l0[u] >> sh) | (h0[u] << (64 - sh)) : l0[u];
+                        const uint64_t x1 = sh ? (l1[u] >> sh) | (h1[u] << (64 - sh)) : l1[u];
+                        if (in0[u] && in1[u]) *(ulonglong2 *)(od + row[u]) = make_ulonglong2(x0, x1);
+                        else if (in0[u]) od[row[u]] = x0;
+                        else if (in1[u]) od[row[u] + 1] = x1;
+                    }
+                }
+            } else
             for (int j0 = warp; j0 < nw; j0 += kStep * kExpUnroll) {
                 int64_t row[kExpUnroll];
                 int rank[kExpUnroll];
@@ -1078,35 +1165,82 @@ k_pq_expand(const PqPage *pages, const PqPage *dicts, const PqChunk *chunks, con
     }
     if (varlen) {
         if (!is_dict) {
-            // PLAIN: the page's payload is its value stream without the 4-byte length words.  8 lanes per value, two
-            // values per lane group and three bytes per lane in flight (all loads before the stores); longer
-            // values finish in a byte loop.
+            // PLAIN: the page's payload is its value stream with the 4-byte length words squeezed out.  Batches of
+            // kExpThreads values: the batch's stretch of the stream comes into shared memory with 16-byte async copies
+            // (the NEXT batch is in flight while this one is worked on), every thread moves ONE value byte by byte
+            // inside shared memory (all 32 lanes busy, no global latency), and the batch's contiguous output range
+            // leaves with 16-byte stores.  (8 lanes per value straight on global memory spent ~14 warp instructions
+            // per value and stalled on the gathers: 40 % of this kernel.)  Batches that do not fit the staging buffers
+            // (long values) and pages with more batches than the boundary table holds take the direct path.
             const int nnz = pg.nnz;
             const int64_t pb = pg.payload_base;
-            const int l8 = tid & 7;
-            for (int j = tid >> 3; j < nnz; j += 2 * (kExpThreads / 8)) {
-                const int jb = j + kExpThreads / 8;
-                const int sa = vs[j], ea = vs[j + 1];
-                int sb = 0, eb = 0;
-                if (jb < nnz) { sb = vs[jb]; eb = vs[jb + 1]; }
-                const uint8_t *pa = values + (4 * (int64_t)(j + 1) - pb);      // pa[o] = source of output byte o
-                const uint8_t *pbb = values + (4 * (int64_t)(jb + 1) - pb);
-                const int ia = sa + l8, ib = sb + l8;
-                uint8_t xa0 = 0, xa1 = 0, xa2 = 0, xb0 = 0, xb1 = 0, xb2 = 0;
-                if (ia < ea) xa0 = pa[ia];
-                if (ia + 8 < ea) xa1 = pa[ia + 8];
-                if (ia + 16 < ea) xa2 = pa[ia + 16];
-                if (ib < eb) xb0 = pbb[ib];
-                if (ib + 8 < eb) xb1 = pbb[ib + 8];
-                if (ib + 16 < eb) xb2 = pbb[ib + 16];
-                if (ia < ea) payload[ia] = xa0;
-                if (ia + 8 < ea) payload[ia + 8] = xa1;
-                if (ia + 16 < ea) payload[ia + 16] = xa2;
-                if (ib < eb) payload[ib] = xb0;
-                if (ib + 8 < eb) payload[ib + 8] = xb1;
-                if (ib + 16 < eb) payload[ib + 16] = xb2;
-                for (int b = ia + 24; b < ea; b += 8) payload[b] = pa[b];
-                for (int b = ib + 24; b < eb; b += 8) payload[b] = pbb[b];
+            const int nb = (nnz + kExpThreads - 1) / kExpThreads;
+            const bool staged_page = nb <= kPayBatches;
+            __syncthreads();
+            if (staged_page) for (int i = tid; i <= nb; i += kExpThreads) s_bnd[i] = vs[min(i * kExpThreads, nnz)];
+            __syncthreads();
+            // batch b: values [b T, b T + jn), output bytes [s_bnd[b], s_bnd[b + 1]), stream bytes from value b T's length word
+            auto batch_src = [&](int b2) -> const uint8_t * { return values + ((int64_t)s_bnd[b2] - pb) + 4 * (int64_t)b2 * kExpThreads; };
+            auto batch_fits = [&](int b2) -> bool {
+                const int jn = min(kExpThreads, nnz - b2 * kExpThreads);
+                const int out_len = s_bnd[b2 + 1] - s_bnd[b2];
+                const int iskew = (int)((uintptr_t)batch_src(b2) & 15), oskew = (int)((uintptr_t)(payload + s_bnd[b2]) & 15);
+                return iskew + out_len + 4 * jn <= kPayIn && oskew + out_len <= kPayOut;
+            };
+            auto prefetch = [&](int b2) {
+                const int jn = min(kExpThreads, nnz - b2 * kExpThreads);
+                int *dv = s_vs[b2 & 1];
+                for (int i = tid; i <= jn; i += kExpThreads) cp_async4(dv + i, vs + b2 * kExpThreads + i);
+                if (batch_fits(b2)) {
+                    const uint8_t *src0 = batch_src(b2);
+                    const int iskew = (int)((uintptr_t)src0 & 15);
+                    const int n16 = (iskew + (s_bnd[b2 + 1] - s_bnd[b2]) + 4 * jn + 15) >> 4;
+                    uint8_t *di = s_in[b2 & 1];
+                    for (int i = tid; i < n16; i += kExpThreads) cp_async16(di + 16 * i, src0 - iskew + 16 * i);   // (<= 15 bytes past the page)
+                }
+                cp_async_commit();
+            };
+            if (staged_page && nb > 0) prefetch(0);
+            for (int b2 = 0; b2 < nb; b2++) {
+                const int j0 = b2 * kExpThreads, jn = min(kExpThreads, nnz - j0);
+                if (!staged_page) {
+                    for (int t = tid >> 3; t < jn; t += kExpThreads / 8) {
+                        const int st = vs[j0 + t], len = vs[j0 + t + 1] - st;
+                        const uint8_t *src = values + ((int64_t)st - pb) + 4 * (int64_t)(j0 + t + 1);
+                        for (int b3 = tid & 7; b3 < len; b3 += 8) payload[(int64_t)st + b3] = src[b3];
+                    }
+                    continue;
+                }
+                if (b2 + 1 < nb) { prefetch(b2 + 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+                __syncthreads();                                            // batch b2 has landed for every thread
+                const int *cvs = s_vs[b2 & 1];
+                const int out0 = s_bnd[b2], out_len = s_bnd[b2 + 1] - out0;
+                if (batch_fits(b2)) {
+                    const uint8_t *src0 = batch_src(b2);
+                    const int iskew = (int)((uintptr_t)src0 & 15), oskew = (int)((uintptr_t)(payload + out0) & 15);
+                    if (tid < jn) {
+                        const int o = cvs[tid] - out0, len = cvs[tid + 1] - cvs[tid];
+                        const uint8_t *sp = s_in[b2 & 1] + iskew + o + 4 * (tid + 1);
+                        uint8_t *dp = s_out + oskew + o;
+                        for (int b3 = 0; b3 < len; b3++) dp[b3] = sp[b3];
+                    }
+                    __syncthreads();
+                    // s_out[oskew + i] is output byte out0 + i: whole 16-byte chunks as vectors, the edges byte-wise
+                    uint8_t *dst16 = payload + out0 - oskew;                // 16-byte aligned
+                    const int end = oskew + out_len;
+                    for (int c = tid; c * 16 < end; c += kExpThreads) {
+                        const int c0 = c * 16;
+                        if (c0 >= oskew && c0 + 16 <= end) *(uint4 *)(dst16 + c0) = *(const uint4 *)(s_out + c0);
+                        else for (int b3 = max(c0, oskew); b3 < min(c0 + 16, end); b3++) dst16[b3] = s_out[b3];
+                    }
+                } else {
+                    for (int t = tid >> 3; t < jn; t += kExpThreads / 8) {
+                        const int st = cvs[t], len = cvs[t + 1] - st;
+                        const uint8_t *src = values + ((int64_t)st - pb) + 4 * (int64_t)(j0 + t + 1);
+                        for (int b3 = tid & 7; b3 < len; b3 += 8) payload[(int64_t)st + b3] = src[b3];
+                    }
+                }
+                __syncthreads();                                            // s_out / the buffers of batch b2 are free again
             }
         }
         if (pg.is_last && tid == 0) out.offsets[row1] = (int32_t)(pg.payload_base + pg.payload_bytes);
@@ -1593,13 +1727,31 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
     }
     if (np > 0) {
         if (n_pairs) {
-            k_pq_walk_values<<<(np + kWalkLaneThreads - 1) / kWalkLaneThreads, kWalkLaneThreads, 0, sm>>>(
+            // the value walk (one lane per page: latency-bound at low occupancy) runs beside the expansion of the pages
+            // that do not need it; the PLAIN BYTE_ARRAY pages follow when both are done
+            static thread_local cudaStream_t side = nullptr;
+            static thread_local cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+            if (!side) {
+                PG_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+                PG_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+                PG_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+            }
+            PG_CUDA(cudaEventRecord(ev_fork, sm));
+            PG_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+            k_pq_walk_values<<<(np + kWvWarps * 32 - 1) / (kWvWarps * 32), kWvWarps * 32, 0, side>>>(
                 d_pages, np, d_chunks, d_vstart, d_err);
+            PG_CUDA(cudaEventRecord(ev_join, side));
+            k_pq_expand<<<np, kExpThreads, 0, sm>>>(d_pages, d_dicts, d_chunks, d_outs, nc, d_ids, d_vstart, d_dict_off,
+                                                    d_dict_len, d_err, 1);
+            PG_CUDA(cudaStreamWaitEvent(sm, ev_join, 0));
+            k_pq_expand<<<np, kExpThreads, 0, sm>>>(d_pages, d_dicts, d_chunks, d_outs, nc, d_ids, d_vstart, d_dict_off,
+                                                    d_dict_len, d_err, 2);
+            launches += 3;
+        } else {
+            k_pq_expand<<<np, kExpThreads, 0, sm>>>(d_pages, d_dicts, d_chunks, d_outs, nc, d_ids, d_vstart, d_dict_off,
+                                                    d_dict_len, d_err, 0);
             launches++;
         }
-        k_pq_expand<<<np, kExpThreads, 0, sm>>>(d_pages, d_dicts, d_chunks, d_outs, nc, d_ids, d_vstart, d_dict_off,
-                                                d_dict_len, d_err);
-        launches++;
     }
     if (any_empty && n_pairs) {
         k_pq_zero_first_offset<<<(n_runs * nc + 127) / 128, 128, 0, sm>>>(d_outs, n_runs * nc);

@@ -237,12 +237,9 @@ struct EmitArgs {
     const uint32_t *gplan;             // sequence-group marks (see PlanArgs), NULL without groups
     const uint32_t *gagg;
     const ColDesc *cols;
-    const int32_t *col_order;          // device [n_passes]: the emit kernel's pass list, column | phase << 16
+    const int32_t *col_order;          // device [n_passes]: the emit kernel's pass list (column indexes)
     int n_passes;
-    int single_winner;                 // deduplicate / first-row: one member of a key group provides every cell
     const int32_t *varlen_cols;        // device [n_varlen]: column of var-len index v
-    uint16_t *vsrc;                    // [n_varlen][vsrc_stride] scratch: source member of every var-len output cell
-    int64_t vsrc_stride;
     ColPtrs ptrs;
     const int64_t *run_rows;           // device [k] rows per run
     int n_cols;
