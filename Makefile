@@ -4,7 +4,7 @@ ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Iinclude -Ipaimon_b200/csrc
 SRCS := paimon_b200/csrc/merge.cu paimon_b200/csrc/emit.cu paimon_b200/csrc/api.cu \
 	paimon_b200/csrc/parquet_decode.cu paimon_b200/csrc/parquet_encode.cu paimon_b200/csrc/parquet_meta.cc \
-	paimon_b200/csrc/arrow_export.cu paimon_b200/csrc/upload.cu paimon_b200/csrc/orc_decode.cu paimon_b200/csrc/orc_meta.cc
+	paimon_b200/csrc/arrow_export.cu paimon_b200/csrc/upload.cu paimon_b200/csrc/readback.cu paimon_b200/csrc/orc_decode.cu paimon_b200/csrc/orc_meta.cc
 HDRS := include/paimon_gpu.h paimon_b200/csrc/pg_internal.h paimon_b200/csrc/device_utils.cuh paimon_b200/csrc/parquet_meta.h \
 	paimon_b200/csrc/zstd_device.cuh paimon_b200/csrc/inflate_device.cuh paimon_b200/csrc/orc_device.cuh paimon_b200/csrc/orc_meta.h \
 	paimon_b200/csrc/scan_kernels.cuh

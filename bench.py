@@ -564,7 +564,7 @@ def main():
                     help="timed region starts from Parquet file bytes in HBM (default for c3) or from decoded columns")
     ap.add_argument("--rows", type=int, default=None, help="override total input rows per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-range-rows", type=int, default=8 << 20,
                     help="e2e (--source columns): input rows per key range of the streaming reader (0 = one batch)")

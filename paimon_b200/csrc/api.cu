@@ -476,7 +476,7 @@ static pg_status build_descriptors(Merge *m) {
         PG_CUDA(cudaMalloc(&m->d_desc, total));
         m->desc_cap = total;
     }
-    PG_CUDA(cudaMemcpyAsync(m->d_desc, host.data(), total, cudaMemcpyHostToDevice, m->stream));
+    { pg_status ts = small_h2d(m->d_desc, host.data(), total, m->stream); if (ts) return ts; }
     PG_CUDA(cudaStreamSynchronize(m->stream));
     unsigned char *d = (unsigned char *)m->d_desc;
     m->d_key_ptrs = (const void **)(d + o_key);
@@ -668,9 +668,13 @@ static pg_status execute(Merge *m) {
     launch_scan(sm, tile_rows, T, row_base, m->d_totals);
     launches += 2;
     PG_CUDA(cudaEventRecord(m->ev[2], sm));
-    PG_CUDA(cudaMemcpyAsync(m->h_totals, m->d_totals, sizeof(int64_t), cudaMemcpyDeviceToHost, sm));
-    PG_CUDA(cudaMemcpyAsync(m->h_err, m->d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, sm));
-    PG_CUDA(cudaStreamSynchronize(sm));      // the one size read-back: output buffers are sized exactly
+    {
+        SmallReads rb(sm);                   // the one size read-back: output buffers are sized exactly
+        pg_status rs = rb.add(m->h_totals, m->d_totals, sizeof(int64_t));
+        if (!rs) rs = rb.add(m->h_err, m->d_err, sizeof(int32_t));
+        if (!rs) rs = rb.finish();
+        if (rs) { free_temps(); return rs; }
+    }
     if (*m->h_err != KERR_NONE) {
         free_temps();
         return fail(*m->h_err == KERR_TILE_OVERFLOW || *m->h_err == KERR_OFFSET_OVERFLOW ? PG_ERR_INTERNAL
@@ -735,8 +739,7 @@ static pg_status execute(Merge *m) {
         if (cd.width > 0) bytes_out += oc.data_bytes;
     }
     m->stats.bytes_out = bytes_out;
-    PG_CUDA(cudaMemcpyAsync(m->d_out_cols, m->out_cols.data(), sizeof(pg_out_column) * nc,
-                            cudaMemcpyHostToDevice, sm));
+    { pg_status ts = small_h2d(m->d_out_cols, m->out_cols.data(), sizeof(pg_out_column) * nc, sm); if (ts) return ts; }
 
     // ---- emit
     EmitArgs ea{};
@@ -769,10 +772,14 @@ static pg_status execute(Merge *m) {
     launch_emit(ea);
     launches++;
     PG_CUDA(cudaEventRecord(m->ev[3], sm));
-    PG_CUDA(cudaMemcpyAsync(m->h_err, m->d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, sm));
-    PG_CUDA(cudaMemcpyAsync(m->h_totals, m->d_totals, sizeof(int64_t) * (nv + 1), cudaMemcpyDeviceToHost, sm));
-    free_temps();
-    PG_CUDA(cudaStreamSynchronize(sm));
+    {
+        SmallReads rb(sm);
+        pg_status rs = rb.add(m->h_err, m->d_err, sizeof(int32_t));
+        if (!rs) rs = rb.add(m->h_totals, m->d_totals, sizeof(int64_t) * (nv + 1));
+        free_temps();
+        if (!rs) rs = rb.finish();
+        if (rs) return rs;
+    }
     PG_CUDA(cudaGetLastError());
     m->has_batch = true;
     if (*m->h_err != KERR_NONE) {

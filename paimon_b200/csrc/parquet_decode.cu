@@ -839,6 +839,14 @@ k_pq_walk_dicts(const PqPage *dicts, int n_dicts, const PqChunk *chunks, int32_t
 // 8 KiB in flight per warp), then every lane walks the values whose length word lies inside its window at
 // shared-memory latency.  Rows of the window buffer are XOR-swizzled per 16-byte chunk (lanes walk their rows at
 // similar offsets: without it every access is a 32-way bank conflict).
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 constexpr int kWvWarps = 4, kWvWin = 256;
 __global__ void __launch_bounds__(kWvWarps * 32)
 k_pq_walk_values(PqPage *pages, int n_pages, const PqChunk *chunks, int32_t *vstart, int32_t *err) {
@@ -866,23 +874,17 @@ k_pq_walk_values(PqPage *pages, int n_pages, const PqChunk *chunks, int32_t *vst
         // ---- load every live lane's window [wb, wb + kWvWin): wb = the 16-byte boundary at or below its position
         const uint8_t *wb = done ? nullptr : (const uint8_t *)((uintptr_t)(stream + q) & ~(uintptr_t)15);
         const uint8_t *wend = done ? nullptr : stream + slen;
-#pragma unroll
-        for (int i0 = 0; i0 < 16; i0 += 4) {
-            uint4 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int w = 2 * (i0 + u) + (lane >> 4), c = lane & 15;
-                const uint8_t *wbw = (const uint8_t *)__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)wb, w);
-                const uint8_t *wew = (const uint8_t *)__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)wend, w);
-                v[u] = make_uint4(0, 0, 0, 0);
-                if (wbw != nullptr && wbw + 16 * c < wew) v[u] = __ldg((const uint4 *)(wbw + 16 * c));   // (<= 15 bytes past the page)
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int w = 2 * (i0 + u) + (lane >> 4), c = lane & 15;
-                *(uint4 *)&rows[w][((c ^ (w & 15)) << 4)] = v[u];
-            }
+        // (16 async 16-byte copies per lane, all in flight together: one round trip per round; chunks past the stream's
+        // end are not loaded — the walk never reads a length word it has not bounds-checked against the stream)
+#pragma unroll 4
+        for (int i = 0; i < 16; i++) {
+            const int w = 2 * i + (lane >> 4), c = lane & 15;
+            const uint8_t *wbw = (const uint8_t *)__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)wb, w);
+            const uint8_t *wew = (const uint8_t *)__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)wend, w);
+            if (wbw != nullptr && wbw + 16 * c < wew) cp_async16(&rows[w][((c ^ (w & 15)) << 4)], wbw + 16 * c);   // (<= 15 bytes past the page)
         }
+        cp_async_commit();
+        cp_async_wait<0>();
         __syncwarp();
         // ---- walk the values whose length word lies inside the window
         if (!done) {
@@ -891,12 +893,11 @@ k_pq_walk_values(PqPage *pages, int n_pages, const PqChunk *chunks, int32_t *vst
             const int sw = lane & 15;
             while (j < nnz && rel + 4 <= kWvWin) {
                 if (q + 4 > slen) { bad = true; break; }
-                uint32_t len = 0;
-#pragma unroll
-                for (int b2 = 0; b2 < 4; b2++) {
-                    const int a2 = rel + b2;
-                    len |= (uint32_t)row[(((a2 >> 4) ^ sw) << 4) | (a2 & 15)] << (8 * b2);
-                }
+                // the length word: two aligned words of the (chunk-swizzled) row, funnel-shifted
+                const int wi = rel >> 2, wj = min(wi + 1, kWvWin / 4 - 1);
+                const uint32_t lo = *(const uint32_t *)(row + ((((wi >> 2) ^ sw) << 4) | ((wi & 3) << 2)));
+                const uint32_t hi = *(const uint32_t *)(row + ((((wj >> 2) ^ sw) << 4) | ((wj & 3) << 2)));
+                const uint32_t len = __funnelshift_r(lo, hi, (rel & 3) * 8);
                 if ((int64_t)len > slen - q - 4) { bad = true; break; }
                 vs[j] = (int32_t)(q + bias);
                 bias -= 4;
@@ -925,14 +926,6 @@ constexpr int kExpThreads = 256;
 constexpr int kPayIn = 8 * 1024, kPayOut = 7 * 1024;      // staging of a batch of kExpThreads PLAIN BYTE_ARRAY values
 constexpr int kPayBatches = 1023;                          // batch boundaries kept per page (pages beyond: direct path)
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ uint64_t pq_load_unaligned(const uint8_t *p, int w) {
     if (w == 8) {
@@ -1440,20 +1433,22 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
             else if (files[f].mem == PG_MEM_DEVICE) need.push_back(f);
         }
         std::vector<uint8_t> tails(8 * need.size() + 8);
-        for (size_t i = 0; i < need.size(); i++)
-            PG_CUDA(cudaMemcpyAsync(tails.data() + 8 * i, files[need[i]].bytes + files[need[i]].size - 8, 8,
-                                    cudaMemcpyDeviceToHost, sm));
-        if (!need.empty()) PG_CUDA(cudaStreamSynchronize(sm));
+        SmallReads rb(sm);
+        for (size_t i = 0; i < need.size(); i++) {
+            pg_status rs = rb.add(tails.data() + 8 * i, files[need[i]].bytes + files[need[i]].size - 8, 8);
+            if (rs) return rs;
+        }
+        if (!need.empty()) { pg_status rs = rb.finish(); if (rs) return rs; }
         std::vector<std::vector<uint8_t>> footers(need.size());
         try {
             for (size_t i = 0; i < need.size(); i++) {
                 const int64_t flen = pq::footer_length(tails.data() + 8 * i);
                 if (flen + 12 > files[need[i]].size) return fail(PG_ERR_FORMAT, "parquet: bad footer length");
                 footers[i].resize((size_t)flen + 8);
-                PG_CUDA(cudaMemcpyAsync(footers[i].data(), files[need[i]].bytes + files[need[i]].size - 8 - flen,
-                                        (size_t)flen, cudaMemcpyDeviceToHost, sm));
+                pg_status rs = rb.add(footers[i].data(), files[need[i]].bytes + files[need[i]].size - 8 - flen, (size_t)flen);
+                if (rs) return rs;
             }
-            if (!need.empty()) PG_CUDA(cudaStreamSynchronize(sm));
+            if (!need.empty()) { pg_status rs = rb.finish(); if (rs) return rs; }
             for (size_t i = 0; i < need.size(); i++) {
                 own_meta[need[i]] = pq::parse_footer_thrift(footers[i].data(), (int64_t)footers[i].size() - 8);
                 meta[need[i]] = &own_meta[need[i]];
@@ -1625,16 +1620,22 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
     int64_t *d_totals = (int64_t *)(tb + tb_chunks + tb_outs + tb_pairs);      // [0..5] chunk totals, [8..] pair totals
     int32_t *d_err = (int32_t *)(d_totals + 6);
     PG_CUDA(cudaMemsetAsync(d_totals, 0, tb_tot, sm));
-    if (n_chunks) PG_CUDA(cudaMemcpyAsync(d_chunks, chunks.data(), sizeof(PqChunk) * n_chunks, cudaMemcpyHostToDevice, sm));
-    PG_CUDA(cudaMemcpyAsync(d_outs, outs.data(), sizeof(PqOut) * outs.size(), cudaMemcpyHostToDevice, sm));
-    if (n_pairs) PG_CUDA(cudaMemcpyAsync(d_pairs, pairs.data(), sizeof(PqPair) * n_pairs, cudaMemcpyHostToDevice, sm));
+    // (tables go through small_h2d: a kernel reads them out of mapped host memory, so they do not queue behind an
+    // asynchronous upload of the next section on the copy engine)
+    if (n_chunks) { pg_status ts = small_h2d(d_chunks, chunks.data(), sizeof(PqChunk) * n_chunks, sm); if (ts) return ts; }
+    { pg_status ts = small_h2d(d_outs, outs.data(), sizeof(PqOut) * outs.size(), sm); if (ts) return ts; }
+    if (n_pairs) { pg_status ts = small_h2d(d_pairs, pairs.data(), sizeof(PqPair) * n_pairs, sm); if (ts) return ts; }
     int64_t h_tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (n_chunks) {
         k_pq_walk<false><<<(n_chunks + 63) / 64, 64, 0, sm>>>(d_chunks, n_chunks, nullptr, nullptr, nullptr, d_err);
         k_pq_chunk_scan<<<1, kScanThreads, 0, sm>>>(d_chunks, n_chunks, d_totals);
         launches += 2;
-        PG_CUDA(cudaMemcpyAsync(h_tot, d_totals, sizeof(int64_t) * 8, cudaMemcpyDeviceToHost, sm));
-        PG_CUDA(cudaStreamSynchronize(sm));              // read-back 1: how many pages the section has
+        {
+            SmallReads rb(sm);                           // read-back 1: how many pages the section has
+            pg_status rs = rb.add(h_tot, d_totals, sizeof(int64_t) * 8);
+            if (!rs) rs = rb.finish();
+            if (rs) return rs;
+        }
         const int herr = (int)(h_tot[6] & 0xffffffff);
         if (herr != KERR_NONE) return kernel_error_status(herr);
     }
@@ -1696,9 +1697,13 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
         if (n_pairs) {
             k_pq_scan_pages<<<(n_pairs * 32 + 127) / 128, 128, 0, sm>>>(d_pages, d_chunks, d_pairs, n_pairs, d_totals + 8, d_err);
             launches++;
-            PG_CUDA(cudaMemcpyAsync(pair_tot.data(), d_totals + 8, sizeof(int64_t) * n_pairs, cudaMemcpyDeviceToHost, sm));
-            PG_CUDA(cudaMemcpyAsync(h_tot, d_totals, sizeof(int64_t) * 8, cudaMemcpyDeviceToHost, sm));
-            PG_CUDA(cudaStreamSynchronize(sm));          // read-back 2: exact payload sizes of the var-len columns
+            {
+                SmallReads rb(sm);                       // read-back 2: exact payload sizes of the var-len columns
+                pg_status rs = rb.add(pair_tot.data(), d_totals + 8, sizeof(int64_t) * n_pairs);
+                if (!rs) rs = rb.add(h_tot, d_totals, sizeof(int64_t) * 8);
+                if (!rs) rs = rb.finish();
+                if (rs) return rs;
+            }
             const int herr = (int)(h_tot[6] & 0xffffffff);
             if (herr != KERR_NONE) return kernel_error_status(herr);
         }
@@ -1723,7 +1728,7 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
                 pt += pad((size_t)pair_tot[pr.idx] + 64);
             }
         }
-        PG_CUDA(cudaMemcpyAsync(d_outs, outs.data(), sizeof(PqOut) * outs.size(), cudaMemcpyHostToDevice, sm));
+        { pg_status ts = small_h2d(d_outs, outs.data(), sizeof(PqOut) * outs.size(), sm); if (ts) return ts; }
     }
     if (np > 0) {
         if (n_pairs) {
@@ -1758,8 +1763,12 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
         launches++;
     }
     PG_CUDA(cudaEventRecord(e1, sm));
-    PG_CUDA(cudaMemcpyAsync(h_tot, d_totals, sizeof(int64_t) * 8, cudaMemcpyDeviceToHost, sm));
-    PG_CUDA(cudaStreamSynchronize(sm));
+    {
+        SmallReads rb(sm);
+        pg_status rs = rb.add(h_tot, d_totals, sizeof(int64_t) * 8);
+        if (!rs) rs = rb.finish();
+        if (rs) return rs;
+    }
     PG_CUDA(cudaGetLastError());
     {
         const int herr = (int)(h_tot[6] & 0xffffffff);

@@ -253,4 +253,22 @@ struct EmitArgs {
 };
 void launch_emit(const EmitArgs &ea);
 
+// readback.cu: small device -> host reads through device-mapped page-locked memory (a kernel stores them), so that
+// they do not queue behind another thread's large copies on the device -> host copy engine.  add() enqueues on the
+// stream, finish() synchronises the stream and delivers the bytes.  One object per synchronisation point, per thread.
+pg_status small_h2d(void *dev_dst, const void *host_src, size_t n, cudaStream_t stream);   // tables / descriptors
+
+class SmallReads {
+ public:
+    explicit SmallReads(cudaStream_t s) : stream_(s) {}
+    pg_status add(void *host_dst, const void *dev_src, size_t n);
+    pg_status finish();
+
+ private:
+    struct Item { void *dst; size_t off, n; };
+    cudaStream_t stream_;
+    std::vector<Item> items_;
+    size_t used_ = 0;
+};
+
 }  // namespace pg
