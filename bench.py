@@ -302,9 +302,12 @@ def schema_c5():
 
 
 def c5_bucket(schema, codec, seed=5):
-    """One C5 bucket as parquet-mr-style files written by pyarrow on the host (dictionary on, data page V1, 1 MiB
-    pages, ~128 MiB row groups; DECIMAL(15,2) / DATE in their physical INT64 / INT32 form): 1 base run (83.3 %) + 4
-    update runs whose keys are resampled from the base.  Returns ([(file bytes, run)], rows in, expected columns)."""
+    """One C5 bucket as parquet-mr-style files written by pyarrow on the host (dictionary on with parquet-mr's 1 MiB
+    dictionary page limit, data page V1, ~128 MiB row groups; DECIMAL(15,2) / DATE in their physical INT64 / INT32
+    form): 1 base run (83.3 %) + 4 update runs whose keys are resampled from the base.  parquet-mr closes a page at
+    1 MiB OR 20 000 rows (parquet.page.row.count.limit, RowDataParquetBuilder.java:63-99 keeps the defaults), pyarrow
+    only knows a byte limit: 160 KiB pages give the 20 000-row pages an 8-byte column gets from parquet-mr.
+    Returns ([(file bytes, run)], rows in, expected columns)."""
     import pyarrow as pa
     import pyarrow.parquet as pq
     rng = np.random.default_rng(seed)
@@ -345,13 +348,13 @@ def c5_bucket(schema, codec, seed=5):
         else:
             exp_part[idx] = part; exp_ship[idx] = ship; exp_seq[idx] = seq0 + np.arange(n_upd, dtype=np.int64)
         sink = pa.BufferOutputStream()
-        pq.write_table(tb, sink, compression=codec, use_dictionary=True, data_page_version="1.0", data_page_size=1 << 20,
+        pq.write_table(tb, sink, compression=codec, use_dictionary=True, data_page_version="1.0", data_page_size=160 << 10,
                        row_group_size=800_000, write_statistics=False, **({"compression_level": 1} if codec == "zstd" else {}))
         files.append((np.frombuffer(sink.getvalue(), np.uint8), r))
     return files, n_base + 4 * n_upd, {"l_partkey": exp_part, "l_shipdate": exp_ship, "_SEQUENCE_NUMBER": exp_seq}
 
 
-def extra_c5(local_rank, peak, steps=3):
+def extra_c5(local_rank, peak, steps=3, codecs=("none", "zstd")):
     """Decode + merge of a C5 bucket from file bytes resident in HBM, `none` and zstd-1 (run A / run B)."""
     from paimon_b200.format import FileUpload, read_section
     from paimon_b200.merge_function import DeduplicateMergeFunction
@@ -359,8 +362,8 @@ def extra_c5(local_rank, peak, steps=3):
     schema = schema_c5()
     spec = DeduplicateMergeFunction.factory().create()
     out = {"what": "SURVEY C5: one bucket of lineitem-shaped Parquet (15.6 M rows: base run + 4 update runs; dictionary on, "
-                   "page V1, 1 MiB pages) -> device decode -> 5-run deduplicate, timed from file bytes in HBM"}
-    for codec in ("none", "zstd"):
+                   "page V1, 160 KiB pages = 20 000 rows of an 8-byte column) -> device decode -> 5-run deduplicate, timed from file bytes in HBM"}
+    for codec in codecs:
         t0 = time.perf_counter()
         files, n_in, expect = c5_bucket(schema, codec)
         gen_s = time.perf_counter() - t0
@@ -700,7 +703,14 @@ def main():
         dev_ms = e0.elapsed_time(e1)
         dec_ms = ms_dec / args.steps
         dec_alg = page_bytes + in_bytes
-        roofline_decode = {"bound": "hbm", "stage": "parquet decode (page walk + levels + value walk + expand)",
+        dec_traffic = None
+        try:
+            tjd = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if args.workload == "c3" and rows == w["rows"]:
+                dec_traffic = tjd["c3_decode"]["traffic"]
+        except Exception:
+            pass
+        roofline_decode = {"bound": "hbm", "stage": "parquet decode (page walk + levels + value walk + expand)", "traffic": dec_traffic,
                            "achieved": dec_alg / (dec_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                            "frac": dec_alg / (dec_ms * 1e-3) / 1e9 / peak, "stage_ms": dec_ms,
                            "algorithmic_bytes": int(dec_alg), "encoded_page_bytes": int(page_bytes),
