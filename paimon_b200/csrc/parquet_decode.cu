@@ -1655,7 +1655,7 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        zs_ctas = (int)std::min<int64_t>((int64_t)sms * 4, (n_pages + n_dicts + kZsWarps - 1) / kZsWarps);
+        zs_ctas = (int)std::min<int64_t>((int64_t)sms * 5, (n_pages + n_dicts + kZsWarps - 1) / kZsWarps);
     }
     const size_t sb_zs = pad((size_t)zs_ctas * kZsWarps * (size_t)(zs::kMaxBlock + 64));
     unsigned char *sbuf = (unsigned char *)scratch.take(sb_pages + sb_dicts + sb_sc + 2 * sb_de + sb_ids + sb_vs + sb_zs + 256);

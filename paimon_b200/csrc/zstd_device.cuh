@@ -76,10 +76,14 @@ ZS_HD inline int highbit(uint32_t v) {                 // position of the highes
 #endif
 }
 
-// forward copy dst[i] = src[i], the regions do not overlap (or src is behind dst by at least n)
+// forward copy dst[i] = src[i], the regions do not overlap (or src is behind dst by at least n).
+// (sequences of columnar data are short — a few literal bytes, a match of the previous value's high bytes — so the
+// <= 32-byte case is one predicated byte move, no loop)
 ZS_HD inline void copy_bytes(uint8_t *dst, const uint8_t *src, int64_t n) {
 #if defined(__CUDA_ARCH__)
-    for (int64_t i = lane_id(); i < n; i += 32) dst[i] = src[i];
+    const int l = lane_id(), m = (int)n;
+    if (m <= 32) { if (l < m) dst[l] = src[l]; }
+    else for (int i = l; i < m; i += 32) dst[i] = src[i];
     __syncwarp();
 #else
     for (int64_t i = 0; i < n; i++) dst[i] = src[i];
@@ -87,18 +91,27 @@ ZS_HD inline void copy_bytes(uint8_t *dst, const uint8_t *src, int64_t n) {
 }
 ZS_HD inline void fill_bytes(uint8_t *dst, uint8_t v, int64_t n) {
 #if defined(__CUDA_ARCH__)
-    for (int64_t i = lane_id(); i < n; i += 32) dst[i] = v;
+    for (int i = lane_id(); i < (int)n; i += 32) dst[i] = v;
     __syncwarp();
 #else
     for (int64_t i = 0; i < n; i++) dst[i] = v;
 #endif
 }
-// match copy: dst[i] = dst[i - offset]; overlapping when offset < n
+// match copy: dst[i] = dst[i - offset]; overlapping when offset < n (then dst[i] = from[i mod offset])
 ZS_HD inline void copy_match(uint8_t *dst, int64_t offset, int64_t n) {
     const uint8_t *from = dst - offset;
 #if defined(__CUDA_ARCH__)
-    if (offset >= n) { for (int64_t i = lane_id(); i < n; i += 32) dst[i] = from[i]; }
-    else { for (int64_t i = lane_id(); i < n; i += 32) dst[i] = from[i % offset]; }
+    const int l = lane_id(), m = (int)n;
+    if (offset >= n) {
+        if (m <= 32) { if (l < m) dst[l] = from[l]; }
+        else for (int i = l; i < m; i += 32) dst[i] = from[i];
+    } else if (offset == 1) {
+        const uint8_t v = from[0];
+        for (int i = l; i < m; i += 32) dst[i] = v;
+    } else {
+        const uint32_t o = (uint32_t)offset;
+        for (int i = l; i < m; i += 32) dst[i] = from[(uint32_t)i % o];
+    }
     __syncwarp();
 #else
     for (int64_t i = 0; i < n; i++) dst[i] = from[i];
@@ -109,28 +122,47 @@ ZS_HD inline void copy_match(uint8_t *dst, int64_t offset, int64_t n) {
 // byte carries a 1-bit end mark above the last data bit
 struct BitsR {
     const uint8_t *p;
+    int64_t len;          // bytes in the stream
     int64_t nbits;        // bits not read yet
     int bad;
+    uint64_t w;           // cached window: stream bits [base, base + 64), refilled as the read position moves down
+    int64_t base;         // (a read costs a shift and a mask instead of up to 8 byte loads; ~2 refills per 3 sequences)
 };
 ZS_HD inline void bits_init(BitsR &b, const uint8_t *p, int64_t len) {
     b.p = p;
+    b.len = len;
     b.bad = 0;
+    b.w = 0;
+    b.base = -1;                                        // no window yet
     if (len <= 0 || p[len - 1] == 0) { b.nbits = 0; b.bad = 1; return; }
     b.nbits = 8 * (len - 1) + highbit(p[len - 1]);
 }
 // the n bits below the read position (n <= 32); positions before the start of the stream read as zero
-ZS_HD inline uint32_t bits_peek_at(const BitsR &b, int64_t pos, int n) {
+ZS_HD inline uint32_t bits_peek_at(BitsR &b, int64_t pos, int n) {
     if (n == 0) return 0;
+    const uint32_t mask = n >= 32 ? 0xffffffffu : ((1u << n) - 1);
+    if (pos >= 0) {
+        if (b.base < 0 || pos < b.base || pos + n > b.base + 64) {
+            // window whose top byte holds bit pos + n - 1: it reaches 57+ bits below the read position
+            int64_t nb = ((pos + n + 7) & ~(int64_t)7) - 64;
+            if (nb < 0) nb = 0;
+            const int64_t byte0 = nb >> 3;
+            uint64_t v = 0;
+            for (int i = 0; i < 8; i++)
+                if (byte0 + i < b.len) v |= (uint64_t)b.p[byte0 + i] << (8 * i);
+            b.w = v;
+            b.base = nb;
+        }
+        return (uint32_t)(b.w >> (pos - b.base)) & mask;
+    }
+    // (rare: the read reaches below the first bit)
+    const int shift = (int)(-pos);
+    if (shift >= n) return 0;
     uint64_t v = 0;
-    int64_t lo = pos;                                   // bit index of the lowest wanted bit
-    int shift = 0;
-    if (lo < 0) { shift = (int)(-lo); lo = 0; if (shift >= n) return 0; }
-    const int64_t byte0 = lo >> 3;
-    const int need = (int)(((pos + n + 7) >> 3) - byte0);   // bytes that hold the bits
-    for (int i = 0; i < need && i < 8; i++) v |= (uint64_t)b.p[byte0 + i] << (8 * i);
-    v >>= (lo & 7);
+    const int need = (int)((pos + n + 7) >> 3);            // bytes that hold the bits
+    for (int i = 0; i < need && i < 8; i++) v |= (uint64_t)b.p[i] << (8 * i);
     v <<= shift;
-    return (uint32_t)(v & (n >= 32 ? 0xffffffffull : ((1ull << n) - 1)));
+    return (uint32_t)v & mask;
 }
 ZS_HD inline uint32_t bits_read(BitsR &b, int n) {
     b.nbits -= n;
