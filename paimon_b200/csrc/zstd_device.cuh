@@ -122,44 +122,51 @@ ZS_HD inline void copy_match(uint8_t *dst, int64_t offset, int64_t n) {
 // byte carries a 1-bit end mark above the last data bit
 struct BitsR {
     const uint8_t *p;
-    int64_t len;          // bytes in the stream
-    int64_t nbits;        // bits not read yet
+    int len;              // bytes in the stream (a block is <= 128 KiB: bit positions fit an int)
+    int nbits;            // bits not read yet
     int bad;
     uint64_t w;           // cached window: stream bits [base, base + 64), refilled as the read position moves down
-    int64_t base;         // (a read costs a shift and a mask instead of up to 8 byte loads; ~2 refills per 3 sequences)
+    int base;             // (a read costs a shift and a mask instead of up to 8 byte loads)
 };
 ZS_HD inline void bits_init(BitsR &b, const uint8_t *p, int64_t len) {
     b.p = p;
-    b.len = len;
+    b.len = (int)len;
     b.bad = 0;
     b.w = 0;
-    b.base = -1;                                        // no window yet
-    if (len <= 0 || p[len - 1] == 0) { b.nbits = 0; b.bad = 1; return; }
-    b.nbits = 8 * (len - 1) + highbit(p[len - 1]);
+    b.base = 1 << 30;                                   // no window yet: every position is below it
+    if (len <= 0 || len > (1 << 27) || p[len - 1] == 0) { b.nbits = 0; b.bad = 1; return; }
+    b.nbits = 8 * ((int)len - 1) + highbit(p[len - 1]);
 }
 // the n bits below the read position (n <= 32); positions before the start of the stream read as zero
-ZS_HD inline uint32_t bits_peek_at(BitsR &b, int64_t pos, int n) {
+ZS_HD inline uint32_t bits_peek_at(BitsR &b, int pos, int n) {
     if (n == 0) return 0;
     const uint32_t mask = n >= 32 ? 0xffffffffu : ((1u << n) - 1);
     if (pos >= 0) {
-        if (b.base < 0 || pos < b.base || pos + n > b.base + 64) {
+        // (unsigned compare: pos below the window wraps to a huge value)
+        if ((unsigned)(pos - b.base) > (unsigned)(64 - n)) {
             // window whose top byte holds bit pos + n - 1: it reaches 57+ bits below the read position
-            int64_t nb = ((pos + n + 7) & ~(int64_t)7) - 64;
+            int nb = ((pos + n + 7) & ~7) - 64;
             if (nb < 0) nb = 0;
-            const int64_t byte0 = nb >> 3;
+            const int byte0 = nb >> 3;
+            const uint8_t *q = b.p + byte0;
             uint64_t v = 0;
-            for (int i = 0; i < 8; i++)
-                if (byte0 + i < b.len) v |= (uint64_t)b.p[byte0 + i] << (8 * i);
+            if (byte0 + 8 <= b.len) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) v |= (uint64_t)q[i] << (8 * i);
+            } else {
+                for (int i = 0; i < 8; i++)
+                    if (byte0 + i < b.len) v |= (uint64_t)q[i] << (8 * i);
+            }
             b.w = v;
             b.base = nb;
         }
         return (uint32_t)(b.w >> (pos - b.base)) & mask;
     }
     // (rare: the read reaches below the first bit)
-    const int shift = (int)(-pos);
+    const int shift = -pos;
     if (shift >= n) return 0;
     uint64_t v = 0;
-    const int need = (int)((pos + n + 7) >> 3);            // bytes that hold the bits
+    const int need = (pos + n + 7) >> 3;                   // bytes that hold the bits
     for (int i = 0; i < need && i < 8; i++) v |= (uint64_t)b.p[i] << (8 * i);
     v <<= shift;
     return (uint32_t)v & mask;
