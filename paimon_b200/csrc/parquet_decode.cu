@@ -1737,20 +1737,43 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
             static thread_local cudaStream_t side = nullptr;
             static thread_local cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
             if (!side) {
-                PG_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+                // (highest priority: its few, long-running CTAs must get their slots before the expansion's 250 k short
+                // ones fill every SM — otherwise the walk only starts when the expansion drains)
+                int prio_lo = 0, prio_hi = 0;
+                cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+                PG_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_hi));
                 PG_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
                 PG_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
             }
+            // PAIMON_GPU_TRACE=1: per-phase times of this part of the section on stderr (experiments)
+            static const bool trace = getenv("PAIMON_GPU_TRACE") != nullptr;
+            cudaEvent_t tv[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+            if (trace) for (auto &e : tv) cudaEventCreate(&e);
             PG_CUDA(cudaEventRecord(ev_fork, sm));
+            if (trace) cudaEventRecord(tv[0], sm);
             PG_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
             k_pq_walk_values<<<(np + kWvWarps * 32 - 1) / (kWvWarps * 32), kWvWarps * 32, 0, side>>>(
                 d_pages, np, d_chunks, d_vstart, d_err);
             PG_CUDA(cudaEventRecord(ev_join, side));
+            if (trace) cudaEventRecord(tv[1], side);
             k_pq_expand<<<np, kExpThreads, 0, sm>>>(d_pages, d_dicts, d_chunks, d_outs, nc, d_ids, d_vstart, d_dict_off,
                                                     d_dict_len, d_err, 1);
+            if (trace) cudaEventRecord(tv[2], sm);
             PG_CUDA(cudaStreamWaitEvent(sm, ev_join, 0));
+            if (trace) cudaEventRecord(tv[3], sm);
             k_pq_expand<<<np, kExpThreads, 0, sm>>>(d_pages, d_dicts, d_chunks, d_outs, nc, d_ids, d_vstart, d_dict_off,
                                                     d_dict_len, d_err, 2);
+            if (trace) {
+                cudaEventRecord(tv[4], sm);
+                cudaEventSynchronize(tv[4]);
+                float a = 0, b = 0, c = 0, d = 0;
+                cudaEventElapsedTime(&a, tv[0], tv[1]);
+                cudaEventElapsedTime(&b, tv[0], tv[2]);
+                cudaEventElapsedTime(&c, tv[0], tv[3]);
+                cudaEventElapsedTime(&d, tv[0], tv[4]);
+                fprintf(stderr, "[decode trace] since fork: value walk done %.2f ms, expand(no walk) done %.2f, join %.2f, expand(byte arrays) done %.2f\n", a, b, c, d);
+                for (auto &e : tv) cudaEventDestroy(e);
+            }
             launches += 3;
         } else {
             k_pq_expand<<<np, kExpThreads, 0, sm>>>(d_pages, d_dicts, d_chunks, d_outs, nc, d_ids, d_vstart, d_dict_off,

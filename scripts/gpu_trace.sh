@@ -1,0 +1,7 @@
+export PYTHONPATH=.
+echo "=== decode trace"
+PAIMON_GPU_TRACE=1 timeout 900 python bench.py --steps 3 --warmup 3 --no-e2e --no-extra --no-cpu-baseline --no-parity-sample 2>&1 | grep -E "decode trace|metric" | tail -4 | cut -c1-260
+echo "=== bench (no trace)"
+timeout 900 python bench.py --steps 5 --warmup 3 --no-e2e --no-extra --no-cpu-baseline 2>/dev/null | tail -1 | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], json.dumps(d['roofline']['phase_ms']), d['roofline_decode']['frac'], d.get('parity_sample'))"
