@@ -1732,8 +1732,8 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
     }
     if (np > 0) {
         if (n_pairs) {
-            // the value walk (one lane per page: latency-bound at low occupancy) runs beside the expansion of the pages
-            // that do not need it; the PLAIN BYTE_ARRAY pages follow when both are done
+            // the value walk (one lane per page: latency-bound at low occupancy) and the PLAIN BYTE_ARRAY pages that need it
+            // run on a side stream beside the expansion of all other pages
             static thread_local cudaStream_t side = nullptr;
             static thread_local cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
             if (!side) {
@@ -1754,15 +1754,16 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
             PG_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
             k_pq_walk_values<<<(np + kWvWarps * 32 - 1) / (kWvWarps * 32), kWvWarps * 32, 0, side>>>(
                 d_pages, np, d_chunks, d_vstart, d_err);
-            PG_CUDA(cudaEventRecord(ev_join, side));
             if (trace) cudaEventRecord(tv[1], side);
+            // the PLAIN BYTE_ARRAY pages follow their walk on the side stream; everything else expands on the main one
+            k_pq_expand<<<np, kExpThreads, 0, side>>>(d_pages, d_dicts, d_chunks, d_outs, nc, d_ids, d_vstart, d_dict_off,
+                                                      d_dict_len, d_err, 2);
+            PG_CUDA(cudaEventRecord(ev_join, side));
+            if (trace) cudaEventRecord(tv[3], side);
             k_pq_expand<<<np, kExpThreads, 0, sm>>>(d_pages, d_dicts, d_chunks, d_outs, nc, d_ids, d_vstart, d_dict_off,
                                                     d_dict_len, d_err, 1);
             if (trace) cudaEventRecord(tv[2], sm);
             PG_CUDA(cudaStreamWaitEvent(sm, ev_join, 0));
-            if (trace) cudaEventRecord(tv[3], sm);
-            k_pq_expand<<<np, kExpThreads, 0, sm>>>(d_pages, d_dicts, d_chunks, d_outs, nc, d_ids, d_vstart, d_dict_off,
-                                                    d_dict_len, d_err, 2);
             if (trace) {
                 cudaEventRecord(tv[4], sm);
                 cudaEventSynchronize(tv[4]);
@@ -1771,7 +1772,7 @@ static pg_status decode_section(const Schema *s, const std::vector<SectionFile> 
                 cudaEventElapsedTime(&b, tv[0], tv[2]);
                 cudaEventElapsedTime(&c, tv[0], tv[3]);
                 cudaEventElapsedTime(&d, tv[0], tv[4]);
-                fprintf(stderr, "[decode trace] since fork: value walk done %.2f ms, expand(no walk) done %.2f, join %.2f, expand(byte arrays) done %.2f\n", a, b, c, d);
+                fprintf(stderr, "[decode trace] since fork: value walk done %.2f ms, expand(no walk) done %.2f, expand(byte arrays) done %.2f, joined %.2f\n", a, b, c, d);
                 for (auto &e : tv) cudaEventDestroy(e);
             }
             launches += 3;
