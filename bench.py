@@ -844,8 +844,25 @@ def main():
     if not args.no_e2e and source == "parquet":
         # the files move to page-locked host memory; the device copies are dropped
         host_files = []
+        pinned = True
+        try:                                  # every rank of the node locks its files + its output arena
+            import psutil
+            local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+            need_host = (sum(sz for _, sz in images) + int(out_bytes * 1.02)) * local_world
+            if psutil.virtual_memory().available < 1.3 * need_host:
+                pinned = False                # (pageable buffers: the copies get staged by the driver, slower but safe)
+        except Exception:
+            pass
+
+        def host_buffer(nbytes):
+            if pinned:
+                try:
+                    return torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+                except RuntimeError:
+                    pass
+            return torch.empty(nbytes, dtype=torch.uint8)
         for fh, (ptr, size) in zip(enc_handles, images):
-            hb = torch.empty(size, dtype=torch.uint8, pin_memory=True)
+            hb = host_buffer(size)
             N.check(lib.pg_parquet_file_fetch(fh, hb.data_ptr(), size))
             host_files.append(hb.numpy())
             lib.pg_parquet_file_free(fh)
@@ -853,7 +870,7 @@ def main():
         rd.close()
         torch.cuda.empty_cache()
         lib.pg_trim()
-        arena = torch.empty(int(out_bytes * 1.02) + (64 << 20), dtype=torch.uint8, pin_memory=True)
+        arena = host_buffer(int(out_bytes * 1.02) + (64 << 20))
         arena_np = arena.numpy()
         hfiles = [(hf, r) for r, hf in enumerate(host_files)]
         mrs = [SortMergeReader([], spec, None, local_rank, schema=schema) for _ in range(2)]
@@ -985,6 +1002,7 @@ def main():
                       "(library upload stream) and the D2H of bucket i-1's batch (second merge handle) overlap the decode + "
                       "merge of bucket i; pinned buffers bound to the GPU's NUMA node",
                "upload_overlapped": overlap, "h2d_alone_ms": h2d_only_ms, "link_probes": link,
+               "host_buffers": "page-locked" if pinned else "pageable (not enough free host memory to lock every rank's buffers)",
                "h2d_alone_gbs": sum(len(hf) for hf in host_files) / (h2d_only_ms * 1e-3) / 1e9,
                "pcie_floor_ms": 1e3 * max(h2d, int(d2h_bytes[0])) / 55e9}
         for m_ in mrs:
