@@ -1,7 +1,4 @@
 export PYTHONPATH=.
-echo "=== TESTS"; timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -5
-echo "=== C5 probe"
-timeout 600 python scripts/c5_probe.py 2>&1 | tail -1 | python -c "
+timeout 900 python bench.py --steps 2 --warmup 3 --no-extra --no-cpu-baseline --e2e-steps 2 2>/tmp/e.log | tail -1 | python -c "
 import sys,json
-d=json.loads(sys.stdin.read())
-for k in ('run_A_none','run_B_zstd1'): print(k, {x:d[k][x] for x in ('rows_per_s','ms_per_step','decode_ms','merge_ms','data_pages','decode_frac_of_hbm_peak','parity')})"
+d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['parity_sample'], json.dumps({k:v for k,v in d['e2e'].items() if k not in ('api','sample')})[:700])"; tail -3 /tmp/e.log
