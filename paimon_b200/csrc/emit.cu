@@ -17,7 +17,9 @@
 // bitmap select, a single-winner path for deduplicate, deeper payload gathers and an L2 prefetch of the payload.  All
 // lost (C3 50-60 ms vs 45.5 ms).  What did help: pointers to the staged data are computed from the shared-memory
 // symbol at every use (picked out of a local array they became generic loads through L1TEX: -5 %), global stores /
-// loads are marked global, and the tile prologue loads its run bounds with one lane per run.
+// loads are marked global, the tile prologue loads its run bounds with one lane per run, and the pass descriptors
+// (column, ColDesc, output buffers) are staged in shared memory once per tile instead of being read from the device
+// tables at the top of every pass (two dependent global round trips in front of all 16 warps: C3 -4 %, C2 -6 %).
 #include <stdio.h>
 
 #include "device_utils.cuh"
@@ -387,10 +389,14 @@ __device__ long long g_emit_ts[64 * 256];
 
 // GAGG: the merge has aggregate functions inside sequence groups (the fold for them is compiled into its own
 // kernel variant: inlined into the common one it costs every workload registers and spills)
+struct PassEnt { ColDesc cd; pg_out_column oc; int32_t c, pad; };
+constexpr int kPassCache = 64;
+
 template <bool GAGG>
 __global__ void __launch_bounds__(kEmitThreads, 2)
 k_emit(EmitArgs ea) {
     extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ PassEnt s_pass[kPassCache];
     const int k = ea.k, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const EmitLayout L = emit_layout(k);
     auto stage_vals = [&](int s) -> unsigned char * { return smem + (size_t)s * L.stage_bytes; };
@@ -417,6 +423,12 @@ k_emit(EmitArgs ea) {
     }
     __syncthreads();
     const int tile = s_i32[0];
+    if (tid < ea.n_passes && tid < kPassCache) {
+        const int c = ea.col_order[tid];
+        s_pass[tid].c = c;
+        s_pass[tid].cd = ea.cols[c];
+        s_pass[tid].oc = ea.out_cols[c];
+    }
 #ifdef PG_EMIT_TIMING
     const bool ts_on = tile >= 2000 && tile < 2064;
     const int ts_tile = tile - 2000;
@@ -514,10 +526,13 @@ k_emit(EmitArgs ea) {
     uint32_t phase = 0;                                // bit s = parity to wait for on stage s
 
     auto col_staged = [&](const ColDesc &cd) { return cd.mode != CM_SEQ && cd.mode != CM_KIND; };
+    // pass descriptors of the tile (column, ColDesc, output buffers) come into shared memory once: read from the device
+    // tables at the top of every pass they are two dependent global round trips in front of all 16 warps
+    auto pass_col = [&](int ci) -> int { return ci < kPassCache ? s_pass[ci].c : ea.col_order[ci]; };
+    auto pass_desc = [&](int ci, int c) -> ColDesc { return ci < kPassCache ? s_pass[ci].cd : ea.cols[c]; };
 
     // issue the bulk copies of column c into stage s (warp 0; lane r = run r)
-    auto issue = [&](int c, int s) {
-        const ColDesc cd = ea.cols[c];
+    auto issue = [&](int c, const ColDesc &cd, int s) {
         if (!col_staged(cd)) return;
         // the stage was last touched through the generic proxy (scratch + validity words)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -560,18 +575,18 @@ k_emit(EmitArgs ea) {
     // ---- prologue: column 0
     // columns are walked in ea.col_order (var-len columns first: their look-back then happens while the
     // CTAs of a wave are still close together in time)
-    if (warp == 0 && ncols > 0) issue(ea.col_order[0], 0);
-    if (tid < n_vw && ncols > 0) stage_vw(0)[tid] = load_vw(ea.col_order[0]);
+    if (warp == 0 && ncols > 0) issue(pass_col(0), pass_desc(0, pass_col(0)), 0);
+    if (tid < n_vw && ncols > 0) stage_vw(0)[tid] = load_vw(pass_col(0));
     __syncthreads();
 
     TS(1);
     for (int ci = 0; ci < ncols; ci++) {
         const int s = ci & 1;
-        const int c = ea.col_order[ci];
-        const int cn = ci + 1 < ncols ? ea.col_order[ci + 1] : -1;
-        const ColDesc cd = ea.cols[c];
-        const pg_out_column oc = ea.out_cols[c];
-        if (warp == 0 && cn >= 0) issue(cn, s ^ 1);
+        const int c = pass_col(ci);
+        const int cn = ci + 1 < ncols ? pass_col(ci + 1) : -1;
+        const ColDesc cd = pass_desc(ci, c);
+        const pg_out_column oc = ci < kPassCache ? s_pass[ci].oc : ea.out_cols[c];
+        if (warp == 0 && cn >= 0) issue(cn, pass_desc(ci + 1, cn), s ^ 1);
         uint32_t next_vw = (cn >= 0 && tid < n_vw) ? load_vw(cn) : 0;
         if (col_staged(cd)) {
             mbar_wait(&mbar[s], (phase >> s) & 1);
